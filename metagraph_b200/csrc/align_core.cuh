@@ -1,0 +1,1523 @@
+// Seed-and-extend for one read, executed by one warp.
+//
+// Restates, on device data structures, the reference's per-read pipeline
+//   DBGAligner::align_batch / align_both_directions / align_core   (dbg_aligner.cpp:251-384, 531-758)
+//   ExactSeeder / MEMSeeder(UniMEM) / SuffixSeeder                 (aligner_seeder_methods.cpp:37-424)
+//   SeedFilteringExtender + DefaultColumnExtender                  (aligner_extender_methods.cpp:66-1034)
+//   Alignment::{trim_offset, reverse_complement (RCDBG)}           (alignment.cpp:177-190, 540-561)
+//   AlignmentAggregator (unlabeled queue)                          (aligner_aggregator.hpp:59-202)
+// Execution model: scalar state is warp-uniform (every lane holds the same value and takes
+// the same branch; scalar stores are issued by all lanes with identical values), DP columns
+// and copies are strided over the 32 lanes, rank/select go through the quad primitives of
+// index.cuh. All dynamic containers live in a per-warp arena in HBM (no malloc); running out
+// of arena marks the read MGB_READ_OVERFLOW and the host re-runs it with a larger arena.
+#pragma once
+#include "index.cuh"
+#include "seed_core.cuh"
+
+namespace mgb {
+
+// ------------------------------------------------------------------------------------
+// Configuration as consumed on the device (DBGAlignerConfig, aligner_config.hpp:18-94)
+// ------------------------------------------------------------------------------------
+struct DevConfig {
+    uint32_t num_alternative_paths;
+    uint32_t min_seed_length;      // after the DBGAligner ctor normalisation (dbg_aligner.cpp:37-48)
+    uint32_t max_seed_length;      // saturated to 0xffffffff
+    uint64_t max_num_seeds_per_locus;
+    score_t min_cell_score, min_path_score, xdrop;
+    double min_exact_match, max_nodes_per_seq_char, max_ram_per_alignment, rel_score_cutoff;
+    int32_t gap_open, gap_ext, left_end_bonus, right_end_bonus;
+    uint8_t forward_and_reverse_complement, allow_left_trim, no_backtrack, pad0;
+    int8_t diag[128];              // score_matrix[c][c]
+    int8_t prof[kSigmaDNA + 1][128];   // score_matrix[decode(i)][q], row sigma = '\0'
+    uint8_t opmatch[kSigmaDNA + 1][128]; // kCharToOp[decode(i)][q] == MATCH (aligner_cigar.cpp:11-51)
+};
+
+static constexpr int kMaxAlt = 4;            // supported num_alternative_paths
+static constexpr int kMaxOut = 8;            // max outgoing edges handled per column (sigma <= 8)
+
+enum ReadStatus : uint32_t { MGB_READ_OK = 0, MGB_READ_OVERFLOW = 1 };
+
+// Capacities of the per-warp arena (host chooses them from the batch's longest read).
+struct Caps {
+    uint32_t L_max;            // longest read
+    uint32_t max_cols;         // DP table columns
+    uint32_t max_cells;        // DP cells (each = S,E,F)
+    uint32_t hash_size;        // conv-checker hash slots, power of two
+    uint32_t max_conv_entries;
+    uint32_t max_conv_cells;
+    uint32_t max_seeds;        // per strand
+    uint32_t aln_nodes, aln_seq, aln_cigar;   // per alignment slot
+};
+
+struct ColMeta {              // DefaultColumnExtender::DPTColumn (extender.hpp:129-147)
+    uint64_t node;
+    uint64_t trail;           // rc graph only: bwd^{k-2}(node) if known, else 0 (NodeFirstCache role)
+    uint32_t parent;
+    uint32_t cells_off;       // index of the first cell in the cells arena
+    int32_t size;             // S.size()
+    int32_t trim;
+    int32_t offset;
+    int32_t max_pos;
+    int32_t score;            // added score (always 0 on real edges)
+    uint8_t c;                // upper-cased character
+    uint8_t is_tip;
+    uint8_t started;          // prev_starts membership
+    uint8_t pad;
+};
+
+struct HeapItem { int32_t score, neg_off_diag; uint32_t idx; int32_t max_score; };
+struct BtStart { int32_t score, neg_off_diag, neg_i, pos; };
+struct ConvSlot { uint64_t key; uint32_t epoch; uint32_t entry; };
+struct ConvEntry { int32_t start, size, seg_start, seg_cap; uint32_t seg_off; uint32_t pad; };
+struct SeedRec { uint32_t clip, len, offset, n_nodes; uint64_t node0; uint32_t alive, pad; };
+
+struct AlnHdr {
+    int32_t q_len;        // query_view size
+    int32_t n_nodes, seq_len, n_cigar;
+    int32_t score;
+    uint32_t offset;
+    uint32_t orientation;
+    uint32_t used;
+};
+
+struct AlnSlot { AlnHdr *h; uint64_t *nodes; char *seq; uint32_t *cigar; };
+
+struct ConvTable {
+    ConvSlot *slots; ConvEntry *entries; score_t *cells;
+    uint32_t epoch, n_entries, cells_used;
+};
+
+// Per-read output record header; followed in the output heap by packed alignments.
+struct OutAln {
+    uint32_t orientation; int32_t score; uint32_t offset; uint32_t query_begin, query_len;
+    uint32_t n_nodes, seq_len, n_cigar;
+};
+
+struct ReadStats { uint32_t num_seeds, num_extensions, num_explored_nodes, dp_columns; uint64_t dp_cells; };
+
+static constexpr int kNumSlots = 3 * kMaxAlt + 2;   // seed, ext[alt], bwd[alt], agg[alt], tmp
+enum { SLOT_SEED = 0, SLOT_TMP = 1, SLOT_EXT = 2, SLOT_BWD = 2 + kMaxAlt, SLOT_AGG = 2 + 2 * kMaxAlt };
+
+// ------------------------------------------------------------------------------------
+// Arena carving (shared by host sizing code and the kernel)
+// ------------------------------------------------------------------------------------
+MGB_HOSTDEV size_t align_up(size_t x) { return (x + 15) & ~(size_t)15; }
+
+struct WarpMem {
+    ColMeta *cols; score_t *cells; HeapItem *heap; HeapItem *next_nodes;
+    BtStart *starts; ConvTable conv[2]; SeedRec *seeds[2]; int32_t *psum[2];
+    AlnSlot slots[kNumSlots];
+    uint32_t *bt_ops; uint64_t *bt_path; char *bt_seq;
+    uint8_t *sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
+    uint32_t *epoch_store;  // conv-table epochs survive across the reads a warp processes
+
+    MGB_HOSTDEV size_t carve(char *base, const Caps &c) {
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return base ? base + r : (char*)nullptr; };
+        epoch_store = (uint32_t*)take(16);
+        cols = (ColMeta*)take(sizeof(ColMeta) * c.max_cols);
+        cells = (score_t*)take(sizeof(score_t) * 3 * (size_t)c.max_cells);
+        heap = (HeapItem*)take(sizeof(HeapItem) * c.max_cols);
+        next_nodes = (HeapItem*)take(sizeof(HeapItem) * c.max_cols);
+        starts = (BtStart*)take(sizeof(BtStart) * 2 * c.max_cols);
+        for (int e = 0; e < 2; ++e) {
+            conv[e].slots = (ConvSlot*)take(sizeof(ConvSlot) * c.hash_size);
+            conv[e].entries = (ConvEntry*)take(sizeof(ConvEntry) * c.max_conv_entries);
+            conv[e].cells = (score_t*)take(sizeof(score_t) * c.max_conv_cells);
+            seeds[e] = (SeedRec*)take(sizeof(SeedRec) * c.max_seeds);
+            psum[e] = (int32_t*)take(sizeof(int32_t) * (c.L_max + 8));
+        }
+        for (int s = 0; s < kNumSlots; ++s) {
+            slots[s].h = (AlnHdr*)take(sizeof(AlnHdr));
+            slots[s].nodes = (uint64_t*)take(8 * (size_t)c.aln_nodes);
+            slots[s].seq = (char*)take(c.aln_seq);
+            slots[s].cigar = (uint32_t*)take(4 * (size_t)c.aln_cigar);
+        }
+        bt_ops = (uint32_t*)take(4 * (size_t)c.aln_cigar);
+        bt_path = (uint64_t*)take(8 * (size_t)c.aln_nodes);
+        bt_seq = (char*)take(c.aln_seq);
+        sfx_min = (uint8_t*)take(c.L_max + 8);
+        return o;
+    }
+};
+
+MGB_HOSTDEV uint32_t cig_pack(uint32_t op, uint32_t len) { return (len << 3) | op; }
+MGB_HOSTDEV uint32_t cig_op(uint32_t x) { return x & 7u; }
+MGB_HOSTDEV uint32_t cig_len(uint32_t x) { return x >> 3; }
+enum { OP_S = 0, OP_X = 1, OP_M = 2, OP_D = 3, OP_I = 4, OP_G = 5 };
+
+// ------------------------------------------------------------------------------------
+// The per-read aligner
+// ------------------------------------------------------------------------------------
+struct ReadAligner {
+    const IndexView &ix;
+    const DevConfig &cfg;
+    const Caps &caps;
+    WarpMem &m;
+
+    // read
+    int L;
+    const char *q[2];            // upper-cased forward / reverse-complement strings
+    const uint8_t *codes[2];     // alphabet codes of q[s]
+    const uint64_t *qnodes[2];   // map_to_nodes_sequentially per strand (may be nullptr if L < k)
+    int n_seeds[2];
+    uint32_t num_matching[2];
+
+    bool overflow;
+    ReadStats stats;
+
+    // extender state (index = query strand the extender was built on)
+    uint32_t ext_table_cap[2];   // std::vector<DPTColumn>::capacity() emulation
+    uint32_t ext_num_ext[2];
+    uint32_t ext_explored_prev[2];
+    bool ext_rc[2];              // set_graph(): true = RCDBG view
+
+    // DP table of the extension in flight
+    uint32_t n_cols;
+    uint32_t cells_used;
+    int n_agg;
+
+    MGB_HD ReadAligner(const IndexView &ix_, const DevConfig &cfg_, const Caps &caps_, WarpMem &m_)
+        : ix(ix_), cfg(cfg_), caps(caps_), m(m_) {}
+
+    // --------------------------------------------------------------------------------
+    // small helpers
+    // --------------------------------------------------------------------------------
+    MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j)]; }
+    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j) + 1]; }
+    MGB_HD score_t& cellF(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j) + 2]; }
+
+    MGB_HD int prof_score(int s, int x, int code) const {   // profile_score_[code][x]
+        return (x >= 1 && x <= L) ? cfg.prof[code][(uint8_t)q[s][x - 1]] : 0;
+    }
+    MGB_HD bool prof_is_match(int s, int x, int code) const {
+        return (x >= 1 && x <= L) ? cfg.opmatch[code][(uint8_t)q[s][x - 1]] : false;
+    }
+    MGB_HD uint32_t encode_char(uint8_t ch) const { return encode_dna(ch); }
+
+    MGB_HD int aln_clipping(const AlnSlot &a) const {
+        return a.h->n_cigar && cig_op(a.cigar[0]) == OP_S ? (int)cig_len(a.cigar[0]) : 0;
+    }
+    MGB_HD int aln_end_clipping(const AlnSlot &a) const {
+        int n = a.h->n_cigar;
+        return n && cig_op(a.cigar[n - 1]) == OP_S ? (int)cig_len(a.cigar[n - 1]) : 0;
+    }
+
+    MGB_HD void copy_slot(int dst, int src) {
+        AlnSlot &d = m.slots[dst]; const AlnSlot &s = m.slots[src];
+        wsync();
+        AlnHdr h = *s.h;
+        for (int i = wlane(); i < h.n_nodes; i += kWarp) d.nodes[i] = s.nodes[i];
+        for (int i = wlane(); i < h.seq_len; i += kWarp) d.seq[i] = s.seq[i];
+        for (int i = wlane(); i < h.n_cigar; i += kWarp) d.cigar[i] = s.cigar[i];
+        *d.h = h;
+        wsync();
+    }
+
+    // Alignment(const Seed&, config) (alignment.hpp:154-165) materialised into a slot
+    MGB_HD void seed_to_slot(int slot, int s, const SeedRec &sd) {
+        AlnSlot &a = m.slots[slot];
+        wsync();
+        for (int i = wlane(); i < (int)sd.n_nodes; i += kWarp)
+            a.nodes[i] = sd.n_nodes == 1 ? sd.node0 : qnodes[s][sd.clip + i];
+        for (int i = wlane(); i < (int)sd.len; i += kWarp) a.seq[i] = q[s][sd.clip + i];
+        int end_clip = L - (int)sd.clip - (int)sd.len;
+        int nc = 0;
+        if (sd.clip) a.cigar[nc++] = cig_pack(OP_S, sd.clip);
+        a.cigar[nc++] = cig_pack(OP_M, sd.len);
+        if (end_clip) a.cigar[nc++] = cig_pack(OP_S, end_clip);
+        AlnHdr h;
+        h.q_len = sd.len; h.n_nodes = sd.n_nodes; h.seq_len = sd.len; h.n_cigar = nc;
+        h.score = m.psum[s][sd.clip] - m.psum[s][sd.clip + sd.len]
+                + (!sd.clip ? cfg.left_end_bonus : 0) + (!end_clip ? cfg.right_end_bonus : 0);
+        h.offset = sd.offset; h.orientation = s; h.used = 1;
+        *a.h = h;
+        wsync();
+    }
+
+    // alignment.cpp:177-190 (no npos nodes on this path)
+    MGB_HD void trim_offset(int slot) {
+        AlnSlot &a = m.slots[slot];
+        AlnHdr h = *a.h;
+        if (!h.offset || h.n_nodes <= 1) return;
+        int trim = imin((int)h.offset, h.n_nodes - 1);
+        wsync();
+        // shift nodes down by `trim` (chunked so that reads precede overlapping writes)
+        for (int base = 0; base < h.n_nodes - trim; base += kWarp) {
+            int i = base + wlane();
+            uint64_t v = i < h.n_nodes - trim ? a.nodes[i + trim] : 0;
+            wsync();
+            if (i < h.n_nodes - trim) a.nodes[i] = v;
+            wsync();
+        }
+        h.offset -= trim; h.n_nodes -= trim;
+        *a.h = h;
+        wsync();
+    }
+
+    // alignment.cpp:540-561, RCDBG branch. Returns false if the alignment became empty.
+    MGB_HD bool reverse_complement_slot(int slot) {
+        trim_offset(slot);
+        AlnSlot &a = m.slots[slot];
+        AlnHdr h = *a.h;
+        if (h.offset) { h.used = 0; h.n_nodes = 0; *a.h = h; return false; }
+        wsync();
+        for (int base = 0; base < (h.n_cigar + 1) / 2; base += kWarp) {
+            int i = base + wlane();
+            if (i < h.n_cigar / 2) {
+                uint32_t x = a.cigar[i], y = a.cigar[h.n_cigar - 1 - i];
+                a.cigar[i] = y; a.cigar[h.n_cigar - 1 - i] = x;
+            }
+        }
+        for (int base = 0; base < (h.n_nodes + 1) / 2; base += kWarp) {
+            int i = base + wlane();
+            if (i < h.n_nodes / 2) {
+                uint64_t x = a.nodes[i], y = a.nodes[h.n_nodes - 1 - i];
+                a.nodes[i] = y; a.nodes[h.n_nodes - 1 - i] = x;
+            }
+        }
+        for (int base = 0; base < (h.seq_len + 1) / 2; base += kWarp) {
+            int i = base + wlane();
+            if (i < (h.seq_len + 1) / 2) {
+                int jj = h.seq_len - 1 - i;
+                char x = complement_char(a.seq[i]), y = complement_char(a.seq[jj]);
+                a.seq[i] = y; a.seq[jj] = x;
+            }
+        }
+        h.orientation ^= 1u;
+        *a.h = h;
+        wsync();
+        h.q_len = L - aln_clipping(a) - aln_end_clipping(a);
+        *a.h = h;
+        wsync();
+        return true;
+    }
+
+    // --------------------------------------------------------------------------------
+    // graph access for the extender
+    // --------------------------------------------------------------------------------
+    // DBGSuccinct::call_outgoing_kmers (dbg_succinct.cpp:110-139); '$' targets are skipped
+    // as the extender does (extender.cpp:381-384). Returns the number of (node, char) pairs.
+    MGB_HD int outgoing_fwd(uint64_t node, uint64_t *nodes, uint8_t *chars) {
+        LineCache lc;
+        uint32_t w = 0;
+        if (node > 1) {
+            w = lc.get_W(ix, node);
+            if (!w) return 0;
+        }
+        uint64_t lst = fwd(ix, lc, node, w % ix.sigma);
+        uint64_t first = pred_last(ix, lc, lst - 1) + 1;
+        int n = 0;
+        for (uint64_t i = first > 2 ? first : 2; i <= lst; ++i) {
+            if (!in_graph(ix, i)) continue;
+            uint32_t c = lc.get_W(ix, i) % ix.sigma;
+            if (c == 0) continue;                    // '$'
+            if (n < kMaxOut) { nodes[n] = i; chars[n] = "$ACGT"[c]; }
+            ++n;
+        }
+        return n;
+    }
+
+    // first character of the k-mer of BOSS edge e (NodeFirstCache::get_first_char,
+    // node_first_cache.cpp:10-24): node_last_value(bwd^{k-2}(e)); *trail = bwd^{k-2}(e)
+    MGB_HD uint32_t first_char_full(uint64_t e, uint64_t *trail) {
+        LineCache lc;
+        uint64_t i = e;
+        for (uint32_t s = 0; s + 2 < ix.k; ++s) i = bwd(ix, lc, i);
+        *trail = i;
+        return node_last_value(ix, i);
+    }
+
+    // RCDBG::call_outgoing_kmers (rc_dbg.hpp:86-97) -> NodeFirstCache::call_incoming_kmers
+    // (node_first_cache.cpp:40-50): incoming nodes in call_incoming_to_target order
+    // (boss.cpp:766-786) with the complement of their first character.
+    MGB_HD int outgoing_rc(uint64_t node, uint64_t node_trail, uint64_t *nodes, uint8_t *chars,
+                           uint64_t *trails) {
+        LineCache lc;
+        uint64_t x = bwd(ix, lc, node);
+        uint32_t d = node_last_value(ix, node);
+        int n = 0;
+        uint64_t edge = x;
+        bool first = true;
+        while (true) {
+            if (in_graph(ix, edge)) {
+                uint64_t tr;
+                uint32_t c;
+                if (first && node_trail) {
+                    // the un-flagged incoming edge: bwd^{k-2}(bwd(node)) = bwd(bwd^{k-2}(node))
+                    LineCache l2;
+                    tr = bwd(ix, l2, node_trail);
+                    c = node_last_value(ix, tr);
+                } else {
+                    c = first_char_full(edge, &tr);
+                }
+                uint8_t ch = complement_char((uint8_t)"$ACGT"[c]);
+                if (ch != '$') {
+                    if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; trails[n] = tr; }
+                    ++n;
+                }
+            }
+            first = false;
+            if (++edge > ix.n) break;
+            uint32_t w;
+            edge = succ_W2(ix, lc, edge, d, &w);
+            if (w != d + ix.sigma) break;
+        }
+        return n;
+    }
+
+    // dbg_succinct.cpp:617-630
+    MGB_HD bool has_multiple_outgoing(uint64_t node) {
+        LineCache lc;
+        if (node == 1) return succ_last(ix, lc, 1) > 2;
+        uint32_t d = lc.get_W(ix, node) % ix.sigma;
+        if (!d) return false;
+        uint64_t t = fwd(ix, lc, node, d);
+        return !lc.get_last(ix, t - 1);
+    }
+    // dbg_succinct.cpp:662-680
+    MGB_HD bool has_single_incoming(uint64_t node) {
+        if (node == 1) return false;
+        LineCache lc;
+        uint64_t x = bwd(ix, lc, node);
+        uint32_t w = node_last_value(ix, node);
+        bool first_valid = !ix.valid || in_graph(ix, x);
+        if (x + 1 == ix.n + 1) return first_valid;
+        uint32_t wn;
+        if (first_valid) {
+            // BOSS::is_single_incoming (boss.cpp:803-816)
+            succ_W2(ix, lc, x + 1, w, &wn);
+            return wn != w + ix.sigma;
+        }
+        // num_incoming_to_target(x, w) == 2
+        int indeg = 1;
+        uint64_t e = x;
+        while (++e <= ix.n) {
+            e = succ_W2(ix, lc, e, w, &wn);
+            if (wn != w + ix.sigma) break;
+            ++indeg;
+            if (indeg > 2) break;
+        }
+        return indeg == 2;
+    }
+
+    // --------------------------------------------------------------------------------
+    // seeding (aligner_seeder_methods.cpp)
+    // --------------------------------------------------------------------------------
+    MGB_HD uint64_t qnode(int s, int i) const { return qnodes[s] ? qnodes[s][i] : 0; }
+
+    MGB_HD void push_seed(int s, uint32_t clip, uint32_t len, uint32_t off, uint32_t nn, uint64_t node0) {
+        if (n_seeds[s] >= (int)caps.max_seeds) { overflow = true; return; }
+        SeedRec r; r.clip = clip; r.len = len; r.offset = off; r.n_nodes = nn; r.node0 = node0;
+        r.alive = 1; r.pad = 0;
+        m.seeds[s][n_seeds[s]++] = r;
+    }
+
+    // ExactSeeder::num_exact_matching (:49-65)
+    MGB_HD uint32_t num_exact_matching(int s, int nk) {
+        const int k = ix.k;
+        // lane-parallel: a matched k-mer at i contributes min(k, distance to the previous match run end)
+        // sequential restatement is cheap enough (nk <= L) and avoids subtle differences
+        uint32_t nm = 0; int last_match_count = 0;
+        for (int i = 0; i < nk; ++i) {
+            if (qnode(s, i)) {
+                int j = i + 1;
+                while (j < nk && qnode(s, j)) ++j;
+                nm += k + (j - i) - 1 - last_match_count;
+                last_match_count = k;
+                i = j - 1;
+            } else if (last_match_count) {
+                --last_match_count;
+            }
+        }
+        return nm;
+    }
+
+    // ExactSeeder::get_seeds (:67-93)
+    MGB_HD void exact_seeds(int s, int nk) {
+        const int k = ix.k;
+        if (num_matching[s] < cfg.min_exact_match * L) return;
+        if (cfg.max_seed_length < (uint32_t)k) return;
+        for (int i = 0; i < nk; ++i) {
+            uint64_t nd = qnode(s, i);
+            if (nd) push_seed(s, i, k, 0, 1, nd);
+        }
+    }
+
+    // MEMSeeder::get_seeds (:360-424) with the UniMEM terminator (seeder.hpp:116-135)
+    MGB_HD void mem_seeds(int s, int nk) {
+        const int k = ix.k;
+        if ((uint32_t)k >= cfg.max_seed_length) { exact_seeds(s, nk); return; }
+        if (num_matching[s] < cfg.min_exact_match * L) return;
+        int i = 0;
+        while (i < nk) {
+            if (!qnode(s, i)) { ++i; continue; }
+            // [i, next): run of matched nodes ending at the first terminator (inclusive)
+            int j = i;
+            while (true) {
+                uint64_t nd = qnode(s, j);
+                bool term = j + 1 == nk || !qnode(s, j + 1)
+                            || has_multiple_outgoing(nd) || !has_single_incoming(nd);
+                ++j;
+                if (term) break;
+            }
+            int mem_length = (j - i) + k - 1;
+            if (mem_length >= (int)cfg.min_seed_length)
+                push_seed(s, i, mem_length, 0, j - i, qnode(s, i));
+            i = j;
+        }
+    }
+
+    // DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix (dbg_succinct.cpp:307-393),
+    // max_num_allowed_matches == SIZE_MAX; str = q[s][pos, pos+len), len <= k - 1.
+    // Appends matches as seeds at query position `pos` unless they exceed `max_per_locus`
+    // (then none is appended). Returns the number of alternative nodes found and the match
+    // length; *first_node = the first one.
+    MGB_HD int suffix_matches(int s, int pos, int len, int min_match, int *match_len,
+                              uint64_t *first_node, bool append) {
+        *match_len = 0;
+        if (len < min_match) return 0;
+        const uint8_t *cd = codes[s] + pos;
+        for (int i = 0; i < len; ++i)
+            if (cd[i] >= ix.sigma) return 0;
+        uint64_t first, lst; int matched;
+        boss_index_range(ix, cd, imin(len, (int)ix.k - 1), &first, &lst, &matched);
+        *match_len = matched;
+        if (matched < min_match) return 0;
+        LineCache lc;
+        uint64_t rank_first = rank_last(ix, lc, first);
+        uint64_t rank_lst = rank_last(ix, lc, lst);
+        int count = 0;
+        int seeds_before = n_seeds[s];
+        for (uint64_t r = rank_first; r <= rank_lst; ++r) {
+            LineCache l2;
+            uint64_t e = select_last(ix, l2, r);
+            uint64_t x = bwd(ix, l2, e);
+            uint32_t d = node_last_value(ix, e);
+            uint64_t edge = x;
+            while (true) {
+                if (in_graph(ix, edge)) {
+                    if (count == 0) *first_node = edge;
+                    ++count;
+                    if (append && (uint64_t)count <= cfg.max_num_seeds_per_locus)
+                        push_seed(s, pos, matched, ix.k - matched, 1, edge);
+                }
+                if (++edge > ix.n) break;
+                uint32_t w;
+                edge = succ_W2(ix, l2, edge, d, &w);
+                if (w != d + ix.sigma) break;
+            }
+            if (overflow) break;
+        }
+        if (append && (uint64_t)count > cfg.max_num_seeds_per_locus)
+            n_seeds[s] = seeds_before;   // locus dropped (:340-345)
+        return count;
+    }
+
+    // SuffixSeeder<UniMEMSeeder>::generate_seeds (:153-358), non-canonical part
+    MGB_HD void build_seeds(int s) {
+        const int k = ix.k;
+        const int nk = L >= k ? L - k + 1 : 0;
+        n_seeds[s] = 0;
+        num_matching[s] = num_exact_matching(s, nk);
+        if (L < (int)cfg.min_seed_length) return;
+        if ((int)cfg.min_seed_length >= k) { mem_seeds(s, nk); return; }
+
+        // base (MEM) seeds first, into the tail of the seed array as scratch: they are merged
+        // with the sub-k seeds in query order below.
+        const int n_pos = L - (int)cfg.min_seed_length + 1;
+        for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
+        wsync();
+        mem_seeds(s, nk);
+        const int n_base = n_seeds[s];
+        if (overflow) return;
+        // move base seeds to the end of the array (scratch), keep order
+        if (2 * n_base > (int)caps.max_seeds) { overflow = true; return; }
+        SeedRec *base_seeds = m.seeds[s] + caps.max_seeds - n_base;
+        wsync();
+        for (int i = n_base - 1; i >= 0; --i) base_seeds[i] = m.seeds[s][i];
+        for (int b = 0; b < n_base; ++b) {
+            SeedRec sd = base_seeds[b];
+            for (int j = 0; j < (int)sd.n_nodes; ++j) m.sfx_min[sd.clip + j] = (uint8_t)k;
+            if ((int)(sd.clip + sd.n_nodes) < n_pos) m.sfx_min[sd.clip + sd.n_nodes] = (uint8_t)k;
+        }
+        n_seeds[s] = 0;
+        int b_next = 0;
+
+        const int last_full_id = L >= k ? L - k + 1 : n_pos;
+        // state of suffix_seeds[last_full_id - 1] for the skip rule (:240-244)
+        int lf_count = 0; uint64_t lf_node = 0;
+        uint32_t nm = 0; int last_end = 0;
+        for (int i = 0; i < n_pos; ++i) {
+            int pos_first = n_seeds[s];
+            bool has_base = b_next < n_base && (int)base_seeds[b_next].clip == i;
+            int n_here = 0; bool dropped = false;
+            if (has_base) {
+                if (n_seeds[s] >= (int)caps.max_seeds - n_base) { overflow = true; return; }
+                m.seeds[s][n_seeds[s]++] = base_seeds[b_next++];
+                n_here = 1;
+            }
+            uint32_t msl_u = cfg.max_seed_length < (uint32_t)(k - 1) ? cfg.max_seed_length : (uint32_t)(k - 1);
+            int max_seed_length = imin((int)msl_u, L - i);
+            int seed_length = 0; uint64_t first_node = 0;
+            int min_here = m.sfx_min[i];
+            // first pass only counts (needed for the skip rule and the per-locus cap)
+            int cnt = suffix_matches(s, i, max_seed_length, min_here, &seed_length, &first_node, false);
+            if (overflow) return;
+            bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
+                        && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
+            if (cnt && !skip) {
+                // append_suffix_seed (:195-213) for every alternative node
+                if (seed_length > min_here) { n_seeds[s] = pos_first; n_here = 0; }
+                m.sfx_min[i] = (uint8_t)seed_length;
+                if ((uint64_t)cnt <= cfg.max_num_seeds_per_locus) {
+                    if (n_seeds[s] + cnt > (int)caps.max_seeds - n_base) { overflow = true; return; }
+                    int dummy_len; uint64_t dummy_node;
+                    suffix_matches(s, i, max_seed_length, min_here, &dummy_len, &dummy_node, true);
+                    if (overflow) return;
+                    n_here += cnt;
+                } else {
+                    dropped = n_here == 0;
+                    n_here += cnt;   // counted for the offset test below, none stored
+                }
+                int sl = seed_length;
+                for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j)
+                    m.sfx_min[j] = (uint8_t)(sl--);
+            }
+            if (i == last_full_id - 1) {
+                lf_count = n_here;
+                lf_node = n_here ? m.seeds[s][pos_first].node0 : 0;
+            }
+            // aggregation (:316-357)
+            if (n_here == 0) continue;
+            bool no_offset = has_base && n_seeds[s] > pos_first && m.seeds[s][pos_first].offset == 0;
+            if (!no_offset && !cnt) continue;
+            bool kept = no_offset || (!dropped && (uint64_t)n_here <= cfg.max_num_seeds_per_locus);
+            if (!no_offset && (uint64_t)n_here > cfg.max_num_seeds_per_locus) {
+                n_seeds[s] = pos_first;   // locus with too many alternatives is dropped
+                kept = false;
+            }
+            if (kept && n_seeds[s] > 0) {
+                const SeedRec &bk = m.seeds[s][n_seeds[s] - 1];
+                int begin = bk.clip, end = begin + (int)bk.len;
+                if (begin < last_end) nm += end - begin - (last_end - begin);
+                else nm += end - begin;
+                last_end = end;
+            }
+        }
+        num_matching[s] = nm;
+    }
+
+    // --------------------------------------------------------------------------------
+    // convergence filter (SeedFilteringExtender, extender.cpp:66-207)
+    // --------------------------------------------------------------------------------
+    MGB_HD uint32_t hash_node(uint64_t key) const {
+        key ^= key >> 33; key *= 0xff51afd7ed558ccdULL; key ^= key >> 33;
+        return (uint32_t)key & (caps.hash_size - 1);
+    }
+    MGB_HD void conv_clear(int e) {
+        ConvTable &t = m.conv[e];
+        ext_explored_prev[e] += t.n_entries;
+        t.n_entries = 0; t.cells_used = 0;
+        ++t.epoch;
+    }
+    MGB_HD int conv_find(int e, uint64_t key) {
+        ConvTable &t = m.conv[e];
+        uint32_t h = hash_node(key);
+        for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
+            ConvSlot sl = t.slots[(h + probe) & (caps.hash_size - 1)];
+            if (sl.epoch != t.epoch) return -1;
+            if (sl.key == key) return (int)sl.entry;
+        }
+        return -1;
+    }
+    // new entry covering [start, start + size), cells uninitialised
+    MGB_HD int conv_insert(int e, uint64_t key, int start, int size) {
+        ConvTable &t = m.conv[e];
+        if (t.n_entries >= caps.max_conv_entries || 2 * (t.n_entries + 1) > caps.hash_size) {
+            overflow = true; return -1;
+        }
+        int seg_start = imax(0, start - 8);
+        int seg_cap = imin(L + 1, start + size + 8) - seg_start;
+        if (t.cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return -1; }
+        ConvEntry en; en.start = start; en.size = size; en.seg_start = seg_start; en.seg_cap = seg_cap;
+        en.seg_off = t.cells_used; en.pad = 0;
+        t.cells_used += seg_cap;
+        int id = t.n_entries++;
+        t.entries[id] = en;
+        uint32_t h = hash_node(key);
+        for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
+            uint32_t p = (h + probe) & (caps.hash_size - 1);
+            if (t.slots[p].epoch != t.epoch) {
+                ConvSlot sl; sl.key = key; sl.epoch = t.epoch; sl.entry = id;
+                t.slots[p] = sl;
+                break;
+            }
+        }
+        return id;
+    }
+    // make the stored vector cover [new_start, new_end) (superset of the current range),
+    // new cells = ninf. Mirrors vec.insert(begin, n, ninf) / resize(n, ninf).
+    MGB_HD bool conv_grow(int e, int id, int new_start, int new_end) {
+        ConvTable &t = m.conv[e];
+        ConvEntry en = t.entries[id];
+        int old_start = en.start, old_end = en.start + en.size;
+        if (new_start < en.seg_start || new_end > en.seg_start + en.seg_cap) {
+            int seg_start = imax(0, new_start - 16);
+            int seg_cap = imin(L + 1, new_end + 16) - seg_start;
+            if (t.cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return false; }
+            score_t *src = t.cells + en.seg_off, *dst = t.cells + t.cells_used;
+            wsync();
+            for (int p = old_start + wlane(); p < old_end; p += kWarp)
+                dst[p - seg_start] = src[p - en.seg_start];
+            en.seg_off = t.cells_used; en.seg_start = seg_start; en.seg_cap = seg_cap;
+            t.cells_used += seg_cap;
+        }
+        score_t *c = t.cells + en.seg_off;
+        for (int p = new_start + wlane(); p < old_start; p += kWarp) c[p - en.seg_start] = kNinf;
+        for (int p = old_end + wlane(); p < new_end; p += kWarp) c[p - en.seg_start] = kNinf;
+        en.start = new_start; en.size = new_end - new_start;
+        t.entries[id] = en;
+        wsync();
+        return true;
+    }
+
+    // extender.cpp:100-156; s = cells S[s_first .. s_first + size) of column `col`
+    MGB_HD score_t update_seed_filter(int e, uint64_t node, int query_start, const ColMeta &col,
+                                      int s_first, int size) {
+        // max over the passed range
+        score_t mx = kNinf;
+        bool any = false;
+        for (int j = wlane(); j < size; j += kWarp) { mx = imax(mx, cellS(col, s_first + j)); any = true; }
+        mx = wreduce_max(mx);
+        (void)any;
+        if (node == 0) return mx;
+        uint64_t key = node + (ext_rc[e] ? ix.n : 0);
+        ConvTable &t = m.conv[e];
+        int id = conv_find(e, key);
+        if (id < 0) {
+            id = conv_insert(e, key, query_start, size);
+            if (id < 0) return kNinf;
+            ConvEntry en = t.entries[id];
+            score_t *c = t.cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp)
+                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+            wsync();
+            return mx;
+        }
+        ConvEntry en = t.entries[id];
+        if (query_start + size <= en.start) {
+            if (!conv_grow(e, id, query_start, en.start + en.size)) return kNinf;
+            en = t.entries[id];
+            score_t *c = t.cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp)
+                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+            wsync();
+            return mx;
+        }
+        if (query_start >= en.start + en.size) {
+            if (!conv_grow(e, id, en.start, query_start + size)) return kNinf;
+            en = t.entries[id];
+            score_t *c = t.cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp)
+                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+            wsync();
+            return mx;
+        }
+        int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
+        if (ns != en.start || ne != en.start + en.size) {
+            if (!conv_grow(e, id, ns, ne)) return kNinf;
+            en = t.entries[id];
+        }
+        score_t *v = t.cells + en.seg_off + (query_start - en.seg_start);
+        score_t max_changed = kNinf;
+        for (int j = wlane(); j < size; j += kWarp) {
+            score_t sj = cellS(col, s_first + j);
+            score_t vj = v[j];
+            if ((double)sj > (double)vj * cfg.rel_score_cutoff) {
+                vj = imax(vj, sj);
+                v[j] = vj;
+                max_changed = imax(max_changed, vj);
+            }
+        }
+        max_changed = wreduce_max(max_changed);
+        wsync();
+        return max_changed;
+    }
+
+    // extender.cpp:158-207
+    MGB_HD void filter_nodes(int e, uint64_t node, int query_start, int query_end) {
+        const score_t mscore = -kNinf;
+        int size = query_end - query_start;
+        ConvTable &t = m.conv[e];
+        int id = conv_find(e, node);
+        int fill_from, fill_to;          // cells set to mscore unconditionally
+        if (id < 0) {
+            id = conv_insert(e, node, query_start, size);
+            if (id < 0) return;
+            fill_from = query_start; fill_to = query_end;
+        } else {
+            ConvEntry en = t.entries[id];
+            if (query_start + size <= en.start) {
+                if (!conv_grow(e, id, query_start, en.start + en.size)) return;
+                fill_from = query_start; fill_to = query_end;
+            } else if (query_start >= en.start + en.size) {
+                if (!conv_grow(e, id, en.start, query_start + size)) return;
+                fill_from = query_start; fill_to = query_end;
+            } else {
+                int ns = imin(query_start, en.start), ne = imax(query_end, en.start + en.size);
+                if (ns != en.start || ne != en.start + en.size)
+                    if (!conv_grow(e, id, ns, ne)) return;
+                // mscore > v[j] for every representable v except mscore itself
+                fill_from = query_start; fill_to = query_end;
+            }
+        }
+        ConvEntry en = t.entries[id];
+        score_t *c = t.cells + en.seg_off;
+        for (int p = fill_from + wlane(); p < fill_to; p += kWarp) c[p - en.seg_start] = mscore;
+        wsync();
+    }
+
+    // extender.cpp:66-88
+    MGB_HD bool check_seed_vals(int e, uint64_t last_node, int pos, score_t score) {
+        uint64_t key = last_node + (ext_rc[e] ? ix.n : 0);
+        int id = conv_find(e, key);
+        if (id < 0) return true;
+        ConvEntry en = m.conv[e].entries[id];
+        if (pos < en.start || pos - en.start >= en.size) return true;
+        return m.conv[e].cells[en.seg_off + (pos - en.seg_start)] < score;
+    }
+
+    // --------------------------------------------------------------------------------
+    // DP table
+    // --------------------------------------------------------------------------------
+    MGB_HD bool heap_less(const HeapItem &a, const HeapItem &b) const {   // std::less<TableIt>
+        if (a.score != b.score) return a.score < b.score;
+        if (a.neg_off_diag != b.neg_off_diag) return a.neg_off_diag < b.neg_off_diag;
+        if (a.idx != b.idx) return a.idx < b.idx;
+        return a.max_score < b.max_score;
+    }
+    MGB_HD void heap_push(int &n, HeapItem it) {
+        int i = n++;
+        while (i > 0) {
+            int p = (i - 1) >> 1;
+            HeapItem pi = m.heap[p];
+            if (!heap_less(pi, it)) break;
+            m.heap[i] = pi;
+            i = p;
+        }
+        m.heap[i] = it;
+    }
+    MGB_HD HeapItem heap_pop(int &n) {
+        HeapItem top = m.heap[0];
+        HeapItem last = m.heap[--n];
+        int i = 0;
+        while (true) {
+            int l = 2 * i + 1, r = l + 1;
+            if (l >= n) break;
+            int c = l;
+            if (r < n && heap_less(m.heap[l], m.heap[r])) c = r;
+            HeapItem ci = m.heap[c];
+            if (!heap_less(last, ci)) break;
+            m.heap[i] = ci;
+            i = c;
+        }
+        if (n > 0) m.heap[i] = last;
+        return top;
+    }
+
+    // allocate a column with `size` cells and room to grow to `max_final` (+ padding)
+    MGB_HD bool new_column(int size, int max_final, ColMeta *out) {
+        if (n_cols >= caps.max_cols || (uint64_t)cells_used + max_final + 5 > caps.max_cells) {
+            overflow = true; return false;
+        }
+        out->cells_off = cells_used;
+        out->size = size;
+        // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
+        for (int j = wlane(); j < size + 5; j += kWarp) {
+            size_t b = 3 * ((size_t)cells_used + j);
+            m.cells[b] = kNinf; m.cells[b + 1] = kNinf; m.cells[b + 2] = kNinf;
+        }
+        wsync();
+        return true;
+    }
+
+    // std::vector<score_t> capacity after DPTColumn::create(size0) + p push_backs + reserve(size + 5)
+    MGB_HD static uint32_t vec_capacity(int size0, int size_final) {
+        uint32_t cap = size0 + 5;
+        if (size_final == size0) return cap;
+        while ((uint32_t)size_final > cap) cap *= 2;
+        if ((uint32_t)size_final + 5 > cap) cap = size_final + 5;
+        return cap;
+    }
+
+    // extend_ins_end (extender.cpp:293-328); returns the new size
+    MGB_HD int extend_ins_end(ColMeta &col, int max_size, score_t cutoff) {
+        int size = col.size;
+        if (size >= max_size) return size;
+        score_t ins = imax(cellS(col, size - 1) + cfg.gap_open, cellE(col, size - 1) + cfg.gap_ext);
+        if (ins < cutoff) return size;
+        int64_t extra = cfg.gap_ext < 0 ? ((int64_t)ins - cutoff) / (-cfg.gap_ext) : (int64_t)0x7fffffff;
+        int cnt = 1 + (int)(extra < (int64_t)(max_size - size - 1) ? extra : (int64_t)(max_size - size - 1));
+        for (int t = wlane(); t < cnt + 5; t += kWarp) {
+            size_t b = 3 * ((size_t)col.cells_off + size + t);
+            score_t v = t < cnt ? ins + t * cfg.gap_ext : kNinf;
+            m.cells[b] = v; m.cells[b + 1] = v; m.cells[b + 2] = kNinf;
+        }
+        wsync();
+        return size + cnt;
+    }
+
+    // update_column (extender.cpp:209-290), restated as a max-plus scan
+    MGB_HD void update_column(int s, const ColMeta &par, ColMeta &col, int prev_end, int start,
+                              score_t cutoff, int code) {
+        const int trim = col.trim;
+        const int n = prev_end - trim;                 // parent rows inside the band
+        const int n4 = (n + 3) & ~3;
+        const int shift = trim - par.trim;
+        const score_t go = cfg.gap_open, ge = cfg.gap_ext, add = col.score;
+        const bool use_del = col.offset > 1;
+        int carry = kNinf + ge;                        // a[-1] = E[0] + ge, E[0] = ninf
+        for (int base = 0; base < n4; base += kWarp) {
+            int j = base + wlane();
+            bool act = j < n4;
+            score_t mval = kNinf, del = kNinf;
+            if (act) {
+                score_t match = kNinf;
+                if (j) match = cellS(par, shift + j - 1) + prof_score(s, start + trim + j, code) + add;
+                if (use_del)
+                    del = imax(cellS(par, shift + j) + go, cellF(par, shift + j) + ge) + add;
+                mval = imax(match, del);
+            }
+            // a[j] = m[j] + go - j*ge ; E[j+1] = prefmax(a)[j] + j*ge
+            int a = act ? mval + go - j * ge : INT32_MIN;
+            int incl = wscan_max(a);
+            incl = imax(incl, carry);
+            int excl = wshfl_up1(incl, carry);         // prefix max over i < j (incl. a[-1])
+            if (act) {
+                score_t e_j = j ? excl + (j - 1) * ge : kNinf;    // E[j]
+                score_t e_next = incl + j * ge;                   // E[j + 1]
+                score_t sv = imax(mval, e_j);
+                sv = sv > cutoff - 1 ? sv : kNinf;
+                cellF(col, j) = del;
+                cellE(col, j + 1) = e_next;
+                cellS(col, j) = sv;
+            }
+            carry = wbcast(incl, kWarp - 1);
+        }
+        wsync();
+        if (col.size > imax(1, n)) {                   // scalar tail (:284-289)
+            int j = col.size - 1;
+            score_t t = imax(cellS(par, shift + j - 1) + add + prof_score(s, start + trim + j, code),
+                             cellE(col, j));
+            if (t >= cutoff) cellS(col, j) = t;
+        }
+        wsync();
+    }
+
+    // --------------------------------------------------------------------------------
+    // DefaultColumnExtender::extend (extender.cpp:412-772) + backtrack (:800-1034)
+    //   e      extender (query strand) index, seed in slot `seed_slot`
+    //   results are written to slots out_base .. out_base + n_out
+    // --------------------------------------------------------------------------------
+    MGB_HD int extend(int e, int seed_slot, score_t min_path_score, bool force_fixed_seed, int out_base) {
+        const int s = e;                                 // query strand of this extender
+        const AlnSlot &seed = m.slots[seed_slot];
+        const AlnHdr sh = *seed.h;
+        const bool rc = ext_rc[e];
+        const int K = ix.k;
+        ++ext_num_ext[e];
+        min_path_score = imax(0, min_path_score);
+        n_cols = 0; cells_used = 0;
+
+        const score_t xdrop = cfg.xdrop;
+        score_t cutoff = imax(-xdrop, kNinf + 1);
+        const int start = aln_clipping(seed);
+        const int wlen = L - start;                       // |window|
+        const int seed_off_m1 = (int)sh.offset - 1;       // seed_offset
+        const int seed_seq_len = sh.seq_len;
+        const score_t partial_sum_offset = m.psum[s][start + wlen];
+
+        // root column (:455-470)
+        {
+            ColMeta root;
+            if (!new_column(1, wlen + 1, &root)) return 0;
+            root.node = seed.nodes[0]; root.trail = 0; root.parent = 0xffffffffu; root.c = 0;
+            root.offset = seed_off_m1; root.max_pos = 0; root.trim = 0; root.score = 0;
+            root.is_tip = 0; root.started = 0; root.pad = 0;
+            cellS(root, 0) = cfg.left_end_bonus && !start ? cfg.left_end_bonus : 0;
+            wsync();
+            int size0 = root.size;
+            root.size = extend_ins_end(root, wlen + 1, cutoff);
+            cells_used += root.size + 5;
+            m.cols[n_cols++] = root;
+            if (n_cols > ext_table_cap[e]) ext_table_cap[e] = ext_table_cap[e] ? 2 * ext_table_cap[e] : 1;
+            stats.dp_cells += root.size; ++stats.dp_columns;
+            table_size_bytes = 136ull * ext_table_cap[e] + 3ull * vec_capacity(size0, root.size) * 4;
+        }
+
+        score_t min_cell_score = 0, best_score = 0;
+        int heap_n = 0, nn_n = 0;
+        { HeapItem r0; r0.score = 0; r0.neg_off_diag = 0; r0.idx = 0; r0.max_score = 0; heap_push(heap_n, r0); }
+
+        while (heap_n) {
+            nn_n = 0;
+            m.next_nodes[nn_n++] = heap_pop(heap_n);
+            while (heap_n && m.heap[0].score == m.next_nodes[nn_n - 1].score)
+                m.next_nodes[nn_n++] = heap_pop(heap_n);
+
+            while (nn_n) {
+                const uint32_t i = m.next_nodes[--nn_n].idx;
+                ColMeta par = m.cols[i];
+                const int next_offset = par.offset + 1;
+                const bool in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
+
+                if (cellS(par, par.max_pos - par.trim) < best_score) {
+                    double node_counter = (double)n_cols;
+                    if (node_counter / wlen >= cfg.max_nodes_per_seq_char) {
+                        heap_n = 0; nn_n = 0;            // global_xdrop
+                        continue;
+                    }
+                    if ((double)table_size_bytes / 1000000 > cfg.max_ram_per_alignment) {
+                        heap_n = 0; nn_n = 0;
+                        continue;
+                    }
+                }
+                // band within the xdrop cutoff (:549-560)
+                int begin, prev_end;
+                {
+                    int lo = 0x7fffffff, hi = -1;
+                    for (int j = wlane(); j < par.size; j += kWarp) {
+                        if (cellS(par, j) >= cutoff) { lo = imin(lo, j); hi = imax(hi, j); }
+                    }
+                    lo = wreduce_min(lo); hi = wreduce_max(hi);
+                    if (hi < 0) continue;                 // prev_end <= begin
+                    begin = lo + par.trim; prev_end = hi + 1 + par.trim;
+                }
+
+                // call_outgoing (:330-387)
+                uint64_t out_nodes[kMaxOut]; uint8_t out_chars[kMaxOut]; uint64_t out_trails[kMaxOut];
+                score_t out_scores[kMaxOut];
+                int n_out = 0;
+                {
+                    uint32_t seed_pos = (uint32_t)(next_offset - (int)sh.offset);
+                    if (in_seed && next_offset < K) {
+                        out_nodes[0] = seed.nodes[0]; out_chars[0] = seed.seq[seed_pos];
+                        out_trails[0] = 0; out_scores[0] = 0; n_out = 1;
+                    } else if (in_seed && force_fixed_seed) {
+                        int node_i = next_offset - K + 1;
+                        uint64_t next_node = seed.nodes[node_i];
+                        out_nodes[0] = next_node; out_chars[0] = seed.seq[seed_pos]; out_trails[0] = 0;
+                        out_scores[0] = next_node ? 0 : (!par.node ? cfg.gap_ext : cfg.gap_open);
+                        n_out = 1;
+                    } else if (!rc) {
+                        n_out = outgoing_fwd(par.node, out_nodes, out_chars);
+                        for (int t = 0; t < kMaxOut; ++t) { out_scores[t] = 0; out_trails[t] = 0; }
+                    } else {
+                        n_out = outgoing_rc(par.node, par.trail, out_nodes, out_chars, out_trails);
+                        for (int t = 0; t < kMaxOut; ++t) out_scores[t] = 0;
+                    }
+                    if (n_out > kMaxOut) { overflow = true; return 0; }
+                }
+                if (n_out == 0) { m.cols[i].is_tip = 1; continue; }
+
+                const int end = imin(prev_end, wlen) + 1;
+
+                for (int t = 0; t < n_out; ++t) {
+                    uint8_t ch = out_chars[t];
+                    if (ch >= 'a' && ch <= 'z') ch -= 32;      // toupper (:564)
+                    ColMeta col;
+                    if (!new_column(end - begin, wlen + 1 - begin, &col)) return 0;
+                    col.node = out_nodes[t]; col.trail = out_trails[t]; col.parent = i; col.c = ch;
+                    col.offset = next_offset; col.max_pos = begin; col.trim = begin;
+                    col.score = out_scores[t]; col.is_tip = 0; col.started = 0; col.pad = 0;
+                    const int size0 = col.size;
+                    const uint32_t cap_before = ext_table_cap[e];
+                    if (n_cols + 1 > ext_table_cap[e]) ext_table_cap[e] = ext_table_cap[e] ? 2 * ext_table_cap[e] : 1;
+                    const int code = encode_char(ch);
+
+                    update_column(s, par, col, prev_end, start, cutoff, code);
+                    col.size = extend_ins_end(col, wlen + 1 - col.trim, cutoff);
+                    stats.dp_cells += col.size; ++stats.dp_columns;
+
+                    // per-column scan (:643-669)
+                    const int diag_i = col.offset - seed_off_m1;
+                    bool has_extension = in_seed;
+                    const score_t extension_cutoff
+                        = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
+                    {
+                        score_t mn = 0x7fffffff; score_t bs = INT32_MIN; int bd = 0x7fffffff, bj = 0x7fffffff;
+                        bool he = false;
+                        for (int j = wlane(); j < col.size; j += kWarp) {
+                            score_t v = cellS(col, j);
+                            if (v != kNinf) mn = imin(mn, v);
+                            int d = iabs(j + begin - diag_i);
+                            if (v > bs || (v == bs && d < bd)) { bs = v; bd = d; bj = j; }
+                            if (v + m.psum[s][start + col.trim + j] >= extension_cutoff) he = true;
+                        }
+                        min_cell_score = imin(min_cell_score, wreduce_min(mn));
+                        score_t gbs = wreduce_max(bs);
+                        int gd = wreduce_min(bs == gbs ? bd : 0x7fffffff);
+                        int gj = wreduce_min(bs == gbs && bd == gd ? bj : 0x7fffffff);
+                        col.max_pos = gj + begin;
+                        if (!has_extension && wballot(he)) has_extension = true;
+                    }
+                    const score_t max_val = cellS(col, col.max_pos - col.trim);
+
+                    if (!in_seed && (max_val < cutoff || !has_extension)) {
+                        ext_table_cap[e] = imax(ext_table_cap[e], cap_before);   // capacity never shrinks
+                        continue;                        // pop(table.size() - 1)
+                    }
+
+                    table_size_bytes += 136ull * (ext_table_cap[e] - cap_before)
+                        + 3ull * vec_capacity(size0, col.size) * 4;
+
+                    if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
+                    best_score = imax(best_score, max_val);
+
+                    const uint32_t idx = n_cols;
+                    cells_used += col.size + 5;
+                    m.cols[n_cols++] = col;
+
+                    const int vec_offset = start + begin - (begin ? 1 : 0);
+                    const int s_first = begin ? 0 : 1;
+                    score_t converged = update_seed_filter(e, col.node, vec_offset, col, s_first,
+                                                           col.size - s_first);
+                    if (overflow) return 0;
+                    if (converged != kNinf) {
+                        HeapItem it; it.score = converged; it.neg_off_diag = -iabs(col.max_pos - diag_i);
+                        it.idx = idx; it.max_score = max_val;
+                        if (nn_n && converged == m.next_nodes[0].score) m.next_nodes[nn_n++] = it;
+                        else heap_push(heap_n, it);
+                    }
+                }
+            }
+        }
+
+        if (cfg.no_backtrack) {
+            copy_slot(out_base, seed_slot);
+            return 1;
+        }
+        int n_res = backtrack(e, seed_slot, min_path_score, start, wlen, min_cell_score, out_base);
+        for (int r = 0; r < n_res; ++r) trim_offset(out_base + r);
+        return n_res;
+    }
+
+    uint64_t table_size_bytes;
+
+    MGB_HD void cig_append(int &n_ops, uint32_t op) {       // Cigar::append(op, 1)
+        if (n_ops && cig_op(m.bt_ops[n_ops - 1]) == op) m.bt_ops[n_ops - 1] += 8u;
+        else {
+            if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return; }
+            m.bt_ops[n_ops++] = cig_pack(op, 1);
+        }
+    }
+
+    MGB_HD int backtrack(int e, int seed_slot, score_t min_path_score, int start, int wlen,
+                         score_t min_cell_score, int out_base) {
+        const int s = e;
+        const AlnSlot &seed = m.slots[seed_slot];
+        const AlnHdr sh = *seed.h;
+        const int K = ix.k;
+        const int seed_clipping = start;
+        const int seed_off_m1 = (int)sh.offset - 1;
+        const int k_minus_1 = K - 1;
+        const int last_pos = wlen;
+        const int seed_dist = imax(K, sh.seq_len) - 1;
+        const score_t min_start_score = min_path_score;
+        const int min_trace_length = K - (int)sh.offset;
+        const score_t right_end_bonus = cfg.right_end_bonus;
+
+        // start candidates (:815-867), two slots per column
+        for (uint32_t i = wlane(); i < n_cols; i += kWarp) {
+            BtStart a, b; a.score = INT32_MIN; b.score = INT32_MIN;
+            a.neg_off_diag = b.neg_off_diag = a.neg_i = b.neg_i = a.pos = b.pos = 0;
+            if (i >= 1) {
+                const ColMeta col = m.cols[i];
+                if (col.offset >= seed_dist) {
+                    const ColMeta par = m.cols[col.parent];
+                    const int code = encode_char(col.c);
+                    for (int which = 0; which < 2; ++which) {
+                        int start_pos;
+                        if (which == 0) start_pos = col.max_pos;
+                        else {
+                            if (!(col.size + col.trim == wlen + 1 && col.max_pos != last_pos)) continue;
+                            start_pos = last_pos;
+                        }
+                        if (start_pos < par.trim + 1) continue;
+                        int pos = start_pos - col.trim, pos_p = start_pos - par.trim - 1;
+                        score_t sv = cellS(col, pos), sp = cellS(par, pos_p);
+                        if (sv == kNinf || sp == kNinf) continue;
+                        score_t end_bonus = start_pos == last_pos ? right_end_bonus : 0;
+                        if (sv + end_bonus >= min_start_score) {
+                            bool is_match = sv == sp + col.score + prof_score(s, seed_clipping + start_pos, code)
+                                && prof_is_match(s, seed_clipping + start_pos, code);
+                            if (is_match || start_pos == last_pos || col.is_tip) {
+                                BtStart &o = which ? b : a;
+                                o.score = sv + end_bonus;
+                                o.neg_off_diag = -iabs(start_pos - col.offset + seed_off_m1);
+                                o.neg_i = -(int)i; o.pos = start_pos;
+                            }
+                        }
+                    }
+                }
+            }
+            m.starts[2 * i] = a; m.starts[2 * i + 1] = b;
+        }
+        wsync();
+
+        int n_ext = 0;
+        score_t best_score = INT32_MIN;
+        const uint32_t n_cand = 2 * n_cols;
+
+        while (true) {
+            // pop the largest remaining start (heap order of :873-879)
+            BtStart best; best.score = INT32_MIN; best.neg_off_diag = INT32_MIN; best.neg_i = INT32_MIN; best.pos = INT32_MIN;
+            uint32_t best_idx = 0xffffffffu;
+            for (uint32_t c = wlane(); c < n_cand; c += kWarp) {
+                BtStart x = m.starts[c];
+                if (x.score == INT32_MIN) continue;
+                bool gt = x.score != best.score ? x.score > best.score
+                        : x.neg_off_diag != best.neg_off_diag ? x.neg_off_diag > best.neg_off_diag
+                        : x.neg_i != best.neg_i ? x.neg_i > best.neg_i : x.pos > best.pos;
+                if (best_idx == 0xffffffffu || gt) { best = x; best_idx = c; }
+            }
+            {
+                int has = best_idx != 0xffffffffu;
+                int v0 = wreduce_max(has ? best.score : INT32_MIN);
+                if (!wballot(has)) break;
+                bool ok = has && best.score == v0;
+                int v1 = wreduce_max(ok ? best.neg_off_diag : INT32_MIN); ok = ok && best.neg_off_diag == v1;
+                int v2 = wreduce_max(ok ? best.neg_i : INT32_MIN); ok = ok && best.neg_i == v2;
+                int v3 = wreduce_max(ok ? best.pos : INT32_MIN); ok = ok && best.pos == v3;
+                unsigned who = wballot(ok);
+                int src = ffs32(who) - 1;
+                best.score = v0; best.neg_off_diag = v1; best.neg_i = v2; best.pos = v3;
+                best_idx = wbcast(best_idx, src);
+            }
+            m.starts[best_idx].score = INT32_MIN;
+            wsync();
+
+            if (n_ext >= (int)cfg.num_alternative_paths) break;          // terminate_backtrack_start
+            uint32_t j = (uint32_t)(-best.neg_i);
+            if (m.cols[j].started) continue;                             // skip_backtrack_start
+            m.cols[j].started = 1;
+
+            score_t score = best.score;
+            if ((int64_t)score - min_cell_score < best_score) break;
+
+            int n_ops = 0, n_path = 0, n_seq = 0, n_trace = 0;
+            int pos = best.pos;
+            const int end_pos = pos;
+            int align_offset = sh.offset;
+            bool path_back_nonzero = false;
+
+            while (j) {
+                const ColMeta col = m.cols[j];
+                const ColMeta par = m.cols[col.parent];
+                const int trim = col.trim, trim_p = par.trim;
+                align_offset = imin(col.offset, k_minus_1);
+                if (pos == col.max_pos) m.cols[j].started = 1;
+                const int code = encode_char(col.c);
+                const score_t sv = cellS(col, pos - trim);
+                const uint32_t last_op = n_ops ? cig_op(m.bt_ops[n_ops - 1]) : 0xffu;
+
+                if (sv == kNinf) {
+                    j = 0;
+                } else if (pos && sv == cellE(col, pos - trim) && (n_ops == 0 || last_op != OP_D)) {
+                    // insertion run (:943-959)
+                    bool again = true;
+                    while (again) {
+                        cig_append(n_ops, OP_I);
+                        again = cellE(col, pos - trim) == cellE(col, pos - trim - 1) + cfg.gap_ext;
+                        --pos;
+                    }
+                } else if (pos && pos >= trim_p + 1
+                        && sv == cellS(par, pos - trim_p - 1) + col.score
+                                + prof_score(s, seed_clipping + pos, code)) {
+                    ++n_trace;
+                    if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
+                    m.bt_seq[n_seq++] = col.c;
+                    cig_append(n_ops, prof_is_match(s, seed_clipping + pos, code) ? OP_M : OP_X);
+                    if (col.offset >= k_minus_1) {
+                        if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
+                        m.bt_path[n_path++] = col.node; path_back_nonzero = col.node != 0;
+                    }
+                    --pos;
+                    j = col.parent;
+                } else if (sv == cellF(col, pos - trim) && (n_ops == 0 || last_op != OP_I)) {
+                    // deletion run (:972-999)
+                    bool again = true;
+                    while (again && j) {
+                        const ColMeta c2 = m.cols[j];
+                        const ColMeta p2 = m.cols[c2.parent];
+                        align_offset = imin(c2.offset, k_minus_1);
+                        again = cellF(c2, pos - c2.trim)
+                                == cellF(p2, pos - p2.trim) + c2.score + cfg.gap_ext;
+                        ++n_trace;
+                        if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
+                        m.bt_seq[n_seq++] = c2.c;
+                        cig_append(n_ops, OP_D);
+                        if (c2.offset >= k_minus_1) {
+                            if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
+                            m.bt_path[n_path++] = c2.node; path_back_nonzero = c2.node != 0;
+                        }
+                        j = c2.parent;
+                    }
+                } else {
+                    break;                                   // backtracking failed
+                }
+                if (overflow) return 0;
+            }
+
+            if (n_trace >= min_trace_length && n_path && path_back_nonzero) {
+                const ColMeta cj = m.cols[j];
+                score_t cur_cell_score = cellS(cj, pos - cj.trim);
+                best_score = imax(best_score, score - cur_cell_score);
+                if ((int64_t)score - min_cell_score < best_score) break;
+
+                const ColMeta root = m.cols[0];
+                if (score >= min_start_score
+                        && (!pos || cur_cell_score == 0)
+                        && (pos || cur_cell_score == cellS(root, 0))
+                        && (cfg.allow_left_trim || !j)) {
+                    // construct_alignment (:774-798)
+                    AlnSlot &o = m.slots[out_base + n_ext];
+                    wsync();
+                    for (int t = wlane(); t < n_path; t += kWarp) o.nodes[t] = m.bt_path[n_path - 1 - t];
+                    for (int t = wlane(); t < n_seq; t += kWarp) o.seq[t] = m.bt_seq[n_seq - 1 - t];
+                    int lead = start + pos;
+                    int tail = L - start - end_pos;
+                    int nc = 0;
+                    if (lead) nc = 1;
+                    for (int t = wlane(); t < n_ops; t += kWarp) o.cigar[nc + t] = m.bt_ops[n_ops - 1 - t];
+                    if (lead) o.cigar[0] = cig_pack(OP_S, lead);
+                    nc += n_ops;
+                    if (tail) o.cigar[nc++] = cig_pack(OP_S, tail);
+                    AlnHdr h;
+                    h.q_len = end_pos - pos; h.n_nodes = n_path; h.seq_len = n_seq; h.n_cigar = nc;
+                    h.score = score; h.offset = align_offset; h.orientation = sh.orientation; h.used = 1;
+                    *o.h = h;
+                    wsync();
+                    ++n_ext;
+                }
+            }
+        }
+
+        if (n_ext == 0 && sh.score >= min_path_score) {
+            copy_slot(out_base, seed_slot);
+            n_ext = 1;
+        }
+        return n_ext;
+    }
+
+    // --------------------------------------------------------------------------------
+    // aggregator (aligner_aggregator.hpp:59-149, unlabeled queue)
+    // --------------------------------------------------------------------------------
+    MGB_HD bool aln_less(const AlnSlot &a, const AlnSlot &b) const {     // LocalAlignmentLess
+        int as = a.h->score, bs = b.h->score;
+        if (bs != as) return bs > as;
+        int aq = a.h->q_len, bq = b.h->q_len;
+        if (aq != bq) return aq > bq;
+        int ao = a.h->orientation, bo = b.h->orientation;
+        if (ao != bo) return ao > bo;
+        return aln_clipping(a) > aln_clipping(b);
+    }
+    MGB_HD bool aln_equal(const AlnSlot &a, const AlnSlot &b) {
+        const AlnHdr x = *a.h, y = *b.h;
+        if (x.orientation != y.orientation || x.offset != y.offset || x.score != y.score
+                || x.q_len != y.q_len || x.seq_len != y.seq_len || x.n_cigar != y.n_cigar
+                || x.n_nodes != y.n_nodes)
+            return false;
+        bool diff = false;
+        int ca = aln_clipping(a), cb = aln_clipping(b);
+        for (int i = wlane(); i < x.q_len; i += kWarp)
+            if (q[x.orientation][ca + i] != q[y.orientation][cb + i]) diff = true;
+        for (int i = wlane(); i < x.seq_len; i += kWarp) if (a.seq[i] != b.seq[i]) diff = true;
+        for (int i = wlane(); i < x.n_cigar; i += kWarp) if (a.cigar[i] != b.cigar[i]) diff = true;
+        for (int i = wlane(); i < x.n_nodes; i += kWarp) if (a.nodes[i] != b.nodes[i]) diff = true;
+        return !wballot(diff);
+    }
+    MGB_HD score_t agg_global_cutoff() {
+        if (!n_agg) return kNinf;
+        int mx = 0;
+        for (int i = 1; i < n_agg; ++i)
+            if (aln_less(m.slots[SLOT_AGG + mx], m.slots[SLOT_AGG + i])) mx = i;
+        score_t cur_max = m.slots[SLOT_AGG + mx].h->score;
+        return cur_max > 0 ? (score_t)((double)cur_max * cfg.rel_score_cutoff) : cur_max;
+    }
+    MGB_HD void agg_add(int slot) {
+        if (!n_agg) { copy_slot(SLOT_AGG, slot); n_agg = 1; return; }
+        if (m.slots[slot].h->score < agg_global_cutoff()) return;
+        for (int i = 0; i < n_agg; ++i)
+            if (aln_equal(m.slots[slot], m.slots[SLOT_AGG + i])) return;
+        if (n_agg < (int)cfg.num_alternative_paths) { copy_slot(SLOT_AGG + n_agg, slot); ++n_agg; return; }
+        int mn = 0;
+        for (int i = 1; i < n_agg; ++i)
+            if (aln_less(m.slots[SLOT_AGG + i], m.slots[SLOT_AGG + mn])) mn = i;
+        if (aln_less(m.slots[slot], m.slots[SLOT_AGG + mn])) return;
+        copy_slot(SLOT_AGG + mn, slot);
+    }
+    MGB_HD score_t get_min_path_score() { return imax(cfg.min_path_score, agg_global_cutoff()); }
+
+    // --------------------------------------------------------------------------------
+    // drivers (dbg_aligner.cpp:360-384, 657-755)
+    // --------------------------------------------------------------------------------
+    MGB_HD bool check_seed_rec(int e, int s, const SeedRec &sd) {
+        // Alignment(seed): last node, pos = |query_view| + clipping - 1, score
+        uint64_t last_node = sd.n_nodes == 1 ? sd.node0 : qnodes[s][sd.clip + sd.n_nodes - 1];
+        int end_clip = L - (int)sd.clip - (int)sd.len;
+        score_t score = m.psum[s][sd.clip] - m.psum[s][sd.clip + sd.len]
+            + (!sd.clip ? cfg.left_end_bonus : 0) + (!end_clip ? cfg.right_end_bonus : 0);
+        return check_seed_vals(e, last_node, (int)sd.len + (int)sd.clip - 1, score);
+    }
+
+    MGB_HD void set_seed(int e) { conv_clear(e); }
+
+    // aln_both for query strand s
+    MGB_HD void align_strand(int s) {
+        const int fe = s, be = 1 - s;
+        ext_rc[fe] = false; ext_rc[be] = true;
+        stats.num_seeds += n_seeds[s];
+        for (int i = 0; i < n_seeds[s] && !overflow; ++i) {
+            SeedRec sd = m.seeds[s][i];
+            if (!sd.alive) continue;
+            seed_to_slot(SLOT_SEED, s, sd);
+            set_seed(fe);
+            int n_res = extend(fe, SLOT_SEED, cfg.min_cell_score, false, SLOT_EXT);
+            if (overflow) return;
+            int n_rc = 0;
+            for (int r = 0; r < n_res; ++r) {
+                const int slot = SLOT_EXT + r;
+                if (m.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
+                if (!aln_clipping(m.slots[slot]) || m.slots[slot].h->offset) continue;
+                if (!reverse_complement_slot(slot)) continue;
+                if (n_rc != r) copy_slot(SLOT_EXT + n_rc, slot);
+                ++n_rc;
+            }
+            // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
+            for (int r = 0; r < n_rc && !overflow; ++r) {
+                if (!m.slots[SLOT_EXT + r].h->used) continue;
+                score_t mps = get_min_path_score();
+                set_seed(be);
+                int nb = extend(be, SLOT_EXT + r, mps, true, SLOT_BWD);
+                if (overflow) return;
+                for (int b = 0; b < nb; ++b) {
+                    const int slot = SLOT_BWD + b;
+                    if (!reverse_complement_slot(slot)) continue;
+                    const AlnHdr h = *m.slots[slot].h;
+                    int clip = aln_clipping(m.slots[slot]), eclip = aln_end_clipping(m.slots[slot]);
+                    for (int t = 0; t < h.n_nodes && !overflow; ++t)
+                        filter_nodes(fe, m.slots[slot].nodes[t], clip, L - eclip);
+                    agg_add(slot);
+                }
+                for (int r2 = r + 1; r2 < n_rc; ++r2) {
+                    AlnSlot &a = m.slots[SLOT_EXT + r2];
+                    if (!a.h->used) continue;
+                    const AlnHdr h = *a.h;
+                    if (!check_seed_vals(be, a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
+                        a.h->used = 0;
+                }
+            }
+            for (int j = i + 1; j < n_seeds[s]; ++j) {
+                if (m.seeds[s][j].alive && !check_seed_rec(fe, s, m.seeds[s][j]))
+                    m.seeds[s][j].alive = 0;
+            }
+        }
+    }
+
+    // forward-only: align_core(*seeder, extender, add_alignment, get_min_path_score, false)
+    MGB_HD void align_forward_only() {
+        ext_rc[0] = false;
+        stats.num_seeds += n_seeds[0];
+        for (int i = 0; i < n_seeds[0] && !overflow; ++i) {
+            SeedRec sd = m.seeds[0][i];
+            if (!sd.alive) continue;
+            seed_to_slot(SLOT_SEED, 0, sd);
+            score_t mps = get_min_path_score();
+            set_seed(0);
+            int n_res = extend(0, SLOT_SEED, mps, false, SLOT_EXT);
+            if (overflow) return;
+            for (int r = 0; r < n_res; ++r) agg_add(SLOT_EXT + r);
+            for (int j = i + 1; j < n_seeds[0]; ++j) {
+                if (m.seeds[0][j].alive && !check_seed_rec(0, 0, m.seeds[0][j]))
+                    m.seeds[0][j].alive = 0;
+            }
+        }
+    }
+
+    // suffix sums of the self-match scores (extender.cpp:26-36)
+    MGB_HD void build_psum(int s) {
+        // sequential suffix sum chunked over the warp
+        int carry = 0;
+        if (wlane() == 0) m.psum[s][L] = 0;
+        for (int base = L - 1; base >= 0; base -= kWarp) {
+            int i = base - wlane();
+            int v = i >= 0 ? cfg.diag[(uint8_t)q[s][i]] : 0;
+#if MGB_DEVICE_CODE
+            for (int d = 1; d < 32; d <<= 1) {
+                int o = __shfl_up_sync(0xffffffffu, v, d);
+                if (wlane() >= d) v += o;
+            }
+#endif
+            v += carry;
+            if (i >= 0) m.psum[s][i] = v;
+            carry = wbcast(v, kWarp - 1);
+        }
+        wsync();
+    }
+
+    // whole pipeline for one read; returns the number of alignments left in SLOT_AGG.. (sorted)
+    MGB_HD int run(int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
+                   const uint64_t *nf, const uint64_t *nr, int *order) {
+        L = L_; q[0] = qf; q[1] = qr; codes[0] = cf; codes[1] = cr; qnodes[0] = nf; qnodes[1] = nr;
+        overflow = false; n_agg = 0;
+        stats.num_seeds = stats.num_extensions = stats.num_explored_nodes = stats.dp_columns = 0;
+        stats.dp_cells = 0;
+        for (int e = 0; e < 2; ++e) {
+            ext_table_cap[e] = 0; ext_num_ext[e] = 0; ext_explored_prev[e] = 0; ext_rc[e] = false;
+            m.conv[e].n_entries = 0; m.conv[e].cells_used = 0; m.conv[e].epoch = m.epoch_store[e];
+            n_seeds[e] = 0; num_matching[e] = 0;
+        }
+        const bool both = cfg.forward_and_reverse_complement;
+        build_psum(0);
+        if (both) build_psum(1);
+        build_seeds(0);
+        if (overflow) return 0;
+        if ((double)L * cfg.min_exact_match > (double)num_matching[0]) { n_seeds[0] = 0; num_matching[0] = 0; }
+        if (both) {
+            build_seeds(1);
+            if (overflow) return 0;
+            if ((double)L * cfg.min_exact_match > (double)num_matching[1]) { n_seeds[1] = 0; num_matching[1] = 0; }
+            uint32_t fm = num_matching[0], bm = num_matching[1];
+            if (fm >= bm) {
+                align_strand(0);
+                if (!overflow && (double)bm >= (double)fm * cfg.rel_score_cutoff) align_strand(1);
+            } else {
+                align_strand(1);
+                if (!overflow && (double)fm >= (double)bm * cfg.rel_score_cutoff) align_strand(0);
+            }
+        } else {
+            align_forward_only();
+        }
+        if (overflow) return 0;
+        for (int e = 0; e < 2; ++e) {
+            stats.num_extensions += ext_num_ext[e];
+            stats.num_explored_nodes += ext_explored_prev[e] + m.conv[e].n_entries;
+        }
+        // AlignmentAggregator::get_alignments: descending LocalAlignmentLess order
+        for (int i = 0; i < n_agg; ++i) order[i] = i;
+        for (int i = 1; i < n_agg; ++i) {
+            int x = order[i], j = i - 1;
+            while (j >= 0 && aln_less(m.slots[SLOT_AGG + order[j]], m.slots[SLOT_AGG + x])) {
+                order[j + 1] = order[j]; --j;
+            }
+            order[j + 1] = x;
+        }
+        return n_agg;
+    }
+};
+
+} // namespace mgb

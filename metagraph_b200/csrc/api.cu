@@ -1,0 +1,680 @@
+// C-ABI (include/mgb.h) of the B200-native `metagraph align` hot path: index upload, the three
+// sm_100a kernels (query preparation, quad-per-strand exact seeding, warp-per-read
+// seed-and-extend) and result unpacking.
+//
+// When compiled by g++ with -DMGB_HOST_EMU (tests/emu/ only) the same logic runs with
+// one-lane "warps" on host memory so that it can be checked against the oracle on a machine
+// without a GPU. That build is test infrastructure; the product library is always the nvcc
+// build and has no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mgb.h"
+#include "align_core.cuh"
+#include "host_common.hpp"
+#include "index_build.hpp"
+
+#if !defined(MGB_HOST_EMU)
+#include <cuda_runtime.h>
+#endif
+
+using namespace mgb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+struct ReadHdr {              // per read, written by the align kernel
+    uint32_t status, n_aln;
+    uint64_t heap_off;
+    ReadStats stats;
+};
+
+// ---------------------------------------------------------------------------------------
+// kernels (device) / loops (host emulation)
+// ---------------------------------------------------------------------------------------
+struct PrepArgs {
+    const char *seqs; const uint64_t *offsets; uint32_t n_reads;
+    char *qf, *qr; uint8_t *cf, *cr;
+};
+
+MGB_HD void prepare_read(const PrepArgs &a, uint32_t r) {
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    for (int i = wlane(); i < L; i += kWarp) {
+        uint8_t f = sanitize_char((uint8_t)a.seqs[b + i]);
+        uint8_t rc = complement_char(sanitize_char((uint8_t)a.seqs[b + L - 1 - i]));
+        a.qf[b + i] = (char)f; a.qr[b + i] = (char)rc;
+        a.cf[b + i] = encode_dna(f); a.cr[b + i] = encode_dna(rc);
+    }
+}
+
+struct SeedArgs {
+    IndexView ix;
+    const uint8_t *cf, *cr; const uint64_t *offsets; const uint64_t *koff;
+    uint64_t *nodes_f, *nodes_r; uint32_t n_reads; uint32_t n_strands;
+};
+
+MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
+    uint32_t r = (uint32_t)(item / a.n_strands);
+    uint32_t s = (uint32_t)(item % a.n_strands);
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r]);
+}
+
+struct AlignArgs {
+    IndexView ix; DevConfig cfg; Caps caps;
+    const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
+    const uint64_t *nodes_f, *nodes_r;
+    const uint32_t *read_list; uint32_t n_list;
+    char *arena; size_t arena_stride;
+    ReadHdr *hdr; char *heap; uint64_t heap_cap; unsigned long long *heap_used;
+    unsigned int *next;
+};
+
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena) {
+    WarpMem mem;
+    mem.carve(arena, a.caps);
+    ReadAligner al(a.ix, a.cfg, a.caps, mem);
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    int order[kMaxAlt];
+    const bool has_k = L >= (int)a.ix.k;
+    int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
+                   has_k ? a.nodes_f + a.koff[r] : nullptr,
+                   has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
+    ReadHdr h;
+    h.status = al.overflow ? MGB_READ_OVERFLOW : MGB_READ_OK;
+    h.n_aln = 0; h.heap_off = 0; h.stats = al.stats;
+    if (!al.overflow && n) {
+        // bytes: per alignment OutAln + nodes*8 + cigar*4 + seq (padded to 8)
+        uint64_t bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            const AlnHdr ah = *mem.slots[SLOT_AGG + order[i]].h;
+            bytes += sizeof(OutAln) + 8ull * ah.n_nodes + ((4ull * ah.n_cigar + 7) & ~7ull)
+                   + (((uint64_t)ah.seq_len + 7) & ~7ull);
+        }
+        unsigned long long off = 0;
+#if MGB_DEVICE_CODE
+        if (wlane() == 0) off = atomicAdd(a.heap_used, (unsigned long long)bytes);
+        off = wbcast64(off, 0);
+#else
+        off = *a.heap_used; *a.heap_used += bytes;
+#endif
+        if (off + bytes > a.heap_cap) {
+            h.status = MGB_READ_OVERFLOW;
+        } else {
+            h.n_aln = n; h.heap_off = off;
+            char *p = a.heap + off;
+            for (int i = 0; i < n; ++i) {
+                const AlnSlot &sl = mem.slots[SLOT_AGG + order[i]];
+                const AlnHdr ah = *sl.h;
+                OutAln o;
+                o.orientation = ah.orientation; o.score = ah.score; o.offset = ah.offset;
+                o.query_begin = al.aln_clipping(sl); o.query_len = ah.q_len;
+                o.n_nodes = ah.n_nodes; o.seq_len = ah.seq_len; o.n_cigar = ah.n_cigar;
+                if (wlane() == 0) *(OutAln*)p = o;
+                p += sizeof(OutAln);
+                uint64_t *pn = (uint64_t*)p;
+                for (int t = wlane(); t < ah.n_nodes; t += kWarp) pn[t] = sl.nodes[t];
+                p += 8ull * ah.n_nodes;
+                uint32_t *pc = (uint32_t*)p;
+                for (int t = wlane(); t < ah.n_cigar; t += kWarp) pc[t] = sl.cigar[t];
+                p += (4ull * ah.n_cigar + 7) & ~7ull;
+                for (int t = wlane(); t < ah.seq_len; t += kWarp) p[t] = sl.seq[t];
+                p += ((uint64_t)ah.seq_len + 7) & ~7ull;
+            }
+        }
+    }
+    if (wlane() == 0) {
+        a.hdr[r] = h;
+        mem.epoch_store[0] = mem.conv[0].epoch; mem.epoch_store[1] = mem.conv[1].epoch;
+    }
+    wsync();
+}
+
+// once per arena: convergence-table slots start with epoch 0 (never equal to a live epoch)
+MGB_HD void init_arena(const AlignArgs &a, char *arena) {
+    WarpMem mem;
+    mem.carve(arena, a.caps);
+    for (int e = 0; e < 2; ++e)
+        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv[e].slots[i].epoch = 0;
+    if (wlane() == 0) { mem.epoch_store[0] = 0; mem.epoch_store[1] = 0; }
+    wsync();
+}
+
+#if !defined(MGB_HOST_EMU)
+__global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < a.n_reads; r += nwarps) prepare_read(a, r);
+}
+
+__global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    uint64_t items = (uint64_t)a.n_reads * a.n_strands;
+    for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
+}
+
+__global__ void __launch_bounds__(128) k_align(const AlignArgs a) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    char *arena = a.arena + (size_t)warp * a.arena_stride;
+    init_arena(a, arena);
+    while (true) {
+        unsigned int t = 0;
+        if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.n_list) break;
+        align_read(a, a.read_list[t], arena);
+    }
+}
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    return fail(MGB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------
+// device memory helpers
+// ---------------------------------------------------------------------------------------
+#if defined(MGB_HOST_EMU)
+struct Stream { int dummy; };
+inline int dev_alloc(void **p, size_t bytes, Stream&) { *p = std::calloc(1, bytes ? bytes : 1); return *p ? 0 : MGB_ERR_CUDA; }
+inline void dev_free(void *p, Stream&) { std::free(p); }
+inline int h2d(void *d, const void *h, size_t bytes, Stream&) { std::memcpy(d, h, bytes); return 0; }
+inline int d2h(void *h, const void *d, size_t bytes, Stream&) { std::memcpy(h, d, bytes); return 0; }
+inline int dev_zero(void *d, size_t bytes, Stream&) { std::memset(d, 0, bytes); return 0; }
+#else
+struct Stream { cudaStream_t s; };
+inline int dev_alloc(void **p, size_t bytes, Stream &st) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, st.s);
+    if (e != cudaSuccess) { g_err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); return MGB_ERR_CUDA; }
+    return 0;
+}
+inline void dev_free(void *p, Stream &st) { if (p) cudaFreeAsync(p, st.s); }
+inline int h2d(void *d, const void *h, size_t bytes, Stream &st) {
+    cudaError_t e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st.s);
+    if (e != cudaSuccess) { g_err = std::string("H2D: ") + cudaGetErrorString(e); return MGB_ERR_CUDA; }
+    return 0;
+}
+inline int d2h(void *h, const void *d, size_t bytes, Stream &st) {
+    cudaError_t e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st.s);
+    if (e != cudaSuccess) { g_err = std::string("D2H: ") + cudaGetErrorString(e); return MGB_ERR_CUDA; }
+    return 0;
+}
+inline int dev_zero(void *d, size_t bytes, Stream &st) {
+    cudaError_t e = cudaMemsetAsync(d, 0, bytes, st.s);
+    if (e != cudaSuccess) { g_err = std::string("memset: ") + cudaGetErrorString(e); return MGB_ERR_CUDA; }
+    return 0;
+}
+#endif
+
+struct DevBufs {               // frees everything it owns on scope exit
+    Stream &st;
+    std::vector<void*> ptrs;
+    explicit DevBufs(Stream &s) : st(s) {}
+    ~DevBufs() { for (void *p : ptrs) dev_free(p, st); }
+    template <class T> int alloc(T **p, size_t count) {
+        void *v = nullptr;
+        int rc = dev_alloc(&v, count * sizeof(T), st);
+        if (rc) return rc;
+        ptrs.push_back(v);
+        *p = (T*)v;
+        return 0;
+    }
+};
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// opaque types
+// ---------------------------------------------------------------------------------------
+struct mgb_index {
+    IndexView view;            // device pointers (host pointers in the emulation build)
+    int device = 0;
+    uint64_t device_bytes = 0;
+    int num_sms = 1;
+    std::vector<void*> bufs;
+#if defined(MGB_HOST_EMU)
+    HostIndex host;
+#endif
+};
+
+struct mgb_results {
+    uint32_t n_reads = 0;
+    std::vector<uint64_t> first;
+    std::vector<uint32_t> count;
+    std::vector<mgb_alignment_t> alns;
+    std::vector<std::vector<char>> heaps;    // host copies of the output heaps
+    mgb_stats_t stats;
+};
+
+extern "C" {
+
+const char* mgb_last_error(void) { return g_err.c_str(); }
+
+int mgb_device_count(void) {
+#if defined(MGB_HOST_EMU)
+    return 1;
+#else
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+#endif
+}
+
+int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, const uint64_t *F,
+                     const uint8_t *valid, uint32_t k, int alphabet, uint32_t suffix_len,
+                     int device, mgb_index_t **out) {
+    if (!W || !last || !F || !out) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    if (alphabet != MGB_ALPHABET_DNA)
+        return fail(MGB_ERR_UNSUPPORTED, "only the DNA alphabet is implemented in this build");
+    std::unique_ptr<mgb_index> idx(new mgb_index());
+    HostIndex hloc;
+#if defined(MGB_HOST_EMU)
+    HostIndex &h = idx->host;
+#else
+    HostIndex &h = hloc;
+#endif
+    if (suffix_len == 0) {
+        // reference default 12 (cli/config/config.cpp:24-25), capped so the table stays
+        // well below the index size
+        uint64_t n = n_plus_1 - 1;
+        suffix_len = 1;
+        uint64_t entries = 4;
+        while (suffix_len < 12 && suffix_len + 1 <= k - 1 && entries * 4 * 8 <= n / 2 + 1024) {
+            entries *= 4; ++suffix_len;
+        }
+    }
+    try {
+        build_host_index(W, last, n_plus_1, F, valid, k, suffix_len, &h);
+    } catch (const std::exception &e) {
+        return fail(MGB_ERR_INVALID_ARGUMENT, e.what());
+    }
+#if defined(MGB_HOST_EMU)
+    (void)device; (void)hloc;
+    idx->view = h.view();
+    idx->device_bytes = h.blocks.size() * 4;
+#else
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MGB_ERR_NO_DEVICE, "no CUDA device available (the B200 kernels have no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(MGB_ERR_INVALID_ARGUMENT, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    idx->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    idx->num_sms = prop.multiProcessorCount;
+    IndexView v = h.view();
+    auto upload = [&](const std::vector<uint32_t> &src, const uint32_t **dst) -> int {
+        if (src.empty()) { *dst = nullptr; return 0; }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, src.size() * 4);
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        idx->bufs.push_back(p);
+        e = cudaMemcpy(p, src.data(), src.size() * 4, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+        idx->device_bytes += src.size() * 4;
+        *dst = (const uint32_t*)p;
+        return 0;
+    };
+    int rc;
+    if ((rc = upload(h.blocks, &v.blocks))) return rc;
+    if ((rc = upload(h.blk_rank, &v.blk_rank))) return rc;
+    if ((rc = upload(h.sel_last, &v.sel_last))) return rc;
+    for (int c = 0; c < kSigmaDNA; ++c)
+        if ((rc = upload(h.sel_W[c], &v.sel_W[c]))) return rc;
+    if ((rc = upload(h.valid, &v.valid))) return rc;
+    if ((rc = upload(h.sfx, &v.sfx))) return rc;
+    idx->view = v;
+#endif
+    *out = idx.release();
+    return MGB_OK;
+}
+
+void mgb_index_destroy(mgb_index_t *index) {
+    if (!index) return;
+#if !defined(MGB_HOST_EMU)
+    cudaSetDevice(index->device);
+    for (void *p : index->bufs) cudaFree(p);
+#endif
+    delete index;
+}
+
+uint64_t mgb_index_num_edges(const mgb_index_t *index) { return index->view.n; }
+uint64_t mgb_index_device_bytes(const mgb_index_t *index) { return index->device_bytes; }
+uint32_t mgb_index_k(const mgb_index_t *index) { return index->view.k; }
+
+void mgb_config_init(mgb_config_t *c) {
+    std::memset(c, 0, sizeof(*c));
+    c->num_alternative_paths = 1;
+    c->max_num_seeds_per_locus = UINT64_MAX;
+    c->min_cell_score = INT32_MIN + 100;
+    c->min_path_score = 0;
+    c->xdrop = INT32_MAX;
+    c->max_nodes_per_seq_char = 1.7976931348623157e308;
+    c->max_ram_per_alignment = 1.7976931348623157e308;
+    c->gap_opening_penalty = -5; c->gap_extension_penalty = -2;
+    c->forward_and_reverse_complement = 1; c->global_xdrop = 1; c->allow_left_trim = 1;
+    // dna_scoring_matrix(2, -1, -2) (aligner_config.cpp:164-183)
+    std::memset(c->score_matrix, -2, sizeof(c->score_matrix));
+    c->score_matrix['A']['G'] = c->score_matrix['G']['A'] = -1;
+    c->score_matrix['C']['T'] = c->score_matrix['T']['C'] = -1;
+    for (const char *p = "ACGT"; *p; ++p) c->score_matrix[(int)*p][(int)*p] = 2;
+}
+
+void mgb_config_init_cli(mgb_config_t *c, uint32_t k, int alphabet) {
+    (void)alphabet;
+    mgb_config_init(c);
+    c->min_seed_length = k < 19 ? k : 19;           // cli/align.cpp:42-43
+    c->max_seed_length = UINT64_MAX;
+    c->max_num_seeds_per_locus = 1000;
+    c->xdrop = 27;
+    c->min_exact_match = 0.7;
+    c->max_nodes_per_seq_char = 5.0;
+    c->max_ram_per_alignment = 200;
+    c->rel_score_cutoff = 0.95;
+    c->gap_opening_penalty = -6; c->gap_extension_penalty = -2;
+    c->left_end_bonus = 5; c->right_end_bonus = 5;
+    std::memset(c->score_matrix, -3, sizeof(c->score_matrix));
+    for (const char *p = "ACGT"; *p; ++p) c->score_matrix[(int)*p][(int)*p] = 2;
+}
+
+} // extern "C"
+
+namespace {
+
+struct Batch {                 // device-resident read batch
+    uint32_t n_reads = 0; uint64_t total_chars = 0, total_kmers = 0; uint32_t L_max = 0;
+    char *seqs = nullptr, *qf = nullptr, *qr = nullptr; uint8_t *cf = nullptr, *cr = nullptr;
+    uint64_t *offsets = nullptr, *koff = nullptr, *nodes_f = nullptr, *nodes_r = nullptr;
+};
+
+int upload_batch(const mgb_index_t *index, const char *seqs, const uint64_t *offsets, uint32_t n_reads,
+                 bool need_rc_nodes, Stream &st, DevBufs &bufs, Batch *b, std::vector<uint64_t> *koff_host,
+                 mgb_stats_t *stats) {
+    const uint32_t k = index->view.k;
+    b->n_reads = n_reads;
+    b->total_chars = offsets[n_reads];
+    koff_host->assign(n_reads + 1, 0);
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        if (offsets[r + 1] < offsets[r]) return fail(MGB_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+        uint64_t L = offsets[r + 1] - offsets[r];
+        if (L > 0x3fffffffull) return fail(MGB_ERR_INVALID_ARGUMENT, "read too long");
+        if (L > b->L_max) b->L_max = (uint32_t)L;
+        (*koff_host)[r + 1] = (*koff_host)[r] + (L >= k ? L - k + 1 : 0);
+    }
+    b->total_kmers = (*koff_host)[n_reads];
+    int rc;
+    const size_t pad = 64;
+    if ((rc = bufs.alloc(&b->seqs, b->total_chars + pad))) return rc;
+    if ((rc = bufs.alloc(&b->qf, b->total_chars + pad))) return rc;
+    if ((rc = bufs.alloc(&b->qr, b->total_chars + pad))) return rc;
+    if ((rc = bufs.alloc(&b->cf, b->total_chars + pad))) return rc;
+    if ((rc = bufs.alloc(&b->cr, b->total_chars + pad))) return rc;
+    if ((rc = bufs.alloc(&b->offsets, (size_t)n_reads + 1))) return rc;
+    if ((rc = bufs.alloc(&b->koff, (size_t)n_reads + 1))) return rc;
+    if ((rc = bufs.alloc(&b->nodes_f, b->total_kmers + 1))) return rc;
+    if (need_rc_nodes && (rc = bufs.alloc(&b->nodes_r, b->total_kmers + 1))) return rc;
+    if ((rc = h2d(b->seqs, seqs, b->total_chars, st))) return rc;
+    if ((rc = h2d(b->offsets, offsets, ((size_t)n_reads + 1) * 8, st))) return rc;
+    if ((rc = h2d(b->koff, koff_host->data(), ((size_t)n_reads + 1) * 8, st))) return rc;
+    stats->h2d_bytes += b->total_chars + 2 * ((size_t)n_reads + 1) * 8;
+    return 0;
+}
+
+int launch_prepare(const Batch &b, Stream &st, int num_sms) {
+    PrepArgs a { b.seqs, b.offsets, b.n_reads, b.qf, b.qr, b.cf, b.cr };
+#if defined(MGB_HOST_EMU)
+    (void)st; (void)num_sms;
+    for (uint32_t r = 0; r < b.n_reads; ++r) prepare_read(a, r);
+#else
+    if (!b.n_reads) return 0;
+    int blocks = std::min<uint64_t>((b.n_reads + 7) / 8, (uint64_t)num_sms * 8);
+    k_prepare<<<blocks, 256, 0, st.s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+#endif
+    return 0;
+}
+
+int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, Stream &st) {
+    SeedArgs a { index->view, b.cf, b.cr, b.offsets, b.koff, b.nodes_f, b.nodes_r, b.n_reads, n_strands };
+    uint64_t items = (uint64_t)b.n_reads * n_strands;
+#if defined(MGB_HOST_EMU)
+    (void)st;
+    for (uint64_t it = 0; it < items; ++it) seed_item(a, it);
+#else
+    if (!items) return 0;
+    // 32 quads per block; enough blocks to fill the machine, grid-stride beyond that
+    uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
+    k_seed<<<(unsigned)blocks, 128, 0, st.s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+#endif
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t *offsets,
+                     uint32_t n_seqs, uint64_t *out_nodes) {
+    if (!index || !seqs || !offsets || !out_nodes) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    Stream st;
+#if !defined(MGB_HOST_EMU)
+    CUDA_TRY(cudaSetDevice(index->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+#endif
+    int rc = 0;
+    {
+        DevBufs bufs(st);
+        Batch b; std::vector<uint64_t> koff; mgb_stats_t stats; std::memset(&stats, 0, sizeof(stats));
+        rc = upload_batch(index, seqs, offsets, n_seqs, false, st, bufs, &b, &koff, &stats);
+        if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
+        if (!rc) rc = launch_prepare(b, st, index->num_sms);
+        if (!rc) rc = launch_seed(index, b, 1, st);
+        if (!rc) rc = d2h(out_nodes, b.nodes_f, b.total_kmers * 8, st);
+#if !defined(MGB_HOST_EMU)
+        if (!rc) { cudaError_t e = cudaStreamSynchronize(st.s); if (e != cudaSuccess) rc = fail(MGB_ERR_CUDA, cudaGetErrorString(e)); }
+#endif
+    }
+#if !defined(MGB_HOST_EMU)
+    cudaStreamSynchronize(st.s);
+    cudaStreamDestroy(st.s);
+#endif
+    return rc;
+}
+
+int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
+                    const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out) {
+    if (!index || !config || !offsets || !out || (!seqs && n_reads && offsets[n_reads]))
+        return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    DevConfig dcfg;
+    std::string err;
+    int rc = lower_config(*config, index->view.k, &dcfg, &err);
+    if (rc) return fail(rc, err);
+
+    std::unique_ptr<mgb_results> res(new mgb_results());
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    res->n_reads = n_reads;
+    res->first.assign(n_reads, 0);
+    res->count.assign(n_reads, 0);
+
+    Stream st;
+#if !defined(MGB_HOST_EMU)
+    CUDA_TRY(cudaSetDevice(index->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    cudaEvent_t ev[6];
+    for (auto &e : ev) cudaEventCreate(&e);
+#endif
+    std::vector<ReadHdr> hdr_host(n_reads);
+    {
+        DevBufs bufs(st);
+        Batch b; std::vector<uint64_t> koff;
+        const bool both = dcfg.forward_and_reverse_complement;
+        const bool map_nodes = dcfg.max_seed_length >= index->view.k;
+#if !defined(MGB_HOST_EMU)
+        cudaEventRecord(ev[0], st.s);
+#endif
+        rc = upload_batch(index, seqs, offsets, n_reads, both, st, bufs, &b, &koff, &res->stats);
+        if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
+        if (!rc && both) rc = dev_zero(b.nodes_r, (b.total_kmers + 1) * 8, st);
+#if !defined(MGB_HOST_EMU)
+        cudaEventRecord(ev[1], st.s);
+#endif
+        if (!rc) rc = launch_prepare(b, st, index->num_sms);
+        if (!rc && map_nodes) rc = launch_seed(index, b, both ? 2 : 1, st);
+        res->stats.kernel_launches += 1 + (map_nodes ? 1 : 0);
+#if !defined(MGB_HOST_EMU)
+        cudaEventRecord(ev[2], st.s);
+#endif
+        ReadHdr *d_hdr = nullptr;
+        if (!rc) rc = bufs.alloc(&d_hdr, (size_t)n_reads + 1);
+
+        // align passes: all reads with scale 1, overflowed reads again with larger arenas
+        std::vector<uint32_t> list(n_reads);
+        for (uint32_t r = 0; r < n_reads; ++r) list[r] = r;
+        uint32_t scale = 1;
+        float align_ms = 0, d2h_ms = 0;
+        for (int pass = 0; !rc && !list.empty(); ++pass, scale *= 4) {
+            if (pass == 6) { rc = fail(MGB_ERR_OVERFLOW, "a read exceeded the largest per-read work arena"); break; }
+            Caps caps = choose_caps(b.L_max, dcfg, index->view.k, scale);
+            size_t stride = arena_bytes(caps);
+#if defined(MGB_HOST_EMU)
+            uint32_t n_warps = 1;
+#else
+            int blocks_per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, 0));
+            if (blocks_per_sm < 1) blocks_per_sm = 1;
+            uint64_t n_warps64 = (uint64_t)index->num_sms * blocks_per_sm * 4;
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            uint64_t mem_warps = (uint64_t)(free_b * 0.6) / (stride ? stride : 1);
+            if (mem_warps < 4) mem_warps = 4;
+            if (n_warps64 > mem_warps) n_warps64 = mem_warps & ~3ull;
+            if (n_warps64 > ((uint64_t)list.size() + 3) / 4 * 4) n_warps64 = ((uint64_t)list.size() + 3) / 4 * 4;
+            uint32_t n_warps = (uint32_t)n_warps64;
+#endif
+            // output heap: generous first guess, doubled on retry passes
+            uint64_t per_read = sizeof(OutAln) + 9ull * (b.L_max + 64 + index->view.k) + 4ull * 64;
+            uint64_t heap_cap = (uint64_t)list.size() * per_read * dcfg.num_alternative_paths * scale + 4096;
+            char *d_arena = nullptr, *d_heap = nullptr; uint32_t *d_list = nullptr;
+            unsigned long long *d_used = nullptr; unsigned int *d_next = nullptr;
+            DevBufs pass_bufs(st);
+            if ((rc = pass_bufs.alloc(&d_arena, stride * n_warps))) break;
+            if ((rc = pass_bufs.alloc(&d_heap, heap_cap))) break;
+            if ((rc = pass_bufs.alloc(&d_list, list.size()))) break;
+            if ((rc = pass_bufs.alloc(&d_used, 1))) break;
+            if ((rc = pass_bufs.alloc(&d_next, 1))) break;
+            if ((rc = h2d(d_list, list.data(), list.size() * 4, st))) break;
+            if ((rc = dev_zero(d_used, 8, st))) break;
+            if ((rc = dev_zero(d_next, 4, st))) break;
+            AlignArgs a;
+            a.ix = index->view; a.cfg = dcfg; a.caps = caps;
+            a.qf = b.qf; a.qr = b.qr; a.cf = b.cf; a.cr = b.cr; a.offsets = b.offsets; a.koff = b.koff;
+            a.nodes_f = b.nodes_f; a.nodes_r = b.nodes_r;
+            a.read_list = d_list; a.n_list = (uint32_t)list.size();
+            a.arena = d_arena; a.arena_stride = stride;
+            a.hdr = d_hdr; a.heap = d_heap; a.heap_cap = heap_cap; a.heap_used = d_used; a.next = d_next;
+            unsigned long long used = 0;
+#if defined(MGB_HOST_EMU)
+            init_arena(a, d_arena);
+            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], d_arena);
+            used = *d_used;
+#else
+            cudaEventRecord(ev[3], st.s);
+            k_align<<<n_warps / 4, 128, 0, st.s>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            cudaEventRecord(ev[4], st.s);
+            if ((rc = d2h(&used, d_used, 8, st))) break;
+            CUDA_TRY(cudaStreamSynchronize(st.s));
+            float ms = 0; cudaEventElapsedTime(&ms, ev[3], ev[4]); align_ms += ms;
+            cudaEventRecord(ev[3], st.s);
+#endif
+            res->stats.kernel_launches += 1;
+            if (used > heap_cap) used = heap_cap;
+            res->heaps.emplace_back((size_t)used);
+            std::vector<char> &heap_host = res->heaps.back();
+            if (used && (rc = d2h(heap_host.data(), d_heap, used, st))) break;
+            if ((rc = d2h(hdr_host.data(), d_hdr, (size_t)n_reads * sizeof(ReadHdr), st))) break;
+#if !defined(MGB_HOST_EMU)
+            CUDA_TRY(cudaStreamSynchronize(st.s));
+            cudaEventRecord(ev[4], st.s);
+            CUDA_TRY(cudaStreamSynchronize(st.s));
+            { float ms = 0; cudaEventElapsedTime(&ms, ev[3], ev[4]); d2h_ms += ms; }
+#endif
+            res->stats.d2h_bytes += used + (size_t)n_reads * sizeof(ReadHdr);
+            // unpack this pass
+            std::vector<uint32_t> retry;
+            const size_t heap_id = res->heaps.size() - 1;
+            for (uint32_t r : list) {
+                const ReadHdr &h = hdr_host[r];
+                if (h.status == MGB_READ_OVERFLOW) { retry.push_back(r); continue; }
+                res->stats.num_seeds += h.stats.num_seeds;
+                res->stats.num_extensions += h.stats.num_extensions;
+                res->stats.num_explored_nodes += h.stats.num_explored_nodes;
+                res->stats.dp_cells += h.stats.dp_cells;
+                res->stats.dp_columns += h.stats.dp_columns;
+                res->count[r] = h.n_aln;
+                res->first[r] = (uint64_t)heap_id << 48 | 0;   // patched below once all are known
+                const char *p = res->heaps[heap_id].data() + h.heap_off;
+                // temporarily store alignments tagged with the read; sorted into read order later
+                for (uint32_t i = 0; i < h.n_aln; ++i) {
+                    const OutAln *o = (const OutAln*)p;
+                    mgb_alignment_t al;
+                    std::memset(&al, 0, sizeof(al));
+                    al.read_index = r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
+                    al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
+                    al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
+                    p += sizeof(OutAln);
+                    al.nodes = (const uint64_t*)p; p += 8ull * o->n_nodes;
+                    al.cigar = (const uint32_t*)p; p += (4ull * o->n_cigar + 7) & ~7ull;
+                    al.sequence = p; p += ((uint64_t)o->seq_len + 7) & ~7ull;
+                    res->alns.push_back(al);
+                }
+            }
+            res->stats.num_reads_retried += retry.size();
+            list.swap(retry);
+        }
+#if !defined(MGB_HOST_EMU)
+        if (!rc) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[0], ev[1]); res->stats.h2d_ms = ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); res->stats.seed_kernel_ms = ms;
+            res->stats.align_kernel_ms = align_ms; res->stats.d2h_ms = d2h_ms;
+        }
+#endif
+    }
+#if !defined(MGB_HOST_EMU)
+    cudaStreamSynchronize(st.s);
+    for (auto &e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(st.s);
+#endif
+    if (rc) return rc;
+    // bring alignments into read order (stable: per-read order is the aggregator's order)
+    std::stable_sort(res->alns.begin(), res->alns.end(),
+                     [](const mgb_alignment_t &x, const mgb_alignment_t &y) { return x.read_index < y.read_index; });
+    uint64_t pos = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
+    *out = res.release();
+    return MGB_OK;
+}
+
+uint32_t mgb_results_num_reads(const mgb_results_t *r) { return r->n_reads; }
+void mgb_results_read_range(const mgb_results_t *r, uint32_t read, uint64_t *first, uint32_t *count) {
+    *first = r->first[read]; *count = r->count[read];
+}
+uint64_t mgb_results_num_alignments(const mgb_results_t *r) { return r->alns.size(); }
+const mgb_alignment_t* mgb_results_alignments(const mgb_results_t *r) { return r->alns.data(); }
+const mgb_stats_t* mgb_results_stats(const mgb_results_t *r) { return &r->stats; }
+void mgb_results_free(mgb_results_t *r) { delete r; }
+
+} // extern "C"

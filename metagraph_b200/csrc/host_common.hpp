@@ -1,0 +1,102 @@
+// Host-side helpers shared by the C-ABI implementation: config validation / lowering
+// (DBGAligner ctor, dbg_aligner.cpp:33-61) and arena sizing.
+#pragma once
+#include <cstring>
+#include <string>
+
+#include "../../include/mgb.h"
+#include "align_core.cuh"
+
+namespace mgb {
+
+// DBGAlignerConfig::check_config_scores (aligner_config.cpp:39-66)
+inline bool check_config_scores(const mgb_config_t &c) {
+    int8_t min_penalty = 127;
+    for (int i = 0; i < 128; ++i)
+        for (int j = 0; j < 128; ++j)
+            if (c.score_matrix[i][j] < min_penalty) min_penalty = c.score_matrix[i][j];
+    if (c.gap_opening_penalty * 2 >= min_penalty) return false;
+    if (c.gap_opening_penalty < min_penalty) min_penalty = c.gap_opening_penalty;
+    if (c.gap_extension_penalty < min_penalty) min_penalty = c.gap_extension_penalty;
+    return (int64_t)c.min_cell_score >= (int64_t)INT32_MIN - min_penalty;
+}
+
+// Returns MGB_OK or an error code; fills `d`.
+inline int lower_config(const mgb_config_t &c, uint32_t k, DevConfig *d, std::string *err) {
+    if (c.seed_complexity_filter) {
+        *err = "seed_complexity_filter requires sdust, which the reference does not vendor; "
+               "run with --align-no-seed-complexity-filter semantics (set it to 0)";
+        return MGB_ERR_UNSUPPORTED;
+    }
+    if (!c.global_xdrop) { *err = "global_xdrop = false is not supported"; return MGB_ERR_UNSUPPORTED; }
+    if (c.num_alternative_paths < 1 || c.num_alternative_paths > (uint64_t)kMaxAlt) {
+        *err = "num_alternative_paths must be in [1, " + std::to_string(kMaxAlt) + "]";
+        return MGB_ERR_UNSUPPORTED;
+    }
+    if (!check_config_scores(c)) {
+        *err = "Error: sum of min_cell_score and lowest penalty too low.";   // dbg_aligner.cpp:55-56
+        return MGB_ERR_BAD_CONFIG;
+    }
+    std::memset(d, 0, sizeof(*d));
+    uint64_t min_seed = c.min_seed_length ? c.min_seed_length : k;
+    uint64_t max_seed = c.max_seed_length ? c.max_seed_length : k;
+    if (min_seed > max_seed) { uint64_t t = min_seed; min_seed = max_seed; max_seed = t; }
+    d->num_alternative_paths = (uint32_t)c.num_alternative_paths;
+    d->min_seed_length = min_seed > 0xffffffffull ? 0xffffffffu : (uint32_t)min_seed;
+    d->max_seed_length = max_seed > 0xffffffffull ? 0xffffffffu : (uint32_t)max_seed;
+    d->max_num_seeds_per_locus = c.max_num_seeds_per_locus;
+    d->min_cell_score = c.min_cell_score; d->min_path_score = c.min_path_score; d->xdrop = c.xdrop;
+    if (c.xdrop <= 0) { *err = "xdrop must be positive"; return MGB_ERR_BAD_CONFIG; }
+    d->min_exact_match = c.min_exact_match; d->max_nodes_per_seq_char = c.max_nodes_per_seq_char;
+    d->max_ram_per_alignment = c.max_ram_per_alignment; d->rel_score_cutoff = c.rel_score_cutoff;
+    d->gap_open = c.gap_opening_penalty; d->gap_ext = c.gap_extension_penalty;
+    d->left_end_bonus = c.left_end_bonus; d->right_end_bonus = c.right_end_bonus;
+    d->forward_and_reverse_complement = c.forward_and_reverse_complement;
+    d->allow_left_trim = c.allow_left_trim; d->no_backtrack = c.no_backtrack;
+    const char letters[] = "$ACGT";
+    for (int q = 0; q < 128; ++q) {
+        d->diag[q] = c.score_matrix[q][q];
+        for (int i = 0; i <= kSigmaDNA; ++i) {
+            int ch = i < kSigmaDNA ? letters[i] : 0;
+            d->prof[i][q] = c.score_matrix[ch][q];
+            // kCharToOp (aligner_cigar.cpp:11-51): MATCH iff same valid letter, any case
+            int uq = (q >= 'a' && q <= 'z') ? q - 32 : q;
+            d->opmatch[i][q] = (i >= 1 && i < kSigmaDNA && uq == ch) ? 1 : 0;
+        }
+    }
+    return MGB_OK;
+}
+
+// Arena capacities for reads up to L_max; `scale` = 1, 4, 16, ... on overflow retries.
+inline Caps choose_caps(uint32_t L_max, const DevConfig &d, uint32_t k, uint32_t scale) {
+    Caps c;
+    uint32_t L = L_max < 16 ? 16 : L_max;
+    c.L_max = L_max;
+    uint64_t cols = (uint64_t)scale * (8ull * L + 256);
+    uint64_t band = (uint64_t)L + 6;
+    if (d.gap_ext < 0 && d.xdrop < (1 << 20)) {
+        uint64_t b = 2ull * (d.xdrop / (-d.gap_ext)) + 16;
+        if (b < band) band = b;
+    }
+    c.max_cols = (uint32_t)(cols > 0x3fffffffull ? 0x3fffffffull : cols);
+    uint64_t cells = cols * (band + 5) + 4ull * (L + 16);
+    c.max_cells = (uint32_t)(cells > 0x7fffffffull / 3 ? 0x7fffffffull / 3 : cells);
+    uint32_t hs = 1024;
+    while (hs < 4 * c.max_cols && hs < (1u << 30)) hs <<= 1;
+    c.hash_size = hs;
+    c.max_conv_entries = c.max_cols;
+    uint64_t ccells = cols * (band + 24);
+    c.max_conv_cells = (uint32_t)(ccells > 0x7fffffffull ? 0x7fffffffull : ccells);
+    c.max_seeds = scale * (4 * L + 64);
+    c.aln_nodes = scale * (3 * L + 128 + k);
+    c.aln_seq = scale * (3 * L + 128 + 2 * k);
+    c.aln_cigar = scale * (2 * L + 64);
+    return c;
+}
+
+inline size_t arena_bytes(const Caps &c) {
+    WarpMem m;
+    return m.carve(nullptr, c);
+}
+
+} // namespace mgb

@@ -1,0 +1,394 @@
+// Flat BOSS index in HBM and the rank/select primitives on top of it.
+//
+// Layout (DNA, sigma = 5): one 64-byte block per 64 consecutive BOSS edges
+//     words 0..7   W, 4 bits per edge (edge j: (w[j>>3] >> 4*(j&7)) & 15; 0xF = padding / W[0])
+//     words 8..9   `last`, 1 bit per edge
+//     word  10     number of set `last` bits before the block
+//     words 11..15 number of W == c (c = 0..4, un-flagged) before the block
+// so one 64-byte (two sector) access answers get_W, get_last, rank_W and rank_last for any
+// position of the block.  A quad (4 consecutive lanes) loads a block with one 16-byte load
+// per lane.  Auxiliary arrays: blk_rank (compact copy of word 10), sel_last / sel_W (block
+// of every 64th set bit / 32nd occurrence) for select, the optional dummy mask and the
+// suffix-range table (boss.hpp:516-525).
+//
+// Semantics follow graph/representation/succinct/boss.{hpp,cpp} (cited per function);
+// only the values returned are observable, the layout is ours.
+#pragma once
+#include "common.cuh"
+
+namespace mgb {
+
+static constexpr int kSigmaDNA = 5;
+static constexpr int kBlkEdges = 64;
+static constexpr int kBlkWords = 16;
+static constexpr int kSelLastRate = 64;
+static constexpr int kSelWRate = 32;
+
+struct IndexView {
+    const uint32_t *blocks;     // nblk * 16 words
+    const uint32_t *blk_rank;   // nblk + 1
+    const uint32_t *sel_last;   // ceil(ones / 64) + 1 (sentinel = last block)
+    const uint32_t *sel_W[kSigmaDNA];   // per symbol, ceil(cnt / 32) + 1
+    const uint32_t *valid;      // bit per edge or nullptr (mask dropped)
+    const uint32_t *sfx;        // 2 words per indexed suffix: [begin, end) edge range
+    uint64_t n;                 // number of edges (ids 1..n)
+    uint32_t nblk;
+    uint32_t k;                 // DBG k; BOSS node length = k - 1
+    uint32_t sfx_len;
+    uint32_t sigma;
+    uint64_t F[kSigmaDNA];
+    uint64_t NF[kSigmaDNA];
+    uint32_t total_W[kSigmaDNA];
+    uint64_t num_ones;
+};
+
+// ---------------------------------------------------------------------------------------
+// A 64-byte block held by a quad (device) or by the single host lane (emulation).
+// ---------------------------------------------------------------------------------------
+#if MGB_DEVICE_CODE
+struct Line { uint32_t x, y, z, w; };
+static constexpr int kGroup = 4;
+MGB_D int glane() { return quad_lane(); }
+MGB_D Line load_line(const IndexView &ix, uint32_t blk) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(ix.blocks) + (size_t)blk * 4 + quad_lane());
+    Line l; l.x = v.x; l.y = v.y; l.z = v.z; l.w = v.w;
+    return l;
+}
+MGB_D uint32_t line_word(const Line &l, int idx) {
+    int c = idx & 3;
+    uint32_t v = c == 0 ? l.x : c == 1 ? l.y : c == 2 ? l.z : l.w;
+    return qbcast(v, idx >> 2);
+}
+MGB_D uint32_t gsum_or(uint32_t s) {   // lanes 2,3 contribute 0 to sums over W words
+    s += qxor(s, 1);
+    s |= qxor(s, 2);
+    return s;
+}
+MGB_D uint32_t gmin(uint32_t s) {
+    uint32_t o = qxor(s, 1); s = o < s ? o : s;
+    o = qxor(s, 2); s = o < s ? o : s;
+    return s;
+}
+MGB_D unsigned gballot(bool p) { return (__ballot_sync(quad_mask(), p) >> (threadIdx.x & 28)) & 0xFu; }
+MGB_D uint32_t ldg32(const uint32_t *p) { return __ldg(p); }
+#else
+struct Line { uint32_t w16[16]; };
+static constexpr int kGroup = 1;
+inline int glane() { return 0; }
+inline Line load_line(const IndexView &ix, uint32_t blk) {
+    Line l;
+    for (int i = 0; i < 16; ++i) l.w16[i] = ix.blocks[(size_t)blk * 16 + i];
+    return l;
+}
+inline uint32_t line_word(const Line &l, int idx) { return l.w16[idx]; }
+inline uint32_t gsum_or(uint32_t s) { return s; }
+inline uint32_t gmin(uint32_t s) { return s; }
+inline unsigned gballot(bool p) { return p ? 1u : 0u; }
+inline uint32_t ldg32(const uint32_t *p) { return *p; }
+#endif
+
+// one bit per nibble of x that equals c
+MGB_HD uint32_t nib_eq(uint32_t x, uint32_t c) {
+    uint32_t y = x ^ (c * 0x11111111u);
+    y |= y >> 1;
+    y |= y >> 2;
+    return ~y & 0x11111111u;
+}
+// nibble positions 0..m of a word (m may be < 0 or > 7)
+MGB_HD uint32_t nib_prefix(int m) {
+    return m < 0 ? 0u : (m >= 7 ? 0x11111111u : (0x11111111u >> (4 * (7 - m))));
+}
+MGB_HD uint32_t nib_suffix(int m) {   // nibble positions m..7
+    return m <= 0 ? 0x11111111u : (m > 7 ? 0u : (0x11111111u << (4 * m)));
+}
+
+// number of W == c among in-block offsets [0, off]
+MGB_HD uint32_t line_count_W(const Line &l, int off, uint32_t c) {
+    uint32_t cnt = 0;
+#if MGB_DEVICE_CODE
+    int q = quad_lane();
+    if (q < 2) {
+        int base = 32 * q;
+        cnt += popc32(nib_eq(l.x, c) & nib_prefix(off - base));
+        cnt += popc32(nib_eq(l.y, c) & nib_prefix(off - base - 8));
+        cnt += popc32(nib_eq(l.z, c) & nib_prefix(off - base - 16));
+        cnt += popc32(nib_eq(l.w, c) & nib_prefix(off - base - 24));
+    }
+    cnt = gsum_or(cnt);
+#else
+    for (int t = 0; t < 8; ++t)
+        cnt += popc32(nib_eq(l.w16[t], c) & nib_prefix(off - 8 * t));
+#endif
+    return cnt;
+}
+
+MGB_HD uint32_t line_get_W(const Line &l, int off) {
+    return (line_word(l, off >> 3) >> (4 * (off & 7))) & 15u;
+}
+MGB_HD bool line_get_last(const Line &l, int off) {
+    return (line_word(l, 8 + (off >> 5)) >> (off & 31)) & 1u;
+}
+MGB_HD uint32_t line_count_last(const Line &l, int off) {   // set bits at offsets [0, off]
+    uint32_t lo = line_word(l, 8), hi = line_word(l, 9);
+    if (off < 32)
+        return popc32(lo & (off == 31 ? 0xffffffffu : ((2u << off) - 1u)));
+    off -= 32;
+    return popc32(lo) + popc32(hi & (off == 31 ? 0xffffffffu : ((2u << off) - 1u)));
+}
+
+// A cached block: re-loaded only when another block is touched.
+struct LineCache {
+    Line line;
+    uint32_t blk;
+    bool valid_;
+    MGB_HD LineCache() : blk(0), valid_(false) {}
+    MGB_HD void touch(const IndexView &ix, uint64_t edge) {
+        uint32_t b = (uint32_t)(edge >> 6);
+        if (!valid_ || b != blk) { line = load_line(ix, b); blk = b; valid_ = true; }
+    }
+    MGB_HD uint32_t get_W(const IndexView &ix, uint64_t e) { touch(ix, e); return line_get_W(line, (int)(e & 63)); }
+    MGB_HD bool get_last(const IndexView &ix, uint64_t e) { touch(ix, e); return line_get_last(line, (int)(e & 63)); }
+};
+
+// boss.cpp:437-441; positions [1..i], un-flagged symbol c only
+MGB_HD uint64_t rank_W(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t c) {
+    if (i == 0) return 0;
+    lc.touch(ix, i);
+    return (uint64_t)line_word(lc.line, 11 + c) + line_count_W(lc.line, (int)(i & 63), c);
+}
+// boss.cpp:577-581
+MGB_HD uint64_t rank_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    if (i == 0) return 0;
+    lc.touch(ix, i);
+    return (uint64_t)line_word(lc.line, 10) + line_count_last(lc.line, (int)(i & 63));
+}
+
+// boss.cpp:588-592: position of the r-th set bit of `last` (r >= 1); leaves its block in lc
+MGB_HD uint64_t select_last(const IndexView &ix, LineCache &lc, uint64_t r) {
+    if (r == 0) return 0;
+    uint64_t j = (r - 1) / kSelLastRate;
+    uint32_t b = ldg32(ix.sel_last + j), b1 = ldg32(ix.sel_last + j + 1);
+    // largest block b in [b, b1] with blk_rank[b] < r
+    for (uint32_t base = b + 1; base <= b1; base += kGroup) {
+        uint32_t cand = base + glane();
+        bool p = cand <= b1 && ldg32(ix.blk_rank + cand) < r;
+        int cnt = popc32(gballot(p));
+        b += cnt;
+        if (cnt < kGroup) break;
+    }
+    lc.touch(ix, (uint64_t)b << 6);
+    int t = (int)(r - line_word(lc.line, 10));
+    uint32_t lo = line_word(lc.line, 8), hi = line_word(lc.line, 9);
+    int plo = popc32(lo);
+    int pos = t <= plo ? nth_set32(lo, t) : 32 + nth_set32(hi, t - plo);
+    return ((uint64_t)b << 6) + pos;
+}
+
+// wavelet_tree::select(c, r) (wavelet_tree.cpp:352-357) for un-flagged c, r >= 1
+MGB_HD uint64_t select_W(const IndexView &ix, LineCache &lc, uint32_t c, uint64_t r) {
+    uint64_t j = (r - 1) / kSelWRate;
+    uint32_t b = ldg32(ix.sel_W[c] + j), b1 = ldg32(ix.sel_W[c] + j + 1);
+    for (uint32_t base = b + 1; base <= b1; base += kGroup) {
+        uint32_t cand = base + glane();
+        bool p = cand <= b1 && ldg32(ix.blocks + (size_t)cand * kBlkWords + 11 + c) < r;
+        int cnt = popc32(gballot(p));
+        b += cnt;
+        if (cnt < kGroup) break;
+    }
+    lc.touch(ix, (uint64_t)b << 6);
+    int t = (int)(r - line_word(lc.line, 11 + c));   // t-th occurrence inside the block
+    // every lane scans the 8 W words (uniform result)
+    int pos = -1;
+    for (int w = 0; w < 8 && pos < 0; ++w) {
+        uint32_t m = nib_eq(line_word(lc.line, w), c);
+        int pc = popc32(m);
+        if (t <= pc) pos = 8 * w + (nth_set32(m, t) >> 2);
+        else t -= pc;
+    }
+    return ((uint64_t)b << 6) + pos;
+}
+
+// boss.cpp:598-607: last set bit of `last` in [1..i], 0 if none
+MGB_HD uint64_t pred_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    while (i) {
+        lc.touch(ix, i);
+        int off = (int)(i & 63);
+        uint32_t lo = line_word(lc.line, 8), hi = line_word(lc.line, 9);
+        uint64_t bits = ((uint64_t)hi << 32) | lo;
+        bits &= off == 63 ? ~0ull : ((2ull << off) - 1ull);
+        if (bits) {
+            uint32_t h = (uint32_t)(bits >> 32);
+            int p = h ? 63 - clz32(h) : 31 - clz32((uint32_t)bits);
+            return (i & ~63ull) + p;
+        }
+        if ((i >> 6) == 0) return 0;
+        i = (i & ~63ull) - 1;
+    }
+    return 0;
+}
+
+// boss.cpp:613-617: first set bit of `last` at a position >= i; n + 1 if none
+MGB_HD uint64_t succ_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    while (i <= ix.n) {
+        lc.touch(ix, i);
+        int off = (int)(i & 63);
+        uint32_t lo = line_word(lc.line, 8), hi = line_word(lc.line, 9);
+        uint64_t bits = (((uint64_t)hi << 32) | lo) >> off << off;
+        if (bits) {
+            uint32_t l = (uint32_t)bits;
+            int p = l ? ffs32(l) - 1 : 32 + ffs32((uint32_t)(bits >> 32)) - 1;
+            return (i & ~63ull) + p;
+        }
+        i = (i & ~63ull) + 64;
+    }
+    return ix.n + 1;
+}
+
+// boss.cpp:679-690
+MGB_HD uint32_t node_last_value(const IndexView &ix, uint64_t i) {
+    if (i == 0) return 0;
+    for (uint32_t c = 0; c < ix.sigma; ++c)
+        if (ix.F[c] >= i) return c - 1;
+    return ix.sigma - 1;
+}
+
+// boss.cpp:642-652
+MGB_HD uint64_t fwd(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t c) {
+    return select_last(ix, lc, ix.NF[c] + rank_W(ix, lc, i, c));
+}
+
+// boss.cpp:623-636
+MGB_HD uint64_t bwd(const IndexView &ix, LineCache &lc, uint64_t i) {
+    uint64_t target_node = rank_last(ix, lc, i - 1) + 1;
+    if (target_node == 1) return 1;
+    uint32_t c = node_last_value(ix, i);
+    return select_W(ix, lc, c, target_node - ix.NF[c]);
+}
+
+// boss.cpp:710-722
+MGB_HD uint64_t pick_edge(const IndexView &ix, LineCache &lc, uint64_t edge, uint32_t c) {
+    do {
+        uint32_t w = lc.get_W(ix, edge);
+        if (w == c || w == c + ix.sigma) return edge;
+    } while (--edge && !lc.get_last(ix, edge));
+    return 0;
+}
+
+// First position p >= i with W[p] in { d, d + sigma } (boss.cpp:515-570 succ_W with two
+// symbols); returns n + 1 and *w = 0 if none.
+MGB_HD uint64_t succ_W2(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t d, uint32_t *w) {
+    while (i <= ix.n) {
+        lc.touch(ix, i);
+        int off = (int)(i & 63);
+        uint32_t best = 64;
+#if MGB_DEVICE_CODE
+        int q = quad_lane();
+        if (q < 2) {
+            uint32_t ws[4] = { lc.line.x, lc.line.y, lc.line.z, lc.line.w };
+#pragma unroll
+            for (int t = 3; t >= 0; --t) {
+                int base = 32 * q + 8 * t;
+                uint32_t m = (nib_eq(ws[t], d) | nib_eq(ws[t], d + ix.sigma)) & nib_suffix(off - base);
+                if (m) best = base + ((ffs32(m) - 1) >> 2);
+            }
+        }
+        best = gmin(best);
+#else
+        for (int t = 7; t >= 0; --t) {
+            uint32_t x = lc.line.w16[t];
+            uint32_t m = (nib_eq(x, d) | nib_eq(x, d + ix.sigma)) & nib_suffix(off - 8 * t);
+            if (m) best = 8 * t + ((ffs32(m) - 1) >> 2);
+        }
+#endif
+        if (best < 64) {
+            uint64_t p = (i & ~63ull) + best;
+            if (p > ix.n) break;
+            *w = line_get_W(lc.line, (int)best);
+            return p;
+        }
+        i = (i & ~63ull) + 64;
+    }
+    *w = 0;
+    return ix.n + 1;
+}
+
+// dbg_succinct.cpp:934-939
+MGB_HD bool in_graph(const IndexView &ix, uint64_t node) {
+    if (node == 0 || node > ix.n) return false;
+    if (!ix.valid) return true;
+    return (ldg32(ix.valid + (node >> 5)) >> (node & 31)) & 1u;
+}
+
+// boss.hpp:682-693. Both ends are advanced together so their loads overlap.
+MGB_HD bool tighten_range(const IndexView &ix, uint64_t *rl, uint64_t *ru, uint32_t s) {
+    LineCache la, lb;
+    uint64_t rk_rl = rank_W(ix, la, *rl - 1, s) + 1;
+    uint64_t rk_ru = rank_W(ix, lb, *ru, s);
+    if (rk_rl > rk_ru) return false;
+    *rl = select_last(ix, la, ix.NF[s] + rk_rl - 1) + 1;
+    *ru = select_last(ix, lb, ix.NF[s] + rk_ru);
+    return true;
+}
+
+// boss.hpp:636-680 (codes must be < sigma)
+MGB_HD void initial_range(const IndexView &ix, const uint8_t *begin, int len,
+                          uint64_t *rl, uint64_t *ru, int *offset) {
+    bool use_sfx = ix.sfx_len && (int)ix.sfx_len <= len;
+    if (use_sfx) {
+        for (uint32_t i = 0; i < ix.sfx_len; ++i)
+            if (begin[i] == 0) use_sfx = false;
+    }
+    if (use_sfx) {
+        uint64_t index = 0;
+        for (int i = (int)ix.sfx_len - 1; i >= 0; --i)
+            index = index * (ix.sigma - 1) + (begin[i] - 1);
+        *rl = ldg32(ix.sfx + 2 * index);
+        *ru = (uint64_t)ldg32(ix.sfx + 2 * index + 1) - 1;
+        *offset = ix.sfx_len;
+    } else {
+        uint32_t s = begin[0];
+        *rl = ix.F[s] + 1 < ix.n + 1 ? ix.F[s] + 1 : ix.n + 1;
+        *ru = s + 1 < ix.sigma ? ix.F[s + 1] : ix.n;
+        *offset = 1;
+    }
+}
+
+// boss.hpp:695-718: last edge of the node spelled by codes[0..len) (len == k - 1), 0 if absent.
+// Codes equal to sigma are invalid.
+MGB_HD uint64_t boss_index(const IndexView &ix, const uint8_t *codes, int len) {
+    for (int i = 0; i < len; ++i)
+        if (codes[i] >= ix.sigma) return 0;
+    uint64_t rl, ru; int off;
+    initial_range(ix, codes, len, &rl, &ru, &off);
+    if (rl > ru) return 0;
+    for (int i = off; i < len; ++i)
+        if (!tighten_range(ix, &rl, &ru, codes[i])) return 0;
+    return ru;
+}
+
+// boss.hpp:720-764: longest matching prefix of codes[0..len) (len <= k - 1) and its edge
+// range; *matched = number of matched characters (0 -> (0, 0)).
+MGB_HD void boss_index_range(const IndexView &ix, const uint8_t *codes, int len,
+                             uint64_t *first, uint64_t *lst, int *matched) {
+    if (len == 0) { *first = 1; *lst = 1; *matched = 0; return; }
+    for (int i = 0; i < len; ++i)
+        if (codes[i] >= ix.sigma) { *first = 0; *lst = 0; *matched = 0; return; }
+    uint64_t rl, ru; int off;
+    initial_range(ix, codes, len, &rl, &ru, &off);
+    if (rl > ru) {
+        uint32_t s = codes[0];
+        rl = ix.F[s] + 1 < ix.n + 1 ? ix.F[s] + 1 : ix.n + 1;
+        ru = s + 1 < ix.sigma ? ix.F[s + 1] : ix.n;
+        if (rl > ru) { *first = 0; *lst = 0; *matched = 0; return; }
+        off = 1;
+    }
+    int i = off;
+    for (; i < len; ++i)
+        if (!tighten_range(ix, &rl, &ru, codes[i])) break;
+    LineCache lc;
+    *first = succ_last(ix, lc, rl);
+    *lst = ru;
+    *matched = i;
+}
+
+} // namespace mgb

@@ -1,0 +1,171 @@
+// Host-side construction of the flat GPU index (layout: index.cuh) from BOSS arrays
+// W / last / F, as handed over by the reference's DBGSuccinct (boss.hpp:499-525).
+// Pure C++; used by the C-ABI (api.cu) and by the host-emulation test harness.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "index.cuh"
+
+namespace mgb {
+
+struct HostIndex {
+    std::vector<uint32_t> blocks, blk_rank, sel_last, valid, sfx;
+    std::vector<uint32_t> sel_W[kSigmaDNA];
+    uint64_t n = 0; uint32_t nblk = 0, k = 0, sfx_len = 0, sigma = kSigmaDNA;
+    uint64_t F[kSigmaDNA], NF[kSigmaDNA]; uint32_t total_W[kSigmaDNA]; uint64_t num_ones = 0;
+
+    // view over the host vectors (emulation) — the device view is assembled in api.cu
+    IndexView view() const {
+        IndexView v;
+        v.blocks = blocks.data(); v.blk_rank = blk_rank.data(); v.sel_last = sel_last.data();
+        for (int c = 0; c < kSigmaDNA; ++c) v.sel_W[c] = sel_W[c].data();
+        v.valid = valid.empty() ? nullptr : valid.data();
+        v.sfx = sfx.empty() ? nullptr : sfx.data();
+        v.n = n; v.nblk = nblk; v.k = k; v.sfx_len = sfx_len; v.sigma = sigma;
+        for (int c = 0; c < kSigmaDNA; ++c) { v.F[c] = F[c]; v.NF[c] = NF[c]; v.total_W[c] = total_W[c]; }
+        v.num_ones = num_ones;
+        return v;
+    }
+};
+
+// n_plus_1 = number of edges + 1 (position 0 is the placeholder, boss_chunk.cpp:60-62)
+inline void build_host_index(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1,
+                             const uint64_t *F, const uint8_t *valid_bytes, uint32_t k,
+                             uint32_t suffix_len, HostIndex *out) {
+    HostIndex &h = *out;
+    if (n_plus_1 < 2) throw std::invalid_argument("empty BOSS table");
+    if (n_plus_1 - 1 >= (1ull << 32) - 64) throw std::invalid_argument("more than 2^32 edges");
+    if (k < 2) throw std::invalid_argument("k must be >= 2");
+    h.n = n_plus_1 - 1; h.k = k; h.sigma = kSigmaDNA;
+    h.nblk = (uint32_t)((h.n >> 6) + 1);
+    h.blocks.assign((size_t)h.nblk * kBlkWords, 0);
+    h.blk_rank.assign(h.nblk + 1, 0);
+    uint32_t cnt[kSigmaDNA] = { 0, 0, 0, 0, 0 };
+    uint32_t ones = 0;
+    h.sel_last.clear();
+    for (int c = 0; c < kSigmaDNA; ++c) h.sel_W[c].clear();
+    for (uint32_t b = 0; b < h.nblk; ++b) {
+        uint32_t *blk = &h.blocks[(size_t)b * kBlkWords];
+        blk[10] = ones;
+        h.blk_rank[b] = ones;
+        for (int c = 0; c < kSigmaDNA; ++c) blk[11 + c] = cnt[c];
+        for (int off = 0; off < kBlkEdges; ++off) {
+            uint64_t i = ((uint64_t)b << 6) + off;
+            uint32_t w = 0xF; uint32_t l = 0;
+            if (i >= 1 && i <= h.n) {
+                w = W[i];
+                if (w >= 2 * kSigmaDNA) throw std::invalid_argument("W value out of range");
+                l = last[i] ? 1 : 0;
+            }
+            blk[off >> 3] |= w << (4 * (off & 7));
+            blk[8 + (off >> 5)] |= l << (off & 31);
+            if (l) {
+                if (ones % kSelLastRate == 0) h.sel_last.push_back(b);
+                ++ones;
+            }
+            if (w < kSigmaDNA) {
+                if (cnt[w] % kSelWRate == 0) h.sel_W[w].push_back(b);
+                ++cnt[w];
+            }
+        }
+    }
+    h.blk_rank[h.nblk] = ones;
+    h.num_ones = ones;
+    h.sel_last.push_back(h.nblk - 1);
+    h.sel_last.push_back(h.nblk - 1);
+    for (int c = 0; c < kSigmaDNA; ++c) {
+        h.total_W[c] = cnt[c];
+        h.sel_W[c].push_back(h.nblk - 1);
+        h.sel_W[c].push_back(h.nblk - 1);
+    }
+    for (int c = 0; c < kSigmaDNA; ++c) h.F[c] = F[c];
+    // NF[c] = rank_last(F[c]) (boss.cpp:1095-1101)
+    {
+        std::vector<uint64_t> pref;   // computed lazily via blk_rank + scan
+        for (int c = 0; c < kSigmaDNA; ++c) {
+            uint64_t i = F[c], r = 0;
+            if (i) {
+                r = h.blk_rank[i >> 6];
+                for (uint64_t p = (i >> 6) << 6; p <= i; ++p) r += (p >= 1 && last[p]) ? 1 : 0;
+            }
+            h.NF[c] = r;
+        }
+    }
+    h.valid.clear();
+    if (valid_bytes) {
+        h.valid.assign((n_plus_1 + 31) / 32 + 1, 0);
+        for (uint64_t i = 1; i <= h.n; ++i)
+            if (valid_bytes[i]) h.valid[i >> 5] |= 1u << (i & 31);
+    }
+    // suffix ranges (boss.hpp:516-525, boss_chunk_construct.cpp:260-320): for every string
+    // over the sigma-1 real symbols of length s, the [begin, end) edge range of the nodes
+    // ending with it, in co-lex index order. Computed by refinement from length s-1 with
+    // host-only rank/select over the byte arrays (tighten_range, boss.hpp:682-693).
+    h.sfx.clear(); h.sfx_len = 0;
+    uint32_t s = suffix_len;
+    if (s > k - 1) s = k - 1;
+    if (s) {
+        // rank_W(i, c) for c in 1..4 sampled every 64 positions; positions of set `last` bits
+        const uint64_t np1 = n_plus_1;
+        std::vector<uint32_t> wr((np1 / 64 + 1) * kSigmaDNA, 0);
+        std::vector<uint32_t> ones_pos;   // select_last(r) = ones_pos[r - 1]
+        ones_pos.reserve(ones);
+        {
+            uint32_t c2[kSigmaDNA] = { 0, 0, 0, 0, 0 };
+            for (uint64_t i = 0; i < np1; ++i) {
+                if (i % 64 == 0) for (int c = 0; c < kSigmaDNA; ++c) wr[(i / 64) * kSigmaDNA + c] = c2[c];
+                if (i >= 1) {
+                    if (W[i] < kSigmaDNA) ++c2[W[i]];
+                    if (last[i]) ones_pos.push_back((uint32_t)i);
+                }
+            }
+        }
+        auto rankW = [&](uint64_t i, uint32_t c) -> uint64_t {     // occurrences in [1..i]
+            if (i == 0) return 0;
+            uint64_t r = wr[(i / 64) * kSigmaDNA + c];
+            for (uint64_t p = (i / 64) * 64; p <= i; ++p) r += (p >= 1 && W[p] == c);
+            return r;
+        };
+        auto selectLast = [&](uint64_t r) -> uint64_t { return r == 0 ? 0 : ones_pos[r - 1]; };
+        auto tighten = [&](uint64_t *rl, uint64_t *ru, uint32_t c) -> bool {
+            uint64_t rk_rl = rankW(*rl - 1, c) + 1, rk_ru = rankW(*ru, c);
+            if (rk_rl > rk_ru) return false;
+            *rl = selectLast(h.NF[c] + rk_rl - 1) + 1;
+            *ru = selectLast(h.NF[c] + rk_ru);
+            return true;
+        };
+        std::vector<uint32_t> cur(2 * (kSigmaDNA - 1)), nxt;
+        for (uint32_t c = 1; c < kSigmaDNA; ++c) {   // length 1: [F[c] + 1, F[c + 1] + 1)
+            uint64_t rl = F[c] + 1 < h.n + 1 ? F[c] + 1 : h.n + 1;
+            uint64_t ru = c + 1 < kSigmaDNA ? F[c + 1] : h.n;
+            cur[2 * (c - 1)] = (uint32_t)rl;
+            cur[2 * (c - 1) + 1] = (uint32_t)(ru + 1);
+        }
+        uint64_t cur_num = kSigmaDNA - 1;
+        for (uint32_t len = 2; len <= s; ++len) {
+            // new index = old_index + (c - 1) * (sigma-1)^(len-1): the appended character is
+            // the most significant digit (boss.hpp:651-655)
+            nxt.assign(2 * cur_num * (kSigmaDNA - 1), 1);
+            for (uint32_t c = 1; c < kSigmaDNA; ++c) {
+                for (uint64_t idx = 0; idx < cur_num; ++idx) {
+                    uint64_t rl = cur[2 * idx], ru = (uint64_t)cur[2 * idx + 1] - 1;
+                    uint64_t o = idx + (uint64_t)(c - 1) * cur_num;
+                    if (rl <= ru && tighten(&rl, &ru, c)) {
+                        nxt[2 * o] = (uint32_t)rl; nxt[2 * o + 1] = (uint32_t)(ru + 1);
+                    }
+                }
+            }
+            cur.swap(nxt);
+            cur_num *= (kSigmaDNA - 1);
+        }
+        for (uint64_t idx = 0; idx < cur_num; ++idx)
+            if (cur[2 * idx] >= cur[2 * idx + 1]) { cur[2 * idx] = 1; cur[2 * idx + 1] = 1; }
+        h.sfx = std::move(cur);
+        h.sfx_len = s;
+    }
+}
+
+} // namespace mgb

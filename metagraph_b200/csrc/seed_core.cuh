@@ -1,0 +1,80 @@
+// Exact seeding: BOSS::map_to_edges (boss.cpp:996-1045) for one strand of one read, executed
+// by one quad (4 lanes share every 64-byte index block; 8 strands per warp are in flight).
+// Also the query preparation (upper-casing, reverse complement, alphabet codes:
+// alignment.cpp:1348-1372, kmer_extractor.cpp:30-44, seq_tools/reverse_complement.hpp).
+#pragma once
+#include "index.cuh"
+
+namespace mgb {
+
+// kBOSSCharToDNA (kmer/alphabets.hpp:67-76) restated as arithmetic: A/a=1 C/c=2 G/g=3
+// T/t/U/u=4, everything else (and bytes >= 128) = 5 = sigma (invalid).
+MGB_HD uint8_t encode_dna(uint8_t ch) {
+    if (ch >= 128) return 5;
+    uint8_t u = ch & 0xDF;   // fold case for letters
+    if (ch < 64) return 5;
+    return u == 'A' ? 1 : u == 'C' ? 2 : u == 'G' ? 3 : (u == 'T' || u == 'U') ? 4 : 5;
+}
+
+// COMPL_TAB (seq_tools/reverse_complement.hpp:31-48) restated: IUPAC complement for both
+// cases, 'U' -> 'A', '`' -> '@', identity elsewhere.
+MGB_HD uint8_t complement_char(uint8_t ch) {
+    if (ch == 96) return 64;
+    uint8_t u = ch & 0xDF;
+    if (ch < 64 || ch >= 128 || u < 'A' || u > 'Z') return ch;
+    uint8_t lower = ch & 0x20;
+    uint8_t r;
+    switch (u) {
+        case 'A': r = 'T'; break; case 'B': r = 'V'; break; case 'C': r = 'G'; break;
+        case 'D': r = 'H'; break; case 'G': r = 'C'; break; case 'H': r = 'D'; break;
+        case 'K': r = 'M'; break; case 'M': r = 'K'; break; case 'R': r = 'Y'; break;
+        case 'T': r = 'A'; break; case 'U': r = 'A'; break; case 'V': r = 'B'; break;
+        case 'Y': r = 'R'; break; default: r = u;
+    }
+    return r | lower;
+}
+
+// AlignmentResults ctor (alignment.cpp:1357-1358): toupper, bytes >= 128 -> 127
+MGB_HD uint8_t sanitize_char(uint8_t ch) {
+    if (ch >= 128) return 127;
+    return (ch >= 'a' && ch <= 'z') ? ch - 32 : ch;
+}
+
+// map_to_edges for codes[0..L). Writes L - K + 1 node ids (validate_edge applied) to `out`
+// and, if `flags` != nullptr, per k-mer bit0 = "BOSS fwd() of this edge lands on a node with
+// more than one outgoing edge" when the walk continued from it (used for the UniMEM
+// terminator, dbg_succinct.cpp:617-630 has_multiple_outgoing).
+// All lanes of the group execute this with identical arguments; lane 0 of the group stores.
+MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint64_t *out) {
+    const int K = (int)ix.k;
+    if (L < K) return;
+    const bool writer = glane() == 0;
+    // index of the last invalid character seen in the current window, or -1
+    int last_inv = -1;
+    for (int j = 0; j < K - 1; ++j)
+        if (codes[j] >= ix.sigma) last_inv = j;
+    LineCache lc;
+    for (int i = 0; i + K <= L; ++i) {
+        if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
+        if (last_inv >= i) {              // invalid[i + k_]
+            if (writer) out[i] = 0;
+            continue;
+        }
+        // map_to_edge (boss.hpp:766-777)
+        uint64_t edge = boss_index(ix, codes + i, K - 1);
+        if (edge) edge = pick_edge(ix, lc, edge, codes[i + K - 1]);
+        if (writer) out[i] = in_graph(ix, edge) ? edge : 0;
+        while (edge && ++i + K - 1 < L) {
+            if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
+            if (last_inv >= i) {
+                if (writer) out[i] = 0;
+                break;
+            }
+            edge = fwd(ix, lc, edge, codes[i + K - 2]);
+            edge = pick_edge(ix, lc, edge, codes[i + K - 1]);
+            if (writer) out[i] = in_graph(ix, edge) ? edge : 0;
+        }
+    }
+}
+
+} // namespace mgb

@@ -1259,8 +1259,9 @@ class Aggregator {
     std::vector<Alignment> get_alignments() {
         std::vector<Alignment> out = std::move(q_);
         q_.clear();
-        std::stable_sort(out.begin(), out.end(), cmp_);
-        std::reverse(out.begin(), out.end());
+        // descending; ties (std::sort leaves them unspecified in the reference) keep insertion order
+        std::stable_sort(out.begin(), out.end(),
+                         [&](const Alignment &a, const Alignment &b) { return cmp_(b, a); });
         return out;
     }
 
