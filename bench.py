@@ -1,0 +1,318 @@
+#!/usr/bin/env python3
+"""Benchmark of the `metagraph align` hot path on B200 (BASELINE.json metric: aligned reads/sec on
+synthetic 150 bp reads).
+
+Workload at N=1 (BASELINE.json configs[1]): 1 M synthetic 150 bp DNA reads (mt19937-style seed 42, 50 %
+reverse-complemented, error-free) against a k=31 BOSS graph of a 100 Mbp uniform random genome (seed 32,
+~100 M nodes), exact-match seeder (--align-min-seed-length 31 --align-max-seed-length 31), CLI-default
+scoring, seed complexity filter off (sdust is not vendored in the reference tree).
+
+One step = one pass of the hot path (query preparation + exact seeding + seed-and-extend) over the
+whole read batch of this rank. `value` counts device time only (inputs resident in HBM; CUDA events on
+the launching stream around the kernels, reported by the C-ABI in mgb_stats_t). `e2e` is the same metric
+through the reference-facing call mgb_align_batch() with pinned HOST buffers: H2D of the reads, all
+kernels, D2H of the packed results and host unpacking inside the timed region.
+
+Multi-GPU: reads shard across ranks (weak scaling: every rank aligns its own batch), the BOSS index is
+built once on rank 0 and broadcast over NCCL, and per-read result summaries are gathered on rank 0 with
+one NCCL gather; there is no collective on the data path itself.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K = 31
+READ_LEN = 150
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def make_genome(G):
+    rng = np.random.default_rng(32)
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G, dtype=np.uint8)]
+
+
+def make_reads(genome, n, seed):
+    """error-free reads, 50 % reverse-complemented; returns (uint8 buffer, uint64 offsets)"""
+    rng = np.random.default_rng(seed)
+    starts = rng.integers(0, len(genome) - READ_LEN, n)
+    idx = starts[:, None] + np.arange(READ_LEN)[None, :]
+    reads = genome[idx]
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    rc = rng.random(n) < 0.5
+    reads[rc] = comp[reads[rc]][:, ::-1]
+    return np.ascontiguousarray(reads.reshape(-1)), np.arange(n + 1, dtype=np.uint64) * READ_LEN
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def cpu_reference(boss, reads_buf, offsets, cfg, target_seconds, threads, n_max):
+    """Times the CPU restatement of the reference algorithm (oracle/) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    g = O.OracleGraph(K, arrays=(boss.W, boss.last, boss.F))
+    def reads_of(a, b):
+        return [bytes(reads_buf[int(offsets[i]):int(offsets[i + 1])]) for i in range(a, b)]
+    probe = min(n_max, max(threads * 16, 512))
+    t = time.time(); g.align_tsv(cfg, reads_of(0, probe), threads=threads); dt = time.time() - t
+    rate = probe / max(dt, 1e-6)
+    n = int(min(n_max, max(probe, rate * target_seconds)))
+    t = time.time(); g.align_tsv(cfg, reads_of(0, n), threads=threads); dt = time.time() - t
+    return n / dt, n, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    G = env_int("BENCH_GENOME", 100_000_000)
+    N = env_int("BENCH_READS", 1_000_000)
+    host_threads = os.cpu_count() or 1
+
+    from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex
+    from metagraph_b200.config import cli_defaults
+    cfg = cli_defaults(K, min_seed_length=K, max_seed_length=K)
+    workload = ("%d synthetic %d bp DNA reads/GPU (50%% rc, error-free) vs k=%d BOSS graph of a %d bp random "
+                "genome, exact-match seeder, CLI-default scoring" % (N, READ_LEN, K, G))
+    config = {"workload": workload, "reads_per_gpu": N, "read_len": READ_LEN, "k": K, "genome_bp": G,
+              "seeder": "exact (min=max seed length = k)", "l2_policy": "inputs larger than L2 "
+              "(index + node arrays + per-warp arenas >> 126 MB)", "parallelism": "reads sharded x%d" % world}
+
+    # ---------------------------------------------------------------- reference arm (CPU) ----
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        genome = make_genome(G)
+        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
+        buf, offsets = make_reads(genome, min(N, 200_000), 42)
+        per_step = []
+        sample_n = 0
+        for s in range(args.warmup + args.steps):
+            rate, n, dt = cpu_reference(boss, buf, offsets, cfg, 8.0, host_threads, len(offsets) - 1)
+            sample_n = n
+            if s >= args.warmup:
+                per_step.append((rate, dt))
+        value = float(np.mean([r for r, _ in per_step]))
+        line = {"impl": "reference", "metric": "aligned reads/sec (150 bp synthetic)", "value": value,
+                "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(np.mean([d for _, d in per_step]) * 1e3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": "reads/s", "cores": host_threads, "kind": "port",
+                                 "sample": "%d reads of the same workload per step (CPU restatement of the "
+                                           "reference algorithm, oracle/, %d threads)" % (sample_n, host_threads)},
+                "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- B200 arm -----------------
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # index build on rank 0 (host, untimed), broadcast of the BOSS arrays over NCCL
+    genome = make_genome(G)
+    if rank == 0:
+        t0 = time.time()
+        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
+        build_s = time.time() - t0
+        meta = torch.tensor([len(boss.W)] + [int(x) for x in boss.F], dtype=torch.int64, device=dev)
+    else:
+        boss, build_s = None, 0.0
+        meta = torch.zeros(6, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(meta, 0)
+        n1 = int(meta[0].item())
+        Wt = torch.from_numpy(boss.W).to(dev) if rank == 0 else torch.empty(n1, dtype=torch.uint8, device=dev)
+        Lt = torch.from_numpy(boss.last).to(dev) if rank == 0 else torch.empty(n1, dtype=torch.uint8, device=dev)
+        dist.broadcast(Wt, 0)
+        dist.broadcast(Lt, 0)
+        if rank != 0:
+            boss = BOSSTable(K, Wt.cpu().numpy(), Lt.cpu().numpy(), meta[1:6].cpu().numpy().astype(np.uint64))
+        del Wt, Lt
+    index = DBGSuccinctIndex(boss, device=local_rank)
+    aligner = B200Aligner(index, cfg)
+
+    buf_np, off_np = make_reads(genome, N, 42 + rank)
+    del genome
+    buf_pin = torch.empty(len(buf_np), dtype=torch.uint8, pin_memory=True)
+    buf_pin.numpy()[:] = buf_np
+    off_pin = torch.empty(len(off_np), dtype=torch.int64, pin_memory=True)
+    off_pin.numpy()[:] = off_np.astype(np.int64)
+    buf = buf_pin.numpy()
+    offsets = off_pin.numpy().view(np.uint64)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        res = aligner.align_batch_raw(buf, offsets)
+        st = aligner.stats_of(res)
+        n_aln = aligner._L.mgb_results_num_alignments(res)
+        # the step's result is read on the host: per-read best score checksum
+        alns = aligner._L.mgb_results_alignments(res)
+        chk = int(alns[0].score) + int(alns[int(n_aln) - 1].score) if n_aln else 0
+        aligner.free_raw(res)
+        return st, int(n_aln), chk
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.time()
+    stats = [step() for _ in range(args.steps)]
+    barrier()
+    wall = time.time() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    dev_ms = sum(s["seed_kernel_ms"] + s["align_kernel_ms"] for s, _, _ in stats)
+    seed_ms = sum(s["seed_kernel_ms"] for s, _, _ in stats) / args.steps
+    align_ms = sum(s["align_kernel_ms"] for s, _, _ in stats) / args.steps
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = t.tolist()
+
+    # final gather of per-rank result summaries on rank 0 over NCCL (north_star: "only a final NCCL
+    # gather of per-read results")
+    summ = torch.tensor([stats[-1][1], stats[-1][2], stats[-1][0]["dp_cells"], stats[-1][0]["dp_columns"]],
+                        dtype=torch.int64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(summ) for _ in range(world)] if rank == 0 else None
+        dist.gather(summ, gathered, dst=0)
+        total_aln = sum(int(g[0]) for g in gathered) if rank == 0 else 0
+    else:
+        total_aln = int(summ[0])
+
+    if rank == 0:
+        total_reads = N * world
+        value = total_reads * args.steps / (dev_ms_max / 1e3)
+        e2e = total_reads * args.steps / (wall_ms_max / 1e3)
+        st = stats[-1][0]
+        peak, peak_kind = measured_peaks()
+        # dominant kernel and its algorithmic bytes per launch (DESIGN.md "Roofline")
+        cols, cells = st["dp_columns"], st["dp_cells"]
+        if align_ms >= seed_ms:
+            kname, kms = "k_align", align_ms
+            alg_bytes = cols * 128 + cells * 12
+        else:
+            kname, kms = "k_seed", seed_ms
+            alg_bytes = N * 27520
+        achieved = alg_bytes / (kms / 1e3) / 1e9
+        # int-pipe view of the extension: 12 int32 ops per DP cell
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        gcups = cells / (align_ms / 1e3) / 1e9
+        gcups_peak = 148 * 128 * sm_clock * 1e6 / 12 / 1e9
+        line = {
+            "metric": "aligned reads/sec (150 bp synthetic)", "value": value, "unit": "reads/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": wall_ms_max / args.steps},
+            "gpu_launches": int(sum(s["kernel_launches"] for s, _, _ in stats)),
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": kms},
+            "kernels_ms_per_step": {"prepare+seed": seed_ms, "align": align_ms},
+            "extension": {"gcups": gcups, "gcups_int32_peak": gcups_peak, "frac": gcups / gcups_peak,
+                          "dp_cells_per_step": int(cells), "dp_columns_per_step": int(cols)},
+            "alignments_gathered": total_aln, "index_build_s": build_s,
+            "index_device_bytes": int(index.device_bytes),
+        }
+        if world == 1:
+            # CPU baseline: oracle (port of the reference algorithm) on all host cores, bounded sample
+            rate, n, dt = cpu_reference(boss, buf_np, off_np, cfg, 10.0, host_threads, min(N, 200_000))
+            line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": host_threads, "kind": "port",
+                                    "sample": "first %d reads of the same workload, %.1f s wall, CPU restatement "
+                                              "of the reference algorithm (oracle/), %d threads" % (n, dt, host_threads)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""Shared parity drivers: run the same inputs through the oracle and through a C-ABI library
+(the sm_100a product library on a GPU box, or the host-emulation build of the same kernel sources
+on a CPU-only machine) and demand identical TSV lines + node paths."""
+import json
+import os
+
+import numpy as np
+
+import oracle_lib as O
+from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex, format_alignment
+from metagraph_b200.config import SIZE_MAX, cli_defaults, struct_defaults
+from test_oracle_golden import GOLD, make_cfg, read_fasta, read_fastq, revcomp
+
+COMP = str.maketrans("ACGT", "TGCA")
+
+
+def mutate(rng, r, rate):
+    out = []
+    for c in r:
+        if rng.random() < rate:
+            y = rng.random()
+            if y < 0.8:
+                out.append("ACGT"[int(rng.integers(0, 4))])
+            elif y < 0.9:
+                out.append(c); out.append("ACGT"[int(rng.integers(0, 4))])
+        else:
+            out.append(c)
+    return "".join(out)
+
+
+def run_lines(idx, cfg, reads, headers=None):
+    headers = headers or [""] * len(reads)
+    al = B200Aligner(idx, cfg)
+    res = al.align_batch(list(zip(headers, reads)))
+    return [format_alignment(h, r, cfg.min_path_score, with_nodes=True) for h, r in zip(headers, res)], al.last_stats
+
+
+def check_goldens(lib):
+    G = json.load(open(os.path.join(GOLD, "test_aligner_goldens.json")))
+    for gold in G:
+        g = O.OracleGraph(gold["k"], gold["refs"], mask=gold["mask"], dynamic=not gold["mask"])
+        W, last, F, valid = g.arrays()
+        idx = DBGSuccinctIndex(BOSSTable(gold["k"], W, last, F), valid=valid if gold["mask"] else None, lib=lib)
+        query = revcomp(gold["query"]) if gold["rc_query"] else gold["query"]
+        for uni in ([False, True] if gold["extend"] else [False]):
+            cfg = make_cfg(gold["cfg"])
+            if uni:
+                cfg.max_seed_length = SIZE_MAX
+            exp = g.align_tsv(cfg, [query], with_nodes=True)
+            got, _ = run_lines(idx, cfg, [query])
+            assert got == exp, (gold["name"], uni, exp, got)
+        idx.close()
+
+
+def check_mt(lib, both):
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    names, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    boss = BOSSTable.from_sequences(11, seqs, lib=lib)
+    g = O.OracleGraph(11, seqs, mask=False)
+    W, last, F, _ = g.arrays()
+    assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
+    idx = DBGSuccinctIndex(boss, lib=lib)
+    cfg = cli_defaults(11, min_exact_match=0.0, forward_and_reverse_complement=both)
+    got, _ = run_lines(idx, cfg, reads, names)
+    exp = g.align_tsv(cfg, reads, headers=names, with_nodes=True)
+    assert got == exp
+    return got
+
+
+def random_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=1):
+    rng = np.random.default_rng(seed)
+    seqs = ["".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])]
+    seqs += [mutate(rng, seqs[0], 0.02) for _ in range(nseq - 1)]
+    g = O.OracleGraph(k, seqs, mask=mask)
+    W, last, F, valid = g.arrays()
+    boss = BOSSTable.from_sequences(k, seqs, lib=lib)
+    assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
+    if mask:
+        assert (boss.dummy_mask(lib=lib) == valid).all()
+    idx = DBGSuccinctIndex(boss, valid=valid if mask else None, lib=lib)
+    reads = []
+    for i in range(nreads):
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        p = int(rng.integers(0, max(1, len(s) - L)))
+        r = mutate(rng, s[p:p + L], rate)
+        if rng.random() < 0.5:
+            r = r.translate(COMP)[::-1]
+        if rng.random() < 0.05 and len(r) > 2:
+            r = r[:len(r) // 2] + "N" + r[len(r) // 2 + 1:]
+        reads.append(r)
+    reads += ["", "A", "ACGT" * 3, "N" * 40]          # empty / shorter than k / all-invalid
+    exp = g.align_tsv(cfg, reads, with_nodes=True)
+    got, stats = run_lines(idx, cfg, reads)
+    bad = [i for i in range(len(reads)) if exp[i] != got[i]]
+    assert not bad, (seed, bad[:3], exp[bad[0]], got[bad[0]])
+    # map_to_nodes parity
+    nodes = idx.map_to_nodes_sequentially(reads)
+    for r, n in zip(reads, nodes):
+        assert list(n) == list(g.map_to_nodes(r)), r
+    idx.close()
+    return stats
+
+
+def sd(**kw):
+    return struct_defaults(**kw)
+
+
+RANDOM_CASES = [
+    # seed, k, G, nreads, L, rate, cfg, mask, nseq
+    (1, 11, 3000, 40, 100, 0.0, lambda k: cli_defaults(k, min_exact_match=0.0), False, 1),
+    (2, 11, 3000, 40, 100, 0.05, lambda k: cli_defaults(k, min_exact_match=0.0), False, 1),
+    (3, 15, 5000, 40, 150, 0.05, lambda k: cli_defaults(k, min_exact_match=0.0), False, 3),
+    (4, 31, 20000, 40, 150, 0.05, lambda k: cli_defaults(k, min_exact_match=0.0), False, 2),
+    (5, 31, 20000, 40, 150, 0.0, lambda k: cli_defaults(k, min_seed_length=31, max_seed_length=31), False, 1),
+    (6, 31, 20000, 40, 150, 0.03, lambda k: cli_defaults(k, min_seed_length=31, max_seed_length=31), False, 3),
+    (7, 9, 2000, 30, 60, 0.05, lambda k: sd(), True, 2),
+    (8, 7, 500, 30, 40, 0.08, lambda k: sd(xdrop=20), True, 2),
+    (9, 21, 10000, 40, 120, 0.08, lambda k: cli_defaults(k, min_exact_match=0.0, num_alternative_paths=2), False, 4),
+    (10, 12, 4000, 30, 300, 0.03, lambda k: cli_defaults(k), False, 2),
+    (11, 31, 20000, 40, 150, 0.05,
+     lambda k: cli_defaults(k, min_exact_match=0.0, forward_and_reverse_complement=False), False, 2),
+]

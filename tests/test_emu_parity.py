@@ -1,0 +1,44 @@
+"""Kernel logic vs oracle on a machine without a GPU: the kernel sources (metagraph_b200/csrc/*.cuh,
+api.cu) compiled by g++ with one-lane warps (tests/emu/, test infrastructure) must reproduce the
+oracle's TSV lines and node paths bit-exactly. The real sm_100a build is checked by test_gpu_parity.py."""
+import os
+import subprocess
+
+import pytest
+
+import parity_common as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "build", "libmgb_emu.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emu_built():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+
+
+def test_goldens_emu():
+    P.check_goldens(EMU)
+
+
+@pytest.mark.parametrize("both", [False, True])
+def test_mt_integration_emu(both):
+    P.check_mt(EMU, both)
+
+
+@pytest.mark.parametrize("case", P.RANDOM_CASES, ids=[str(c[0]) for c in P.RANDOM_CASES])
+def test_random_emu(case):
+    seed, k, G, n, L, rate, cfgf, mask, nseq = case
+    P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
+def test_unsupported_configs_fail_loudly():
+    from metagraph_b200 import _lib
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex, B200Aligner
+    from metagraph_b200.config import struct_defaults
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(4, ["AGCTTCGAGGCCAA"], lib=EMU), lib=EMU)
+    for kw, code in ((dict(seed_complexity_filter=True), -4), (dict(global_xdrop=False), -4),
+                     (dict(num_alternative_paths=99), -4), (dict(min_cell_score=-2**31), -3)):
+        with pytest.raises(_lib.MgbError) as e:
+            B200Aligner(idx, struct_defaults(**kw)).align("AGCTTCGAGG")
+        assert e.value.code == code

@@ -1,0 +1,60 @@
+"""Parity tests proper: the sm_100a library (through the C-ABI) vs the oracle on a real GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_common as P
+
+pytestmark = pytest.mark.gpu
+LIB = None   # product library (metagraph_b200/_lib/libmgb.so)
+
+
+def test_goldens_gpu():
+    P.check_goldens(LIB)
+
+
+@pytest.mark.parametrize("both", [False, True])
+def test_mt_integration_gpu(both):
+    P.check_mt(LIB, both)
+
+
+@pytest.mark.parametrize("case", P.RANDOM_CASES, ids=[str(c[0]) for c in P.RANDOM_CASES])
+def test_random_gpu(case):
+    seed, k, G, n, L, rate, cfgf, mask, nseq = case
+    P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
+def test_c2_scale_properties():
+    """BASELINE config[1] shape at reduced genome size: every error-free read must align end to end
+    ({L}= with score 2L+10), forward reads on '+', reverse-complemented reads on '-', and the path must
+    spell the read; a 2000-read sample is compared with the oracle line by line."""
+    import oracle_lib as O
+    from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex, format_alignment
+    from metagraph_b200.config import cli_defaults
+    k, G, N = 31, 2_000_000, 20000
+    rng = np.random.default_rng(32)
+    genome = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G, dtype=np.uint8)]
+    boss = BOSSTable.from_sequences(k, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
+    idx = DBGSuccinctIndex(boss)
+    rng = np.random.default_rng(42)
+    comp = np.zeros(256, np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i in range(N):
+        p = int(rng.integers(0, G - 150))
+        r = genome[p:p + 150]
+        reads.append(bytes(comp[r][::-1] if i & 1 else r).decode())
+    cfg = cli_defaults(k, min_seed_length=31, max_seed_length=31)
+    al = B200Aligner(idx, cfg)
+    res = al.align_batch([("", r) for r in reads])
+    for i, (r, ar) in enumerate(zip(reads, res)):
+        assert len(ar) == 1
+        a = ar[0]
+        assert a.get_cigar_string() == "150=" and a.score == 310 and a.offset == 0
+        assert a.orientation == bool(i & 1)
+        assert a.sequence == (r.translate(P.COMP)[::-1] if i & 1 else r)
+        assert len(a.nodes) == 120
+    o = O.OracleGraph(k, arrays=(boss.W, boss.last, boss.F))
+    exp = o.align_tsv(cfg, reads[:2000], with_nodes=True, threads=8)
+    got = [format_alignment("", r, 0, with_nodes=True) for r in res[:2000]]
+    assert got == exp
