@@ -69,8 +69,8 @@ struct ColMeta {              // DefaultColumnExtender::DPTColumn (extender.hpp:
 
 struct HeapItem { int32_t score, neg_off_diag; uint32_t idx; int32_t max_score; };
 struct BtStart { int32_t score, neg_off_diag, neg_i, pos; };
-struct ConvSlot { uint64_t key; uint32_t epoch; uint32_t entry; };
-struct ConvEntry { int32_t start, size, seg_start, seg_cap; uint32_t seg_off; uint32_t pad; };
+// convergence-table slot with the entry stored inline (one 32-byte load per probe)
+struct ConvSlot { uint64_t key; uint32_t epoch; int32_t start, size, seg_start, seg_cap; uint32_t seg_off; };
 struct SeedRec { uint32_t clip, len, offset, n_nodes; uint64_t node0; uint32_t alive, pad; };
 
 struct AlnHdr {
@@ -84,9 +84,22 @@ struct AlnHdr {
 
 struct AlnSlot { AlnHdr *h; uint64_t *nodes; char *seq; uint32_t *cigar; };
 
-struct ConvTable {
-    ConvSlot *slots; ConvEntry *entries; score_t *cells;
-    uint32_t epoch, n_entries, cells_used;
+// Per-strand state. Lives in shared memory so that it can be indexed with a run-time strand
+// number without forcing the aligner object out of registers.
+struct StrandCtx {
+    const char *q;               // upper-cased query strand (on-chip copy if staged)
+    int32_t *ps;                 // suffix sums of self-match scores (extender.cpp:26-36)
+    const uint8_t *codes;        // alphabet codes of q
+    const uint64_t *qnodes;      // map_to_nodes_sequentially (nullptr if L < k)
+    SeedRec *seeds;
+    ConvSlot *conv_slots; score_t *conv_cells;      // convergence table of the extender built on this strand
+    uint32_t conv_epoch, conv_n, conv_cells_used;
+    int32_t n_seeds; uint32_t num_matching;
+    uint32_t table_cap;          // std::vector<DPTColumn>::capacity() emulation
+    uint32_t num_ext, explored_prev;
+    uint32_t rc;                 // set_graph(): 1 = RCDBG view
+    uint32_t implicit_seeds;     // 1: seeds are the set bits of `mask` (one k-mer seed per matched k-mer)
+    uint32_t *mask;              // alive bits of implicit seeds (shared memory)
 };
 
 // Per-read output record header; followed in the output heap by packed alignments.
@@ -107,7 +120,7 @@ MGB_HOSTDEV size_t align_up(size_t x) { return (x + 15) & ~(size_t)15; }
 
 struct WarpMem {
     ColMeta *cols; score_t *cells; HeapItem *heap; HeapItem *next_nodes;
-    BtStart *starts; ConvTable conv[2]; SeedRec *seeds[2]; int32_t *psum[2];
+    BtStart *starts; ConvSlot *conv_slots[2]; score_t *conv_cells[2]; SeedRec *seeds[2]; int32_t *psum[2];
     AlnSlot slots[kNumSlots];
     uint32_t *bt_ops; uint64_t *bt_path; char *bt_seq;
     uint8_t *sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
@@ -123,9 +136,8 @@ struct WarpMem {
         next_nodes = (HeapItem*)take(sizeof(HeapItem) * c.max_cols);
         starts = (BtStart*)take(sizeof(BtStart) * 2 * c.max_cols);
         for (int e = 0; e < 2; ++e) {
-            conv[e].slots = (ConvSlot*)take(sizeof(ConvSlot) * c.hash_size);
-            conv[e].entries = (ConvEntry*)take(sizeof(ConvEntry) * c.max_conv_entries);
-            conv[e].cells = (score_t*)take(sizeof(score_t) * c.max_conv_cells);
+            conv_slots[e] = (ConvSlot*)take(sizeof(ConvSlot) * c.hash_size);
+            conv_cells[e] = (score_t*)take(sizeof(score_t) * c.max_conv_cells);
             seeds[e] = (SeedRec*)take(sizeof(SeedRec) * c.max_seeds);
             psum[e] = (int32_t*)take(sizeof(int32_t) * (c.L_max + 8));
         }
@@ -143,6 +155,38 @@ struct WarpMem {
     }
 };
 
+// Per-warp on-chip working set (shared memory on the device, a heap block in the host
+// emulation): two DP column buffers (parent / child ping-pong), the query strands and their
+// suffix sums, the best-first queue and the outgoing-edge scratch.
+struct WarpSmem {
+    score_t *buf0;            // two buffers, each: S[bmax] | E[bmax] | F[bmax]
+    int bmax;
+    char *q0, *q1; int32_t *psum0, *psum1; int lq;     // lq = capacity in characters (0: not staged)
+    StrandCtx *ctx;           // [2]
+    uint32_t *mask0, *mask1;  // (lq / 32 + 2) words each
+    AlnSlot *slots;           // [kNumSlots]
+    MGB_HOSTDEV score_t* buf(int b) const { return buf0 + (size_t)b * 3 * bmax; }
+    HeapItem *heap, *nn; int hcap;
+    uint64_t *out_nodes, *out_trails; int32_t *out_scores; uint8_t *out_chars;
+
+    MGB_HOSTDEV size_t carve(char *base, int bmax_, int lq_, int hcap_) {
+        size_t o = 0;
+        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return base ? base + r : (char*)nullptr; };
+        bmax = bmax_; lq = lq_; hcap = hcap_;
+        buf0 = (score_t*)take(sizeof(score_t) * 6 * (size_t)bmax);
+        psum0 = (int32_t*)take(4 * ((size_t)lq + 8)); psum1 = (int32_t*)take(4 * ((size_t)lq + 8));
+        q0 = (char*)take((size_t)lq + 8); q1 = (char*)take((size_t)lq + 8);
+        ctx = (StrandCtx*)take(sizeof(StrandCtx) * 2);
+        mask0 = (uint32_t*)take(4 * ((size_t)lq / 32 + 2)); mask1 = (uint32_t*)take(4 * ((size_t)lq / 32 + 2));
+        slots = (AlnSlot*)take(sizeof(AlnSlot) * kNumSlots);
+        heap = (HeapItem*)take(sizeof(HeapItem) * hcap);
+        nn = (HeapItem*)take(sizeof(HeapItem) * hcap);
+        out_nodes = (uint64_t*)take(8 * 8); out_trails = (uint64_t*)take(8 * 8);
+        out_scores = (int32_t*)take(4 * 8); out_chars = (uint8_t*)take(16);
+        return o;
+    }
+};
+
 MGB_HOSTDEV uint32_t cig_pack(uint32_t op, uint32_t len) { return (len << 3) | op; }
 MGB_HOSTDEV uint32_t cig_op(uint32_t x) { return x & 7u; }
 MGB_HOSTDEV uint32_t cig_len(uint32_t x) { return x >> 3; }
@@ -156,44 +200,38 @@ struct ReadAligner {
     const DevConfig &cfg;
     const Caps &caps;
     WarpMem &m;
+    WarpSmem &sm;
 
     // read
     int L;
-    const char *q[2];            // upper-cased forward / reverse-complement strings
-    const uint8_t *codes[2];     // alphabet codes of q[s]
-    const uint64_t *qnodes[2];   // map_to_nodes_sequentially per strand (may be nullptr if L < k)
-    int n_seeds[2];
-    uint32_t num_matching[2];
+    StrandCtx *cx;               // sm.ctx: per-strand state (query, seeds, extender bookkeeping)
 
     bool overflow;
     ReadStats stats;
 
-    // extender state (index = query strand the extender was built on)
-    uint32_t ext_table_cap[2];   // std::vector<DPTColumn>::capacity() emulation
-    uint32_t ext_num_ext[2];
-    uint32_t ext_explored_prev[2];
-    bool ext_rc[2];              // set_graph(): true = RCDBG view
 
     // DP table of the extension in flight
     uint32_t n_cols;
     uint32_t cells_used;
     int n_agg;
 
-    MGB_HD ReadAligner(const IndexView &ix_, const DevConfig &cfg_, const Caps &caps_, WarpMem &m_)
-        : ix(ix_), cfg(cfg_), caps(caps_), m(m_) {}
+    MGB_HD ReadAligner(const IndexView &ix_, const DevConfig &cfg_, const Caps &caps_, WarpMem &m_,
+                       WarpSmem &sm_)
+        : ix(ix_), cfg(cfg_), caps(caps_), m(m_), sm(sm_), cx(sm_.ctx) {}
 
     // --------------------------------------------------------------------------------
     // small helpers
     // --------------------------------------------------------------------------------
-    MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j)]; }
-    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j) + 1]; }
-    MGB_HD score_t& cellF(const ColMeta &c, int j) { return m.cells[3 * ((size_t)c.cells_off + j) + 2]; }
+    // committed columns: S[size+5] | E[size+5] | F[size+5] starting at cells_off
+    MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + j]; }
+    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + (c.size + 5) + j]; }
+    MGB_HD score_t& cellF(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + 2 * (c.size + 5) + j]; }
 
     MGB_HD int prof_score(int s, int x, int code) const {   // profile_score_[code][x]
-        return (x >= 1 && x <= L) ? cfg.prof[code][(uint8_t)q[s][x - 1]] : 0;
+        return (x >= 1 && x <= L) ? cfg.prof[code][(uint8_t)cx[s].q[x - 1]] : 0;
     }
     MGB_HD bool prof_is_match(int s, int x, int code) const {
-        return (x >= 1 && x <= L) ? cfg.opmatch[code][(uint8_t)q[s][x - 1]] : false;
+        return (x >= 1 && x <= L) ? cfg.opmatch[code][(uint8_t)cx[s].q[x - 1]] : false;
     }
     MGB_HD uint32_t encode_char(uint8_t ch) const { return encode_dna(ch); }
 
@@ -206,7 +244,7 @@ struct ReadAligner {
     }
 
     MGB_HD void copy_slot(int dst, int src) {
-        AlnSlot &d = m.slots[dst]; const AlnSlot &s = m.slots[src];
+        AlnSlot &d = sm.slots[dst]; const AlnSlot &s = sm.slots[src];
         wsync();
         AlnHdr h = *s.h;
         for (int i = wlane(); i < h.n_nodes; i += kWarp) d.nodes[i] = s.nodes[i];
@@ -218,11 +256,11 @@ struct ReadAligner {
 
     // Alignment(const Seed&, config) (alignment.hpp:154-165) materialised into a slot
     MGB_HD void seed_to_slot(int slot, int s, const SeedRec &sd) {
-        AlnSlot &a = m.slots[slot];
+        AlnSlot &a = sm.slots[slot];
         wsync();
         for (int i = wlane(); i < (int)sd.n_nodes; i += kWarp)
-            a.nodes[i] = sd.n_nodes == 1 ? sd.node0 : qnodes[s][sd.clip + i];
-        for (int i = wlane(); i < (int)sd.len; i += kWarp) a.seq[i] = q[s][sd.clip + i];
+            a.nodes[i] = sd.n_nodes == 1 ? sd.node0 : cx[s].qnodes[sd.clip + i];
+        for (int i = wlane(); i < (int)sd.len; i += kWarp) a.seq[i] = cx[s].q[sd.clip + i];
         int end_clip = L - (int)sd.clip - (int)sd.len;
         int nc = 0;
         if (sd.clip) a.cigar[nc++] = cig_pack(OP_S, sd.clip);
@@ -230,7 +268,7 @@ struct ReadAligner {
         if (end_clip) a.cigar[nc++] = cig_pack(OP_S, end_clip);
         AlnHdr h;
         h.q_len = sd.len; h.n_nodes = sd.n_nodes; h.seq_len = sd.len; h.n_cigar = nc;
-        h.score = m.psum[s][sd.clip] - m.psum[s][sd.clip + sd.len]
+        h.score = cx[s].ps[sd.clip] - cx[s].ps[sd.clip + sd.len]
                 + (!sd.clip ? cfg.left_end_bonus : 0) + (!end_clip ? cfg.right_end_bonus : 0);
         h.offset = sd.offset; h.orientation = s; h.used = 1;
         *a.h = h;
@@ -239,7 +277,7 @@ struct ReadAligner {
 
     // alignment.cpp:177-190 (no npos nodes on this path)
     MGB_HD void trim_offset(int slot) {
-        AlnSlot &a = m.slots[slot];
+        AlnSlot &a = sm.slots[slot];
         AlnHdr h = *a.h;
         if (!h.offset || h.n_nodes <= 1) return;
         int trim = imin((int)h.offset, h.n_nodes - 1);
@@ -260,7 +298,7 @@ struct ReadAligner {
     // alignment.cpp:540-561, RCDBG branch. Returns false if the alignment became empty.
     MGB_HD bool reverse_complement_slot(int slot) {
         trim_offset(slot);
-        AlnSlot &a = m.slots[slot];
+        AlnSlot &a = sm.slots[slot];
         AlnHdr h = *a.h;
         if (h.offset) { h.used = 0; h.n_nodes = 0; *a.h = h; return false; }
         wsync();
@@ -301,20 +339,15 @@ struct ReadAligner {
     // DBGSuccinct::call_outgoing_kmers (dbg_succinct.cpp:110-139); '$' targets are skipped
     // as the extender does (extender.cpp:381-384). Returns the number of (node, char) pairs.
     MGB_HD int outgoing_fwd(uint64_t node, uint64_t *nodes, uint8_t *chars) {
-        LineCache lc;
-        uint32_t w = 0;
-        if (node > 1) {
-            w = lc.get_W(ix, node);
-            if (!w) return 0;
-        }
-        uint64_t lst = fwd(ix, lc, node, w % ix.sigma);
-        uint64_t first = pred_last(ix, lc, lst - 1) + 1;
+        // the record of the most recently created column was requested while its DP was computed
+        const uint2 a = node == pf_node ? pf_adj : load_adj(ix, node);
+        if (!a.x) return 0;
+        const uint32_t all = a.y & 31u, ok = (a.y >> 8) & 31u;
+        const uint64_t first = (uint64_t)a.x - popc32(all) + 1;
         int n = 0;
-        for (uint64_t i = first > 2 ? first : 2; i <= lst; ++i) {
-            if (!in_graph(ix, i)) continue;
-            uint32_t c = lc.get_W(ix, i) % ix.sigma;
-            if (c == 0) continue;                    // '$'
-            if (n < kMaxOut) { nodes[n] = i; chars[n] = "$ACGT"[c]; }
+        for (uint32_t c = 1; c < ix.sigma; ++c) {
+            if (!((ok >> c) & 1u)) continue;
+            if (n < kMaxOut) { nodes[n] = first + popc32(all & ((1u << c) - 1u)); chars[n] = "$ACGT"[c]; }
             ++n;
         }
         return n;
@@ -370,12 +403,9 @@ struct ReadAligner {
 
     // dbg_succinct.cpp:617-630
     MGB_HD bool has_multiple_outgoing(uint64_t node) {
-        LineCache lc;
-        if (node == 1) return succ_last(ix, lc, 1) > 2;
-        uint32_t d = lc.get_W(ix, node) % ix.sigma;
-        if (!d) return false;
-        uint64_t t = fwd(ix, lc, node, d);
-        return !lc.get_last(ix, t - 1);
+        // !get_last(fwd(node, d) - 1): the target node has more than one edge
+        const uint2 a = load_adj(ix, node);
+        return a.x && popc32(a.y & 31u) > 1;
     }
     // dbg_succinct.cpp:662-680
     MGB_HD bool has_single_incoming(uint64_t node) {
@@ -406,13 +436,13 @@ struct ReadAligner {
     // --------------------------------------------------------------------------------
     // seeding (aligner_seeder_methods.cpp)
     // --------------------------------------------------------------------------------
-    MGB_HD uint64_t qnode(int s, int i) const { return qnodes[s] ? qnodes[s][i] : 0; }
+    MGB_HD uint64_t qnode(int s, int i) const { return cx[s].qnodes ? cx[s].qnodes[i] : 0; }
 
     MGB_HD void push_seed(int s, uint32_t clip, uint32_t len, uint32_t off, uint32_t nn, uint64_t node0) {
-        if (n_seeds[s] >= (int)caps.max_seeds) { overflow = true; return; }
+        if (cx[s].n_seeds >= (int)caps.max_seeds) { overflow = true; return; }
         SeedRec r; r.clip = clip; r.len = len; r.offset = off; r.n_nodes = nn; r.node0 = node0;
         r.alive = 1; r.pad = 0;
-        m.seeds[s][n_seeds[s]++] = r;
+        cx[s].seeds[cx[s].n_seeds++] = r;
     }
 
     // ExactSeeder::num_exact_matching (:49-65)
@@ -438,7 +468,7 @@ struct ReadAligner {
     // ExactSeeder::get_seeds (:67-93)
     MGB_HD void exact_seeds(int s, int nk) {
         const int k = ix.k;
-        if (num_matching[s] < cfg.min_exact_match * L) return;
+        if (cx[s].num_matching < cfg.min_exact_match * L) return;
         if (cfg.max_seed_length < (uint32_t)k) return;
         for (int i = 0; i < nk; ++i) {
             uint64_t nd = qnode(s, i);
@@ -450,7 +480,7 @@ struct ReadAligner {
     MGB_HD void mem_seeds(int s, int nk) {
         const int k = ix.k;
         if ((uint32_t)k >= cfg.max_seed_length) { exact_seeds(s, nk); return; }
-        if (num_matching[s] < cfg.min_exact_match * L) return;
+        if (cx[s].num_matching < cfg.min_exact_match * L) return;
         int i = 0;
         while (i < nk) {
             if (!qnode(s, i)) { ++i; continue; }
@@ -471,7 +501,7 @@ struct ReadAligner {
     }
 
     // DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix (dbg_succinct.cpp:307-393),
-    // max_num_allowed_matches == SIZE_MAX; str = q[s][pos, pos+len), len <= k - 1.
+    // max_num_allowed_matches == SIZE_MAX; str = cx[s].q[pos, pos+len), len <= k - 1.
     // Appends matches as seeds at query position `pos` unless they exceed `max_per_locus`
     // (then none is appended). Returns the number of alternative nodes found and the match
     // length; *first_node = the first one.
@@ -479,7 +509,7 @@ struct ReadAligner {
                               uint64_t *first_node, bool append) {
         *match_len = 0;
         if (len < min_match) return 0;
-        const uint8_t *cd = codes[s] + pos;
+        const uint8_t *cd = cx[s].codes + pos;
         for (int i = 0; i < len; ++i)
             if (cd[i] >= ix.sigma) return 0;
         uint64_t first, lst; int matched;
@@ -490,7 +520,7 @@ struct ReadAligner {
         uint64_t rank_first = rank_last(ix, lc, first);
         uint64_t rank_lst = rank_last(ix, lc, lst);
         int count = 0;
-        int seeds_before = n_seeds[s];
+        int seeds_before = cx[s].n_seeds;
         for (uint64_t r = rank_first; r <= rank_lst; ++r) {
             LineCache l2;
             uint64_t e = select_last(ix, l2, r);
@@ -512,16 +542,64 @@ struct ReadAligner {
             if (overflow) break;
         }
         if (append && (uint64_t)count > cfg.max_num_seeds_per_locus)
-            n_seeds[s] = seeds_before;   // locus dropped (:340-345)
+            cx[s].n_seeds = seeds_before;   // locus dropped (:340-345)
         return count;
+    }
+
+    // first index >= pos (< n) whose bit equals `want`; n if none
+    MGB_HD int mask_next(const uint32_t *mask, int n, int pos, bool want) const {
+        while (pos < n) {
+            uint32_t wd = mask[pos >> 5];
+            if (!want) wd = ~wd;
+            wd &= ~0u << (pos & 31);
+            if (wd) { int r = (pos & ~31) + ffs32(wd) - 1; return r < n ? r : n; }
+            pos = (pos & ~31) + 32;
+        }
+        return n;
     }
 
     // SuffixSeeder<UniMEMSeeder>::generate_seeds (:153-358), non-canonical part
     MGB_HD void build_seeds(int s) {
         const int k = ix.k;
         const int nk = L >= k ? L - k + 1 : 0;
-        n_seeds[s] = 0;
-        num_matching[s] = num_exact_matching(s, nk);
+        cx[s].n_seeds = 0;
+        // Exact seeder with staged query (the BASELINE configs[1] path): one k-mer seed per matched
+        // k-mer, kept as a bit mask on chip instead of a seed array
+        if ((int)cfg.min_seed_length >= k && (uint32_t)k >= cfg.max_seed_length && sm.lq && L + 1 <= sm.lq) {
+            uint32_t *mask = cx[s].mask;
+            const uint64_t *qn = cx[s].qnodes;
+            const int nw = (nk + 31) / 32;
+            int total = 0;
+            for (int w = 0; w < nw; ++w) {
+                unsigned word = 0;
+                for (int b = 0; b < 32; b += kWarp) {        // one pass on the device
+                    int i = 32 * w + b + wlane();
+                    word |= wballot(i < nk && qn[i] != 0) << b;
+                }
+                mask[w] = word;
+                total += popc32(word);
+            }
+            mask[nw] = 0;
+            wsync();
+            // ExactSeeder::num_exact_matching (:49-65) over the runs of set bits
+            uint32_t nm = 0; int pos = 0, prev_end = -1;
+            while (pos < nk) {
+                int i = mask_next(mask, nk, pos, true);
+                if (i >= nk) break;
+                int j = mask_next(mask, nk, i, false);
+                int lmc = prev_end < 0 ? 0 : imax(k - (i - prev_end), 0);
+                nm += k + (j - i) - 1 - lmc;
+                prev_end = j; pos = j;
+            }
+            cx[s].num_matching = nm;
+            cx[s].implicit_seeds = 1;
+            // ExactSeeder::get_seeds (:67-93)
+            if (L < (int)cfg.min_seed_length || (double)nm < cfg.min_exact_match * L || cfg.max_seed_length < (uint32_t)k)
+                total = 0;
+            cx[s].n_seeds = total;
+            return;
+        }
+        cx[s].num_matching = num_exact_matching(s, nk);
         if (L < (int)cfg.min_seed_length) return;
         if ((int)cfg.min_seed_length >= k) { mem_seeds(s, nk); return; }
 
@@ -531,19 +609,19 @@ struct ReadAligner {
         for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
         wsync();
         mem_seeds(s, nk);
-        const int n_base = n_seeds[s];
+        const int n_base = cx[s].n_seeds;
         if (overflow) return;
         // move base seeds to the end of the array (scratch), keep order
         if (2 * n_base > (int)caps.max_seeds) { overflow = true; return; }
-        SeedRec *base_seeds = m.seeds[s] + caps.max_seeds - n_base;
+        SeedRec *base_seeds = cx[s].seeds + caps.max_seeds - n_base;
         wsync();
-        for (int i = n_base - 1; i >= 0; --i) base_seeds[i] = m.seeds[s][i];
+        for (int i = n_base - 1; i >= 0; --i) base_seeds[i] = cx[s].seeds[i];
         for (int b = 0; b < n_base; ++b) {
             SeedRec sd = base_seeds[b];
             for (int j = 0; j < (int)sd.n_nodes; ++j) m.sfx_min[sd.clip + j] = (uint8_t)k;
             if ((int)(sd.clip + sd.n_nodes) < n_pos) m.sfx_min[sd.clip + sd.n_nodes] = (uint8_t)k;
         }
-        n_seeds[s] = 0;
+        cx[s].n_seeds = 0;
         int b_next = 0;
 
         const int last_full_id = L >= k ? L - k + 1 : n_pos;
@@ -551,12 +629,12 @@ struct ReadAligner {
         int lf_count = 0; uint64_t lf_node = 0;
         uint32_t nm = 0; int last_end = 0;
         for (int i = 0; i < n_pos; ++i) {
-            int pos_first = n_seeds[s];
+            int pos_first = cx[s].n_seeds;
             bool has_base = b_next < n_base && (int)base_seeds[b_next].clip == i;
             int n_here = 0; bool dropped = false;
             if (has_base) {
-                if (n_seeds[s] >= (int)caps.max_seeds - n_base) { overflow = true; return; }
-                m.seeds[s][n_seeds[s]++] = base_seeds[b_next++];
+                if (cx[s].n_seeds >= (int)caps.max_seeds - n_base) { overflow = true; return; }
+                cx[s].seeds[cx[s].n_seeds++] = base_seeds[b_next++];
                 n_here = 1;
             }
             uint32_t msl_u = cfg.max_seed_length < (uint32_t)(k - 1) ? cfg.max_seed_length : (uint32_t)(k - 1);
@@ -570,10 +648,10 @@ struct ReadAligner {
                         && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
             if (cnt && !skip) {
                 // append_suffix_seed (:195-213) for every alternative node
-                if (seed_length > min_here) { n_seeds[s] = pos_first; n_here = 0; }
+                if (seed_length > min_here) { cx[s].n_seeds = pos_first; n_here = 0; }
                 m.sfx_min[i] = (uint8_t)seed_length;
                 if ((uint64_t)cnt <= cfg.max_num_seeds_per_locus) {
-                    if (n_seeds[s] + cnt > (int)caps.max_seeds - n_base) { overflow = true; return; }
+                    if (cx[s].n_seeds + cnt > (int)caps.max_seeds - n_base) { overflow = true; return; }
                     int dummy_len; uint64_t dummy_node;
                     suffix_matches(s, i, max_seed_length, min_here, &dummy_len, &dummy_node, true);
                     if (overflow) return;
@@ -588,153 +666,151 @@ struct ReadAligner {
             }
             if (i == last_full_id - 1) {
                 lf_count = n_here;
-                lf_node = n_here ? m.seeds[s][pos_first].node0 : 0;
+                lf_node = n_here ? cx[s].seeds[pos_first].node0 : 0;
             }
             // aggregation (:316-357)
             if (n_here == 0) continue;
-            bool no_offset = has_base && n_seeds[s] > pos_first && m.seeds[s][pos_first].offset == 0;
+            bool no_offset = has_base && cx[s].n_seeds > pos_first && cx[s].seeds[pos_first].offset == 0;
             if (!no_offset && !cnt) continue;
             bool kept = no_offset || (!dropped && (uint64_t)n_here <= cfg.max_num_seeds_per_locus);
             if (!no_offset && (uint64_t)n_here > cfg.max_num_seeds_per_locus) {
-                n_seeds[s] = pos_first;   // locus with too many alternatives is dropped
+                cx[s].n_seeds = pos_first;   // locus with too many alternatives is dropped
                 kept = false;
             }
-            if (kept && n_seeds[s] > 0) {
-                const SeedRec &bk = m.seeds[s][n_seeds[s] - 1];
+            if (kept && cx[s].n_seeds > 0) {
+                const SeedRec &bk = cx[s].seeds[cx[s].n_seeds - 1];
                 int begin = bk.clip, end = begin + (int)bk.len;
                 if (begin < last_end) nm += end - begin - (last_end - begin);
                 else nm += end - begin;
                 last_end = end;
             }
         }
-        num_matching[s] = nm;
+        cx[s].num_matching = nm;
     }
 
     // --------------------------------------------------------------------------------
     // convergence filter (SeedFilteringExtender, extender.cpp:66-207)
+    // Open-addressing table keyed by node id; the per-node score vector lives in a
+    // segment of the conv cell arena, indexed by absolute query position.
     // --------------------------------------------------------------------------------
     MGB_HD uint32_t hash_node(uint64_t key) const {
-        key ^= key >> 33; key *= 0xff51afd7ed558ccdULL; key ^= key >> 33;
-        return (uint32_t)key & (caps.hash_size - 1);
+        uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+        h ^= h >> 15;
+        return h & (caps.hash_size - 1);
     }
     MGB_HD void conv_clear(int e) {
-        ConvTable &t = m.conv[e];
-        ext_explored_prev[e] += t.n_entries;
-        t.n_entries = 0; t.cells_used = 0;
-        ++t.epoch;
+        StrandCtx &t = cx[e];
+        t.explored_prev += t.conv_n;
+        t.conv_n = 0; t.conv_cells_used = 0;
+        ++t.conv_epoch;
     }
-    MGB_HD int conv_find(int e, uint64_t key) {
-        ConvTable &t = m.conv[e];
+    // returns the slot index or -1; *out = slot contents. No collectives: may be called with
+    // lane-divergent keys.
+    MGB_HD int conv_find(const ConvSlot *slots, uint32_t epoch, uint64_t key, ConvSlot *out,
+                         bool use_prefetch = false) {
         uint32_t h = hash_node(key);
         for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
-            ConvSlot sl = t.slots[(h + probe) & (caps.hash_size - 1)];
-            if (sl.epoch != t.epoch) return -1;
-            if (sl.key == key) return (int)sl.entry;
+            uint32_t p = (h + probe) & (caps.hash_size - 1);
+            ConvSlot sl = (use_prefetch && probe == 0 && key == pf_key && p == pf_slot_idx) ? pf_slot : slots[p];
+            if (sl.epoch != epoch) return -1;
+            if (sl.key == key) { *out = sl; return (int)p; }
         }
         return -1;
     }
     // new entry covering [start, start + size), cells uninitialised
-    MGB_HD int conv_insert(int e, uint64_t key, int start, int size) {
-        ConvTable &t = m.conv[e];
-        if (t.n_entries >= caps.max_conv_entries || 2 * (t.n_entries + 1) > caps.hash_size) {
+    MGB_HD int conv_insert(int e, uint64_t key, int start, int size, ConvSlot *out) {
+        StrandCtx &t = cx[e];
+        const uint32_t n_entries = t.conv_n, cells_used = t.conv_cells_used, epoch = t.conv_epoch;
+        ConvSlot *slots = t.conv_slots;
+        if (n_entries >= caps.max_conv_entries || 2 * (n_entries + 1) > caps.hash_size) {
             overflow = true; return -1;
         }
         int seg_start = imax(0, start - 8);
         int seg_cap = imin(L + 1, start + size + 8) - seg_start;
-        if (t.cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return -1; }
-        ConvEntry en; en.start = start; en.size = size; en.seg_start = seg_start; en.seg_cap = seg_cap;
-        en.seg_off = t.cells_used; en.pad = 0;
-        t.cells_used += seg_cap;
-        int id = t.n_entries++;
-        t.entries[id] = en;
+        if (cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return -1; }
+        ConvSlot sl; sl.key = key; sl.epoch = epoch; sl.start = start; sl.size = size;
+        sl.seg_start = seg_start; sl.seg_cap = seg_cap; sl.seg_off = cells_used;
+        t.conv_cells_used = cells_used + seg_cap;
+        t.conv_n = n_entries + 1;
         uint32_t h = hash_node(key);
         for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
             uint32_t p = (h + probe) & (caps.hash_size - 1);
-            if (t.slots[p].epoch != t.epoch) {
-                ConvSlot sl; sl.key = key; sl.epoch = t.epoch; sl.entry = id;
-                t.slots[p] = sl;
-                break;
+            if (slots[p].epoch != epoch) {
+                slots[p] = sl;
+                *out = sl;
+                return (int)p;
             }
         }
-        return id;
+        overflow = true;
+        return -1;
     }
     // make the stored vector cover [new_start, new_end) (superset of the current range),
     // new cells = ninf. Mirrors vec.insert(begin, n, ninf) / resize(n, ninf).
-    MGB_HD bool conv_grow(int e, int id, int new_start, int new_end) {
-        ConvTable &t = m.conv[e];
-        ConvEntry en = t.entries[id];
-        int old_start = en.start, old_end = en.start + en.size;
-        if (new_start < en.seg_start || new_end > en.seg_start + en.seg_cap) {
+    MGB_HD bool conv_grow(int e, int slot, ConvSlot *en, int new_start, int new_end) {
+        StrandCtx &t = cx[e];
+        score_t *cells = t.conv_cells;
+        int old_start = en->start, old_end = en->start + en->size;
+        if (new_start < en->seg_start || new_end > en->seg_start + en->seg_cap) {
+            const uint32_t cells_used = t.conv_cells_used;
             int seg_start = imax(0, new_start - 16);
             int seg_cap = imin(L + 1, new_end + 16) - seg_start;
-            if (t.cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return false; }
-            score_t *src = t.cells + en.seg_off, *dst = t.cells + t.cells_used;
+            if (cells_used + seg_cap > caps.max_conv_cells) { overflow = true; return false; }
+            score_t *src = cells + en->seg_off, *dst = cells + cells_used;
             wsync();
             for (int p = old_start + wlane(); p < old_end; p += kWarp)
-                dst[p - seg_start] = src[p - en.seg_start];
-            en.seg_off = t.cells_used; en.seg_start = seg_start; en.seg_cap = seg_cap;
-            t.cells_used += seg_cap;
+                dst[p - seg_start] = src[p - en->seg_start];
+            en->seg_off = cells_used; en->seg_start = seg_start; en->seg_cap = seg_cap;
+            t.conv_cells_used = cells_used + seg_cap;
         }
-        score_t *c = t.cells + en.seg_off;
-        for (int p = new_start + wlane(); p < old_start; p += kWarp) c[p - en.seg_start] = kNinf;
-        for (int p = old_end + wlane(); p < new_end; p += kWarp) c[p - en.seg_start] = kNinf;
-        en.start = new_start; en.size = new_end - new_start;
-        t.entries[id] = en;
+        score_t *c = cells + en->seg_off;
+        for (int p = new_start + wlane(); p < old_start; p += kWarp) c[p - en->seg_start] = kNinf;
+        for (int p = old_end + wlane(); p < new_end; p += kWarp) c[p - en->seg_start] = kNinf;
+        en->start = new_start; en->size = new_end - new_start;
+        t.conv_slots[slot] = *en;
         wsync();
         return true;
     }
 
-    // extender.cpp:100-156; s = cells S[s_first .. s_first + size) of column `col`
-    MGB_HD score_t update_seed_filter(int e, uint64_t node, int query_start, const ColMeta &col,
-                                      int s_first, int size) {
-        // max over the passed range
+    // extender.cpp:100-156; sv = S[s_first .. s_first + size) of the column being committed
+    MGB_HD score_t update_seed_filter(int e, uint64_t node, int query_start, const score_t *sv, int size) {
         score_t mx = kNinf;
-        bool any = false;
-        for (int j = wlane(); j < size; j += kWarp) { mx = imax(mx, cellS(col, s_first + j)); any = true; }
+        for (int j = wlane(); j < size; j += kWarp) mx = imax(mx, sv[j]);
         mx = wreduce_max(mx);
-        (void)any;
         if (node == 0) return mx;
-        uint64_t key = node + (ext_rc[e] ? ix.n : 0);
-        ConvTable &t = m.conv[e];
-        int id = conv_find(e, key);
-        if (id < 0) {
-            id = conv_insert(e, key, query_start, size);
-            if (id < 0) return kNinf;
-            ConvEntry en = t.entries[id];
-            score_t *c = t.cells + en.seg_off;
-            for (int j = wlane(); j < size; j += kWarp)
-                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+        StrandCtx &t = cx[e];
+        uint64_t key = node + (t.rc ? ix.n : 0);
+        score_t *cells = t.conv_cells;
+        ConvSlot en;
+        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en);
+        if (slot < 0) {
+            slot = conv_insert(e, key, query_start, size, &en);
+            if (slot < 0) return kNinf;
+            score_t *c = cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
             wsync();
             return mx;
         }
-        ConvEntry en = t.entries[id];
         if (query_start + size <= en.start) {
-            if (!conv_grow(e, id, query_start, en.start + en.size)) return kNinf;
-            en = t.entries[id];
-            score_t *c = t.cells + en.seg_off;
-            for (int j = wlane(); j < size; j += kWarp)
-                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+            if (!conv_grow(e, slot, &en, query_start, en.start + en.size)) return kNinf;
+            score_t *c = cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
             wsync();
             return mx;
         }
         if (query_start >= en.start + en.size) {
-            if (!conv_grow(e, id, en.start, query_start + size)) return kNinf;
-            en = t.entries[id];
-            score_t *c = t.cells + en.seg_off;
-            for (int j = wlane(); j < size; j += kWarp)
-                c[query_start + j - en.seg_start] = cellS(col, s_first + j);
+            if (!conv_grow(e, slot, &en, en.start, query_start + size)) return kNinf;
+            score_t *c = cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
             wsync();
             return mx;
         }
         int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
-        if (ns != en.start || ne != en.start + en.size) {
-            if (!conv_grow(e, id, ns, ne)) return kNinf;
-            en = t.entries[id];
-        }
-        score_t *v = t.cells + en.seg_off + (query_start - en.seg_start);
+        if (ns != en.start || ne != en.start + en.size)
+            if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
+        score_t *v = cells + en.seg_off + (query_start - en.seg_start);
         score_t max_changed = kNinf;
         for (int j = wlane(); j < size; j += kWarp) {
-            score_t sj = cellS(col, s_first + j);
+            score_t sj = sv[j];
             score_t vj = v[j];
             if ((double)sj > (double)vj * cfg.rel_score_cutoff) {
                 vj = imax(vj, sj);
@@ -747,52 +823,93 @@ struct ReadAligner {
         return max_changed;
     }
 
-    // extender.cpp:158-207
+#if MGB_DEVICE_CODE
+    // update_seed_filter with the passed range held one value per lane: lane holds s[vi] if
+    // 0 <= vi < size (size <= 32)
+    MGB_HD score_t update_seed_filter_reg(int e, uint64_t node, int query_start, score_t val, int vi, int size) {
+        const bool has = vi >= 0 && vi < size;
+        const score_t mx = wreduce_max(has ? val : kNinf);
+        if (node == 0) return mx;
+        StrandCtx &t = cx[e];
+        uint64_t key = node + (t.rc ? ix.n : 0);
+        score_t *cells = t.conv_cells;
+        ConvSlot en;
+        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, true);
+        if (slot < 0) {
+            slot = conv_insert(e, key, query_start, size, &en);
+            if (slot < 0) return kNinf;
+            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
+            wsync();
+            return mx;
+        }
+        if (query_start + size <= en.start) {
+            if (!conv_grow(e, slot, &en, query_start, en.start + en.size)) return kNinf;
+            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
+            wsync();
+            return mx;
+        }
+        if (query_start >= en.start + en.size) {
+            if (!conv_grow(e, slot, &en, en.start, query_start + size)) return kNinf;
+            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
+            wsync();
+            return mx;
+        }
+        int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
+        if (ns != en.start || ne != en.start + en.size)
+            if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
+        score_t max_changed = kNinf;
+        if (has) {
+            score_t *v = cells + en.seg_off + (query_start + vi - en.seg_start);
+            score_t vj = *v;
+            if ((double)val > (double)vj * cfg.rel_score_cutoff) {
+                vj = imax(vj, val);
+                *v = vj;
+                max_changed = vj;
+            }
+        }
+        max_changed = wreduce_max(max_changed);
+        wsync();
+        return max_changed;
+    }
+#endif
+
+    // extender.cpp:158-207 (every cell of [query_start, query_end) ends up at -ninf)
     MGB_HD void filter_nodes(int e, uint64_t node, int query_start, int query_end) {
         const score_t mscore = -kNinf;
         int size = query_end - query_start;
-        ConvTable &t = m.conv[e];
-        int id = conv_find(e, node);
-        int fill_from, fill_to;          // cells set to mscore unconditionally
-        if (id < 0) {
-            id = conv_insert(e, node, query_start, size);
-            if (id < 0) return;
-            fill_from = query_start; fill_to = query_end;
+        StrandCtx &t = cx[e];
+        ConvSlot en;
+        int slot = conv_find(t.conv_slots, t.conv_epoch, node, &en);
+        if (slot < 0) {
+            slot = conv_insert(e, node, query_start, size, &en);
+            if (slot < 0) return;
         } else {
-            ConvEntry en = t.entries[id];
-            if (query_start + size <= en.start) {
-                if (!conv_grow(e, id, query_start, en.start + en.size)) return;
-                fill_from = query_start; fill_to = query_end;
-            } else if (query_start >= en.start + en.size) {
-                if (!conv_grow(e, id, en.start, query_start + size)) return;
-                fill_from = query_start; fill_to = query_end;
-            } else {
-                int ns = imin(query_start, en.start), ne = imax(query_end, en.start + en.size);
-                if (ns != en.start || ne != en.start + en.size)
-                    if (!conv_grow(e, id, ns, ne)) return;
-                // mscore > v[j] for every representable v except mscore itself
-                fill_from = query_start; fill_to = query_end;
-            }
+            int ns = imin(query_start, en.start), ne = imax(query_end, en.start + en.size);
+            if (ns != en.start || ne != en.start + en.size)
+                if (!conv_grow(e, slot, &en, ns, ne)) return;
         }
-        ConvEntry en = t.entries[id];
-        score_t *c = t.cells + en.seg_off;
-        for (int p = fill_from + wlane(); p < fill_to; p += kWarp) c[p - en.seg_start] = mscore;
+        score_t *c = t.conv_cells + en.seg_off;
+        for (int p = query_start + wlane(); p < query_end; p += kWarp) c[p - en.seg_start] = mscore;
         wsync();
     }
 
-    // extender.cpp:66-88
-    MGB_HD bool check_seed_vals(int e, uint64_t last_node, int pos, score_t score) {
-        uint64_t key = last_node + (ext_rc[e] ? ix.n : 0);
-        int id = conv_find(e, key);
-        if (id < 0) return true;
-        ConvEntry en = m.conv[e].entries[id];
+    // extender.cpp:66-88 (lane-divergent arguments allowed)
+    MGB_HD bool check_seed_vals(const ConvSlot *slots, const score_t *cells, uint32_t epoch, bool rc,
+                                uint64_t last_node, int pos, score_t score) {
+        uint64_t key = last_node + (rc ? ix.n : 0);
+        ConvSlot en;
+        if (conv_find(slots, epoch, key, &en) < 0) return true;
         if (pos < en.start || pos - en.start >= en.size) return true;
-        return m.conv[e].cells[en.seg_off + (pos - en.seg_start)] < score;
+        return cells[en.seg_off + (pos - en.seg_start)] < score;
     }
 
     // --------------------------------------------------------------------------------
-    // DP table
+    // best-first queue (std::priority_queue<TableIt>, extender.cpp:477-504); lives in shared
+    // memory and migrates to the arena when it outgrows it
     // --------------------------------------------------------------------------------
+    HeapItem *hp, *np;           // heap / next_nodes storage
+    int hp_cap, np_cap;
+
     MGB_HD bool heap_less(const HeapItem &a, const HeapItem &b) const {   // std::less<TableIt>
         if (a.score != b.score) return a.score < b.score;
         if (a.neg_off_diag != b.neg_off_diag) return a.neg_off_diag < b.neg_off_diag;
@@ -800,50 +917,52 @@ struct ReadAligner {
         return a.max_score < b.max_score;
     }
     MGB_HD void heap_push(int &n, HeapItem it) {
+        if (n >= hp_cap) {
+            if (hp == m.heap) { overflow = true; return; }
+            for (int t = wlane(); t < n; t += kWarp) m.heap[t] = hp[t];
+            wsync();
+            hp = m.heap; hp_cap = caps.max_cols;
+        }
         int i = n++;
         while (i > 0) {
             int p = (i - 1) >> 1;
-            HeapItem pi = m.heap[p];
+            HeapItem pi = hp[p];
             if (!heap_less(pi, it)) break;
-            m.heap[i] = pi;
+            hp[i] = pi;
             i = p;
         }
-        m.heap[i] = it;
+        hp[i] = it;
     }
     MGB_HD HeapItem heap_pop(int &n) {
-        HeapItem top = m.heap[0];
-        HeapItem last = m.heap[--n];
+        HeapItem top = hp[0];
+        HeapItem last = hp[--n];
         int i = 0;
         while (true) {
             int l = 2 * i + 1, r = l + 1;
             if (l >= n) break;
             int c = l;
-            if (r < n && heap_less(m.heap[l], m.heap[r])) c = r;
-            HeapItem ci = m.heap[c];
+            if (r < n && heap_less(hp[l], hp[r])) c = r;
+            HeapItem ci = hp[c];
             if (!heap_less(last, ci)) break;
-            m.heap[i] = ci;
+            hp[i] = ci;
             i = c;
         }
-        if (n > 0) m.heap[i] = last;
+        if (n > 0) hp[i] = last;
         return top;
     }
-
-    // allocate a column with `size` cells and room to grow to `max_final` (+ padding)
-    MGB_HD bool new_column(int size, int max_final, ColMeta *out) {
-        if (n_cols >= caps.max_cols || (uint64_t)cells_used + max_final + 5 > caps.max_cells) {
-            overflow = true; return false;
+    MGB_HD void nn_push(int &n, HeapItem it) {
+        if (n >= np_cap) {
+            if (np == m.next_nodes) { overflow = true; return; }
+            for (int t = wlane(); t < n; t += kWarp) m.next_nodes[t] = np[t];
+            wsync();
+            np = m.next_nodes; np_cap = caps.max_cols;
         }
-        out->cells_off = cells_used;
-        out->size = size;
-        // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
-        for (int j = wlane(); j < size + 5; j += kWarp) {
-            size_t b = 3 * ((size_t)cells_used + j);
-            m.cells[b] = kNinf; m.cells[b + 1] = kNinf; m.cells[b + 2] = kNinf;
-        }
-        wsync();
-        return true;
+        np[n++] = it;
     }
 
+    // --------------------------------------------------------------------------------
+    // DP columns
+    // --------------------------------------------------------------------------------
     // std::vector<score_t> capacity after DPTColumn::create(size0) + p push_backs + reserve(size + 5)
     MGB_HD static uint32_t vec_capacity(int size0, int size_final) {
         uint32_t cap = size0 + 5;
@@ -853,32 +972,54 @@ struct ReadAligner {
         return cap;
     }
 
-    // extend_ins_end (extender.cpp:293-328); returns the new size
-    MGB_HD int extend_ins_end(ColMeta &col, int max_size, score_t cutoff) {
-        int size = col.size;
+    // Working buffer of the column being computed: S | E | F with stride `cap`
+    struct Scratch { score_t *S, *E, *F; int cap; bool on_chip; };
+
+    MGB_HD Scratch scratch_smem(int b) const {
+        Scratch r; r.S = sm.buf(b); r.E = r.S + sm.bmax; r.F = r.E + sm.bmax; r.cap = sm.bmax; r.on_chip = true;
+        return r;
+    }
+    // arena scratch above the commit area of the column in flight; `cells` must be the largest
+    // size the column can reach (so that an arena scratch never has to move)
+    MGB_HD bool scratch_arena(int cells, Scratch *r) {
+        uint64_t need = (uint64_t)cells_used + 3ull * (cells + 8) /*commit*/ + 3ull * (cells + 8) /*scratch*/;
+        if (need > 3ull * caps.max_cells) { overflow = true; return false; }
+        r->cap = cells + 8;
+        r->S = m.cells + cells_used + 3ull * (cells + 8);
+        r->E = r->S + r->cap; r->F = r->E + r->cap; r->on_chip = false;
+        return true;
+    }
+
+    // extend_ins_end (extender.cpp:293-328); returns the new size. `sc` may migrate to the arena.
+    MGB_HD int extend_ins_end(Scratch &sc, int size, int max_size, score_t cutoff) {
         if (size >= max_size) return size;
-        score_t ins = imax(cellS(col, size - 1) + cfg.gap_open, cellE(col, size - 1) + cfg.gap_ext);
+        score_t ins = imax(sc.S[size - 1] + cfg.gap_open, sc.E[size - 1] + cfg.gap_ext);
         if (ins < cutoff) return size;
         int64_t extra = cfg.gap_ext < 0 ? ((int64_t)ins - cutoff) / (-cfg.gap_ext) : (int64_t)0x7fffffff;
         int cnt = 1 + (int)(extra < (int64_t)(max_size - size - 1) ? extra : (int64_t)(max_size - size - 1));
+        if (size + cnt + 5 > sc.cap) {
+            Scratch big;                               // only an on-chip scratch can be too small
+            if (!sc.on_chip || !scratch_arena(max_size, &big)) { overflow = true; return size; }
+            for (int t = wlane(); t < size + 5 && t < sc.cap; t += kWarp) {
+                big.S[t] = sc.S[t]; big.E[t] = sc.E[t]; big.F[t] = sc.F[t];
+            }
+            wsync();
+            sc = big;
+        }
         for (int t = wlane(); t < cnt + 5; t += kWarp) {
-            size_t b = 3 * ((size_t)col.cells_off + size + t);
             score_t v = t < cnt ? ins + t * cfg.gap_ext : kNinf;
-            m.cells[b] = v; m.cells[b + 1] = v; m.cells[b + 2] = kNinf;
+            sc.S[size + t] = v; sc.E[size + t] = v; sc.F[size + t] = kNinf;
         }
         wsync();
         return size + cnt;
     }
 
-    // update_column (extender.cpp:209-290), restated as a max-plus scan
-    MGB_HD void update_column(int s, const ColMeta &par, ColMeta &col, int prev_end, int start,
-                              score_t cutoff, int code) {
-        const int trim = col.trim;
-        const int n = prev_end - trim;                 // parent rows inside the band
+    // update_column (extender.cpp:209-290), restated as a max-plus scan.
+    // pS / pF: parent's S / F shifted so that index j is the same absolute row as child row j.
+    MGB_HD void update_column(int s, const score_t *pS, const score_t *pF, Scratch &sc, int size0,
+                              int n, int prof_base, score_t cutoff, int code, score_t add, bool use_del) {
         const int n4 = (n + 3) & ~3;
-        const int shift = trim - par.trim;
-        const score_t go = cfg.gap_open, ge = cfg.gap_ext, add = col.score;
-        const bool use_del = col.offset > 1;
+        const score_t go = cfg.gap_open, ge = cfg.gap_ext;
         int carry = kNinf + ge;                        // a[-1] = E[0] + ge, E[0] = ninf
         for (int base = 0; base < n4; base += kWarp) {
             int j = base + wlane();
@@ -886,9 +1027,8 @@ struct ReadAligner {
             score_t mval = kNinf, del = kNinf;
             if (act) {
                 score_t match = kNinf;
-                if (j) match = cellS(par, shift + j - 1) + prof_score(s, start + trim + j, code) + add;
-                if (use_del)
-                    del = imax(cellS(par, shift + j) + go, cellF(par, shift + j) + ge) + add;
+                if (j) match = pS[j - 1] + prof_score(s, prof_base + j, code) + add;
+                if (use_del) del = imax(pS[j] + go, pF[j] + ge) + add;
                 mval = imax(match, del);
             }
             // a[j] = m[j] + go - j*ge ; E[j+1] = prefmax(a)[j] + j*ge
@@ -898,23 +1038,32 @@ struct ReadAligner {
             int excl = wshfl_up1(incl, carry);         // prefix max over i < j (incl. a[-1])
             if (act) {
                 score_t e_j = j ? excl + (j - 1) * ge : kNinf;    // E[j]
-                score_t e_next = incl + j * ge;                   // E[j + 1]
                 score_t sv = imax(mval, e_j);
-                sv = sv > cutoff - 1 ? sv : kNinf;
-                cellF(col, j) = del;
-                cellE(col, j + 1) = e_next;
-                cellS(col, j) = sv;
+                sc.F[j] = del;
+                sc.E[j + 1] = incl + j * ge;                      // E[j + 1]
+                sc.S[j] = sv > cutoff - 1 ? sv : kNinf;
             }
             carry = wbcast(incl, kWarp - 1);
         }
         wsync();
-        if (col.size > imax(1, n)) {                   // scalar tail (:284-289)
-            int j = col.size - 1;
-            score_t t = imax(cellS(par, shift + j - 1) + add + prof_score(s, start + trim + j, code),
-                             cellE(col, j));
-            if (t >= cutoff) cellS(col, j) = t;
+        if (size0 > imax(1, n)) {                      // scalar tail (:284-289)
+            int j = size0 - 1;
+            score_t t = imax(pS[j - 1] + add + prof_score(s, prof_base + j, code), sc.E[j]);
+            if (t >= cutoff) sc.S[j] = t;
+            wsync();
         }
-        wsync();
+    }
+
+    // copy a finished column (incl. 5 padding cells) into the DP table; returns cells_off
+    MGB_HD uint32_t commit_column(const Scratch &sc, int size) {
+        const int cap = size + 5;
+        const uint32_t off = cells_used;
+        score_t *dst = m.cells + off;
+        for (int t = wlane(); t < cap; t += kWarp) {
+            dst[t] = sc.S[t]; dst[cap + t] = sc.E[t]; dst[2 * cap + t] = sc.F[t];
+        }
+        cells_used += 3 * cap;
+        return off;
     }
 
     // --------------------------------------------------------------------------------
@@ -924,13 +1073,15 @@ struct ReadAligner {
     // --------------------------------------------------------------------------------
     MGB_HD int extend(int e, int seed_slot, score_t min_path_score, bool force_fixed_seed, int out_base) {
         const int s = e;                                 // query strand of this extender
-        const AlnSlot &seed = m.slots[seed_slot];
+        const AlnSlot &seed = sm.slots[seed_slot];
         const AlnHdr sh = *seed.h;
-        const bool rc = ext_rc[e];
+        const bool rc = cx[e].rc;
         const int K = ix.k;
-        ++ext_num_ext[e];
+        ++cx[e].num_ext;
         min_path_score = imax(0, min_path_score);
         n_cols = 0; cells_used = 0;
+        hp = sm.heap; hp_cap = sm.hcap; np = sm.nn; np_cap = sm.hcap;
+        pf_node = 0; pf_key = ~0ull; pf_slot_idx = 0;
 
         const score_t xdrop = cfg.xdrop;
         score_t cutoff = imax(-xdrop, kNinf + 1);
@@ -938,24 +1089,37 @@ struct ReadAligner {
         const int wlen = L - start;                       // |window|
         const int seed_off_m1 = (int)sh.offset - 1;       // seed_offset
         const int seed_seq_len = sh.seq_len;
-        const score_t partial_sum_offset = m.psum[s][start + wlen];
+        const score_t partial_sum_offset = cx[s].ps[start + wlen];
+        // seed characters: for plain seeds the sequence equals the query substring (staged on chip)
+        const char *seed_seq = seed_is_query ? cx[s].q + start : seed.seq;
+        const uint64_t seed_node0 = seed.nodes[0];
+        int res0 = -1, res1 = -1;                         // columns resident in sm.buf(0) / sm.buf(1)
+        ColMeta last_col; uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
+
+        if ((uint64_t)3 * (wlen + 16) > 3ull * caps.max_cells) { overflow = true; return 0; }
 
         // root column (:455-470)
         {
-            ColMeta root;
-            if (!new_column(1, wlen + 1, &root)) return 0;
-            root.node = seed.nodes[0]; root.trail = 0; root.parent = 0xffffffffu; root.c = 0;
-            root.offset = seed_off_m1; root.max_pos = 0; root.trim = 0; root.score = 0;
-            root.is_tip = 0; root.started = 0; root.pad = 0;
-            cellS(root, 0) = cfg.left_end_bonus && !start ? cfg.left_end_bonus : 0;
+            Scratch sc;
+            if (1 + 8 <= sm.bmax) sc = scratch_smem(0);
+            else if (!scratch_arena(wlen + 1, &sc)) return 0;
+            for (int t = wlane(); t < 1 + 5; t += kWarp) { sc.S[t] = kNinf; sc.E[t] = kNinf; sc.F[t] = kNinf; }
             wsync();
-            int size0 = root.size;
-            root.size = extend_ins_end(root, wlen + 1, cutoff);
-            cells_used += root.size + 5;
+            sc.S[0] = cfg.left_end_bonus && !start ? cfg.left_end_bonus : 0;
+            wsync();
+            int size = extend_ins_end(sc, 1, wlen + 1, cutoff);
+            if (overflow) return 0;
+            ColMeta root;
+            root.node = seed_node0; root.trail = 0; root.parent = 0xffffffffu; root.c = 0;
+            root.offset = seed_off_m1; root.max_pos = 0; root.trim = 0; root.score = 0;
+            root.is_tip = 0; root.started = 0; root.pad = 0; root.size = size;
+            root.cells_off = commit_column(sc, size);
+            if (sc.on_chip) res0 = 0;
             m.cols[n_cols++] = root;
-            if (n_cols > ext_table_cap[e]) ext_table_cap[e] = ext_table_cap[e] ? 2 * ext_table_cap[e] : 1;
-            stats.dp_cells += root.size; ++stats.dp_columns;
-            table_size_bytes = 136ull * ext_table_cap[e] + 3ull * vec_capacity(size0, root.size) * 4;
+            if (n_cols > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
+            stats.dp_cells += size; ++stats.dp_columns;
+            table_size_bytes = 136ull * cx[e].table_cap + 3ull * vec_capacity(1, size) * 4;
+            wsync();
         }
 
         score_t min_cell_score = 0, best_score = 0;
@@ -964,17 +1128,23 @@ struct ReadAligner {
 
         while (heap_n) {
             nn_n = 0;
-            m.next_nodes[nn_n++] = heap_pop(heap_n);
-            while (heap_n && m.heap[0].score == m.next_nodes[nn_n - 1].score)
-                m.next_nodes[nn_n++] = heap_pop(heap_n);
+            nn_push(nn_n, heap_pop(heap_n));
+            while (heap_n && hp[0].score == np[nn_n - 1].score) nn_push(nn_n, heap_pop(heap_n));
+            if (overflow) return 0;
 
             while (nn_n) {
-                const uint32_t i = m.next_nodes[--nn_n].idx;
-                ColMeta par = m.cols[i];
+                const uint32_t i = np[--nn_n].idx;
+                const ColMeta par = (i == last_idx) ? last_col : m.cols[i];
                 const int next_offset = par.offset + 1;
                 const bool in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
+                // parent cells: on chip if it is one of the two most recent columns
+                const int pb = res0 == (int)i ? 0 : (res1 == (int)i ? 1 : -1);
+                const score_t *parS, *parF;
+                if (pb >= 0) { parS = sm.buf(pb); parF = parS + 2 * sm.bmax; }
+                else { parS = m.cells + par.cells_off; parF = parS + 2 * (par.size + 5); }
+                const int cb = pb >= 0 ? 1 - pb : 0;      // buffer for the children
 
-                if (cellS(par, par.max_pos - par.trim) < best_score) {
+                if (parS[par.max_pos - par.trim] < best_score) {
                     double node_counter = (double)n_cols;
                     if (node_counter / wlen >= cfg.max_nodes_per_seq_char) {
                         heap_n = 0; nn_n = 0;            // global_xdrop
@@ -990,7 +1160,7 @@ struct ReadAligner {
                 {
                     int lo = 0x7fffffff, hi = -1;
                     for (int j = wlane(); j < par.size; j += kWarp) {
-                        if (cellS(par, j) >= cutoff) { lo = imin(lo, j); hi = imax(hi, j); }
+                        if (parS[j] >= cutoff) { lo = imin(lo, j); hi = imax(hi, j); }
                     }
                     lo = wreduce_min(lo); hi = wreduce_max(hi);
                     if (hi < 0) continue;                 // prev_end <= begin
@@ -998,103 +1168,247 @@ struct ReadAligner {
                 }
 
                 // call_outgoing (:330-387)
-                uint64_t out_nodes[kMaxOut]; uint8_t out_chars[kMaxOut]; uint64_t out_trails[kMaxOut];
-                score_t out_scores[kMaxOut];
                 int n_out = 0;
                 {
                     uint32_t seed_pos = (uint32_t)(next_offset - (int)sh.offset);
                     if (in_seed && next_offset < K) {
-                        out_nodes[0] = seed.nodes[0]; out_chars[0] = seed.seq[seed_pos];
-                        out_trails[0] = 0; out_scores[0] = 0; n_out = 1;
+                        sm.out_nodes[0] = seed_node0; sm.out_chars[0] = seed_seq[seed_pos];
+                        sm.out_trails[0] = 0; sm.out_scores[0] = 0; n_out = 1;
                     } else if (in_seed && force_fixed_seed) {
                         int node_i = next_offset - K + 1;
                         uint64_t next_node = seed.nodes[node_i];
-                        out_nodes[0] = next_node; out_chars[0] = seed.seq[seed_pos]; out_trails[0] = 0;
-                        out_scores[0] = next_node ? 0 : (!par.node ? cfg.gap_ext : cfg.gap_open);
+                        sm.out_nodes[0] = next_node; sm.out_chars[0] = seed_seq[seed_pos]; sm.out_trails[0] = 0;
+                        sm.out_scores[0] = next_node ? 0 : (!par.node ? cfg.gap_ext : cfg.gap_open);
                         n_out = 1;
                     } else if (!rc) {
-                        n_out = outgoing_fwd(par.node, out_nodes, out_chars);
-                        for (int t = 0; t < kMaxOut; ++t) { out_scores[t] = 0; out_trails[t] = 0; }
+                        n_out = outgoing_fwd(par.node, sm.out_nodes, sm.out_chars);
+                        for (int t = 0; t < kMaxOut; ++t) { sm.out_scores[t] = 0; sm.out_trails[t] = 0; }
                     } else {
-                        n_out = outgoing_rc(par.node, par.trail, out_nodes, out_chars, out_trails);
-                        for (int t = 0; t < kMaxOut; ++t) out_scores[t] = 0;
+                        n_out = outgoing_rc(par.node, par.trail, sm.out_nodes, sm.out_chars, sm.out_trails);
+                        for (int t = 0; t < kMaxOut; ++t) sm.out_scores[t] = 0;
                     }
+                    wsync();
                     if (n_out > kMaxOut) { overflow = true; return 0; }
                 }
                 if (n_out == 0) { m.cols[i].is_tip = 1; continue; }
 
                 const int end = imin(prev_end, wlen) + 1;
+                const int size0 = end - begin;
+                const int n = prev_end - begin;           // parent rows inside the band
+                const int shift = begin - par.trim;
 
                 for (int t = 0; t < n_out; ++t) {
-                    uint8_t ch = out_chars[t];
+                    uint8_t ch = sm.out_chars[t];
                     if (ch >= 'a' && ch <= 'z') ch -= 32;      // toupper (:564)
-                    ColMeta col;
-                    if (!new_column(end - begin, wlen + 1 - begin, &col)) return 0;
-                    col.node = out_nodes[t]; col.trail = out_trails[t]; col.parent = i; col.c = ch;
-                    col.offset = next_offset; col.max_pos = begin; col.trim = begin;
-                    col.score = out_scores[t]; col.is_tip = 0; col.started = 0; col.pad = 0;
-                    const int size0 = col.size;
-                    const uint32_t cap_before = ext_table_cap[e];
-                    if (n_cols + 1 > ext_table_cap[e]) ext_table_cap[e] = ext_table_cap[e] ? 2 * ext_table_cap[e] : 1;
+                    if (n_cols >= caps.max_cols) { overflow = true; return 0; }
+#if MGB_DEVICE_CODE
+                    // ---- register fast path: the whole column (incl. its 5 padding cells) fits in one
+                    // lane-per-cell pass (n4 <= 28, final size <= 27). Fuses DPTColumn::create, update_column,
+                    // extend_ins_end, the per-column scan, the table commit and the convergence filter.
+                    if (use_fast && n <= 28 && size0 <= 27 && sm.bmax >= 40) {
+                        const int j = wlane();
+                        const score_t go = cfg.gap_open, ge = cfg.gap_ext;
+                        const score_t add = sm.out_scores[t];
+                        {   // requests whose latency overlaps the DP below
+                            const uint64_t cnode = sm.out_nodes[t];
+                            if (!rc && cnode) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                            pf_key = cnode + (rc ? ix.n : 0);
+                            pf_slot_idx = hash_node(pf_key);
+                            pf_slot = cx[e].conv_slots[pf_slot_idx];
+                        }
+                        const int code = encode_char(ch);
+                        const int n4 = (n + 3) & ~3;
+                        const score_t *pS = parS + shift, *pF = parF + shift;
+                        const bool act = j < n4;
+                        const score_t ps_jm1 = (j >= 1 && j <= n4) ? pS[j - 1] : kNinf;
+                        const score_t ps_j = act ? pS[j] : kNinf;
+                        const score_t pf_j = act ? pF[j] : kNinf;
+                        const int pr = prof_score(s, start + begin + j, code);
+                        const score_t match = (act && j) ? ps_jm1 + pr + add : kNinf;
+                        const score_t del = (act && next_offset > 1) ? imax(ps_j + go, pf_j + ge) + add : kNinf;
+                        const score_t mval = imax(match, del);
+                        const int a = act ? mval + go - j * ge : INT32_MIN;
+                        int incl = wscan_max(a);
+                        incl = imax(incl, kNinf + ge);
+                        const int excl = wshfl_up1(incl, kNinf + ge);
+                        score_t E_j = (j >= 1 && j <= n4) ? excl + (j - 1) * ge : kNinf;
+                        score_t F_j = act ? del : kNinf;
+                        score_t S_j = kNinf;
+                        if (act) { score_t sv = imax(mval, E_j); S_j = sv > cutoff - 1 ? sv : kNinf; }
+                        if (size0 > imax(1, n) && j == size0 - 1) {               // scalar tail (:284-289)
+                            score_t tt = imax(ps_jm1 + add + pr, E_j);
+                            if (tt >= cutoff) S_j = tt;
+                        }
+                        // extend_ins_end (:293-328)
+                        int size = size0;
+                        bool fits = true;
+                        const int max_size = wlen + 1 - begin;
+                        if (size0 < max_size) {
+                            const score_t s_last = wbcast(S_j, size0 - 1), e_last = wbcast(E_j, size0 - 1);
+                            const score_t ins = imax(s_last + go, e_last + ge);
+                            if (ins >= cutoff) {
+                                int64_t extra = ge < 0 ? ((int64_t)ins - cutoff) / (-ge) : (int64_t)0x7fffffff;
+                                int cnt = 1 + (int)(extra < (int64_t)(max_size - size0 - 1) ? extra : (int64_t)(max_size - size0 - 1));
+                                if (size0 + cnt > 27) fits = false;
+                                else {
+                                    if (j >= size0) {
+                                        const bool in = j < size0 + cnt;
+                                        S_j = in ? ins + (j - size0) * ge : kNinf;
+                                        E_j = S_j; F_j = kNinf;
+                                    }
+                                    size = size0 + cnt;
+                                }
+                            }
+                        }
+                        if (fits) {
+                            const uint32_t cap_before = cx[e].table_cap;
+                            if (n_cols + 1 > cap_before) cx[e].table_cap = cap_before ? 2 * cap_before : 1;
+                            stats.dp_cells += size; ++stats.dp_columns;
+                            // per-column scan (:643-669)
+                            const int diag_i = next_offset - seed_off_m1;
+                            const score_t extension_cutoff
+                                = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
+                            const bool cell = j < size;
+                            const score_t v = cell ? S_j : kNinf;
+                            min_cell_score = imin(min_cell_score, wreduce_min(cell && v != kNinf ? v : 0x7fffffff));
+                            const score_t gbs = wreduce_max(cell ? v : INT32_MIN);
+                            const int dj = iabs(j + begin - diag_i);
+                            const int gd = wreduce_min(cell && v == gbs ? dj : 0x7fffffff);
+                            const int gj = wreduce_min(cell && v == gbs && dj == gd ? j : 0x7fffffff);
+                            const int max_pos = gj + begin;
+                            const score_t max_val = gbs;
+                            bool has_extension = in_seed;
+                            if (!has_extension)
+                                has_extension = wballot(cell && v + cx[s].ps[start + begin + j] >= extension_cutoff) != 0;
+                            if (!in_seed && (max_val < cutoff || !has_extension))
+                                continue;                        // pop(table.size() - 1)
+                            table_size_bytes += 136ull * (cx[e].table_cap - cap_before)
+                                + 3ull * vec_capacity(size0, size) * 4;
+                            if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
+                            best_score = imax(best_score, max_val);
+                            if ((uint64_t)cells_used + 3ull * (size + 5) + 3ull * (wlen + 16) > 3ull * caps.max_cells) {
+                                overflow = true; return 0;
+                            }
+                            // commit: DP table (global) and the on-chip child buffer
+                            const int cap = size + 5;
+                            const uint32_t off = cells_used;
+                            cells_used += 3 * cap;
+                            score_t *cb_S = sm.buf(cb);
+                            if (j < cap) {
+                                score_t *dst = m.cells + off;
+                                dst[j] = S_j; dst[cap + j] = E_j; dst[2 * cap + j] = F_j;
+                                cb_S[j] = S_j; cb_S[sm.bmax + j] = E_j; cb_S[2 * sm.bmax + j] = F_j;
+                            }
+                            if (j + 32 < cap) {                  // padding cells beyond lane 31 are untouched ninf
+                                score_t *dst = m.cells + off;
+                                dst[j + 32] = kNinf; dst[cap + j + 32] = kNinf; dst[2 * cap + j + 32] = kNinf;
+                                cb_S[j + 32] = kNinf; cb_S[sm.bmax + j + 32] = kNinf; cb_S[2 * sm.bmax + j + 32] = kNinf;
+                            }
+                            ColMeta col;
+                            col.node = sm.out_nodes[t]; col.trail = sm.out_trails[t]; col.parent = i; col.c = ch;
+                            col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
+                            col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size; col.cells_off = off;
+                            const uint32_t idx = n_cols;
+                            m.cols[n_cols++] = col;
+                            last_col = col; last_idx = idx;
+                            if (cb) res1 = (int)idx; else res0 = (int)idx;
+                            wsync();
+                            // convergence filter from registers (update_seed_filter)
+                            const int s_first = begin ? 0 : 1;
+                            const int vec_offset = start + begin - (begin ? 1 : 0);
+                            score_t converged = update_seed_filter_reg(e, col.node, vec_offset, S_j, j - s_first,
+                                                                       size - s_first);
+                            if (overflow) return 0;
+                            if (converged != kNinf) {
+                                HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
+                                it.idx = idx; it.max_score = max_val;
+                                if (nn_n && converged == np[0].score) nn_push(nn_n, it);
+                                else heap_push(heap_n, it);
+                                if (overflow) return 0;
+                            }
+                            continue;
+                        }
+                    }
+#endif
+                    Scratch sc;
+                    if (size0 + 8 <= sm.bmax) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
+                    else if (!scratch_arena(wlen + 1 - begin, &sc)) return 0;
+                    // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
+                    for (int j = wlane(); j < size0 + 5; j += kWarp) { sc.S[j] = kNinf; sc.E[j] = kNinf; sc.F[j] = kNinf; }
+                    wsync();
+                    const score_t add = sm.out_scores[t];
+                    const uint32_t cap_before = cx[e].table_cap;
+                    if (n_cols + 1 > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
                     const int code = encode_char(ch);
 
-                    update_column(s, par, col, prev_end, start, cutoff, code);
-                    col.size = extend_ins_end(col, wlen + 1 - col.trim, cutoff);
-                    stats.dp_cells += col.size; ++stats.dp_columns;
+                    update_column(s, parS + shift, parF + shift, sc, size0, n, start + begin, cutoff,
+                                  code, add, next_offset > 1);
+                    const int size = extend_ins_end(sc, size0, wlen + 1 - begin, cutoff);
+                    if (overflow) return 0;
+                    stats.dp_cells += size; ++stats.dp_columns;
 
                     // per-column scan (:643-669)
-                    const int diag_i = col.offset - seed_off_m1;
+                    const int diag_i = next_offset - seed_off_m1;
                     bool has_extension = in_seed;
                     const score_t extension_cutoff
                         = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
+                    int max_pos;
                     {
                         score_t mn = 0x7fffffff; score_t bs = INT32_MIN; int bd = 0x7fffffff, bj = 0x7fffffff;
                         bool he = false;
-                        for (int j = wlane(); j < col.size; j += kWarp) {
-                            score_t v = cellS(col, j);
+                        for (int j = wlane(); j < size; j += kWarp) {
+                            score_t v = sc.S[j];
                             if (v != kNinf) mn = imin(mn, v);
                             int d = iabs(j + begin - diag_i);
                             if (v > bs || (v == bs && d < bd)) { bs = v; bd = d; bj = j; }
-                            if (v + m.psum[s][start + col.trim + j] >= extension_cutoff) he = true;
+                            if (v + cx[s].ps[start + begin + j] >= extension_cutoff) he = true;
                         }
                         min_cell_score = imin(min_cell_score, wreduce_min(mn));
                         score_t gbs = wreduce_max(bs);
                         int gd = wreduce_min(bs == gbs ? bd : 0x7fffffff);
                         int gj = wreduce_min(bs == gbs && bd == gd ? bj : 0x7fffffff);
-                        col.max_pos = gj + begin;
+                        max_pos = gj + begin;
                         if (!has_extension && wballot(he)) has_extension = true;
                     }
-                    const score_t max_val = cellS(col, col.max_pos - col.trim);
+                    const score_t max_val = sc.S[max_pos - begin];
 
-                    if (!in_seed && (max_val < cutoff || !has_extension)) {
-                        ext_table_cap[e] = imax(ext_table_cap[e], cap_before);   // capacity never shrinks
+                    if (!in_seed && (max_val < cutoff || !has_extension))
                         continue;                        // pop(table.size() - 1)
-                    }
 
-                    table_size_bytes += 136ull * (ext_table_cap[e] - cap_before)
-                        + 3ull * vec_capacity(size0, col.size) * 4;
+                    table_size_bytes += 136ull * (cx[e].table_cap - cap_before)
+                        + 3ull * vec_capacity(size0, size) * 4;
 
                     if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
                     best_score = imax(best_score, max_val);
 
+                    if ((uint64_t)cells_used + 3ull * (size + 5) + 3ull * (wlen + 16) > 3ull * caps.max_cells) {
+                        overflow = true; return 0;
+                    }
+                    ColMeta col;
+                    col.node = sm.out_nodes[t]; col.trail = sm.out_trails[t]; col.parent = i; col.c = ch;
+                    col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
+                    col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size;
+                    col.cells_off = commit_column(sc, size);
                     const uint32_t idx = n_cols;
-                    cells_used += col.size + 5;
                     m.cols[n_cols++] = col;
+                    last_col = col; last_idx = idx;
+                    if (sc.on_chip) { if (cb) res1 = (int)idx; else res0 = (int)idx; }
 
                     const int vec_offset = start + begin - (begin ? 1 : 0);
                     const int s_first = begin ? 0 : 1;
-                    score_t converged = update_seed_filter(e, col.node, vec_offset, col, s_first,
-                                                           col.size - s_first);
+                    score_t converged = update_seed_filter(e, col.node, vec_offset, sc.S + s_first, size - s_first);
                     if (overflow) return 0;
                     if (converged != kNinf) {
-                        HeapItem it; it.score = converged; it.neg_off_diag = -iabs(col.max_pos - diag_i);
+                        HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
                         it.idx = idx; it.max_score = max_val;
-                        if (nn_n && converged == m.next_nodes[0].score) m.next_nodes[nn_n++] = it;
+                        if (nn_n && converged == np[0].score) nn_push(nn_n, it);
                         else heap_push(heap_n, it);
+                        if (overflow) return 0;
                     }
                 }
             }
         }
+        wsync();
 
         if (cfg.no_backtrack) {
             copy_slot(out_base, seed_slot);
@@ -1105,6 +1419,10 @@ struct ReadAligner {
         return n_res;
     }
 
+    bool seed_is_query;          // the seed in SLOT_SEED is a plain query substring
+    bool use_fast = true;        // register fast path for narrow columns (device only)
+    uint64_t pf_node; uint2 pf_adj;        // software prefetch: adjacency record of the newest column
+    uint64_t pf_key; ConvSlot pf_slot; uint32_t pf_slot_idx;   // ... and its first conv-table probe
     uint64_t table_size_bytes;
 
     MGB_HD void cig_append(int &n_ops, uint32_t op) {       // Cigar::append(op, 1)
@@ -1118,7 +1436,7 @@ struct ReadAligner {
     MGB_HD int backtrack(int e, int seed_slot, score_t min_path_score, int start, int wlen,
                          score_t min_cell_score, int out_base) {
         const int s = e;
-        const AlnSlot &seed = m.slots[seed_slot];
+        const AlnSlot &seed = sm.slots[seed_slot];
         const AlnHdr sh = *seed.h;
         const int K = ix.k;
         const int seed_clipping = start;
@@ -1214,23 +1532,33 @@ struct ReadAligner {
             int align_offset = sh.offset;
             bool path_back_nonzero = false;
 
+            // pending CIGAR run lives in registers (Cigar::append merges equal neighbours)
+            uint32_t cur_op = 0xffu, cur_len = 0;
+            auto cig_add = [&](uint32_t op) {
+                if (op == cur_op) { ++cur_len; return; }
+                if (cur_len) {
+                    if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return; }
+                    m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+                }
+                cur_op = op; cur_len = 1;
+            };
+            ColMeta col = m.cols[j];
+            ColMeta par = m.cols[col.parent];
             while (j) {
-                const ColMeta col = m.cols[j];
-                const ColMeta par = m.cols[col.parent];
                 const int trim = col.trim, trim_p = par.trim;
                 align_offset = imin(col.offset, k_minus_1);
                 if (pos == col.max_pos) m.cols[j].started = 1;
                 const int code = encode_char(col.c);
                 const score_t sv = cellS(col, pos - trim);
-                const uint32_t last_op = n_ops ? cig_op(m.bt_ops[n_ops - 1]) : 0xffu;
+                const uint32_t last_op = cur_op;
 
                 if (sv == kNinf) {
                     j = 0;
-                } else if (pos && sv == cellE(col, pos - trim) && (n_ops == 0 || last_op != OP_D)) {
+                } else if (pos && sv == cellE(col, pos - trim) && (last_op == 0xffu || last_op != OP_D)) {
                     // insertion run (:943-959)
                     bool again = true;
                     while (again) {
-                        cig_append(n_ops, OP_I);
+                        cig_add(OP_I);
                         again = cellE(col, pos - trim) == cellE(col, pos - trim - 1) + cfg.gap_ext;
                         --pos;
                     }
@@ -1240,40 +1568,47 @@ struct ReadAligner {
                     ++n_trace;
                     if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
                     m.bt_seq[n_seq++] = col.c;
-                    cig_append(n_ops, prof_is_match(s, seed_clipping + pos, code) ? OP_M : OP_X);
+                    cig_add(prof_is_match(s, seed_clipping + pos, code) ? OP_M : OP_X);
                     if (col.offset >= k_minus_1) {
                         if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
                         m.bt_path[n_path++] = col.node; path_back_nonzero = col.node != 0;
                     }
                     --pos;
                     j = col.parent;
-                } else if (sv == cellF(col, pos - trim) && (n_ops == 0 || last_op != OP_I)) {
+                    col = par;
+                    if (j) par = m.cols[col.parent];
+                } else if (sv == cellF(col, pos - trim) && (last_op == 0xffu || last_op != OP_I)) {
                     // deletion run (:972-999)
                     bool again = true;
                     while (again && j) {
-                        const ColMeta c2 = m.cols[j];
-                        const ColMeta p2 = m.cols[c2.parent];
-                        align_offset = imin(c2.offset, k_minus_1);
-                        again = cellF(c2, pos - c2.trim)
-                                == cellF(p2, pos - p2.trim) + c2.score + cfg.gap_ext;
+                        align_offset = imin(col.offset, k_minus_1);
+                        again = cellF(col, pos - col.trim)
+                                == cellF(par, pos - par.trim) + col.score + cfg.gap_ext;
                         ++n_trace;
                         if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
-                        m.bt_seq[n_seq++] = c2.c;
-                        cig_append(n_ops, OP_D);
-                        if (c2.offset >= k_minus_1) {
+                        m.bt_seq[n_seq++] = col.c;
+                        cig_add(OP_D);
+                        if (col.offset >= k_minus_1) {
                             if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
-                            m.bt_path[n_path++] = c2.node; path_back_nonzero = c2.node != 0;
+                            m.bt_path[n_path++] = col.node; path_back_nonzero = col.node != 0;
                         }
-                        j = c2.parent;
+                        j = col.parent;
+                        col = par;
+                        if (j) par = m.cols[col.parent];
                     }
                 } else {
                     break;                                   // backtracking failed
                 }
                 if (overflow) return 0;
             }
+            if (cur_len) {
+                if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return 0; }
+                m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+            }
+            wsync();
 
             if (n_trace >= min_trace_length && n_path && path_back_nonzero) {
-                const ColMeta cj = m.cols[j];
+                const ColMeta cj = j ? col : m.cols[0];
                 score_t cur_cell_score = cellS(cj, pos - cj.trim);
                 best_score = imax(best_score, score - cur_cell_score);
                 if ((int64_t)score - min_cell_score < best_score) break;
@@ -1284,7 +1619,7 @@ struct ReadAligner {
                         && (pos || cur_cell_score == cellS(root, 0))
                         && (cfg.allow_left_trim || !j)) {
                     // construct_alignment (:774-798)
-                    AlnSlot &o = m.slots[out_base + n_ext];
+                    AlnSlot &o = sm.slots[out_base + n_ext];
                     wsync();
                     for (int t = wlane(); t < n_path; t += kWarp) o.nodes[t] = m.bt_path[n_path - 1 - t];
                     for (int t = wlane(); t < n_seq; t += kWarp) o.seq[t] = m.bt_seq[n_seq - 1 - t];
@@ -1334,7 +1669,7 @@ struct ReadAligner {
         bool diff = false;
         int ca = aln_clipping(a), cb = aln_clipping(b);
         for (int i = wlane(); i < x.q_len; i += kWarp)
-            if (q[x.orientation][ca + i] != q[y.orientation][cb + i]) diff = true;
+            if (cx[x.orientation].q[ca + i] != cx[y.orientation].q[cb + i]) diff = true;
         for (int i = wlane(); i < x.seq_len; i += kWarp) if (a.seq[i] != b.seq[i]) diff = true;
         for (int i = wlane(); i < x.n_cigar; i += kWarp) if (a.cigar[i] != b.cigar[i]) diff = true;
         for (int i = wlane(); i < x.n_nodes; i += kWarp) if (a.nodes[i] != b.nodes[i]) diff = true;
@@ -1344,20 +1679,20 @@ struct ReadAligner {
         if (!n_agg) return kNinf;
         int mx = 0;
         for (int i = 1; i < n_agg; ++i)
-            if (aln_less(m.slots[SLOT_AGG + mx], m.slots[SLOT_AGG + i])) mx = i;
-        score_t cur_max = m.slots[SLOT_AGG + mx].h->score;
+            if (aln_less(sm.slots[SLOT_AGG + mx], sm.slots[SLOT_AGG + i])) mx = i;
+        score_t cur_max = sm.slots[SLOT_AGG + mx].h->score;
         return cur_max > 0 ? (score_t)((double)cur_max * cfg.rel_score_cutoff) : cur_max;
     }
     MGB_HD void agg_add(int slot) {
         if (!n_agg) { copy_slot(SLOT_AGG, slot); n_agg = 1; return; }
-        if (m.slots[slot].h->score < agg_global_cutoff()) return;
+        if (sm.slots[slot].h->score < agg_global_cutoff()) return;
         for (int i = 0; i < n_agg; ++i)
-            if (aln_equal(m.slots[slot], m.slots[SLOT_AGG + i])) return;
+            if (aln_equal(sm.slots[slot], sm.slots[SLOT_AGG + i])) return;
         if (n_agg < (int)cfg.num_alternative_paths) { copy_slot(SLOT_AGG + n_agg, slot); ++n_agg; return; }
         int mn = 0;
         for (int i = 1; i < n_agg; ++i)
-            if (aln_less(m.slots[SLOT_AGG + i], m.slots[SLOT_AGG + mn])) mn = i;
-        if (aln_less(m.slots[slot], m.slots[SLOT_AGG + mn])) return;
+            if (aln_less(sm.slots[SLOT_AGG + i], sm.slots[SLOT_AGG + mn])) mn = i;
+        if (aln_less(sm.slots[slot], sm.slots[SLOT_AGG + mn])) return;
         copy_slot(SLOT_AGG + mn, slot);
     }
     MGB_HD score_t get_min_path_score() { return imax(cfg.min_path_score, agg_global_cutoff()); }
@@ -1365,86 +1700,119 @@ struct ReadAligner {
     // --------------------------------------------------------------------------------
     // drivers (dbg_aligner.cpp:360-384, 657-755)
     // --------------------------------------------------------------------------------
-    MGB_HD bool check_seed_rec(int e, int s, const SeedRec &sd) {
-        // Alignment(seed): last node, pos = |query_view| + clipping - 1, score
-        uint64_t last_node = sd.n_nodes == 1 ? sd.node0 : qnodes[s][sd.clip + sd.n_nodes - 1];
+    // check_seed for a plain seed (Alignment(seed): last node, pos = |query_view| + clipping - 1, score)
+    MGB_HD bool check_seed_rec(const ConvSlot *slots, const score_t *cells, uint32_t epoch, bool rc,
+                               const uint64_t *nodes_s, const int32_t *pss, const SeedRec &sd) {
+        uint64_t last_node = sd.n_nodes == 1 ? sd.node0 : nodes_s[sd.clip + sd.n_nodes - 1];
         int end_clip = L - (int)sd.clip - (int)sd.len;
-        score_t score = m.psum[s][sd.clip] - m.psum[s][sd.clip + sd.len]
+        score_t score = pss[sd.clip] - pss[sd.clip + sd.len]
             + (!sd.clip ? cfg.left_end_bonus : 0) + (!end_clip ? cfg.right_end_bonus : 0);
-        return check_seed_vals(e, last_node, (int)sd.len + (int)sd.clip - 1, score);
+        return check_seed_vals(slots, cells, epoch, rc, last_node, (int)sd.len + (int)sd.clip - 1, score);
     }
 
     MGB_HD void set_seed(int e) { conv_clear(e); }
 
-    // aln_both for query strand s
-    MGB_HD void align_strand(int s) {
+    // Seeds of query strand s, in order (dbg_aligner.cpp:360-384 align_core when `both` is false,
+    // :657-736 aln_both otherwise: forward extension, then backward extension of left-clipped
+    // results through the reverse-complement graph view).
+    MGB_HD void align_strand(int s, bool both) {
         const int fe = s, be = 1 - s;
-        ext_rc[fe] = false; ext_rc[be] = true;
-        stats.num_seeds += n_seeds[s];
-        for (int i = 0; i < n_seeds[s] && !overflow; ++i) {
-            SeedRec sd = m.seeds[s][i];
-            if (!sd.alive) continue;
+        cx[fe].rc = 0;
+        if (both) cx[be].rc = 1;
+        const int n_seeds_s = cx[s].n_seeds;
+        SeedRec *seeds_s = cx[s].seeds;
+        const bool implicit = cx[s].implicit_seeds != 0;
+        const int nk = L >= (int)ix.k ? L - (int)ix.k + 1 : 0;
+        stats.num_seeds += n_seeds_s;
+        if (!n_seeds_s) return;
+        for (int i = implicit ? mask_next(cx[s].mask, nk, 0, true) : 0;
+             (implicit ? i < nk : i < n_seeds_s) && !overflow;
+             i = implicit ? mask_next(cx[s].mask, nk, i + 1, true) : i + 1) {
+            SeedRec sd;
+            if (implicit) {
+                sd.clip = i; sd.len = ix.k; sd.offset = 0; sd.n_nodes = 1; sd.node0 = cx[s].qnodes[i];
+                sd.alive = 1; sd.pad = 0;
+            } else {
+                sd = seeds_s[i];
+                if (!sd.alive) continue;
+            }
             seed_to_slot(SLOT_SEED, s, sd);
+            seed_is_query = true;
+            const score_t mps_fwd = both ? cfg.min_cell_score : get_min_path_score();
             set_seed(fe);
-            int n_res = extend(fe, SLOT_SEED, cfg.min_cell_score, false, SLOT_EXT);
+            int n_res = extend(fe, SLOT_SEED, mps_fwd, false, SLOT_EXT);
             if (overflow) return;
             int n_rc = 0;
             for (int r = 0; r < n_res; ++r) {
                 const int slot = SLOT_EXT + r;
-                if (m.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
-                if (!aln_clipping(m.slots[slot]) || m.slots[slot].h->offset) continue;
+                if (!both) { agg_add(slot); continue; }
+                if (sm.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
+                if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
                 if (!reverse_complement_slot(slot)) continue;
                 if (n_rc != r) copy_slot(SLOT_EXT + n_rc, slot);
                 ++n_rc;
             }
             // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
             for (int r = 0; r < n_rc && !overflow; ++r) {
-                if (!m.slots[SLOT_EXT + r].h->used) continue;
+                if (!sm.slots[SLOT_EXT + r].h->used) continue;
                 score_t mps = get_min_path_score();
                 set_seed(be);
+                seed_is_query = false;
                 int nb = extend(be, SLOT_EXT + r, mps, true, SLOT_BWD);
                 if (overflow) return;
                 for (int b = 0; b < nb; ++b) {
                     const int slot = SLOT_BWD + b;
                     if (!reverse_complement_slot(slot)) continue;
-                    const AlnHdr h = *m.slots[slot].h;
-                    int clip = aln_clipping(m.slots[slot]), eclip = aln_end_clipping(m.slots[slot]);
+                    const AlnHdr h = *sm.slots[slot].h;
+                    int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
                     for (int t = 0; t < h.n_nodes && !overflow; ++t)
-                        filter_nodes(fe, m.slots[slot].nodes[t], clip, L - eclip);
+                        filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
                     agg_add(slot);
                 }
                 for (int r2 = r + 1; r2 < n_rc; ++r2) {
-                    AlnSlot &a = m.slots[SLOT_EXT + r2];
+                    AlnSlot &a = sm.slots[SLOT_EXT + r2];
                     if (!a.h->used) continue;
                     const AlnHdr h = *a.h;
-                    if (!check_seed_vals(be, a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
+                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, true,
+                                         a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
                         a.h->used = 0;
                 }
             }
-            for (int j = i + 1; j < n_seeds[s]; ++j) {
-                if (m.seeds[s][j].alive && !check_seed_rec(fe, s, m.seeds[s][j]))
-                    m.seeds[s][j].alive = 0;
+            // later seeds already covered by this extension are dropped (:731-734, :379-382);
+            // independent probes, one seed per lane
+            wsync();
+            {
+                const ConvSlot *slots = cx[fe].conv_slots; const score_t *cells = cx[fe].conv_cells;
+                const uint32_t epoch = cx[fe].conv_epoch;
+                const uint64_t *nodes_s = cx[s].qnodes; const int32_t *pss = cx[s].ps;
+                if (implicit) {
+                    uint32_t *mask = cx[s].mask;
+                    for (int w = (i + 1) >> 5; 32 * w < nk; ++w) {
+                        const uint32_t word = mask[w];
+                        uint32_t nw = 0;
+                        for (int b = 0; b < 32; b += kWarp) {    // one pass on the device
+                            const int bit = b + wlane();
+                            const int jj = 32 * w + bit;
+                            bool alive = jj > i && ((word >> bit) & 1u);
+                            if (alive) {
+                                SeedRec c; c.clip = jj; c.len = ix.k; c.offset = 0; c.n_nodes = 1;
+                                c.node0 = nodes_s[jj]; c.alive = 1; c.pad = 0;
+                                alive = check_seed_rec(slots, cells, epoch, false, nodes_s, pss, c);
+                            }
+                            nw |= wballot(alive) << b;
+                        }
+                        // bits at positions <= i in the first word stay as they are
+                        if (32 * w <= i) { uint32_t lowmask = (i & 31) == 31 ? ~0u : ((2u << (i & 31)) - 1u); nw |= word & lowmask; }
+                        mask[w] = nw;
+                    }
+                } else {
+                    for (int j = i + 1 + wlane(); j < n_seeds_s; j += kWarp) {
+                        if (seeds_s[j].alive && !check_seed_rec(slots, cells, epoch, false, nodes_s, pss, seeds_s[j]))
+                            seeds_s[j].alive = 0;
+                    }
+                }
             }
-        }
-    }
-
-    // forward-only: align_core(*seeder, extender, add_alignment, get_min_path_score, false)
-    MGB_HD void align_forward_only() {
-        ext_rc[0] = false;
-        stats.num_seeds += n_seeds[0];
-        for (int i = 0; i < n_seeds[0] && !overflow; ++i) {
-            SeedRec sd = m.seeds[0][i];
-            if (!sd.alive) continue;
-            seed_to_slot(SLOT_SEED, 0, sd);
-            score_t mps = get_min_path_score();
-            set_seed(0);
-            int n_res = extend(0, SLOT_SEED, mps, false, SLOT_EXT);
-            if (overflow) return;
-            for (int r = 0; r < n_res; ++r) agg_add(SLOT_EXT + r);
-            for (int j = i + 1; j < n_seeds[0]; ++j) {
-                if (m.seeds[0][j].alive && !check_seed_rec(0, 0, m.seeds[0][j]))
-                    m.seeds[0][j].alive = 0;
-            }
+            wsync();
         }
     }
 
@@ -1452,10 +1820,10 @@ struct ReadAligner {
     MGB_HD void build_psum(int s) {
         // sequential suffix sum chunked over the warp
         int carry = 0;
-        if (wlane() == 0) m.psum[s][L] = 0;
+        if (wlane() == 0) cx[s].ps[L] = 0;
         for (int base = L - 1; base >= 0; base -= kWarp) {
             int i = base - wlane();
-            int v = i >= 0 ? cfg.diag[(uint8_t)q[s][i]] : 0;
+            int v = i >= 0 ? cfg.diag[(uint8_t)cx[s].q[i]] : 0;
 #if MGB_DEVICE_CODE
             for (int d = 1; d < 32; d <<= 1) {
                 int o = __shfl_up_sync(0xffffffffu, v, d);
@@ -1463,7 +1831,7 @@ struct ReadAligner {
             }
 #endif
             v += carry;
-            if (i >= 0) m.psum[s][i] = v;
+            if (i >= 0) cx[s].ps[i] = v;
             carry = wbcast(v, kWarp - 1);
         }
         wsync();
@@ -1472,46 +1840,64 @@ struct ReadAligner {
     // whole pipeline for one read; returns the number of alignments left in SLOT_AGG.. (sorted)
     MGB_HD int run(int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
                    const uint64_t *nf, const uint64_t *nr, int *order) {
-        L = L_; q[0] = qf; q[1] = qr; codes[0] = cf; codes[1] = cr; qnodes[0] = nf; qnodes[1] = nr;
-        overflow = false; n_agg = 0;
+        L = L_;
+        overflow = false; n_agg = 0; seed_is_query = false;
+        wsync();
+        // per-strand context + alignment slot table (shared memory; constant indices only here)
+        {
+            StrandCtx c0, c1;
+            c0.q = qf; c1.q = qr; c0.codes = cf; c1.codes = cr; c0.qnodes = nf; c1.qnodes = nr;
+            c0.ps = m.psum[0]; c1.ps = m.psum[1];
+            c0.seeds = m.seeds[0]; c1.seeds = m.seeds[1];
+            c0.conv_slots = m.conv_slots[0]; c1.conv_slots = m.conv_slots[1];
+            c0.conv_cells = m.conv_cells[0]; c1.conv_cells = m.conv_cells[1];
+            c0.conv_epoch = m.epoch_store[0]; c1.conv_epoch = m.epoch_store[1];
+            c0.conv_n = c1.conv_n = 0; c0.conv_cells_used = c1.conv_cells_used = 0;
+            c0.n_seeds = c1.n_seeds = 0; c0.num_matching = c1.num_matching = 0;
+            c0.table_cap = c1.table_cap = 0; c0.num_ext = c1.num_ext = 0;
+            c0.explored_prev = c1.explored_prev = 0; c0.rc = c1.rc = 0;
+            c0.implicit_seeds = c1.implicit_seeds = 0; c0.mask = sm.mask0; c1.mask = sm.mask1;
+            // stage the query strands (and their suffix sums) on chip when they fit
+            if (L + 1 <= sm.lq) {
+                for (int i = wlane(); i < L; i += kWarp) { sm.q0[i] = qf[i]; sm.q1[i] = qr[i]; }
+                c0.q = sm.q0; c1.q = sm.q1; c0.ps = sm.psum0; c1.ps = sm.psum1;
+            }
+            sm.ctx[0] = c0; sm.ctx[1] = c1;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+            for (int t = 0; t < kNumSlots; ++t) sm.slots[t] = m.slots[t];
+        }
+        wsync();
         stats.num_seeds = stats.num_extensions = stats.num_explored_nodes = stats.dp_columns = 0;
         stats.dp_cells = 0;
-        for (int e = 0; e < 2; ++e) {
-            ext_table_cap[e] = 0; ext_num_ext[e] = 0; ext_explored_prev[e] = 0; ext_rc[e] = false;
-            m.conv[e].n_entries = 0; m.conv[e].cells_used = 0; m.conv[e].epoch = m.epoch_store[e];
-            n_seeds[e] = 0; num_matching[e] = 0;
-        }
         const bool both = cfg.forward_and_reverse_complement;
         build_psum(0);
         if (both) build_psum(1);
         build_seeds(0);
         if (overflow) return 0;
-        if ((double)L * cfg.min_exact_match > (double)num_matching[0]) { n_seeds[0] = 0; num_matching[0] = 0; }
+        if ((double)L * cfg.min_exact_match > (double)cx[0].num_matching) { cx[0].n_seeds = 0; cx[0].num_matching = 0; }
+        int first = 0, n_pass = 1;
         if (both) {
             build_seeds(1);
             if (overflow) return 0;
-            if ((double)L * cfg.min_exact_match > (double)num_matching[1]) { n_seeds[1] = 0; num_matching[1] = 0; }
-            uint32_t fm = num_matching[0], bm = num_matching[1];
-            if (fm >= bm) {
-                align_strand(0);
-                if (!overflow && (double)bm >= (double)fm * cfg.rel_score_cutoff) align_strand(1);
-            } else {
-                align_strand(1);
-                if (!overflow && (double)fm >= (double)bm * cfg.rel_score_cutoff) align_strand(0);
-            }
-        } else {
-            align_forward_only();
+            if ((double)L * cfg.min_exact_match > (double)cx[1].num_matching) { cx[1].n_seeds = 0; cx[1].num_matching = 0; }
+            // the strand with more exact-match bases first; the other only if it is close (:738-755)
+            uint32_t fm = cx[0].num_matching, bm = cx[1].num_matching;
+            first = fm >= bm ? 0 : 1;
+            uint32_t hi = first ? bm : fm, lo = first ? fm : bm;
+            n_pass = (double)lo >= (double)hi * cfg.rel_score_cutoff ? 2 : 1;
         }
+        for (int pass = 0; pass < n_pass && !overflow; ++pass)
+            align_strand(pass ? 1 - first : first, both);
         if (overflow) return 0;
-        for (int e = 0; e < 2; ++e) {
-            stats.num_extensions += ext_num_ext[e];
-            stats.num_explored_nodes += ext_explored_prev[e] + m.conv[e].n_entries;
-        }
+        stats.num_extensions += cx[0].num_ext + cx[1].num_ext;
+        stats.num_explored_nodes += cx[0].explored_prev + cx[0].conv_n + cx[1].explored_prev + cx[1].conv_n;
         // AlignmentAggregator::get_alignments: descending LocalAlignmentLess order
         for (int i = 0; i < n_agg; ++i) order[i] = i;
         for (int i = 1; i < n_agg; ++i) {
             int x = order[i], j = i - 1;
-            while (j >= 0 && aln_less(m.slots[SLOT_AGG + order[j]], m.slots[SLOT_AGG + x])) {
+            while (j >= 0 && aln_less(sm.slots[SLOT_AGG + order[j]], sm.slots[SLOT_AGG + x])) {
                 order[j + 1] = order[j]; --j;
             }
             order[j + 1] = x;

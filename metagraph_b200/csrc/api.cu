@@ -72,6 +72,8 @@ MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
 
 struct AlignArgs {
     IndexView ix; DevConfig cfg; Caps caps;
+    int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
+    int use_fast;               // 0 disables the register fast path (test knob)
     const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
     const uint64_t *nodes_f, *nodes_r;
     const uint32_t *read_list; uint32_t n_list;
@@ -80,10 +82,13 @@ struct AlignArgs {
     unsigned int *next;
 };
 
-MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena) {
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena, char *smem) {
     WarpMem mem;
     mem.carve(arena, a.caps);
-    ReadAligner al(a.ix, a.cfg, a.caps, mem);
+    WarpSmem sm;
+    sm.carve(smem, a.bmax, a.lq, a.hcap);
+    ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
+    al.use_fast = a.use_fast != 0;
     const uint64_t b = a.offsets[r];
     const int L = (int)(a.offsets[r + 1] - b);
     int order[kMaxAlt];
@@ -136,7 +141,7 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena) {
     }
     if (wlane() == 0) {
         a.hdr[r] = h;
-        mem.epoch_store[0] = mem.conv[0].epoch; mem.epoch_store[1] = mem.conv[1].epoch;
+        mem.epoch_store[0] = sm.ctx[0].conv_epoch; mem.epoch_store[1] = sm.ctx[1].conv_epoch;
     }
     wsync();
 }
@@ -146,7 +151,7 @@ MGB_HD void init_arena(const AlignArgs &a, char *arena) {
     WarpMem mem;
     mem.carve(arena, a.caps);
     for (int e = 0; e < 2; ++e)
-        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv[e].slots[i].epoch = 0;
+        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv_slots[e][i].epoch = 0;
     if (wlane() == 0) { mem.epoch_store[0] = 0; mem.epoch_store[1] = 0; }
     wsync();
 }
@@ -165,16 +170,23 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
     for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
 }
 
-__global__ void __launch_bounds__(128) k_align(const AlignArgs a) {
+#ifndef MGB_ALIGN_MIN_BLOCKS
+#define MGB_ALIGN_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     char *arena = a.arena + (size_t)warp * a.arena_stride;
+    extern __shared__ __align__(16) char smem_raw[];
+    WarpSmem probe;
+    const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
+    char *smem = smem_raw + (threadIdx.x >> 5) * smem_per_warp;
     init_arena(a, arena);
     while (true) {
         unsigned int t = 0;
         if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= a.n_list) break;
-        align_read(a, a.read_list[t], arena);
+        align_read(a, a.read_list[t], arena, smem);
     }
 }
 
@@ -334,6 +346,16 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         if ((rc = upload(h.sel_W[c], &v.sel_W[c]))) return rc;
     if ((rc = upload(h.valid, &v.valid))) return rc;
     if ((rc = upload(h.sfx, &v.sfx))) return rc;
+    {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, h.adj.size() * sizeof(uint2));
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(adj): ") + cudaGetErrorString(e));
+        idx->bufs.push_back(p);
+        e = cudaMemcpy(p, h.adj.data(), h.adj.size() * sizeof(uint2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMemcpy(adj): ") + cudaGetErrorString(e));
+        idx->device_bytes += h.adj.size() * sizeof(uint2);
+        v.adj = (const uint2*)p;
+    }
     idx->view = v;
 #endif
     *out = idx.release();
@@ -548,11 +570,25 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             if (pass == 6) { rc = fail(MGB_ERR_OVERFLOW, "a read exceeded the largest per-read work arena"); break; }
             Caps caps = choose_caps(b.L_max, dcfg, index->view.k, scale);
             size_t stride = arena_bytes(caps);
+            // on-chip working set per warp: column buffers hold a full-width column of reads up to
+            // 248 bp; longer reads / wider columns spill to the arena scratch
+            const int bmax = b.L_max + 9 <= 256 ? (int)((b.L_max + 9 + 31) & ~31u) : 256;
+            const int lq = b.L_max + 1 <= 512 ? (int)((b.L_max + 1 + 15) & ~15u) : 0;
+            int hcap = 16;
+            // test knobs: force the spill paths (arena scratch, queue migration, unstaged query)
+            int bmax_v = bmax, lq_v = lq;
+            if (const char *e = std::getenv("MGB_TEST_BMAX")) bmax_v = std::atoi(e);
+            if (const char *e = std::getenv("MGB_TEST_LQ")) lq_v = std::atoi(e);
+            if (const char *e = std::getenv("MGB_TEST_HCAP")) hcap = std::atoi(e);
+            WarpSmem sm_probe;
+            const size_t smem_per_warp = sm_probe.carve(nullptr, bmax_v, lq_v, hcap);
 #if defined(MGB_HOST_EMU)
             uint32_t n_warps = 1;
 #else
             int blocks_per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, 0));
+            const size_t smem_block = smem_per_warp * 4;
+            CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, smem_block));
             if (blocks_per_sm < 1) blocks_per_sm = 1;
             uint64_t n_warps64 = (uint64_t)index->num_sms * blocks_per_sm * 4;
             size_t free_b = 0, total_b = 0;
@@ -578,7 +614,8 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             if ((rc = dev_zero(d_used, 8, st))) break;
             if ((rc = dev_zero(d_next, 4, st))) break;
             AlignArgs a;
-            a.ix = index->view; a.cfg = dcfg; a.caps = caps;
+            a.ix = index->view; a.cfg = dcfg; a.caps = caps; a.bmax = bmax_v; a.lq = lq_v; a.hcap = hcap;
+            a.use_fast = std::getenv("MGB_TEST_NOFAST") ? 0 : 1;
             a.qf = b.qf; a.qr = b.qr; a.cf = b.cf; a.cr = b.cr; a.offsets = b.offsets; a.koff = b.koff;
             a.nodes_f = b.nodes_f; a.nodes_r = b.nodes_r;
             a.read_list = d_list; a.n_list = (uint32_t)list.size();
@@ -587,11 +624,12 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             unsigned long long used = 0;
 #if defined(MGB_HOST_EMU)
             init_arena(a, d_arena);
-            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], d_arena);
+            std::vector<char> smem_emu(smem_per_warp + 64);
+            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], d_arena, smem_emu.data());
             used = *d_used;
 #else
             cudaEventRecord(ev[3], st.s);
-            k_align<<<n_warps / 4, 128, 0, st.s>>>(a);
+            k_align<<<n_warps / 4, 128, smem_block, st.s>>>(a);
             CUDA_TRY(cudaGetLastError());
             cudaEventRecord(ev[4], st.s);
             if ((rc = d2h(&used, d_used, 8, st))) break;

@@ -16,6 +16,10 @@
 #pragma once
 #include "common.cuh"
 
+#if !defined(__CUDACC__)
+struct uint2 { uint32_t x, y; };
+#endif
+
 namespace mgb {
 
 static constexpr int kSigmaDNA = 5;
@@ -31,6 +35,7 @@ struct IndexView {
     const uint32_t *sel_W[kSigmaDNA];   // per symbol, ceil(cnt / 32) + 1
     const uint32_t *valid;      // bit per edge or nullptr (mask dropped)
     const uint32_t *sfx;        // 2 words per indexed suffix: [begin, end) edge range
+    const uint2 *adj;           // per edge: forward adjacency record (see adj_* below), or nullptr
     uint64_t n;                 // number of edges (ids 1..n)
     uint32_t nblk;
     uint32_t k;                 // DBG k; BOSS node length = k - 1
@@ -255,6 +260,26 @@ MGB_HD uint32_t node_last_value(const IndexView &ix, uint64_t i) {
 // boss.cpp:642-652
 MGB_HD uint64_t fwd(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t c) {
     return select_last(ix, lc, ix.NF[c] + rank_W(ix, lc, i, c));
+}
+
+// Forward adjacency record of edge e (denormalised DBGSuccinct::call_outgoing_kmers,
+// dbg_succinct.cpp:110-139 = fwd + pred_last + get_W of the target node, in one 8-byte load):
+//   x        last edge of the target node of e (0: e is a sink dummy, no outgoing edges)
+//   y[0:5)   labels ($ACGT) present among the target node's edges (flagged ones included)
+//   y[8:13)  labels whose edge is a valid, non-'$' DBG node (in_graph)
+// Edges of a node are sorted by label, so the edge with label c is first + popc(mask & ((1<<c)-1)).
+MGB_HD uint2 load_adj(const IndexView &ix, uint64_t e) {
+#if MGB_DEVICE_CODE
+    return __ldg(ix.adj + e);
+#else
+    return ix.adj[e];
+#endif
+}
+MGB_HD uint64_t adj_child(uint2 a, uint32_t c) {   // edge with label c out of the target node, 0 if none
+    uint32_t all = a.y & 31u;
+    if (!a.x || !((all >> c) & 1u)) return 0;
+    uint64_t first = (uint64_t)a.x - popc32(all) + 1;
+    return first + popc32(all & ((1u << c) - 1u));
 }
 
 // boss.cpp:623-636

@@ -13,6 +13,7 @@ namespace mgb {
 
 struct HostIndex {
     std::vector<uint32_t> blocks, blk_rank, sel_last, valid, sfx;
+    std::vector<uint2> adj;
     std::vector<uint32_t> sel_W[kSigmaDNA];
     uint64_t n = 0; uint32_t nblk = 0, k = 0, sfx_len = 0, sigma = kSigmaDNA;
     uint64_t F[kSigmaDNA], NF[kSigmaDNA]; uint32_t total_W[kSigmaDNA]; uint64_t num_ones = 0;
@@ -24,6 +25,7 @@ struct HostIndex {
         for (int c = 0; c < kSigmaDNA; ++c) v.sel_W[c] = sel_W[c].data();
         v.valid = valid.empty() ? nullptr : valid.data();
         v.sfx = sfx.empty() ? nullptr : sfx.data();
+        v.adj = adj.empty() ? nullptr : adj.data();
         v.n = n; v.nblk = nblk; v.k = k; v.sfx_len = sfx_len; v.sigma = sigma;
         for (int c = 0; c < kSigmaDNA; ++c) { v.F[c] = F[c]; v.NF[c] = NF[c]; v.total_W[c] = total_W[c]; }
         v.num_ones = num_ones;
@@ -99,6 +101,34 @@ inline void build_host_index(const uint8_t *W, const uint8_t *last, uint64_t n_p
         h.valid.assign((n_plus_1 + 31) / 32 + 1, 0);
         for (uint64_t i = 1; i <= h.n; ++i)
             if (valid_bytes[i]) h.valid[i >> 5] |= 1u << (i & 31);
+    }
+    // forward adjacency records (index.cuh load_adj): the j-th un-flagged occurrence of label c
+    // points to the j-th node whose last character is c (boss.cpp:642-652 fwd); flagged edges share
+    // the target of the preceding un-flagged one.
+    {
+        std::vector<uint32_t> ones_pos;          // select_last(r) = ones_pos[r - 1]
+        ones_pos.reserve(ones);
+        for (uint64_t i = 1; i <= h.n; ++i) if (last[i]) ones_pos.push_back((uint32_t)i);
+        std::vector<uint16_t> nodemask(ones_pos.size() + 1, 0);   // by node rank (1-based)
+        {
+            uint64_t r = 1; uint16_t all = 0, ok = 0;
+            for (uint64_t i = 1; i <= h.n; ++i) {
+                uint32_t c = W[i] % kSigmaDNA;
+                all |= 1u << c;
+                if (c && (!valid_bytes || valid_bytes[i])) ok |= 1u << c;
+                if (last[i]) { nodemask[r++] = (uint16_t)(all | (ok << 8)); all = 0; ok = 0; }
+            }
+        }
+        h.adj.assign(n_plus_1, uint2{0, 0});
+        uint64_t cur[kSigmaDNA] = { 0, 0, 0, 0, 0 };
+        for (uint64_t i = 1; i <= h.n; ++i) {
+            uint32_t w = W[i], c = w % kSigmaDNA;
+            if (w < (uint32_t)kSigmaDNA) ++cur[c];
+            if (i > 1 && c == 0) continue;                         // sink dummy: no outgoing edges
+            uint64_t r = h.NF[c] + cur[c];
+            if (r == 0 || r > ones_pos.size()) continue;
+            h.adj[i] = uint2{ ones_pos[r - 1], nodemask[r] };
+        }
     }
     // suffix ranges (boss.hpp:516-525, boss_chunk_construct.cpp:260-320): for every string
     // over the sigma-1 real symbols of length s, the [begin, end) edge range of the nodes

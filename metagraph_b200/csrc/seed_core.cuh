@@ -70,9 +70,11 @@ MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint6
                 if (writer) out[i] = 0;
                 break;
             }
-            edge = fwd(ix, lc, edge, codes[i + K - 2]);
-            edge = pick_edge(ix, lc, edge, codes[i + K - 1]);
-            if (writer) out[i] = in_graph(ix, edge) ? edge : 0;
+            // fwd(edge, codes[i+K-2]) + pick_edge(.., codes[i+K-1]) through the adjacency record
+            const uint2 a = load_adj(ix, edge);
+            const uint32_t c = codes[i + K - 1];
+            edge = adj_child(a, c);
+            if (writer) out[i] = (edge && ((a.y >> (8 + c)) & 1u)) ? edge : 0;
         }
     }
 }
