@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -229,6 +230,43 @@ inline int dev_zero(void *d, size_t bytes, Stream &st) {
 }
 #endif
 
+// Host buffers that receive the packed results. On the device build they are pinned and
+// recycled through a process-wide pool (cudaHostAlloc of GB-sized buffers costs 100s of ms), so a
+// mgb_results_t owns its buffers zero-copy and hands them back in mgb_results_free().
+struct HostBuf { char *p = nullptr; size_t cap = 0; };
+#if defined(MGB_HOST_EMU)
+inline HostBuf hostbuf_acquire(size_t bytes) { HostBuf b; b.cap = bytes ? bytes : 1; b.p = (char*)std::malloc(b.cap); return b; }
+inline void hostbuf_release(HostBuf b) { std::free(b.p); }
+#else
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<HostBuf> free_list;
+    HostBuf acquire(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = free_list.size();
+            for (size_t i = 0; i < free_list.size(); ++i)
+                if (free_list[i].cap >= bytes && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best != free_list.size()) { HostBuf b = free_list[best]; free_list.erase(free_list.begin() + best); return b; }
+        }
+        HostBuf b;
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaHostAlloc((void**)&b.p, want, cudaHostAllocDefault) != cudaSuccess) { b.p = nullptr; b.cap = 0; return b; }
+        b.cap = want;
+        return b;
+    }
+    void release(HostBuf b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() >= 16) { cudaFreeHost(b.p); return; }
+        free_list.push_back(b);
+    }
+};
+PinnedPool g_pinned_pool;
+inline HostBuf hostbuf_acquire(size_t bytes) { return g_pinned_pool.acquire(bytes); }
+inline void hostbuf_release(HostBuf b) { g_pinned_pool.release(b); }
+#endif
+
 struct DevBufs {               // frees everything it owns on scope exit
     Stream &st;
     std::vector<void*> ptrs;
@@ -265,7 +303,8 @@ struct mgb_results {
     std::vector<uint64_t> first;
     std::vector<uint32_t> count;
     std::vector<mgb_alignment_t> alns;
-    std::vector<std::vector<char>> heaps;    // host copies of the output heaps
+    std::vector<HostBuf> heaps;              // host copies of the output heaps (recycled on free)
+    ~mgb_results() { for (HostBuf b : heaps) hostbuf_release(b); }
     mgb_stats_t stats;
 };
 
@@ -325,6 +364,13 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     idx->num_sms = prop.multiProcessorCount;
+    {   // keep stream-ordered allocations cached between calls
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     IndexView v = h.view();
     auto upload = [&](const std::vector<uint32_t> &src, const uint32_t **dst) -> int {
         if (src.empty()) { *dst = nullptr; return 0; }
@@ -537,7 +583,11 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     cudaEvent_t ev[6];
     for (auto &e : ev) cudaEventCreate(&e);
 #endif
-    std::vector<ReadHdr> hdr_host(n_reads);
+    HostBuf hdr_buf = hostbuf_acquire(((size_t)n_reads + 1) * sizeof(ReadHdr));
+    if (!hdr_buf.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
+    ReadHdr *hdr_host = (ReadHdr*)hdr_buf.p;
+    struct HdrGuard { HostBuf b; ~HdrGuard() { hostbuf_release(b); } } hdr_guard{ hdr_buf };
+    std::vector<uint32_t> read_heap(n_reads, 0);   // which pass produced the read's alignments
     {
         DevBufs bufs(st);
         Batch b; std::vector<uint64_t> koff;
@@ -639,10 +689,11 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
 #endif
             res->stats.kernel_launches += 1;
             if (used > heap_cap) used = heap_cap;
-            res->heaps.emplace_back((size_t)used);
-            std::vector<char> &heap_host = res->heaps.back();
-            if (used && (rc = d2h(heap_host.data(), d_heap, used, st))) break;
-            if ((rc = d2h(hdr_host.data(), d_hdr, (size_t)n_reads * sizeof(ReadHdr), st))) break;
+            HostBuf heap_host = hostbuf_acquire((size_t)used + 16);
+            if (!heap_host.p) { rc = fail(MGB_ERR_CUDA, "host buffer allocation failed"); break; }
+            res->heaps.push_back(heap_host);
+            if (used && (rc = d2h(heap_host.p, d_heap, used, st))) break;
+            if ((rc = d2h(hdr_host, d_hdr, (size_t)n_reads * sizeof(ReadHdr), st))) break;
 #if !defined(MGB_HOST_EMU)
             CUDA_TRY(cudaStreamSynchronize(st.s));
             cudaEventRecord(ev[4], st.s);
@@ -650,9 +701,9 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             { float ms = 0; cudaEventElapsedTime(&ms, ev[3], ev[4]); d2h_ms += ms; }
 #endif
             res->stats.d2h_bytes += used + (size_t)n_reads * sizeof(ReadHdr);
-            // unpack this pass
+            // classify this pass; alignments are materialised in read order after the last pass
             std::vector<uint32_t> retry;
-            const size_t heap_id = res->heaps.size() - 1;
+            const uint32_t heap_id = (uint32_t)res->heaps.size() - 1;
             for (uint32_t r : list) {
                 const ReadHdr &h = hdr_host[r];
                 if (h.status == MGB_READ_OVERFLOW) { retry.push_back(r); continue; }
@@ -662,22 +713,8 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
                 res->stats.dp_cells += h.stats.dp_cells;
                 res->stats.dp_columns += h.stats.dp_columns;
                 res->count[r] = h.n_aln;
-                res->first[r] = (uint64_t)heap_id << 48 | 0;   // patched below once all are known
-                const char *p = res->heaps[heap_id].data() + h.heap_off;
-                // temporarily store alignments tagged with the read; sorted into read order later
-                for (uint32_t i = 0; i < h.n_aln; ++i) {
-                    const OutAln *o = (const OutAln*)p;
-                    mgb_alignment_t al;
-                    std::memset(&al, 0, sizeof(al));
-                    al.read_index = r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
-                    al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
-                    al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
-                    p += sizeof(OutAln);
-                    al.nodes = (const uint64_t*)p; p += 8ull * o->n_nodes;
-                    al.cigar = (const uint32_t*)p; p += (4ull * o->n_cigar + 7) & ~7ull;
-                    al.sequence = p; p += ((uint64_t)o->seq_len + 7) & ~7ull;
-                    res->alns.push_back(al);
-                }
+                res->first[r] = h.heap_off;          // byte offset for now, patched below
+                read_heap[r] = heap_id;
             }
             res->stats.num_reads_retried += retry.size();
             list.swap(retry);
@@ -697,11 +734,30 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     cudaStreamDestroy(st.s);
 #endif
     if (rc) return rc;
-    // bring alignments into read order (stable: per-read order is the aggregator's order)
-    std::stable_sort(res->alns.begin(), res->alns.end(),
-                     [](const mgb_alignment_t &x, const mgb_alignment_t &y) { return x.read_index < y.read_index; });
-    uint64_t pos = 0;
-    for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
+    // materialise mgb_alignment_t records in read order
+    {
+        std::vector<uint64_t> byte_off(res->first);
+        uint64_t pos = 0;
+        for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
+        res->alns.resize(pos);
+        #pragma omp parallel for schedule(static) if (n_reads > 20000)
+        for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
+            const char *p = res->heaps[read_heap[r]].p + byte_off[r];
+            for (uint32_t i = 0; i < res->count[r]; ++i) {
+                const OutAln *o = (const OutAln*)p;
+                mgb_alignment_t al;
+                std::memset(&al, 0, sizeof(al));
+                al.read_index = (uint32_t)r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
+                al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
+                al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
+                p += sizeof(OutAln);
+                al.nodes = (const uint64_t*)p; p += 8ull * o->n_nodes;
+                al.cigar = (const uint32_t*)p; p += (4ull * o->n_cigar + 7) & ~7ull;
+                al.sequence = p; p += ((uint64_t)o->seq_len + 7) & ~7ull;
+                res->alns[res->first[r] + i] = al;
+            }
+        }
+    }
     *out = res.release();
     return MGB_OK;
 }
