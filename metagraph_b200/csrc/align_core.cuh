@@ -110,6 +110,14 @@ struct OutAln {
 
 struct ReadStats { uint32_t num_seeds, num_extensions, num_explored_nodes, dp_columns; uint64_t dp_cells; };
 
+#if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
+#define MGB_TIC(var) long long var = clock64()
+#define MGB_TOC(var, slot) phase_cycles[slot] += clock64() - var
+#else
+#define MGB_TIC(var)
+#define MGB_TOC(var, slot)
+#endif
+
 static constexpr int kNumSlots = 3 * kMaxAlt + 2;   // seed, ext[alt], bwd[alt], agg[alt], tmp
 enum { SLOT_SEED = 0, SLOT_TMP = 1, SLOT_EXT = 2, SLOT_BWD = 2 + kMaxAlt, SLOT_AGG = 2 + 2 * kMaxAlt };
 
@@ -995,8 +1003,10 @@ struct ReadAligner {
         if (size >= max_size) return size;
         score_t ins = imax(sc.S[size - 1] + cfg.gap_open, sc.E[size - 1] + cfg.gap_ext);
         if (ins < cutoff) return size;
-        int64_t extra = cfg.gap_ext < 0 ? ((int64_t)ins - cutoff) / (-cfg.gap_ext) : (int64_t)0x7fffffff;
-        int cnt = 1 + (int)(extra < (int64_t)(max_size - size - 1) ? extra : (int64_t)(max_size - size - 1));
+        const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;              // ins >= cutoff
+        const uint32_t extra = cfg.gap_ext < 0 ? diff / (uint32_t)(-cfg.gap_ext) : 0x7fffffffu;
+        const uint32_t room = (uint32_t)(max_size - size - 1);
+        int cnt = 1 + (int)(extra < room ? extra : room);
         if (size + cnt + 5 > sc.cap) {
             Scratch big;                               // only an on-chip scratch can be too small
             if (!sc.on_chip || !scratch_arena(max_size, &big)) { overflow = true; return size; }
@@ -1095,8 +1105,11 @@ struct ReadAligner {
         const uint64_t seed_node0 = seed.nodes[0];
         int res0 = -1, res1 = -1;                         // columns resident in sm.buf(0) / sm.buf(1)
         ColMeta last_col; uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
+        bool last_band_valid = false; uint32_t last_band_mask = 0; score_t last_band_cutoff = 0;
 
         if ((uint64_t)3 * (wlen + 16) > 3ull * caps.max_cells) { overflow = true; return 0; }
+        // committing a column is safe while cells_used <= cells_limit (room for it and the next scratch)
+        const uint32_t cells_limit = (uint32_t)(3ull * caps.max_cells - 6ull * (wlen + 16));
 
         // root column (:455-470)
         {
@@ -1122,6 +1135,7 @@ struct ReadAligner {
             wsync();
         }
 
+        MGB_TIC(t_fwd);
         score_t min_cell_score = 0, best_score = 0;
         int heap_n = 0, nn_n = 0;
         { HeapItem r0; r0.score = 0; r0.neg_off_diag = 0; r0.idx = 0; r0.max_score = 0; heap_push(heap_n, r0); }
@@ -1157,7 +1171,12 @@ struct ReadAligner {
                 }
                 // band within the xdrop cutoff (:549-560)
                 int begin, prev_end;
-                {
+                if (i == last_idx && last_band_valid && last_band_cutoff == cutoff) {
+                    // band recorded when the column was committed (same cutoff): no second pass
+                    if (!last_band_mask) continue;
+                    begin = ffs32(last_band_mask) - 1 + par.trim;
+                    prev_end = 32 - clz32(last_band_mask) + par.trim;
+                } else {
                     int lo = 0x7fffffff, hi = -1;
                     for (int j = wlane(); j < par.size; j += kWarp) {
                         if (parS[j] >= cutoff) { lo = imin(lo, j); hi = imax(hi, j); }
@@ -1182,10 +1201,10 @@ struct ReadAligner {
                         n_out = 1;
                     } else if (!rc) {
                         n_out = outgoing_fwd(par.node, sm.out_nodes, sm.out_chars);
-                        for (int t = 0; t < kMaxOut; ++t) { sm.out_scores[t] = 0; sm.out_trails[t] = 0; }
+                        for (int t = 0; t < n_out && t < kMaxOut; ++t) { sm.out_scores[t] = 0; sm.out_trails[t] = 0; }
                     } else {
                         n_out = outgoing_rc(par.node, par.trail, sm.out_nodes, sm.out_chars, sm.out_trails);
-                        for (int t = 0; t < kMaxOut; ++t) sm.out_scores[t] = 0;
+                        for (int t = 0; t < n_out && t < kMaxOut; ++t) sm.out_scores[t] = 0;
                     }
                     wsync();
                     if (n_out > kMaxOut) { overflow = true; return 0; }
@@ -1247,8 +1266,10 @@ struct ReadAligner {
                             const score_t s_last = wbcast(S_j, size0 - 1), e_last = wbcast(E_j, size0 - 1);
                             const score_t ins = imax(s_last + go, e_last + ge);
                             if (ins >= cutoff) {
-                                int64_t extra = ge < 0 ? ((int64_t)ins - cutoff) / (-ge) : (int64_t)0x7fffffff;
-                                int cnt = 1 + (int)(extra < (int64_t)(max_size - size0 - 1) ? extra : (int64_t)(max_size - size0 - 1));
+                                const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;      // ins >= cutoff
+                                const uint32_t extra = ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu;
+                                const uint32_t room = (uint32_t)(max_size - size0 - 1);
+                                int cnt = 1 + (int)(extra < room ? extra : room);
                                 if (size0 + cnt > 27) fits = false;
                                 else {
                                     if (j >= size0) {
@@ -1286,9 +1307,7 @@ struct ReadAligner {
                                 + 3ull * vec_capacity(size0, size) * 4;
                             if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
                             best_score = imax(best_score, max_val);
-                            if ((uint64_t)cells_used + 3ull * (size + 5) + 3ull * (wlen + 16) > 3ull * caps.max_cells) {
-                                overflow = true; return 0;
-                            }
+                            if (cells_used > cells_limit) { overflow = true; return 0; }
                             // commit: DP table (global) and the on-chip child buffer
                             const int cap = size + 5;
                             const uint32_t off = cells_used;
@@ -1311,6 +1330,7 @@ struct ReadAligner {
                             const uint32_t idx = n_cols;
                             m.cols[n_cols++] = col;
                             last_col = col; last_idx = idx;
+                            last_band_mask = wballot(cell && S_j >= cutoff); last_band_cutoff = cutoff; last_band_valid = true;
                             if (cb) res1 = (int)idx; else res0 = (int)idx;
                             wsync();
                             // convergence filter from registers (update_seed_filter)
@@ -1323,7 +1343,11 @@ struct ReadAligner {
                                 HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
                                 it.idx = idx; it.max_score = max_val;
                                 if (nn_n && converged == np[0].score) nn_push(nn_n, it);
-                                else heap_push(heap_n, it);
+                                else if (heap_n == 0 && nn_n == 0 && t + 1 == n_out) {
+                                    // sole candidate: pushing it and popping it in the next round is the
+                                    // identity; np[0] must still hold it for the tie test above
+                                    np[0] = it; nn_n = 1;
+                                } else heap_push(heap_n, it);
                                 if (overflow) return 0;
                             }
                             continue;
@@ -1391,7 +1415,7 @@ struct ReadAligner {
                     col.cells_off = commit_column(sc, size);
                     const uint32_t idx = n_cols;
                     m.cols[n_cols++] = col;
-                    last_col = col; last_idx = idx;
+                    last_col = col; last_idx = idx; last_band_valid = false;
                     if (sc.on_chip) { if (cb) res1 = (int)idx; else res0 = (int)idx; }
 
                     const int vec_offset = start + begin - (begin ? 1 : 0);
@@ -1409,16 +1433,20 @@ struct ReadAligner {
             }
         }
         wsync();
+        MGB_TOC(t_fwd, 2);
 
         if (cfg.no_backtrack) {
             copy_slot(out_base, seed_slot);
             return 1;
         }
+        MGB_TIC(t_bt);
         int n_res = backtrack(e, seed_slot, min_path_score, start, wlen, min_cell_score, out_base);
         for (int r = 0; r < n_res; ++r) trim_offset(out_base + r);
+        MGB_TOC(t_bt, 3);
         return n_res;
     }
 
+    long long phase_cycles[8] = {0,0,0,0,0,0,0,0};   // MGB_PHASE_TIMERS: setup, seeds, fwd loop, backtrack, rest
     bool seed_is_query;          // the seed in SLOT_SEED is a plain query substring
     bool use_fast = true;        // register fast path for narrow columns (device only)
     uint64_t pf_node; uint2 pf_adj;        // software prefetch: adjacency record of the newest column
@@ -1544,6 +1572,10 @@ struct ReadAligner {
             };
             ColMeta col = m.cols[j];
             ColMeta par = m.cols[col.parent];
+            // the grand-parent's record is requested one step ahead so that a move to the parent costs
+            // no dependent round trip
+            ColMeta gpar = par;
+            if (par.parent != 0xffffffffu) gpar = m.cols[par.parent];
             while (j) {
                 const int trim = col.trim, trim_p = par.trim;
                 align_offset = imin(col.offset, k_minus_1);
@@ -1576,7 +1608,7 @@ struct ReadAligner {
                     --pos;
                     j = col.parent;
                     col = par;
-                    if (j) par = m.cols[col.parent];
+                    if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols[par.parent]; }
                 } else if (sv == cellF(col, pos - trim) && (last_op == 0xffu || last_op != OP_I)) {
                     // deletion run (:972-999)
                     bool again = true;
@@ -1594,7 +1626,7 @@ struct ReadAligner {
                         }
                         j = col.parent;
                         col = par;
-                        if (j) par = m.cols[col.parent];
+                        if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols[par.parent]; }
                     }
                 } else {
                     break;                                   // backtracking failed
@@ -1840,6 +1872,7 @@ struct ReadAligner {
     // whole pipeline for one read; returns the number of alignments left in SLOT_AGG.. (sorted)
     MGB_HD int run(int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
                    const uint64_t *nf, const uint64_t *nr, int *order) {
+        MGB_TIC(t_setup);
         L = L_;
         overflow = false; n_agg = 0; seed_is_query = false;
         wsync();
@@ -1874,6 +1907,8 @@ struct ReadAligner {
         const bool both = cfg.forward_and_reverse_complement;
         build_psum(0);
         if (both) build_psum(1);
+        MGB_TOC(t_setup, 0);
+        MGB_TIC(t_seeds);
         build_seeds(0);
         if (overflow) return 0;
         if ((double)L * cfg.min_exact_match > (double)cx[0].num_matching) { cx[0].n_seeds = 0; cx[0].num_matching = 0; }
@@ -1888,8 +1923,11 @@ struct ReadAligner {
             uint32_t hi = first ? bm : fm, lo = first ? fm : bm;
             n_pass = (double)lo >= (double)hi * cfg.rel_score_cutoff ? 2 : 1;
         }
+        MGB_TOC(t_seeds, 1);
+        MGB_TIC(t_align);
         for (int pass = 0; pass < n_pass && !overflow; ++pass)
             align_strand(pass ? 1 - first : first, both);
+        MGB_TOC(t_align, 4);
         if (overflow) return 0;
         stats.num_extensions += cx[0].num_ext + cx[1].num_ext;
         stats.num_explored_nodes += cx[0].explored_prev + cx[0].conv_n + cx[1].explored_prev + cx[1].conv_n;

@@ -75,6 +75,7 @@ struct AlignArgs {
     IndexView ix; DevConfig cfg; Caps caps;
     int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
     int use_fast;               // 0 disables the register fast path (test knob)
+    unsigned long long *phase_out;   // MGB_PHASE_TIMERS builds: cycles per phase (setup, seeds, fwd, backtrack, align total)
     const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
     const uint64_t *nodes_f, *nodes_r;
     const uint32_t *read_list; uint32_t n_list;
@@ -97,6 +98,11 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena, char *smem) 
     int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
                    has_k ? a.nodes_f + a.koff[r] : nullptr,
                    has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
+#if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
+    if (wlane() == 0 && a.phase_out) {
+        for (int p = 0; p < 5; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
+    }
+#endif
     ReadHdr h;
     h.status = al.overflow ? MGB_READ_OVERFLOW : MGB_READ_OK;
     h.n_aln = 0; h.heap_off = 0; h.stats = al.stats;
@@ -666,6 +672,13 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             AlignArgs a;
             a.ix = index->view; a.cfg = dcfg; a.caps = caps; a.bmax = bmax_v; a.lq = lq_v; a.hcap = hcap;
             a.use_fast = std::getenv("MGB_TEST_NOFAST") ? 0 : 1;
+            a.phase_out = nullptr;
+#if defined(MGB_PHASE_TIMERS) && !defined(MGB_HOST_EMU)
+            unsigned long long *d_phase = nullptr;
+            if ((rc = pass_bufs.alloc(&d_phase, 8))) break;
+            if ((rc = dev_zero(d_phase, 64, st))) break;
+            a.phase_out = d_phase;
+#endif
             a.qf = b.qf; a.qr = b.qr; a.cf = b.cf; a.cr = b.cr; a.offsets = b.offsets; a.koff = b.koff;
             a.nodes_f = b.nodes_f; a.nodes_r = b.nodes_r;
             a.read_list = d_list; a.n_list = (uint32_t)list.size();
@@ -688,6 +701,15 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             cudaEventRecord(ev[3], st.s);
 #endif
             res->stats.kernel_launches += 1;
+#if defined(MGB_PHASE_TIMERS) && !defined(MGB_HOST_EMU)
+            {
+                unsigned long long ph[8];
+                cudaMemcpy(ph, a.phase_out, 64, cudaMemcpyDeviceToHost);
+                std::fprintf(stderr, "[phase cycles/read] setup %.0f seeds %.0f fwd %.0f backtrack %.0f align_total %.0f (reads %u)\n",
+                             (double)ph[0] / a.n_list, (double)ph[1] / a.n_list, (double)ph[2] / a.n_list,
+                             (double)ph[3] / a.n_list, (double)ph[4] / a.n_list, a.n_list);
+            }
+#endif
             if (used > heap_cap) used = heap_cap;
             HostBuf heap_host = hostbuf_acquire((size_t)used + 16);
             if (!heap_host.p) { rc = fail(MGB_ERR_CUDA, "host buffer allocation failed"); break; }
