@@ -163,7 +163,28 @@ MGB_HD void init_arena(const AlignArgs &a, char *arena) {
     wsync();
 }
 
+// One refinement level of the suffix-range table (boss.hpp:651-655 index order: the appended
+// character is the most significant digit): entry o = idx + (c-1)*cur_num of the new table is
+// tighten_range(cur[idx], c).
+struct SfxArgs { IndexView ix; const uint32_t *cur; uint32_t *nxt; uint64_t cur_num; };
+
+MGB_HD void sfx_extend_item(const SfxArgs &a, uint64_t o) {
+    const uint64_t idx = o % a.cur_num;
+    const uint32_t c = (uint32_t)(o / a.cur_num) + 1;
+    uint64_t rl = a.cur[2 * idx], ru = (uint64_t)a.cur[2 * idx + 1] - 1;
+    uint32_t b = 1, e = 1;
+    if (rl <= ru && tighten_range(a.ix, &rl, &ru, c)) { b = (uint32_t)rl; e = (uint32_t)(ru + 1); }
+    if (glane() == 0) { a.nxt[2 * o] = b; a.nxt[2 * o + 1] = e; }
+}
+
 #if !defined(MGB_HOST_EMU)
+__global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    const uint64_t total = a.cur_num * (kSigmaDNA - 1);
+    for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
+}
+
 __global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -347,18 +368,35 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         uint64_t n = n_plus_1 - 1;
         suffix_len = 1;
         uint64_t entries = 4;
-        while (suffix_len < 12 && suffix_len + 1 <= k - 1 && entries * 4 * 8 <= n / 2 + 1024) {
+        while (suffix_len < 14 && suffix_len + 1 <= k - 1 && entries * 4 <= 4 * n + 1024) {
             entries *= 4; ++suffix_len;
         }
     }
+    // levels up to 8 are refined on the host, the rest by k_sfx_extend on the device
+    const uint32_t sfx_target = suffix_len > k - 1 ? k - 1 : suffix_len;
+    const uint32_t sfx_host = sfx_target < 8 ? sfx_target : 8;
     try {
-        build_host_index(W, last, n_plus_1, F, valid, k, suffix_len, &h);
+        build_host_index(W, last, n_plus_1, F, valid, k, sfx_host, &h);
     } catch (const std::exception &e) {
         return fail(MGB_ERR_INVALID_ARGUMENT, e.what());
     }
 #if defined(MGB_HOST_EMU)
     (void)device; (void)hloc;
     idx->view = h.view();
+    {
+        uint64_t cur_num = 1;
+        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (kSigmaDNA - 1);
+        for (uint32_t len = sfx_host + 1; len <= sfx_target && sfx_host >= 1; ++len) {
+            const uint64_t nxt_num = cur_num * (kSigmaDNA - 1);
+            std::vector<uint32_t> nxt(2 * nxt_num);
+            SfxArgs sa { idx->view, idx->view.sfx, nxt.data(), cur_num };
+            sa.ix.sfx = nullptr; sa.ix.sfx_len = 0;
+            for (uint64_t o = 0; o < nxt_num; ++o) sfx_extend_item(sa, o);
+            h.sfx.swap(nxt);
+            cur_num = nxt_num;
+            idx->view.sfx = h.sfx.data(); idx->view.sfx_len = len;
+        }
+    }
     idx->device_bytes = h.blocks.size() * 4;
 #else
     int ndev = 0;
@@ -409,6 +447,34 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         v.adj = (const uint2*)p;
     }
     idx->view = v;
+    // deeper suffix-range levels on the device
+    {
+        uint64_t cur_num = 1;
+        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (kSigmaDNA - 1);
+        const uint32_t *cur = v.sfx;
+        for (uint32_t len = sfx_host + 1; len <= sfx_target && sfx_host >= 1; ++len) {
+            uint32_t *nxt = nullptr;
+            const uint64_t nxt_num = cur_num * (kSigmaDNA - 1);
+            cudaError_t e = cudaMalloc((void**)&nxt, nxt_num * 8);
+            if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(sfx): ") + cudaGetErrorString(e));
+            SfxArgs sa { idx->view, cur, nxt, cur_num };
+            sa.ix.sfx = nullptr; sa.ix.sfx_len = 0;
+            uint64_t blocks = std::min<uint64_t>((nxt_num + 31) / 32, (uint64_t)idx->num_sms * 32);
+            k_sfx_extend<<<(unsigned)blocks, 128>>>(sa);
+            e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { cudaFree(nxt); return fail(MGB_ERR_CUDA, std::string("k_sfx_extend: ") + cudaGetErrorString(e)); }
+            // the previous level is no longer needed (the host-built one is freed with the index)
+            if (len > sfx_host + 1) {
+                cudaFree((void*)cur);
+                idx->bufs.erase(std::find(idx->bufs.begin(), idx->bufs.end(), (void*)cur));
+                idx->device_bytes -= cur_num * 8;
+            }
+            idx->bufs.push_back(nxt);
+            idx->device_bytes += nxt_num * 8;
+            cur = nxt; cur_num = nxt_num;
+            idx->view.sfx = nxt; idx->view.sfx_len = len;
+        }
+    }
 #endif
     *out = idx.release();
     return MGB_OK;

@@ -119,4 +119,6 @@ RANDOM_CASES = [
     (10, 12, 4000, 30, 300, 0.03, lambda k: cli_defaults(k), False, 2),
     (11, 31, 20000, 40, 150, 0.05,
      lambda k: cli_defaults(k, min_exact_match=0.0, forward_and_reverse_complement=False), False, 2),
+    # large enough for the device-refined suffix-range levels (s > 8)
+    (12, 31, 400000, 30, 150, 0.02, lambda k: cli_defaults(k, min_seed_length=31, max_seed_length=31), False, 1),
 ]
