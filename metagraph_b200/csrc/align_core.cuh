@@ -132,6 +132,7 @@ struct WarpMem {
     AlnSlot slots[kNumSlots];
     uint32_t *bt_ops; uint64_t *bt_path; char *bt_seq;
     uint8_t *sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
+    uint32_t *sfx_first, *sfx_last; uint8_t *sfx_len;   // index_range result per query position
     uint32_t *epoch_store;  // conv-table epochs survive across the reads a warp processes
 
     MGB_HOSTDEV size_t carve(char *base, const Caps &c) {
@@ -159,6 +160,8 @@ struct WarpMem {
         bt_path = (uint64_t*)take(8 * (size_t)c.aln_nodes);
         bt_seq = (char*)take(c.aln_seq);
         sfx_min = (uint8_t*)take(c.L_max + 8);
+        sfx_first = (uint32_t*)take(4 * ((size_t)c.L_max + 8)); sfx_last = (uint32_t*)take(4 * ((size_t)c.L_max + 8));
+        sfx_len = (uint8_t*)take(c.L_max + 8);
         return o;
     }
 };
@@ -361,46 +364,27 @@ struct ReadAligner {
         return n;
     }
 
-    // first character of the k-mer of BOSS edge e (NodeFirstCache::get_first_char,
-    // node_first_cache.cpp:10-24): node_last_value(bwd^{k-2}(e)); *trail = bwd^{k-2}(e)
-    MGB_HD uint32_t first_char_full(uint64_t e, uint64_t *trail) {
-        LineCache lc;
-        uint64_t i = e;
-        for (uint32_t s = 0; s + 2 < ix.k; ++s) i = bwd(ix, lc, i);
-        *trail = i;
-        return node_last_value(ix, i);
-    }
-
     // RCDBG::call_outgoing_kmers (rc_dbg.hpp:86-97) -> NodeFirstCache::call_incoming_kmers
     // (node_first_cache.cpp:40-50): incoming nodes in call_incoming_to_target order
-    // (boss.cpp:766-786) with the complement of their first character.
-    MGB_HD int outgoing_rc(uint64_t node, uint64_t node_trail, uint64_t *nodes, uint8_t *chars,
+    // (boss.cpp:766-786) with the complement of their first character, through the reverse
+    // adjacency records.
+    MGB_HD int outgoing_rc(uint64_t node, uint64_t /*node_trail*/, uint64_t *nodes, uint8_t *chars,
                            uint64_t *trails) {
-        LineCache lc;
-        uint64_t x = bwd(ix, lc, node);
-        uint32_t d = node_last_value(ix, node);
+        const uint2 r = load_radj(ix, node);
+        const uint32_t d = node_last_value(ix, node);
         int n = 0;
-        uint64_t edge = x;
-        bool first = true;
+        uint64_t edge = r.x;
+        LineCache lc;
         while (true) {
             if (in_graph(ix, edge)) {
-                uint64_t tr;
-                uint32_t c;
-                if (first && node_trail) {
-                    // the un-flagged incoming edge: bwd^{k-2}(bwd(node)) = bwd(bwd^{k-2}(node))
-                    LineCache l2;
-                    tr = bwd(ix, l2, node_trail);
-                    c = node_last_value(ix, tr);
-                } else {
-                    c = first_char_full(edge, &tr);
-                }
+                const uint32_t c = load_radj(ix, edge).y & 7u;
                 uint8_t ch = complement_char((uint8_t)"$ACGT"[c]);
                 if (ch != '$') {
-                    if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; trails[n] = tr; }
+                    if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; trails[n] = 0; }
                     ++n;
                 }
             }
-            first = false;
+            if (!((r.y >> 3) & 1u)) break;              // single incoming edge
             if (++edge > ix.n) break;
             uint32_t w;
             edge = succ_W2(ix, lc, edge, d, &w);
@@ -418,6 +402,7 @@ struct ReadAligner {
     // dbg_succinct.cpp:662-680
     MGB_HD bool has_single_incoming(uint64_t node) {
         if (node == 1) return false;
+        if (!ix.valid) return !((load_radj(ix, node).y >> 3) & 1u);   // mask dropped: !multi-incoming
         LineCache lc;
         uint64_t x = bwd(ix, lc, node);
         uint32_t w = node_last_value(ix, node);
@@ -508,52 +493,6 @@ struct ReadAligner {
         }
     }
 
-    // DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix (dbg_succinct.cpp:307-393),
-    // max_num_allowed_matches == SIZE_MAX; str = cx[s].q[pos, pos+len), len <= k - 1.
-    // Appends matches as seeds at query position `pos` unless they exceed `max_per_locus`
-    // (then none is appended). Returns the number of alternative nodes found and the match
-    // length; *first_node = the first one.
-    MGB_HD int suffix_matches(int s, int pos, int len, int min_match, int *match_len,
-                              uint64_t *first_node, bool append) {
-        *match_len = 0;
-        if (len < min_match) return 0;
-        const uint8_t *cd = cx[s].codes + pos;
-        for (int i = 0; i < len; ++i)
-            if (cd[i] >= ix.sigma) return 0;
-        uint64_t first, lst; int matched;
-        boss_index_range(ix, cd, imin(len, (int)ix.k - 1), &first, &lst, &matched);
-        *match_len = matched;
-        if (matched < min_match) return 0;
-        LineCache lc;
-        uint64_t rank_first = rank_last(ix, lc, first);
-        uint64_t rank_lst = rank_last(ix, lc, lst);
-        int count = 0;
-        int seeds_before = cx[s].n_seeds;
-        for (uint64_t r = rank_first; r <= rank_lst; ++r) {
-            LineCache l2;
-            uint64_t e = select_last(ix, l2, r);
-            uint64_t x = bwd(ix, l2, e);
-            uint32_t d = node_last_value(ix, e);
-            uint64_t edge = x;
-            while (true) {
-                if (in_graph(ix, edge)) {
-                    if (count == 0) *first_node = edge;
-                    ++count;
-                    if (append && (uint64_t)count <= cfg.max_num_seeds_per_locus)
-                        push_seed(s, pos, matched, ix.k - matched, 1, edge);
-                }
-                if (++edge > ix.n) break;
-                uint32_t w;
-                edge = succ_W2(ix, l2, edge, d, &w);
-                if (w != d + ix.sigma) break;
-            }
-            if (overflow) break;
-        }
-        if (append && (uint64_t)count > cfg.max_num_seeds_per_locus)
-            cx[s].n_seeds = seeds_before;   // locus dropped (:340-345)
-        return count;
-    }
-
     // first index >= pos (< n) whose bit equals `want`; n if none
     MGB_HD int mask_next(const uint32_t *mask, int n, int pos, bool want) const {
         while (pos < n) {
@@ -564,6 +503,39 @@ struct ReadAligner {
             pos = (pos & ~31) + 32;
         }
         return n;
+    }
+
+    // Second half of DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix
+    // (dbg_succinct.cpp:355-393, max_num_allowed_matches == SIZE_MAX): enumerate the nodes whose
+    // k-mer suffix matches, given the BOSS range [first, lst] found by index_range. Appends one
+    // seed per node at query position `pos`; returns their number (seeds beyond the capacity set
+    // `overflow`).
+    MGB_HD int suffix_enumerate(int s, int pos, int matched, uint64_t first, uint64_t lst, uint64_t *first_node) {
+        LineCache lc;
+        const uint64_t rank_first = rank_last(ix, lc, first);
+        const uint64_t rank_lst = rank_last(ix, lc, lst);
+        int count = 0;
+        for (uint64_t r = rank_first; r <= rank_lst && !overflow; ++r) {
+            LineCache l2;
+            const uint64_t e = select_last(ix, l2, r);
+            const uint2 ra = load_radj(ix, e);
+            const uint32_t d = node_last_value(ix, e);
+            uint64_t edge = ra.x;
+            while (true) {
+                if (in_graph(ix, edge)) {
+                    if (count == 0) *first_node = edge;
+                    ++count;
+                    push_seed(s, pos, matched, ix.k - matched, 1, edge);
+                    if (overflow) break;
+                }
+                if (!((ra.y >> 3) & 1u)) break;
+                if (++edge > ix.n) break;
+                uint32_t w;
+                edge = succ_W2(ix, l2, edge, d, &w);
+                if (w != d + ix.sigma) break;
+            }
+        }
+        return count;
     }
 
     // SuffixSeeder<UniMEMSeeder>::generate_seeds (:153-358), non-canonical part
@@ -611,17 +583,15 @@ struct ReadAligner {
         if (L < (int)cfg.min_seed_length) return;
         if ((int)cfg.min_seed_length >= k) { mem_seeds(s, nk); return; }
 
-        // base (MEM) seeds first, into the tail of the seed array as scratch: they are merged
-        // with the sub-k seeds in query order below.
+        // base (MEM) seeds first; they are merged with the sub-k seeds in query order below
         const int n_pos = L - (int)cfg.min_seed_length + 1;
         for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
         wsync();
         mem_seeds(s, nk);
         const int n_base = cx[s].n_seeds;
         if (overflow) return;
-        // move base seeds to the end of the array (scratch), keep order
         if (2 * n_base > (int)caps.max_seeds) { overflow = true; return; }
-        SeedRec *base_seeds = cx[s].seeds + caps.max_seeds - n_base;
+        SeedRec *base_seeds = cx[s].seeds + caps.max_seeds - n_base;   // scratch at the end of the array
         wsync();
         for (int i = n_base - 1; i >= 0; --i) base_seeds[i] = cx[s].seeds[i];
         for (int b = 0; b < n_base; ++b) {
@@ -629,63 +599,77 @@ struct ReadAligner {
             for (int j = 0; j < (int)sd.n_nodes; ++j) m.sfx_min[sd.clip + j] = (uint8_t)k;
             if ((int)(sd.clip + sd.n_nodes) < n_pos) m.sfx_min[sd.clip + sd.n_nodes] = (uint8_t)k;
         }
+        wsync();
         cx[s].n_seeds = 0;
-        int b_next = 0;
 
+        // BOSS::index_range (boss.hpp:720-764) of every position not covered by a base seed, one
+        // position per lane group (the searches are independent; only their use below is ordered)
+        const uint32_t msl_u = cfg.max_seed_length < (uint32_t)(k - 1) ? cfg.max_seed_length : (uint32_t)(k - 1);
+        {
+            const int groups = kWarp / kGroup;
+            const int g = wlane() / kGroup;
+            for (int base = 0; base < n_pos; base += groups) {
+                const int i = base + g;
+                if (i < n_pos && m.sfx_min[i] != k) {
+                    const int len = imin((int)msl_u, L - i);
+                    uint64_t first = 0, lst = 0; int matched = 0;
+                    bool ok = len >= (int)cfg.min_seed_length;
+                    const uint8_t *cd = cx[s].codes + i;
+                    for (int t = 0; t < len && ok; ++t) ok = cd[t] < ix.sigma;
+                    if (ok) boss_index_range(ix, cd, imin(len, k - 1), &first, &lst, &matched);
+                    if (glane() == 0) {
+                        m.sfx_first[i] = (uint32_t)first; m.sfx_last[i] = (uint32_t)lst; m.sfx_len[i] = (uint8_t)matched;
+                    }
+                }
+            }
+        }
+        wsync();
+
+        int b_next = 0;
         const int last_full_id = L >= k ? L - k + 1 : n_pos;
         // state of suffix_seeds[last_full_id - 1] for the skip rule (:240-244)
         int lf_count = 0; uint64_t lf_node = 0;
         uint32_t nm = 0; int last_end = 0;
         for (int i = 0; i < n_pos; ++i) {
-            int pos_first = cx[s].n_seeds;
-            bool has_base = b_next < n_base && (int)base_seeds[b_next].clip == i;
-            int n_here = 0; bool dropped = false;
-            if (has_base) {
+            const int pos_first = cx[s].n_seeds;
+            int n_here = 0;
+            if (b_next < n_base && (int)base_seeds[b_next].clip == i) {
+                // a full seed at this position (offset 0): emitted as is (:334-337)
                 if (cx[s].n_seeds >= (int)caps.max_seeds - n_base) { overflow = true; return; }
                 cx[s].seeds[cx[s].n_seeds++] = base_seeds[b_next++];
                 n_here = 1;
-            }
-            uint32_t msl_u = cfg.max_seed_length < (uint32_t)(k - 1) ? cfg.max_seed_length : (uint32_t)(k - 1);
-            int max_seed_length = imin((int)msl_u, L - i);
-            int seed_length = 0; uint64_t first_node = 0;
-            int min_here = m.sfx_min[i];
-            // first pass only counts (needed for the skip rule and the per-locus cap)
-            int cnt = suffix_matches(s, i, max_seed_length, min_here, &seed_length, &first_node, false);
-            if (overflow) return;
-            bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
-                        && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
-            if (cnt && !skip) {
-                // append_suffix_seed (:195-213) for every alternative node
-                if (seed_length > min_here) { cx[s].n_seeds = pos_first; n_here = 0; }
-                m.sfx_min[i] = (uint8_t)seed_length;
-                if ((uint64_t)cnt <= cfg.max_num_seeds_per_locus) {
-                    if (cx[s].n_seeds + cnt > (int)caps.max_seeds - n_base) { overflow = true; return; }
-                    int dummy_len; uint64_t dummy_node;
-                    suffix_matches(s, i, max_seed_length, min_here, &dummy_len, &dummy_node, true);
+            } else if (m.sfx_min[i] != k) {
+                const int min_here = m.sfx_min[i];
+                const int matched = m.sfx_len[i];
+                // call_nodes_with_suffix_matching_longest_prefix (:231-238): nothing below min_match_length
+                if (matched >= min_here && matched > 0) {
+                    uint64_t first_node = 0;
+                    // capacity: the scratch copy of the base seeds lives at the end of the array
+                    int cnt = suffix_enumerate(s, i, matched, m.sfx_first[i], m.sfx_last[i], &first_node);
                     if (overflow) return;
-                    n_here += cnt;
-                } else {
-                    dropped = n_here == 0;
-                    n_here += cnt;   // counted for the offset test below, none stored
+                    if (cx[s].n_seeds > (int)caps.max_seeds - n_base) { overflow = true; return; }
+                    const bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
+                                && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
+                    if (cnt == 0 || skip) {
+                        cx[s].n_seeds = pos_first;
+                    } else {
+                        // append_suffix_seed (:195-213) for every alternative node
+                        m.sfx_min[i] = (uint8_t)matched;
+                        int sl = matched;
+                        for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j)
+                            m.sfx_min[j] = (uint8_t)(sl--);
+                        n_here = cnt;
+                        // a locus with too many alternatives is dropped at aggregation (:340-345)
+                        if ((uint64_t)cnt > cfg.max_num_seeds_per_locus) cx[s].n_seeds = pos_first;
+                    }
                 }
-                int sl = seed_length;
-                for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j)
-                    m.sfx_min[j] = (uint8_t)(sl--);
             }
             if (i == last_full_id - 1) {
                 lf_count = n_here;
-                lf_node = n_here ? cx[s].seeds[pos_first].node0 : 0;
+                lf_node = (n_here && cx[s].n_seeds > pos_first) ? cx[s].seeds[pos_first].node0 : 0;
             }
-            // aggregation (:316-357)
-            if (n_here == 0) continue;
-            bool no_offset = has_base && cx[s].n_seeds > pos_first && cx[s].seeds[pos_first].offset == 0;
-            if (!no_offset && !cnt) continue;
-            bool kept = no_offset || (!dropped && (uint64_t)n_here <= cfg.max_num_seeds_per_locus);
-            if (!no_offset && (uint64_t)n_here > cfg.max_num_seeds_per_locus) {
-                cx[s].n_seeds = pos_first;   // locus with too many alternatives is dropped
-                kept = false;
-            }
-            if (kept && cx[s].n_seeds > 0) {
+            // aggregation (:316-357): num_matching counts the span of the last seed emitted here
+            if (cx[s].n_seeds > pos_first) {
                 const SeedRec &bk = cx[s].seeds[cx[s].n_seeds - 1];
                 int begin = bk.clip, end = begin + (int)bk.len;
                 if (begin < last_end) nm += end - begin - (last_end - begin);

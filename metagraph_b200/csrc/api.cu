@@ -177,6 +177,43 @@ MGB_HD void sfx_extend_item(const SfxArgs &a, uint64_t o) {
     if (glane() == 0) { a.nxt[2 * o] = b; a.nxt[2 * o + 1] = e; }
 }
 
+// Reverse adjacency construction (index.cuh load_radj): per edge bwd(e) + "source node has several
+// incoming edges", then k-2 gather rounds c_{j+1}[e] = c_j[bwd(e)] that move the last node character
+// (boss.cpp:679-690) to the first position of the k-mer.
+struct RadjArgs { IndexView ix; uint32_t *bwd_arr; uint8_t *c_cur; uint8_t *c_nxt; uint8_t *multi; uint2 *radj; uint64_t n; };
+
+MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
+    LineCache lc;
+    uint64_t x = bwd(a.ix, lc, e);
+    uint32_t d = node_last_value(a.ix, e);
+    uint32_t multi = 0;
+    if (x + 1 <= a.ix.n) {
+        uint32_t w;
+        succ_W2(a.ix, lc, x + 1, d, &w);
+        multi = w == d + a.ix.sigma;
+    }
+    if (glane() == 0) { a.bwd_arr[e] = (uint32_t)x; a.c_cur[e] = (uint8_t)d; a.multi[e] = (uint8_t)multi; }
+}
+
+#if !defined(MGB_HOST_EMU)
+__global__ void __launch_bounds__(128) k_radj_bwd(RadjArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    for (uint64_t e = 1 + quad; e <= a.n; e += nquads) radj_bwd_item(a, e);
+}
+__global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = 1 + t; e <= a.n; e += nt) a.c_nxt[e] = a.c_cur[a.bwd_arr[e]];
+}
+__global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = 1 + t; e <= a.n; e += nt)
+        a.radj[e] = make_uint2(a.bwd_arr[e], (uint32_t)a.c_cur[e] | ((uint32_t)a.multi[e] << 3));
+}
+#endif
+
 #if !defined(MGB_HOST_EMU)
 __global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
     uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
@@ -322,6 +359,7 @@ struct mgb_index {
     std::vector<void*> bufs;
 #if defined(MGB_HOST_EMU)
     HostIndex host;
+    std::vector<uint2> radj_host;
 #endif
 };
 
@@ -396,6 +434,21 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             cur_num = nxt_num;
             idx->view.sfx = h.sfx.data(); idx->view.sfx_len = len;
         }
+    }
+    {
+        const uint64_t n = idx->view.n;
+        std::vector<uint32_t> bwd_arr(n + 1, 0);
+        std::vector<uint8_t> c0(n + 1, 0), c1(n + 1, 0), multi(n + 1, 0);
+        idx->radj_host.assign(n + 1, uint2{0, 0});
+        RadjArgs ra { idx->view, bwd_arr.data(), c0.data(), c1.data(), multi.data(), idx->radj_host.data(), n };
+        for (uint64_t e = 1; e <= n; ++e) radj_bwd_item(ra, e);
+        for (uint32_t r = 0; r + 2 < k; ++r) {
+            for (uint64_t e = 1; e <= n; ++e) ra.c_nxt[e] = ra.c_cur[bwd_arr[e]];
+            std::swap(ra.c_cur, ra.c_nxt);
+        }
+        for (uint64_t e = 1; e <= n; ++e)
+            idx->radj_host[e] = uint2{ bwd_arr[e], (uint32_t)ra.c_cur[e] | ((uint32_t)multi[e] << 3) };
+        idx->view.radj = idx->radj_host.data();
     }
     idx->device_bytes = h.blocks.size() * 4;
 #else
@@ -474,6 +527,33 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             cur = nxt; cur_num = nxt_num;
             idx->view.sfx = nxt; idx->view.sfx_len = len;
         }
+    }
+    // reverse adjacency records
+    {
+        const uint64_t n = idx->view.n;
+        uint32_t *bwd_arr = nullptr; uint8_t *c0 = nullptr, *c1 = nullptr, *multi = nullptr; uint2 *radj = nullptr;
+        cudaError_t e = cudaMalloc((void**)&bwd_arr, (n + 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c0, n + 1);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c1, n + 1);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&multi, n + 1);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&radj, (n + 1) * sizeof(uint2));
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(radj): ") + cudaGetErrorString(e));
+        cudaMemset(bwd_arr, 0, 4); cudaMemset(c0, 0, 1); cudaMemset(c1, 0, 1); cudaMemset(multi, 0, 1);
+        cudaMemset(radj, 0, sizeof(uint2));
+        RadjArgs ra { idx->view, bwd_arr, c0, c1, multi, radj, n };
+        const unsigned grid = (unsigned)idx->num_sms * 16;
+        k_radj_bwd<<<grid, 128>>>(ra);
+        for (uint32_t r = 0; r + 2 < k; ++r) {          // k - 2 bwd steps
+            k_radj_gather<<<grid, 256>>>(ra);
+            std::swap(ra.c_cur, ra.c_nxt);
+        }
+        k_radj_pack<<<grid, 256>>>(ra);
+        e = cudaDeviceSynchronize();
+        cudaFree(bwd_arr); cudaFree(c0); cudaFree(c1); cudaFree(multi);
+        if (e != cudaSuccess) { cudaFree(radj); return fail(MGB_ERR_CUDA, std::string("radj build: ") + cudaGetErrorString(e)); }
+        idx->bufs.push_back(radj);
+        idx->device_bytes += (n + 1) * sizeof(uint2);
+        idx->view.radj = radj;
     }
 #endif
     *out = idx.release();

@@ -36,6 +36,7 @@ struct IndexView {
     const uint32_t *valid;      // bit per edge or nullptr (mask dropped)
     const uint32_t *sfx;        // 2 words per indexed suffix: [begin, end) edge range
     const uint2 *adj;           // per edge: forward adjacency record (see adj_* below), or nullptr
+    const uint2 *radj;          // per edge: reverse adjacency record (see load_radj), or nullptr
     uint64_t n;                 // number of edges (ids 1..n)
     uint32_t nblk;
     uint32_t k;                 // DBG k; BOSS node length = k - 1
@@ -280,6 +281,19 @@ MGB_HD uint64_t adj_child(uint2 a, uint32_t c) {   // edge with label c out of t
     if (!a.x || !((all >> c) & 1u)) return 0;
     uint64_t first = (uint64_t)a.x - popc32(all) + 1;
     return first + popc32(all & ((1u << c) - 1u));
+}
+
+// Reverse adjacency record of edge e (backward extension through the RCDBG view, rc_dbg.hpp:86-97):
+//   x        bwd(e): first (un-flagged) edge entering the source node of e (boss.cpp:623-636)
+//   y[0:3)   first character of e's own k-mer = node_last_value(bwd^{k-2}(e))
+//            (NodeFirstCache::get_first_char, node_first_cache.cpp:10-24)
+//   y[3]     the source node of e has more than one incoming edge (!BOSS::is_single_incoming)
+MGB_HD uint2 load_radj(const IndexView &ix, uint64_t e) {
+#if MGB_DEVICE_CODE
+    return __ldg(ix.radj + e);
+#else
+    return ix.radj[e];
+#endif
 }
 
 // boss.cpp:623-636

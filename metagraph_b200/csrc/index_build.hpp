@@ -26,6 +26,7 @@ struct HostIndex {
         v.valid = valid.empty() ? nullptr : valid.data();
         v.sfx = sfx.empty() ? nullptr : sfx.data();
         v.adj = adj.empty() ? nullptr : adj.data();
+        v.radj = nullptr;
         v.n = n; v.nblk = nblk; v.k = k; v.sfx_len = sfx_len; v.sigma = sigma;
         for (int c = 0; c < kSigmaDNA; ++c) { v.F[c] = F[c]; v.NF[c] = NF[c]; v.total_W[c] = total_W[c]; }
         v.num_ones = num_ones;
