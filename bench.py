@@ -118,7 +118,10 @@ _ORACLE_CACHE = {}
 
 
 def cpu_reference(boss, reads_buf, offsets, cfg, target_seconds, threads, n_max):
-    """Times the CPU restatement of the reference algorithm (oracle/) on a bounded sample."""
+    """Times the CPU restatement of the reference algorithm (oracle/) on a bounded sample. The thread
+    count is probed (all hardware threads, half, a quarter): on two-socket hosts the restatement, like
+    any pointer-chasing code over one shared graph, peaks below the full thread count.
+    Returns (reads/s, sample size, seconds, threads used)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     if "g" not in _ORACLE_CACHE:
@@ -126,12 +129,21 @@ def cpu_reference(boss, reads_buf, offsets, cfg, target_seconds, threads, n_max)
     g = _ORACLE_CACHE["g"]
     def reads_of(a, b):
         return [bytes(reads_buf[int(offsets[i]):int(offsets[i + 1])]) for i in range(a, b)]
-    probe = min(n_max, max(threads * 16, 512))
-    t = time.time(); g.align_tsv(cfg, reads_of(0, probe), threads=threads); dt = time.time() - t
-    rate = probe / max(dt, 1e-6)
-    n = int(min(n_max, max(probe, rate * target_seconds)))
-    t = time.time(); g.align_tsv(cfg, reads_of(0, n), threads=threads); dt = time.time() - t
-    return n / dt, n, dt
+    if "threads" not in _ORACLE_CACHE:
+        best = (0.0, threads)
+        for th in sorted({max(1, threads // 4), max(1, threads // 2), threads}):
+            probe = min(n_max, max(th * 200, 2000))
+            rs = reads_of(0, probe)
+            t = time.time(); g.align_tsv(cfg, rs, threads=th); dt = time.time() - t
+            if probe / dt > best[0]:
+                best = (probe / dt, th)
+        _ORACLE_CACHE["threads"] = best[1]
+        _ORACLE_CACHE["rate"] = best[0]
+    th = _ORACLE_CACHE["threads"]
+    n = int(min(n_max, max(2000, _ORACLE_CACHE["rate"] * target_seconds)))
+    rs = reads_of(0, n)
+    t = time.time(); g.align_tsv(cfg, rs, threads=th); dt = time.time() - t
+    return n / dt, n, dt, th
 
 
 def main():
@@ -164,11 +176,11 @@ def main():
             return
         genome = make_genome(G)
         boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
-        buf, offsets = make_reads(genome, min(N, 200_000), 42)
+        buf, offsets = make_reads(genome, min(N, 400_000), 42)
         per_step = []
         sample_n = 0
         for s in range(args.warmup + args.steps):
-            rate, n, dt = cpu_reference(boss, buf, offsets, cfg, 8.0, host_threads, len(offsets) - 1)
+            rate, n, dt, used_threads = cpu_reference(boss, buf, offsets, cfg, 8.0, host_threads, len(offsets) - 1)
             sample_n = n
             if s >= args.warmup:
                 per_step.append((rate, dt))
@@ -177,9 +189,11 @@ def main():
                 "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean([d for _, d in per_step]) * 1e3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": value, "unit": "reads/s", "cores": host_threads, "kind": "port",
+                "cpu_baseline": {"value": value, "unit": "reads/s", "cores": used_threads, "kind": "port",
                                  "sample": "%d reads of the same workload per step (CPU restatement of the "
-                                           "reference algorithm, oracle/, %d threads)" % (sample_n, host_threads)},
+                                           "reference algorithm, oracle/, best of %d/%d/%d threads = %d)"
+                                           % (sample_n, max(1, host_threads // 4), max(1, host_threads // 2),
+                                              host_threads, used_threads)},
                 "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -319,10 +333,12 @@ def main():
         }
         if world == 1:
             # CPU baseline: oracle (port of the reference algorithm) on all host cores, bounded sample
-            rate, n, dt = cpu_reference(boss, buf_np, off_np, cfg, 10.0, host_threads, min(N, 200_000))
-            line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": host_threads, "kind": "port",
+            rate, n, dt, used_threads = cpu_reference(boss, buf_np, off_np, cfg, 10.0, host_threads, min(N, 400_000))
+            line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": used_threads, "kind": "port",
                                     "sample": "first %d reads of the same workload, %.1f s wall, CPU restatement "
-                                              "of the reference algorithm (oracle/), %d threads" % (n, dt, host_threads)}
+                                              "of the reference algorithm (oracle/), best of %d/%d/%d threads = %d"
+                                              % (n, dt, max(1, host_threads // 4), max(1, host_threads // 2),
+                                                 host_threads, used_threads)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
