@@ -1560,7 +1560,79 @@ struct ReadAligner {
             // no dependent round trip
             ColMeta gpar = par;
             if (par.parent != 0xffffffffu) gpar = m.cols[par.parent];
+            bool try_run = true;
             while (j) {
+                // Diagonal runs, one warp-wide step: lane t examines column j - t at query position
+                // pos - t, assuming that j, j-1, ... is a parent chain and that every step before it was a
+                // (mis)match (:961-970). The longest prefix of lanes for which this holds is exactly what
+                // the sequential walk would do, and is committed at once.
+                if (try_run) {
+                    const int t = wlane();
+                    bool good = false, is_m = false;
+                    ColMeta c_t;
+                    c_t.offset = 0; c_t.node = 0; c_t.c = 0; c_t.max_pos = -1;
+                    if ((uint32_t)t < j) {
+                        c_t = m.cols[j - t];
+                        const ColMeta p_t = m.cols[j - t - 1];
+                        const int pos_t = pos - t;
+                        const int ci = pos_t - c_t.trim, pi = pos_t - p_t.trim - 1;
+                        if (c_t.parent == j - t - 1 && pos_t > 0 && ci >= 0 && ci < c_t.size && pi >= 0 && pi < p_t.size) {
+                            const score_t sv = cellS(c_t, ci);
+                            const bool ins = sv == cellE(c_t, ci) && (t || cur_op == 0xffu || cur_op != OP_D);
+                            const int code = encode_char(c_t.c);
+                            good = sv != kNinf && !ins
+                                && sv == cellS(p_t, pi) + c_t.score + prof_score(s, seed_clipping + pos_t, code);
+                            is_m = prof_is_match(s, seed_clipping + pos_t, code);
+                        }
+                    }
+                    const uint32_t bad = ~wballot(good);
+                    const int n_good = bad ? ffs32(bad) - 1 : kWarp;
+                    try_run = n_good == kWarp;                // a short run ends on a step of another kind
+                    if (n_good) {
+                        const bool mine = t < n_good;
+                        const bool has_node = mine && c_t.offset >= k_minus_1;
+                        const uint32_t node_mask = wballot(has_node);
+                        const uint32_t nz_mask = wballot(has_node && c_t.node != 0);
+                        const uint32_t m_mask = wballot(mine && is_m);
+                        if (n_seq + n_good > (int)caps.aln_seq || n_path + popc32(node_mask) > (int)caps.aln_nodes) {
+                            overflow = true; return 0;
+                        }
+                        if (mine) {
+                            m.bt_seq[n_seq + t] = c_t.c;
+                            if (pos - t == c_t.max_pos) m.cols[j - t].started = 1;
+                            if (has_node) m.bt_path[n_path + popc32(node_mask & ((1u << t) - 1u))] = c_t.node;
+                        }
+                        if (node_mask) path_back_nonzero = (nz_mask >> (31 - clz32(node_mask))) & 1u;
+                        for (int b = 0; b < n_good; ) {          // Cigar::append per run of equal ops
+                            const bool mb = (m_mask >> b) & 1u;
+                            const uint32_t valid = n_good >= 32 ? 0xffffffffu : ((1u << n_good) - 1u);
+                            const uint32_t diff = (mb ? ~m_mask : m_mask) & valid & ~((1u << b) - 1u);
+                            const int end = diff ? ffs32(diff) - 1 : n_good;
+                            const uint32_t op = mb ? OP_M : OP_X;
+                            if (op == cur_op) cur_len += end - b;
+                            else {
+                                if (cur_len) {
+                                    if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return 0; }
+                                    m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+                                }
+                                cur_op = op; cur_len = end - b;
+                            }
+                            b = end;
+                        }
+                        n_trace += n_good; n_seq += n_good; n_path += popc32(node_mask);
+                        pos -= n_good;
+                        align_offset = imin(wbcast(c_t.offset, n_good - 1), k_minus_1);
+                        j -= n_good;
+                        col = m.cols[j];
+                        if (j) {
+                            par = m.cols[col.parent];
+                            gpar = par;
+                            if (par.parent != 0xffffffffu) gpar = m.cols[par.parent];
+                        }
+                        continue;
+                    }
+                }
+                try_run = true;
                 const int trim = col.trim, trim_p = par.trim;
                 align_offset = imin(col.offset, k_minus_1);
                 if (pos == col.max_pos) m.cols[j].started = 1;
