@@ -154,6 +154,12 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
 int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
                     const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out);
 
+/* A batch of >= 128k reads is split into up to 8 contiguous pieces that run on two streams, so the
+ * download and unpacking of one piece overlap the kernels of the next (reads are independent,
+ * dbg_aligner.cpp:251-355). max_pieces caps the split; 1 = one piece (device timers in mgb_stats_t
+ * then do not overlap), 0 = automatic (default). Process-wide. */
+void mgb_set_pipeline_pieces(uint32_t max_pieces);
+
 uint32_t mgb_results_num_reads(const mgb_results_t *results);
 /* alignments of read i are [first, first + count) in mgb_results_alignments() */
 void mgb_results_read_range(const mgb_results_t *results, uint32_t read, uint64_t *first,

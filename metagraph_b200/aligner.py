@@ -198,6 +198,10 @@ class B200Aligner:
     def free_raw(self, res):
         self._L.mgb_results_free(res)
 
+    def set_pipeline_pieces(self, max_pieces):
+        """mgb_set_pipeline_pieces: cap on the pieces a batch is split into (0 = automatic)."""
+        self._L.mgb_set_pipeline_pieces(int(max_pieces))
+
     def stats_of(self, res):
         st = self._L.mgb_results_stats(res).contents
         return {n: getattr(st, n) for n, _ in _lib.mgb_stats_t._fields_}

@@ -7,9 +7,13 @@
 // without a GPU. That build is test infrastructure; the product library is always the nvcc
 // build and has no CPU path.
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -322,7 +326,7 @@ struct PinnedPool {
     void release(HostBuf b) {
         if (!b.p) return;
         std::lock_guard<std::mutex> lk(mu);
-        if (free_list.size() >= 16) { cudaFreeHost(b.p); return; }
+        if (free_list.size() >= 32) { cudaFreeHost(b.p); return; }
         free_list.push_back(b);
     }
 };
@@ -331,10 +335,15 @@ inline HostBuf hostbuf_acquire(size_t bytes) { return g_pinned_pool.acquire(byte
 inline void hostbuf_release(HostBuf b) { g_pinned_pool.release(b); }
 #endif
 
+// Device working memory of one call. On the device build the buffers belong to a Workspace that the
+// index keeps between calls (slot i = the i-th request of the call): cudaMalloc of GB-sized arenas per
+// call is slow, and stream-ordered pools stall when two streams trade memory back and forth.
+#if defined(MGB_HOST_EMU)
+struct Workspace {};
 struct DevBufs {               // frees everything it owns on scope exit
     Stream &st;
     std::vector<void*> ptrs;
-    explicit DevBufs(Stream &s) : st(s) {}
+    DevBufs(Stream &s, Workspace*, size_t) : st(s) {}
     ~DevBufs() { for (void *p : ptrs) dev_free(p, st); }
     template <class T> int alloc(T **p, size_t count) {
         void *v = nullptr;
@@ -344,7 +353,60 @@ struct DevBufs {               // frees everything it owns on scope exit
         *p = (T*)v;
         return 0;
     }
+    size_t capacity_of_next() const { return 0; }
 };
+#else
+struct Workspace {
+    std::vector<void*> ptr;
+    std::vector<size_t> cap;
+    cudaStream_t stream = nullptr;       // created on first use, kept with the buffers
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    int ready() {
+        if (stream) return 0;
+        cudaError_t e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+        for (auto &x : ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
+        if (e != cudaSuccess) { g_err = std::string("stream/event creation: ") + cudaGetErrorString(e); return MGB_ERR_CUDA; }
+        return 0;
+    }
+    ~Workspace() {
+        for (void *p : ptr) if (p) cudaFree(p);
+        for (auto &x : ev) if (x) cudaEventDestroy(x);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int get(size_t slot, size_t bytes, void **out) {
+        if (slot >= ptr.size()) { ptr.resize(slot + 1, nullptr); cap.resize(slot + 1, 0); }
+        if (cap[slot] < bytes || !ptr[slot]) {
+            if (ptr[slot]) cudaFree(ptr[slot]);
+            ptr[slot] = nullptr; cap[slot] = 0;
+            size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&ptr[slot], want);
+            if (e != cudaSuccess) { cudaGetLastError(); want = bytes ? bytes : 16; e = cudaMalloc(&ptr[slot], want); }
+            if (e != cudaSuccess) {
+                ptr[slot] = nullptr;
+                g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+                return MGB_ERR_CUDA;
+            }
+            cap[slot] = want;
+        }
+        *out = ptr[slot];
+        return 0;
+    }
+};
+struct DevBufs {
+    Stream &st;
+    Workspace *ws;
+    size_t slot;
+    DevBufs(Stream &s, Workspace *w, size_t slot_base) : st(s), ws(w), slot(slot_base) {}
+    template <class T> int alloc(T **p, size_t count) {
+        void *v = nullptr;
+        int rc = ws->get(slot++, count * sizeof(T), &v);
+        if (rc) return rc;
+        *p = (T*)v;
+        return 0;
+    }
+    size_t capacity_of_next() const { return slot < ws->cap.size() ? ws->cap[slot] : 0; }
+};
+#endif
 
 } // namespace
 
@@ -357,6 +419,18 @@ struct mgb_index {
     uint64_t device_bytes = 0;
     int num_sms = 1;
     std::vector<void*> bufs;
+    // working memory recycled between calls (at most 3 sets are kept)
+    mutable std::mutex ws_mu;
+    mutable std::vector<Workspace*> ws_free;
+    Workspace* ws_acquire() const {
+        std::lock_guard<std::mutex> lk(ws_mu);
+        if (ws_free.empty()) return new Workspace();
+        Workspace *w = ws_free.back(); ws_free.pop_back(); return w;
+    }
+    void ws_release(Workspace *w) const {
+        std::lock_guard<std::mutex> lk(ws_mu);
+        if (ws_free.size() < 3) ws_free.push_back(w); else delete w;
+    }
 #if defined(MGB_HOST_EMU)
     HostIndex host;
     std::vector<uint2> radj_host;
@@ -367,9 +441,11 @@ struct mgb_results {
     uint32_t n_reads = 0;
     std::vector<uint64_t> first;
     std::vector<uint32_t> count;
-    std::vector<mgb_alignment_t> alns;
+    mgb_alignment_t *alns = nullptr;         // n_alns records in read order, inside alns_buf
+    uint64_t n_alns = 0;
+    HostBuf alns_buf;
     std::vector<HostBuf> heaps;              // host copies of the output heaps (recycled on free)
-    ~mgb_results() { for (HostBuf b : heaps) hostbuf_release(b); }
+    ~mgb_results() { for (HostBuf b : heaps) hostbuf_release(b); hostbuf_release(alns_buf); }
     mgb_stats_t stats;
 };
 
@@ -566,6 +642,7 @@ void mgb_index_destroy(mgb_index_t *index) {
     cudaSetDevice(index->device);
     for (void *p : index->bufs) cudaFree(p);
 #endif
+    for (Workspace *w : index->ws_free) delete w;
     delete index;
 }
 
@@ -689,13 +766,15 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
                      uint32_t n_seqs, uint64_t *out_nodes) {
     if (!index || !seqs || !offsets || !out_nodes) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
     Stream st;
+    int rc = 0;
+    struct WsGuard { const mgb_index_t *ix; Workspace *w; ~WsGuard() { ix->ws_release(w); } } wsg{ index, index->ws_acquire() };
 #if !defined(MGB_HOST_EMU)
     CUDA_TRY(cudaSetDevice(index->device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    if ((rc = wsg.w->ready())) return rc;
+    st.s = wsg.w->stream;
 #endif
-    int rc = 0;
     {
-        DevBufs bufs(st);
+        DevBufs bufs(st, wsg.w, 0);
         Batch b; std::vector<uint64_t> koff; mgb_stats_t stats; std::memset(&stats, 0, sizeof(stats));
         rc = upload_batch(index, seqs, offsets, n_seqs, false, st, bufs, &b, &koff, &stats);
         if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
@@ -708,32 +787,64 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
     }
 #if !defined(MGB_HOST_EMU)
     cudaStreamSynchronize(st.s);
-    cudaStreamDestroy(st.s);
 #endif
     return rc;
 }
 
-int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
-                    const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out) {
-    if (!index || !config || !offsets || !out || (!seqs && n_reads && offsets[n_reads]))
-        return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
-    DevConfig dcfg;
-    std::string err;
-    int rc = lower_config(*config, index->view.k, &dcfg, &err);
-    if (rc) return fail(rc, err);
+} // extern "C"
 
-    std::unique_ptr<mgb_results> res(new mgb_results());
+// One contiguous range of reads [lo, lo + n) of a batch, processed start to finish on its own
+// stream: upload, prepare + seed, align passes, download, materialisation. Pieces of one batch are
+// independent (IDBGAligner::align_batch treats every query separately, dbg_aligner.cpp:251-355), so
+// the download and unpacking of one piece overlap the kernels of the next.
+struct Piece {
+    uint32_t lo = 0, n_reads = 0;
+    // views into the arrays of the enclosing mgb_results: entries of reads [lo, lo + n_reads), and a
+    // region of n_reads * num_alternative_paths records that receives n_alns of them (piece-local
+    // indices in `first`)
+    uint64_t *first = nullptr;
+    uint32_t *count = nullptr;
+    mgb_alignment_t *alns = nullptr;
+    uint64_t n_alns = 0;
+    std::vector<HostBuf> heaps;
+    mgb_stats_t stats;
+    int rc = 0;
+    std::string err;
+    ~Piece() { for (HostBuf b : heaps) hostbuf_release(b); }
+};
+
+static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const char *all_seqs,
+                       const uint64_t *all_offsets, uint32_t lo, uint32_t n_reads, Piece *res) {
+    // MGB_DEBUG=1: wall-clock split of the call on stderr
+    const bool dbg_time = std::getenv("MGB_DEBUG") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+        if (!dbg_time) return;
+        auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[mgb] reads %u+%u %-28s %8.2f ms\n", lo, n_reads, what,
+                     std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    int rc = 0;
     std::memset(&res->stats, 0, sizeof(res->stats));
-    res->n_reads = n_reads;
-    res->first.assign(n_reads, 0);
-    res->count.assign(n_reads, 0);
+    res->lo = lo; res->n_reads = n_reads;
+    // offsets relative to the first character of the piece
+    std::vector<uint64_t> offs_local;
+    const uint64_t *offsets = all_offsets + lo;
+    const char *seqs = all_seqs ? all_seqs + all_offsets[lo] : nullptr;
+    if (all_offsets[lo]) {
+        offs_local.resize((size_t)n_reads + 1);
+        for (uint32_t r = 0; r <= n_reads; ++r) offs_local[r] = all_offsets[lo + r] - all_offsets[lo];
+        offsets = offs_local.data();
+    }
 
     Stream st;
+    struct WsGuard { const mgb_index_t *ix; Workspace *w; ~WsGuard() { ix->ws_release(w); } } wsg{ index, index->ws_acquire() };
 #if !defined(MGB_HOST_EMU)
     CUDA_TRY(cudaSetDevice(index->device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    cudaEvent_t ev[6];
-    for (auto &e : ev) cudaEventCreate(&e);
+    if ((rc = wsg.w->ready())) return rc;
+    st.s = wsg.w->stream;
+    cudaEvent_t *ev = wsg.w->ev;
 #endif
     HostBuf hdr_buf = hostbuf_acquire(((size_t)n_reads + 1) * sizeof(ReadHdr));
     if (!hdr_buf.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
@@ -741,14 +852,16 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     struct HdrGuard { HostBuf b; ~HdrGuard() { hostbuf_release(b); } } hdr_guard{ hdr_buf };
     std::vector<uint32_t> read_heap(n_reads, 0);   // which pass produced the read's alignments
     {
-        DevBufs bufs(st);
+        DevBufs bufs(st, wsg.w, 0);
         Batch b; std::vector<uint64_t> koff;
         const bool both = dcfg.forward_and_reverse_complement;
         const bool map_nodes = dcfg.max_seed_length >= index->view.k;
 #if !defined(MGB_HOST_EMU)
         cudaEventRecord(ev[0], st.s);
 #endif
+        tick("setup");
         rc = upload_batch(index, seqs, offsets, n_reads, both, st, bufs, &b, &koff, &res->stats);
+        tick("upload_batch (host part)");
         if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
         if (!rc && both) rc = dev_zero(b.nodes_r, (b.total_kmers + 1) * 8, st);
 #if !defined(MGB_HOST_EMU)
@@ -784,20 +897,39 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             if (const char *e = std::getenv("MGB_TEST_HCAP")) hcap = std::atoi(e);
             WarpSmem sm_probe;
             const size_t smem_per_warp = sm_probe.carve(nullptr, bmax_v, lq_v, hcap);
+            DevBufs pass_bufs(st, wsg.w, 32);          // slot 32: the arena
 #if defined(MGB_HOST_EMU)
             uint32_t n_warps = 1;
 #else
             int blocks_per_sm = 0;
             const size_t smem_block = smem_per_warp * 4;
-            CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, smem_block));
+            {
+                // driver queries serialise against running work: ask once per shared-memory size
+                static std::mutex occ_mu;
+                static std::map<std::pair<int, size_t>, int> occ_cache;
+                std::lock_guard<std::mutex> lk(occ_mu);
+                auto key = std::make_pair(index->device, smem_block);
+                auto it = occ_cache.find(key);
+                if (it == occ_cache.end()) {
+                    CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
+                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, smem_block));
+                    // the attribute is a high-water mark per device: re-assert the largest size seen
+                    size_t mx = smem_block;
+                    for (auto &kv : occ_cache) if (kv.first.first == index->device) mx = std::max(mx, kv.first.second);
+                    if (mx != smem_block)
+                        CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+                    occ_cache[key] = blocks_per_sm;
+                } else blocks_per_sm = it->second;
+            }
             if (blocks_per_sm < 1) blocks_per_sm = 1;
             uint64_t n_warps64 = (uint64_t)index->num_sms * blocks_per_sm * 4;
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            uint64_t mem_warps = (uint64_t)(free_b * 0.6) / (stride ? stride : 1);
-            if (mem_warps < 4) mem_warps = 4;
-            if (n_warps64 > mem_warps) n_warps64 = mem_warps & ~3ull;
+            if (stride * n_warps64 > pass_bufs.capacity_of_next()) {
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                uint64_t mem_warps = (uint64_t)(free_b * 0.6 + pass_bufs.capacity_of_next()) / (stride ? stride : 1);
+                if (mem_warps < 4) mem_warps = 4;
+                if (n_warps64 > mem_warps) n_warps64 = mem_warps & ~3ull;
+            }
             if (n_warps64 > ((uint64_t)list.size() + 3) / 4 * 4) n_warps64 = ((uint64_t)list.size() + 3) / 4 * 4;
             uint32_t n_warps = (uint32_t)n_warps64;
 #endif
@@ -806,12 +938,12 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             uint64_t heap_cap = (uint64_t)list.size() * per_read * dcfg.num_alternative_paths * scale + 4096;
             char *d_arena = nullptr, *d_heap = nullptr; uint32_t *d_list = nullptr;
             unsigned long long *d_used = nullptr; unsigned int *d_next = nullptr;
-            DevBufs pass_bufs(st);
             if ((rc = pass_bufs.alloc(&d_arena, stride * n_warps))) break;
             if ((rc = pass_bufs.alloc(&d_heap, heap_cap))) break;
             if ((rc = pass_bufs.alloc(&d_list, list.size()))) break;
             if ((rc = pass_bufs.alloc(&d_used, 1))) break;
             if ((rc = pass_bufs.alloc(&d_next, 1))) break;
+            tick("pass: arena/heap alloc");
             if ((rc = h2d(d_list, list.data(), list.size() * 4, st))) break;
             if ((rc = dev_zero(d_used, 8, st))) break;
             if ((rc = dev_zero(d_next, 4, st))) break;
@@ -846,6 +978,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             float ms = 0; cudaEventElapsedTime(&ms, ev[3], ev[4]); align_ms += ms;
             cudaEventRecord(ev[3], st.s);
 #endif
+            tick("pass: h2d+seed+align kernels");
             res->stats.kernel_launches += 1;
 #if defined(MGB_PHASE_TIMERS) && !defined(MGB_HOST_EMU)
             {
@@ -858,6 +991,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
 #endif
             if (used > heap_cap) used = heap_cap;
             HostBuf heap_host = hostbuf_acquire((size_t)used + 16);
+            tick("pass: host buffer");
             if (!heap_host.p) { rc = fail(MGB_ERR_CUDA, "host buffer allocation failed"); break; }
             res->heaps.push_back(heap_host);
             if (used && (rc = d2h(heap_host.p, d_heap, used, st))) break;
@@ -869,6 +1003,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             { float ms = 0; cudaEventElapsedTime(&ms, ev[3], ev[4]); d2h_ms += ms; }
 #endif
             res->stats.d2h_bytes += used + (size_t)n_reads * sizeof(ReadHdr);
+            tick("pass: d2h");
             // classify this pass; alignments are materialised in read order after the last pass
             std::vector<uint32_t> retry;
             const uint32_t heap_id = (uint32_t)res->heaps.size() - 1;
@@ -886,6 +1021,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             }
             res->stats.num_reads_retried += retry.size();
             list.swap(retry);
+            tick("pass: classify");
         }
 #if !defined(MGB_HOST_EMU)
         if (!rc) {
@@ -898,16 +1034,15 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     }
 #if !defined(MGB_HOST_EMU)
     cudaStreamSynchronize(st.s);
-    for (auto &e : ev) cudaEventDestroy(e);
-    cudaStreamDestroy(st.s);
 #endif
     if (rc) return rc;
+    tick("free device buffers");
     // materialise mgb_alignment_t records in read order
     {
-        std::vector<uint64_t> byte_off(res->first);
+        std::vector<uint64_t> byte_off(res->first, res->first + n_reads);
         uint64_t pos = 0;
         for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
-        res->alns.resize(pos);
+        res->n_alns = pos;
         #pragma omp parallel for schedule(static) if (n_reads > 20000)
         for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
             const char *p = res->heaps[read_heap[r]].p + byte_off[r];
@@ -915,7 +1050,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
                 const OutAln *o = (const OutAln*)p;
                 mgb_alignment_t al;
                 std::memset(&al, 0, sizeof(al));
-                al.read_index = (uint32_t)r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
+                al.read_index = lo + (uint32_t)r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
                 al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
                 al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
                 p += sizeof(OutAln);
@@ -926,6 +1061,105 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             }
         }
     }
+    tick("materialise");
+    return MGB_OK;
+}
+
+static std::atomic<uint32_t> g_max_pieces{0};      // 0 = automatic
+
+extern "C" {
+
+void mgb_set_pipeline_pieces(uint32_t max_pieces) { g_max_pieces.store(max_pieces); }
+
+int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
+                    const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out) {
+    if (!index || !config || !offsets || !out || (!seqs && n_reads && offsets[n_reads]))
+        return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    DevConfig dcfg;
+    std::string err;
+    int rc = lower_config(*config, index->view.k, &dcfg, &err);
+    if (rc) return fail(rc, err);
+
+    // pieces of >= 64k reads, at most 8; two host threads keep two pieces in flight
+    const uint32_t kMinPiece = 65536, kMaxPieces = 8;
+    uint32_t n_pieces = std::min<uint32_t>(kMaxPieces, n_reads / kMinPiece);
+#if defined(MGB_HOST_EMU)
+    n_pieces = 1;
+#endif
+    if (uint32_t cap = g_max_pieces.load()) n_pieces = std::min<uint32_t>(std::max<uint32_t>(n_pieces, 1), cap);
+    if (const char *e = std::getenv("MGB_TEST_PIECES")) n_pieces = (uint32_t)std::atoi(e);   // test knob
+    if (n_pieces < 1) n_pieces = 1;
+    if (n_pieces > n_reads) n_pieces = n_reads ? n_reads : 1;
+
+    const bool dbg_time = std::getenv("MGB_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+
+    // every piece writes its records straight into the result arrays: a read has at most
+    // num_alternative_paths alignments, so piece i owns the record region starting at lo_i * num_alt
+    std::unique_ptr<mgb_results> res(new mgb_results());
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    res->n_reads = n_reads;
+    res->first.assign(n_reads, 0);
+    res->count.assign(n_reads, 0);
+    const uint64_t num_alt = dcfg.num_alternative_paths;
+    res->alns_buf = hostbuf_acquire(((size_t)n_reads * num_alt + 1) * sizeof(mgb_alignment_t));
+    if (!res->alns_buf.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
+    res->alns = (mgb_alignment_t*)res->alns_buf.p;
+
+    std::vector<Piece> pieces(n_pieces);
+    auto piece_lo = [&](uint32_t i) { return (uint32_t)((uint64_t)n_reads * i / n_pieces); };
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        pieces[i].first = res->first.data() + piece_lo(i);
+        pieces[i].count = res->count.data() + piece_lo(i);
+        pieces[i].alns = res->alns + (uint64_t)piece_lo(i) * num_alt;
+    }
+    if (n_pieces == 1) {
+        rc = align_range(index, dcfg, seqs, offsets, 0, n_reads, &pieces[0]);
+        if (rc) return rc;
+    } else {
+        std::atomic<uint32_t> next{0};
+        std::atomic<bool> failed{false};
+        auto lane = [&]() {
+            for (uint32_t i; !failed.load() && (i = next.fetch_add(1)) < n_pieces; ) {
+                Piece &pc = pieces[i];
+                pc.rc = align_range(index, dcfg, seqs, offsets, piece_lo(i), piece_lo(i + 1) - piece_lo(i), &pc);
+                if (pc.rc) { pc.err = g_err; failed.store(true); }
+            }
+        };
+        std::thread other(lane);
+        lane();
+        other.join();
+        for (Piece &pc : pieces)
+            if (pc.rc) return fail(pc.rc, pc.err);
+    }
+    if (dbg_time) std::fprintf(stderr, "[mgb] %u pieces done at %.2f ms\n", n_pieces, since());
+
+    // close the gaps between the regions (none if every read produced num_alt alignments)
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        Piece &pc = pieces[i];
+        const uint64_t region = (uint64_t)pc.lo * num_alt;
+        if (total != region) {
+            std::memmove(res->alns + total, res->alns + region, pc.n_alns * sizeof(mgb_alignment_t));
+        }
+        if (total) {
+            const int64_t n = pc.n_reads;
+            #pragma omp parallel for schedule(static) if (n > 50000)
+            for (int64_t r = 0; r < n; ++r) pc.first[r] += total;
+        }
+        total += pc.n_alns;
+        for (HostBuf b : pc.heaps) res->heaps.push_back(b);
+        pc.heaps.clear();
+        mgb_stats_t &t = res->stats; const mgb_stats_t &u = pc.stats;
+        t.num_seeds += u.num_seeds; t.num_extensions += u.num_extensions;
+        t.num_explored_nodes += u.num_explored_nodes; t.dp_cells += u.dp_cells; t.dp_columns += u.dp_columns;
+        t.num_reads_retried += u.num_reads_retried; t.seed_kernel_ms += u.seed_kernel_ms;
+        t.align_kernel_ms += u.align_kernel_ms; t.h2d_ms += u.h2d_ms; t.d2h_ms += u.d2h_ms;
+        t.h2d_bytes += u.h2d_bytes; t.d2h_bytes += u.d2h_bytes; t.kernel_launches += u.kernel_launches;
+    }
+    res->n_alns = total;
+    if (dbg_time) std::fprintf(stderr, "[mgb] merged at %.2f ms\n", since());
     *out = res.release();
     return MGB_OK;
 }
@@ -934,8 +1168,8 @@ uint32_t mgb_results_num_reads(const mgb_results_t *r) { return r->n_reads; }
 void mgb_results_read_range(const mgb_results_t *r, uint32_t read, uint64_t *first, uint32_t *count) {
     *first = r->first[read]; *count = r->count[read];
 }
-uint64_t mgb_results_num_alignments(const mgb_results_t *r) { return r->alns.size(); }
-const mgb_alignment_t* mgb_results_alignments(const mgb_results_t *r) { return r->alns.data(); }
+uint64_t mgb_results_num_alignments(const mgb_results_t *r) { return r->n_alns; }
+const mgb_alignment_t* mgb_results_alignments(const mgb_results_t *r) { return r->alns; }
 const mgb_stats_t* mgb_results_stats(const mgb_results_t *r) { return &r->stats; }
 void mgb_results_free(mgb_results_t *r) { delete r; }
 

@@ -32,6 +32,17 @@ def test_random_emu(case):
     P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_random_emu_in_pieces(monkeypatch):
+    """mgb_align_batch splits big batches into pieces run by two host threads; force the split on a
+    small batch (ragged piece boundaries, results merged in read order)."""
+    monkeypatch.setenv("MGB_TEST_PIECES", "3")
+    seed, k, G, n, L, rate, cfgf, mask, nseq = P.RANDOM_CASES[1]
+    P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+    monkeypatch.setenv("MGB_TEST_PIECES", "1000000")      # more pieces than reads: one read each
+    seed, k, G, n, L, rate, cfgf, mask, nseq = P.RANDOM_CASES[2]
+    P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
 def test_unsupported_configs_fail_loudly():
     from metagraph_b200 import _lib
     from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex, B200Aligner

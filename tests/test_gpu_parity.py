@@ -25,6 +25,14 @@ def test_random_gpu(case):
     P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_random_gpu_in_pieces(monkeypatch):
+    """Batch split into pieces on two streams / host threads (forced on small batches)."""
+    monkeypatch.setenv("MGB_TEST_PIECES", "3")
+    for case in P.RANDOM_CASES[:4]:
+        seed, k, G, n, L, rate, cfgf, mask, nseq = case
+        P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
 def test_c2_scale_properties():
     """BASELINE config[1] shape at reduced genome size: every error-free read must align end to end
     ({L}= with score 2L+10), forward reads on '+', reverse-complemented reads on '-', and the path must
@@ -32,7 +40,7 @@ def test_c2_scale_properties():
     import oracle_lib as O
     from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex, format_alignment
     from metagraph_b200.config import cli_defaults
-    k, G, N = 31, 2_000_000, 20000
+    k, G, N = 31, 2_000_000, 140000      # > 128k reads: the batch runs as two pieces
     rng = np.random.default_rng(32)
     genome = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, G, dtype=np.uint8)]
     boss = BOSSTable.from_sequences(k, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
@@ -47,6 +55,7 @@ def test_c2_scale_properties():
     cfg = cli_defaults(k, min_seed_length=31, max_seed_length=31)
     al = B200Aligner(idx, cfg)
     res = al.align_batch([("", r) for r in reads])
+    assert len(res) == N
     for i, (r, ar) in enumerate(zip(reads, res)):
         assert len(ar) == 1
         a = ar[0]
