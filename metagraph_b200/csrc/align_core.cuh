@@ -698,19 +698,22 @@ struct ReadAligner {
     }
     // returns the slot index or -1; *out = slot contents. No collectives: may be called with
     // lane-divergent keys.
+    // *free_at (optional) = the free slot the probe sequence ended on when the key is absent (-1: none)
     MGB_HD int conv_find(const ConvSlot *slots, uint32_t epoch, uint64_t key, ConvSlot *out,
-                         bool use_prefetch = false) {
+                         bool use_prefetch = false, int *free_at = nullptr) {
         uint32_t h = hash_node(key);
+        if (free_at) *free_at = -1;
         for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
             uint32_t p = (h + probe) & (caps.hash_size - 1);
             ConvSlot sl = (use_prefetch && probe == 0 && key == pf_key && p == pf_slot_idx) ? pf_slot : slots[p];
-            if (sl.epoch != epoch) return -1;
+            if (sl.epoch != epoch) { if (free_at) *free_at = (int)p; return -1; }
             if (sl.key == key) { *out = sl; return (int)p; }
         }
         return -1;
     }
     // new entry covering [start, start + size), cells uninitialised
-    MGB_HD int conv_insert(int e, uint64_t key, int start, int size, ConvSlot *out) {
+    // free_at >= 0: the free slot conv_find just ended on for this key (no second probe)
+    MGB_HD int conv_insert(int e, uint64_t key, int start, int size, ConvSlot *out, int free_at = -1) {
         StrandCtx &t = cx[e];
         const uint32_t n_entries = t.conv_n, cells_used = t.conv_cells_used, epoch = t.conv_epoch;
         ConvSlot *slots = t.conv_slots;
@@ -724,6 +727,7 @@ struct ReadAligner {
         sl.seg_start = seg_start; sl.seg_cap = seg_cap; sl.seg_off = cells_used;
         t.conv_cells_used = cells_used + seg_cap;
         t.conv_n = n_entries + 1;
+        if (free_at >= 0) { slots[free_at] = sl; *out = sl; return free_at; }
         uint32_t h = hash_node(key);
         for (uint32_t probe = 0; probe < caps.hash_size; ++probe) {
             uint32_t p = (h + probe) & (caps.hash_size - 1);
@@ -773,9 +777,10 @@ struct ReadAligner {
         uint64_t key = node + (t.rc ? ix.n : 0);
         score_t *cells = t.conv_cells;
         ConvSlot en;
-        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en);
+        int free_at;
+        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, false, &free_at);
         if (slot < 0) {
-            slot = conv_insert(e, key, query_start, size, &en);
+            slot = conv_insert(e, key, query_start, size, &en, free_at);
             if (slot < 0) return kNinf;
             score_t *c = cells + en.seg_off;
             for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
@@ -826,9 +831,10 @@ struct ReadAligner {
         uint64_t key = node + (t.rc ? ix.n : 0);
         score_t *cells = t.conv_cells;
         ConvSlot en;
-        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, true);
+        int free_at;
+        int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, true, &free_at);
         if (slot < 0) {
-            slot = conv_insert(e, key, query_start, size, &en);
+            slot = conv_insert(e, key, query_start, size, &en, free_at);
             if (slot < 0) return kNinf;
             if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
             wsync();

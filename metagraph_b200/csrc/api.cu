@@ -88,11 +88,7 @@ struct AlignArgs {
     unsigned int *next;
 };
 
-MGB_HD void align_read(const AlignArgs &a, uint32_t r, char *arena, char *smem) {
-    WarpMem mem;
-    mem.carve(arena, a.caps);
-    WarpSmem sm;
-    sm.carve(smem, a.bmax, a.lq, a.hcap);
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm) {
     ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
     al.use_fast = a.use_fast != 0;
     const uint64_t b = a.offsets[r];
@@ -250,12 +246,16 @@ __global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const Align
     const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
     char *smem = smem_raw + (threadIdx.x >> 5) * smem_per_warp;
     init_arena(a, arena);
+    WarpMem mem;                 // the warp's arena and on-chip working set are laid out once
+    mem.carve(arena, a.caps);
+    WarpSmem sm;
+    sm.carve(smem, a.bmax, a.lq, a.hcap);
     while (true) {
         unsigned int t = 0;
         if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= a.n_list) break;
-        align_read(a, a.read_list[t], arena, smem);
+        align_read(a, a.read_list[t], mem, sm);
     }
 }
 
@@ -966,7 +966,9 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #if defined(MGB_HOST_EMU)
             init_arena(a, d_arena);
             std::vector<char> smem_emu(smem_per_warp + 64);
-            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], d_arena, smem_emu.data());
+            WarpMem mem_emu; mem_emu.carve(d_arena, a.caps);
+            WarpSmem sm_emu; sm_emu.carve(smem_emu.data(), a.bmax, a.lq, a.hcap);
+            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], mem_emu, sm_emu);
             used = *d_used;
 #else
             cudaEventRecord(ev[3], st.s);

@@ -405,6 +405,17 @@ MGB_HD uint64_t boss_index(const IndexView &ix, const uint8_t *codes, int len) {
     return ru;
 }
 
+// boss_index for codes known to be valid (all < sigma, none 0) with the suffix-table slot of
+// codes[0..sfx_len) already known (map_to_edges keeps it as a rolling value)
+MGB_HD uint64_t boss_index_slot(const IndexView &ix, const uint8_t *codes, int len, uint64_t slot) {
+    uint64_t rl = ldg32(ix.sfx + 2 * slot);
+    uint64_t ru = (uint64_t)ldg32(ix.sfx + 2 * slot + 1) - 1;
+    if (rl > ru) return 0;
+    for (int i = (int)ix.sfx_len; i < len; ++i)
+        if (!tighten_range(ix, &rl, &ru, codes[i])) return 0;
+    return ru;
+}
+
 // boss.hpp:720-764: longest matching prefix of codes[0..len) (len <= k - 1) and its edge
 // range; *matched = number of matched characters (0 -> (0, 0)).
 MGB_HD void boss_index_range(const IndexView &ix, const uint8_t *codes, int len,

@@ -50,22 +50,49 @@ MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint6
     if (L < K) return;
     const bool writer = glane() == 0;
     // index of the last invalid character seen in the current window, or -1
-    int last_inv = -1;
-    for (int j = 0; j < K - 1; ++j)
+    int last_inv = -1, last_zero = -1;         // (code 0, '$', never comes out of encode_dna)
+    for (int j = 0; j < K - 1; ++j) {
         if (codes[j] >= ix.sigma) last_inv = j;
+        if (codes[j] == 0) last_zero = j;
+    }
     LineCache lc;
+    // suffix-table slot of codes[w .. w + S): sum of (code - 1) * (sigma - 1)^j, kept as a rolling value
+    // so that a cold lookup (one per k-mer on a strand that does not match) costs O(1) instead of O(k)
+    const int S = (ix.sfx_len && (int)ix.sfx_len <= K - 1) ? (int)ix.sfx_len : 0;
+    const uint64_t base = ix.sigma - 1;
+    uint64_t top = 1;                                  // base^(S-1)
+    for (int j = 1; j < S; ++j) top *= base;
+    uint64_t slot = 0; int slot_at = -1 - S;           // window start the slot belongs to
     for (int i = 0; i + K <= L; ++i) {
         if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
+        if (codes[i + K - 1] == 0) last_zero = i + K - 1;
         if (last_inv >= i) {              // invalid[i + k_]
             if (writer) out[i] = 0;
             continue;
         }
-        // map_to_edge (boss.hpp:766-777)
-        uint64_t edge = boss_index(ix, codes + i, K - 1);
+        // map_to_edge (boss.hpp:766-777); all K codes are valid here
+        uint64_t edge;
+        if (S && last_zero < i) {
+            if (i - slot_at >= S || i < slot_at) {     // restart (an invalid code, once clamped, never
+                slot = 0;                              // survives S shifts, but a restart is simpler)
+                for (int j = S - 1; j >= 0; --j) slot = slot * base + (codes[i + j] - 1);
+            } else {
+                for (int w = slot_at; w < i; ++w) {
+                    const uint32_t c = codes[w + S];
+                    const uint64_t digit = (c >= ix.sigma ? ix.sigma - 1 : (c ? c : 1)) - 1;   // clamped: unused windows
+                    slot = (base == 4 ? slot >> 2 : slot / base) + digit * top;
+                }
+            }
+            slot_at = i;
+            edge = boss_index_slot(ix, codes + i, K - 1, slot);
+        } else {
+            edge = boss_index(ix, codes + i, K - 1);
+        }
         if (edge) edge = pick_edge(ix, lc, edge, codes[i + K - 1]);
         if (writer) out[i] = in_graph(ix, edge) ? edge : 0;
         while (edge && ++i + K - 1 < L) {
             if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
+            if (codes[i + K - 1] == 0) last_zero = i + K - 1;
             if (last_inv >= i) {
                 if (writer) out[i] = 0;
                 break;
