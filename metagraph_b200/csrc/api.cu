@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
 }
 
 #ifndef MGB_ALIGN_MIN_BLOCKS
-#define MGB_ALIGN_MIN_BLOCKS 3
+#define MGB_ALIGN_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
