@@ -44,11 +44,13 @@ class BOSSTable:
         return len(self.W) - 1
 
     @classmethod
-    def from_sequences(cls, k, seqs, threads=0, force_source_dummies=False, lib=None, packed=None):
+    def from_sequences(cls, k, seqs, threads=0, force_source_dummies=False, lib=None, packed=None,
+                       alphabet=0):
+        """alphabet: 0 = DNA ("$ACGT"), 1 = protein ("$ABCDEFGHIJKLMNOPQRSTUVWYZX")"""
         L = _lib.load_library(lib)
         buf, offsets = packed if packed is not None else _pack(seqs)
         b = _lib.mgb_boss_t()
-        rc = L.mgb_boss_build(buf.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k, 0,
+        rc = L.mgb_boss_build(buf.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k, int(alphabet),
                               int(force_source_dummies), threads, ctypes.byref(b))
         if rc:
             raise _lib.MgbError(rc, "mgb_boss_build failed")
@@ -56,10 +58,10 @@ class BOSSTable:
             n1 = b.n_plus_1
             W = np.ctypeslib.as_array(b.W, shape=(n1,)).copy()
             last = np.ctypeslib.as_array(b.last, shape=(n1,)).copy()
-            F = np.array([b.F[i] for i in range(5)], dtype=np.uint64)
+            F = np.array([b.F[i] for i in range(27 if alphabet == 1 else 5)], dtype=np.uint64)
         finally:
             L.mgb_boss_free(ctypes.byref(b))
-        return cls(k, W, last, F)
+        return cls(k, W, last, F, alphabet=int(alphabet))
 
     def dummy_mask(self, lib=None):
         """valid-edge bytes as DBGSuccinct::mask_dummy_kmers computes them"""
@@ -68,9 +70,10 @@ class BOSSTable:
         b.n_plus_1 = len(self.W)
         b.W = self.W.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
         b.last = self.last.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
-        for i in range(5):
+        for i in range(len(self.F)):
             b.F[i] = int(self.F[i])
         b.k = self.k
+        b.alphabet = self.alphabet
         valid = np.zeros(len(self.W), np.uint8)
         _lib.check(L, L.mgb_boss_mask_dummy(ctypes.byref(b), valid.ctypes.data))
         return valid

@@ -145,15 +145,20 @@ def struct_defaults(**kw):
     return DBGAlignerConfig(**kw)
 
 
-def cli_defaults(k, **kw):
+def cli_defaults(k, alphabet="dna", **kw):
     """`metagraph align` defaults: match 2, mismatch -3/-3, gaps -6/-2, end bonus 5, xdrop 27,
     rel_score_cutoff 0.95, min_seed 19 (capped at k), max_seed inf, 1000 seeds/locus,
-    5 nodes/char, 200 MB, min_exact_match 0.7; seed complexity filter off (no sdust)."""
+    5 nodes/char, 200 MB, min_exact_match 0.7; seed complexity filter off (no sdust).
+    alphabet="protein": BLOSUM62 (DBGAlignerConfig::set_scoring_matrix, aligner_config.cpp:164-205);
+    the reverse-complement strand does not exist there (dbg_aligner.cpp:224-229)."""
     d = dict(num_alternative_paths=1, min_seed_length=min(19, k), max_seed_length=SIZE_MAX,
              max_num_seeds_per_locus=1000, min_path_score=0, xdrop=27, min_exact_match=0.7,
              max_nodes_per_seq_char=5.0, max_ram_per_alignment=200.0, rel_score_cutoff=0.95,
              gap_opening_penalty=-6, gap_extension_penalty=-2, left_end_bonus=5, right_end_bonus=5,
              forward_and_reverse_complement=True, seed_complexity_filter=False,
              score_matrix=dna_scoring_matrix(2, -3, -3))
+    if alphabet == "protein":
+        d["score_matrix"] = blosum62_scoring_matrix()
+        d["forward_and_reverse_complement"] = False
     d.update(kw)
     return DBGAlignerConfig(**d)

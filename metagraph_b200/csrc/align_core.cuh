@@ -30,12 +30,16 @@ struct DevConfig {
     int32_t gap_open, gap_ext, left_end_bonus, right_end_bonus;
     uint8_t forward_and_reverse_complement, allow_left_trim, no_backtrack, pad0;
     int8_t diag[128];              // score_matrix[c][c]
-    int8_t prof[kSigmaDNA + 1][128];   // score_matrix[decode(i)][q], row sigma = '\0'
-    uint8_t opmatch[kSigmaDNA + 1][128]; // kCharToOp[decode(i)][q] == MATCH (aligner_cigar.cpp:11-51)
+    int8_t prof[kMaxSigma + 1][128];   // score_matrix[decode(i)][q], row sigma = '\0'
+    uint8_t opmatch[kMaxSigma + 1][128]; // kCharToOp[decode(i)][q] == MATCH (aligner_cigar.cpp:11-51)
+    uint8_t code_of[256];              // KmerExtractorBOSS::encode (kmer_extractor.cpp:30-44); invalid = sigma
+    char letters[kMaxSigma + 1];       // alphabet, "$ACGT" / "$ABCDEFGHIJKLMNOPQRSTUVWYZX"
+    uint32_t sigma;
+    uint32_t has_complement;           // DNA: reverse complement defined
 };
 
 static constexpr int kMaxAlt = 4;            // supported num_alternative_paths
-static constexpr int kMaxOut = 8;            // max outgoing edges handled per column (sigma <= 8)
+static constexpr int kMaxOut = kMaxSigma;     // max outgoing edges handled per column
 
 enum ReadStatus : uint32_t { MGB_READ_OK = 0, MGB_READ_OVERFLOW = 1 };
 
@@ -192,8 +196,8 @@ struct WarpSmem {
         slots = (AlnSlot*)take(sizeof(AlnSlot) * kNumSlots);
         heap = (HeapItem*)take(sizeof(HeapItem) * hcap);
         nn = (HeapItem*)take(sizeof(HeapItem) * hcap);
-        out_nodes = (uint64_t*)take(8 * 8); out_trails = (uint64_t*)take(8 * 8);
-        out_scores = (int32_t*)take(4 * 8); out_chars = (uint8_t*)take(16);
+        out_nodes = (uint64_t*)take(8 * kMaxOut); out_trails = (uint64_t*)take(8 * kMaxOut);
+        out_scores = (int32_t*)take(4 * kMaxOut); out_chars = (uint8_t*)take(kMaxOut);
         return o;
     }
 };
@@ -244,7 +248,7 @@ struct ReadAligner {
     MGB_HD bool prof_is_match(int s, int x, int code) const {
         return (x >= 1 && x <= L) ? cfg.opmatch[code][(uint8_t)cx[s].q[x - 1]] : false;
     }
-    MGB_HD uint32_t encode_char(uint8_t ch) const { return encode_dna(ch); }
+    MGB_HD uint32_t encode_char(uint8_t ch) const { return cfg.code_of[ch]; }
 
     MGB_HD int aln_clipping(const AlnSlot &a) const {
         return a.h->n_cigar && cig_op(a.cigar[0]) == OP_S ? (int)cig_len(a.cigar[0]) : 0;
@@ -351,14 +355,14 @@ struct ReadAligner {
     // as the extender does (extender.cpp:381-384). Returns the number of (node, char) pairs.
     MGB_HD int outgoing_fwd(uint64_t node, uint64_t *nodes, uint8_t *chars) {
         // the record of the most recently created column was requested while its DP was computed
-        const uint2 a = node == pf_node ? pf_adj : load_adj(ix, node);
-        if (!a.x) return 0;
-        const uint32_t all = a.y & 31u, ok = (a.y >> 8) & 31u;
-        const uint64_t first = (uint64_t)a.x - popc32(all) + 1;
+        const Adj a = (!ix.wide && node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, node);
+        if (!a.last) return 0;
+        const uint32_t all = a.all, ok = a.ok;
+        const uint64_t first = (uint64_t)a.last - popc32(all) + 1;
         int n = 0;
         for (uint32_t c = 1; c < ix.sigma; ++c) {
             if (!((ok >> c) & 1u)) continue;
-            if (n < kMaxOut) { nodes[n] = first + popc32(all & ((1u << c) - 1u)); chars[n] = "$ACGT"[c]; }
+            if (n < kMaxOut) { nodes[n] = first + popc32(all & ((1u << c) - 1u)); chars[n] = cfg.letters[c]; }
             ++n;
         }
         return n;
@@ -377,14 +381,14 @@ struct ReadAligner {
         LineCache lc;
         while (true) {
             if (in_graph(ix, edge)) {
-                const uint32_t c = load_radj(ix, edge).y & 7u;
-                uint8_t ch = complement_char((uint8_t)"$ACGT"[c]);
+                const uint32_t c = radj_char(ix, load_radj(ix, edge).y);
+                uint8_t ch = complement_char((uint8_t)cfg.letters[c]);
                 if (ch != '$') {
                     if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; trails[n] = 0; }
                     ++n;
                 }
             }
-            if (!((r.y >> 3) & 1u)) break;              // single incoming edge
+            if (!radj_multi(ix, r.y)) break;             // single incoming edge
             if (++edge > ix.n) break;
             uint32_t w;
             edge = succ_W2(ix, lc, edge, d, &w);
@@ -396,13 +400,13 @@ struct ReadAligner {
     // dbg_succinct.cpp:617-630
     MGB_HD bool has_multiple_outgoing(uint64_t node) {
         // !get_last(fwd(node, d) - 1): the target node has more than one edge
-        const uint2 a = load_adj(ix, node);
-        return a.x && popc32(a.y & 31u) > 1;
+        const Adj a = load_adj_any(ix, node);
+        return a.last && popc32(a.all) > 1;
     }
     // dbg_succinct.cpp:662-680
     MGB_HD bool has_single_incoming(uint64_t node) {
         if (node == 1) return false;
-        if (!ix.valid) return !((load_radj(ix, node).y >> 3) & 1u);   // mask dropped: !multi-incoming
+        if (!ix.valid) return !radj_multi(ix, load_radj(ix, node).y);   // mask dropped: !multi-incoming
         LineCache lc;
         uint64_t x = bwd(ix, lc, node);
         uint32_t w = node_last_value(ix, node);
@@ -528,7 +532,7 @@ struct ReadAligner {
                     push_seed(s, pos, matched, ix.k - matched, 1, edge);
                     if (overflow) break;
                 }
-                if (!((ra.y >> 3) & 1u)) break;
+                if (!radj_multi(ix, ra.y)) break;
                 if (++edge > ix.n) break;
                 uint32_t w;
                 edge = succ_W2(ix, l2, edge, d, &w);
@@ -1220,7 +1224,7 @@ struct ReadAligner {
                         const score_t add = sm.out_scores[t];
                         {   // requests whose latency overlaps the DP below
                             const uint64_t cnode = sm.out_nodes[t];
-                            if (!rc && cnode) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                            if (!rc && cnode && !ix.wide) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
                             pf_key = cnode + (rc ? ix.n : 0);
                             pf_slot_idx = hash_node(pf_key);
                             pf_slot = cx[e].conv_slots[pf_slot_idx];

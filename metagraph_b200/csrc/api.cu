@@ -48,6 +48,7 @@ struct ReadHdr {              // per read, written by the align kernel
 struct PrepArgs {
     const char *seqs; const uint64_t *offsets; uint32_t n_reads;
     char *qf, *qr; uint8_t *cf, *cr;
+    uint8_t code_of[256];     // KmerExtractorBOSS::encode of the index's alphabet
 };
 
 MGB_HD void prepare_read(const PrepArgs &a, uint32_t r) {
@@ -57,7 +58,7 @@ MGB_HD void prepare_read(const PrepArgs &a, uint32_t r) {
         uint8_t f = sanitize_char((uint8_t)a.seqs[b + i]);
         uint8_t rc = complement_char(sanitize_char((uint8_t)a.seqs[b + L - 1 - i]));
         a.qf[b + i] = (char)f; a.qr[b + i] = (char)rc;
-        a.cf[b + i] = encode_dna(f); a.cr[b + i] = encode_dna(rc);
+        a.cf[b + i] = a.code_of[f]; a.cr[b + i] = a.code_of[rc];
     }
 }
 
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = 1 + t; e <= a.n; e += nt)
-        a.radj[e] = make_uint2(a.bwd_arr[e], (uint32_t)a.c_cur[e] | ((uint32_t)a.multi[e] << 3));
+        a.radj[e] = make_uint2(a.bwd_arr[e], (uint32_t)a.c_cur[e] | ((uint32_t)a.multi[e] << (a.ix.wide ? 7 : 3)));
 }
 #endif
 
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a) {
 __global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
     uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    const uint64_t total = a.cur_num * (kSigmaDNA - 1);
+    const uint64_t total = a.cur_num * (a.ix.sigma - 1);
     for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
 }
 
@@ -419,6 +420,8 @@ struct mgb_index {
     uint64_t device_bytes = 0;
     int num_sms = 1;
     std::vector<void*> bufs;
+    int alphabet = MGB_ALPHABET_DNA;
+    AlphabetTables at;
     // working memory recycled between calls (at most 3 sets are kept)
     mutable std::mutex ws_mu;
     mutable std::vector<Workspace*> ws_free;
@@ -467,9 +470,11 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
                      const uint8_t *valid, uint32_t k, int alphabet, uint32_t suffix_len,
                      int device, mgb_index_t **out) {
     if (!W || !last || !F || !out) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
-    if (alphabet != MGB_ALPHABET_DNA)
-        return fail(MGB_ERR_UNSUPPORTED, "only the DNA alphabet is implemented in this build");
     std::unique_ptr<mgb_index> idx(new mgb_index());
+    if (!alphabet_tables(alphabet, &idx->at)) return fail(MGB_ERR_UNSUPPORTED, "unknown alphabet");
+    idx->alphabet = alphabet;
+    const uint32_t sigma = idx->at.sigma;
+    const bool force_wide = std::getenv("MGB_TEST_WIDE") != nullptr;   // test knob: generic layout for DNA
     HostIndex hloc;
 #if defined(MGB_HOST_EMU)
     HostIndex &h = idx->host;
@@ -481,16 +486,19 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         // well below the index size
         uint64_t n = n_plus_1 - 1;
         suffix_len = 1;
-        uint64_t entries = 4;
-        while (suffix_len < 14 && suffix_len + 1 <= k - 1 && entries * 4 <= 4 * n + 1024) {
-            entries *= 4; ++suffix_len;
+        uint64_t entries = sigma - 1;
+        while (suffix_len < 14 && suffix_len + 1 <= k - 1 && entries * (sigma - 1) <= 4 * n + 1024) {
+            entries *= sigma - 1; ++suffix_len;
         }
     }
     // levels up to 8 are refined on the host, the rest by k_sfx_extend on the device
     const uint32_t sfx_target = suffix_len > k - 1 ? k - 1 : suffix_len;
-    const uint32_t sfx_host = sfx_target < 8 ? sfx_target : 8;
+    // (host levels: at most 4^8 = 65k entries' worth)
+    uint32_t sfx_host = 0;
+    for (uint64_t e = 1; sfx_host < sfx_target && e * (sigma - 1) <= 65536; e *= sigma - 1) ++sfx_host;
+    if (sfx_host == 0 && sfx_target) sfx_host = 1;
     try {
-        build_host_index(W, last, n_plus_1, F, valid, k, sfx_host, &h);
+        build_host_index(W, last, n_plus_1, F, valid, k, sfx_host, &h, sigma, force_wide);
     } catch (const std::exception &e) {
         return fail(MGB_ERR_INVALID_ARGUMENT, e.what());
     }
@@ -499,9 +507,9 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     idx->view = h.view();
     {
         uint64_t cur_num = 1;
-        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (kSigmaDNA - 1);
+        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (sigma - 1);
         for (uint32_t len = sfx_host + 1; len <= sfx_target && sfx_host >= 1; ++len) {
-            const uint64_t nxt_num = cur_num * (kSigmaDNA - 1);
+            const uint64_t nxt_num = cur_num * (sigma - 1);
             std::vector<uint32_t> nxt(2 * nxt_num);
             SfxArgs sa { idx->view, idx->view.sfx, nxt.data(), cur_num };
             sa.ix.sfx = nullptr; sa.ix.sfx_len = 0;
@@ -523,10 +531,10 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             std::swap(ra.c_cur, ra.c_nxt);
         }
         for (uint64_t e = 1; e <= n; ++e)
-            idx->radj_host[e] = uint2{ bwd_arr[e], (uint32_t)ra.c_cur[e] | ((uint32_t)multi[e] << 3) };
+            idx->radj_host[e] = uint2{ bwd_arr[e], (uint32_t)ra.c_cur[e] | ((uint32_t)multi[e] << (idx->view.wide ? 7 : 3)) };
         idx->view.radj = idx->radj_host.data();
     }
-    idx->device_bytes = h.blocks.size() * 4;
+    idx->device_bytes = h.blocks.size() * 4 + h.wW.size();
 #else
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -565,7 +573,18 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         if ((rc = upload(h.sel_W[c], &v.sel_W[c]))) return rc;
     if ((rc = upload(h.valid, &v.valid))) return rc;
     if ((rc = upload(h.sfx, &v.sfx))) return rc;
-    {
+    if (h.wide) {
+        std::vector<uint32_t> wW32((h.wW.size() + 3) / 4);
+        std::memcpy(wW32.data(), h.wW.data(), h.wW.size());
+        const uint32_t *p32 = nullptr;
+        if ((rc = upload(wW32, &p32))) return rc;
+        v.wW = (const uint8_t*)p32;
+        if ((rc = upload(h.wl, &v.wl))) return rc;
+        if ((rc = upload(h.wrank, &v.wrank))) return rc;
+        if ((rc = upload(h.wsel, &v.wsel))) return rc;
+        if ((rc = upload(h.wadj, &v.wadj))) return rc;
+        v.adj = nullptr;
+    } else {
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, h.adj.size() * sizeof(uint2));
         if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(adj): ") + cudaGetErrorString(e));
@@ -579,11 +598,11 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     // deeper suffix-range levels on the device
     {
         uint64_t cur_num = 1;
-        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (kSigmaDNA - 1);
+        for (uint32_t i = 0; i < sfx_host; ++i) cur_num *= (sigma - 1);
         const uint32_t *cur = v.sfx;
         for (uint32_t len = sfx_host + 1; len <= sfx_target && sfx_host >= 1; ++len) {
             uint32_t *nxt = nullptr;
-            const uint64_t nxt_num = cur_num * (kSigmaDNA - 1);
+            const uint64_t nxt_num = cur_num * (sigma - 1);
             cudaError_t e = cudaMalloc((void**)&nxt, nxt_num * 8);
             if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(sfx): ") + cudaGetErrorString(e));
             SfxArgs sa { idx->view, cur, nxt, cur_num };
@@ -728,8 +747,9 @@ int upload_batch(const mgb_index_t *index, const char *seqs, const uint64_t *off
     return 0;
 }
 
-int launch_prepare(const Batch &b, Stream &st, int num_sms) {
-    PrepArgs a { b.seqs, b.offsets, b.n_reads, b.qf, b.qr, b.cf, b.cr };
+int launch_prepare(const mgb_index_t *index, const Batch &b, Stream &st, int num_sms) {
+    PrepArgs a { b.seqs, b.offsets, b.n_reads, b.qf, b.qr, b.cf, b.cr, {0} };
+    std::memcpy(a.code_of, index->at.code_of, sizeof(a.code_of));
 #if defined(MGB_HOST_EMU)
     (void)st; (void)num_sms;
     for (uint32_t r = 0; r < b.n_reads; ++r) prepare_read(a, r);
@@ -778,7 +798,7 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
         Batch b; std::vector<uint64_t> koff; mgb_stats_t stats; std::memset(&stats, 0, sizeof(stats));
         rc = upload_batch(index, seqs, offsets, n_seqs, false, st, bufs, &b, &koff, &stats);
         if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
-        if (!rc) rc = launch_prepare(b, st, index->num_sms);
+        if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
         if (!rc) rc = launch_seed(index, b, 1, st);
         if (!rc) rc = d2h(out_nodes, b.nodes_f, b.total_kmers * 8, st);
 #if !defined(MGB_HOST_EMU)
@@ -867,7 +887,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #if !defined(MGB_HOST_EMU)
         cudaEventRecord(ev[1], st.s);
 #endif
-        if (!rc) rc = launch_prepare(b, st, index->num_sms);
+        if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
         if (!rc && map_nodes) rc = launch_seed(index, b, both ? 2 : 1, st);
         res->stats.kernel_launches += 1 + (map_nodes ? 1 : 0);
 #if !defined(MGB_HOST_EMU)
@@ -1079,7 +1099,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
         return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
     DevConfig dcfg;
     std::string err;
-    int rc = lower_config(*config, index->view.k, &dcfg, &err);
+    int rc = lower_config(*config, index->view.k, index->alphabet, &dcfg, &err);
     if (rc) return fail(rc, err);
 
     // pieces of >= 64k reads, at most 8; two host threads keep two pieces in flight

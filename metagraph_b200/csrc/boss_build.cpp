@@ -32,6 +32,14 @@ Alpha make_dna() {
     return a;
 }
 
+Alpha make_protein() {       // kmer/alphabets.hpp:29-38: "$ABCDEFGHIJKLMNOPQRSTUVWYZX", unknown -> 'X'
+    Alpha a; a.sigma = 27; a.bits = 5;
+    const char *l = "$ABCDEFGHIJKLMNOPQRSTUVWYZX";
+    for (int i = 0; i < 256; ++i) a.code[i] = 26;
+    for (int i = 1; i < 26; ++i) { a.code[(int)l[i]] = i; a.code[(int)l[i] + 32] = i; }
+    return a;
+}
+
 template <class It> void psort(It b, It e, int threads) {
     if (threads > 1 && e - b > 100000) __gnu_parallel::sort(b, e);
     else std::sort(b, e);
@@ -44,9 +52,9 @@ extern "C" {
 int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t K,
                    int alphabet, int force_source_dummies, int num_threads, mgb_boss_t *out) {
     if (!offsets || !out || (n_seqs && !seqs)) return MGB_ERR_INVALID_ARGUMENT;
-    if (alphabet != MGB_ALPHABET_DNA) return MGB_ERR_UNSUPPORTED;
+    if (alphabet != MGB_ALPHABET_DNA && alphabet != MGB_ALPHABET_PROTEIN) return MGB_ERR_UNSUPPORTED;
     if (K < 2) return MGB_ERR_INVALID_ARGUMENT;
-    const Alpha al = make_dna();
+    const Alpha al = alphabet == MGB_ALPHABET_PROTEIN ? make_protein() : make_dna();
     if ((uint64_t)K * al.bits > 128) return MGB_ERR_UNSUPPORTED;
     if (num_threads < 1) num_threads = omp_get_max_threads();
     omp_set_num_threads(num_threads);
@@ -213,17 +221,17 @@ int mgb_boss_mask_dummy(const mgb_boss_t *b, uint8_t *valid) {
     // dbg_succinct.cpp:903-908). Source dummies are found by walking the sentinel tree.
     if (!b || !valid || !b->W) return MGB_ERR_INVALID_ARGUMENT;
     const uint64_t n = b->n_plus_1 - 1;
-    const int sigma = 5;
+    const int sigma = b->alphabet == MGB_ALPHABET_PROTEIN ? 27 : 5;
     const uint32_t k = b->k - 1;
     std::vector<uint64_t> rankW((n / 64 + 2) * sigma, 0), ones;
     {
-        uint64_t c2[8] = { 0 };
+        uint64_t c2[32] = { 0 };
         for (uint64_t i = 0; i <= n; ++i) {
             if (i % 64 == 0) for (int c = 0; c < sigma; ++c) rankW[(i / 64) * sigma + c] = c2[c];
             if (i >= 1) { if (b->W[i] < sigma) ++c2[b->W[i]]; if (b->last[i]) ones.push_back(i); }
         }
     }
-    uint64_t NF[8];
+    uint64_t NF[32];
     for (int c = 0; c < sigma; ++c) {
         NF[c] = std::upper_bound(ones.begin(), ones.end(), b->F[c]) - ones.begin();
     }

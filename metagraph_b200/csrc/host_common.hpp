@@ -21,8 +21,43 @@ inline bool check_config_scores(const mgb_config_t &c) {
     return (int64_t)c.min_cell_score >= (int64_t)INT32_MIN - min_penalty;
 }
 
+// Alphabets of the BOSS graph (kmer/alphabets.hpp:29-38 protein, :64-79 DNA) and
+// KmerExtractorBOSS::encode (kmer_extractor.cpp:30-44): unknown characters (and bytes >= 128) map to
+// `sigma` for DNA (invalid) and to 'X' = 26 for protein (a regular symbol).
+struct AlphabetTables {
+    uint32_t sigma;
+    bool has_complement;
+    char letters[kMaxSigma + 1];
+    uint8_t code_of[256];
+    const char *valid_upper;      // letters that score as a match with themselves (alphabets.hpp:85-161)
+};
+inline bool alphabet_tables(int alphabet, AlphabetTables *t) {
+    std::memset(t, 0, sizeof(*t));
+    if (alphabet == MGB_ALPHABET_DNA) {
+        t->sigma = 5; t->has_complement = true;
+        std::strcpy(t->letters, "$ACGT");
+        std::memset(t->code_of, 5, sizeof(t->code_of));
+        for (int i = 1; i < 5; ++i) { t->code_of[(int)t->letters[i]] = i; t->code_of[(int)t->letters[i] + 32] = i; }
+        t->code_of[(int)'U'] = t->code_of[(int)'u'] = 4;
+        t->valid_upper = "ACGT";
+        return true;
+    }
+    if (alphabet == MGB_ALPHABET_PROTEIN) {
+        t->sigma = 27; t->has_complement = false;
+        std::strcpy(t->letters, "$ABCDEFGHIJKLMNOPQRSTUVWYZX");
+        std::memset(t->code_of, 26, sizeof(t->code_of));
+        for (int i = 1; i < 26; ++i) { t->code_of[(int)t->letters[i]] = i; t->code_of[(int)t->letters[i] + 32] = i; }
+        t->valid_upper = "ABCDEFGHIJKLMNOPQRSTUVWYZ";
+        return true;
+    }
+    return false;
+}
+
 // Returns MGB_OK or an error code; fills `d`.
-inline int lower_config(const mgb_config_t &c, uint32_t k, DevConfig *d, std::string *err) {
+inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConfig *d, std::string *err) {
+    AlphabetTables at;
+    if (!alphabet_tables(alphabet, &at)) { *err = "unknown alphabet"; return MGB_ERR_UNSUPPORTED; }
+
     if (c.seed_complexity_filter) {
         *err = "seed_complexity_filter requires sdust, which the reference does not vendor; "
                "run with --align-no-seed-complexity-filter semantics (set it to 0)";
@@ -51,17 +86,21 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, DevConfig *d, std::st
     d->max_ram_per_alignment = c.max_ram_per_alignment; d->rel_score_cutoff = c.rel_score_cutoff;
     d->gap_open = c.gap_opening_penalty; d->gap_ext = c.gap_extension_penalty;
     d->left_end_bonus = c.left_end_bonus; d->right_end_bonus = c.right_end_bonus;
-    d->forward_and_reverse_complement = c.forward_and_reverse_complement;
+    // protein builds compile the reverse-complement strand out (dbg_aligner.cpp:224-229, 289-293)
+    d->forward_and_reverse_complement = c.forward_and_reverse_complement && at.has_complement;
     d->allow_left_trim = c.allow_left_trim; d->no_backtrack = c.no_backtrack;
-    const char letters[] = "$ACGT";
+    d->sigma = at.sigma; d->has_complement = at.has_complement ? 1 : 0;
+    std::memcpy(d->letters, at.letters, sizeof(d->letters));
+    std::memcpy(d->code_of, at.code_of, sizeof(d->code_of));
+    const int sigma = (int)at.sigma;
     for (int q = 0; q < 128; ++q) {
         d->diag[q] = c.score_matrix[q][q];
-        for (int i = 0; i <= kSigmaDNA; ++i) {
-            int ch = i < kSigmaDNA ? letters[i] : 0;
+        for (int i = 0; i <= sigma; ++i) {
+            int ch = i < sigma ? at.letters[i] : 0;
             d->prof[i][q] = c.score_matrix[ch][q];
             // kCharToOp (aligner_cigar.cpp:11-51): MATCH iff same valid letter, any case
             int uq = (q >= 'a' && q <= 'z') ? q - 32 : q;
-            d->opmatch[i][q] = (i >= 1 && i < kSigmaDNA && uq == ch) ? 1 : 0;
+            d->opmatch[i][q] = (i >= 1 && i < sigma && uq == ch && std::strchr(at.valid_upper, ch)) ? 1 : 0;
         }
     }
     return MGB_OK;

@@ -23,6 +23,7 @@ struct uint2 { uint32_t x, y; };
 namespace mgb {
 
 static constexpr int kSigmaDNA = 5;
+static constexpr int kMaxSigma = 32;         // alphabet-generic ("wide") layout: sigma <= 32 (protein: 27)
 static constexpr int kBlkEdges = 64;
 static constexpr int kBlkWords = 16;
 static constexpr int kSelLastRate = 64;
@@ -42,10 +43,27 @@ struct IndexView {
     uint32_t k;                 // DBG k; BOSS node length = k - 1
     uint32_t sfx_len;
     uint32_t sigma;
-    uint64_t F[kSigmaDNA];
-    uint64_t NF[kSigmaDNA];
-    uint32_t total_W[kSigmaDNA];
+    uint64_t F[kMaxSigma];
+    uint64_t NF[kMaxSigma];
+    uint32_t total_W[kMaxSigma];
     uint64_t num_ones;
+    // Alphabet-generic layout (any sigma <= 32; used for protein, kmer/alphabets.hpp:29-38). Plain arrays
+    // per 64-edge block, no lane cooperation: every lane of a group does the same scalar work.
+    //   wW     one byte per edge (0xFF = padding / position 0)
+    //   wl     4 words per block: `last` bits (2 words), set bits before the block, 0
+    //   wrank  kMaxSigma words per block: number of W == c (un-flagged) before the block
+    //   wsel   per symbol (offset wsel_off[c]): block of every 32nd occurrence, as sel_W
+    //   wadj   4 words per edge: last edge of the target node, label mask (all), label mask (valid
+    //          DBG nodes), 0 -- the adj record with sigma-bit masks
+    // radj is shared; its y word holds the first character in bits 0..6 and the multi-incoming flag in
+    // bit 7 here (bits 0..2 / bit 3 in the DNA layout).
+    uint32_t wide;
+    const uint8_t *wW;
+    const uint32_t *wl;
+    const uint32_t *wrank;
+    const uint32_t *wsel;
+    uint32_t wsel_off[kMaxSigma];
+    const uint32_t *wadj;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -142,6 +160,112 @@ MGB_HD uint32_t line_count_last(const Line &l, int off) {   // set bits at offse
     return popc32(lo) + popc32(hi & (off == 31 ? 0xffffffffu : ((2u << off) - 1u)));
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Alphabet-generic primitives (IndexView::wide): same contracts as the block versions below.
+// ---------------------------------------------------------------------------------------
+MGB_HD uint32_t wide_get_W(const IndexView &ix, uint64_t e) { return ix.wW[e]; }
+MGB_HD bool wide_get_last(const IndexView &ix, uint64_t e) {
+    return (ix.wl[(e >> 6) * 4 + ((e >> 5) & 1)] >> (e & 31)) & 1u;
+}
+MGB_HD uint32_t bytes_eq(uint32_t x, uint32_t c) {        // bit 8j set iff byte j of x == c
+    uint32_t y = x ^ (c * 0x01010101u);
+    y |= y >> 4; y |= y >> 2; y |= y >> 1;
+    return ~y & 0x01010101u;
+}
+MGB_HD uint64_t wide_rank_W(const IndexView &ix, uint64_t i, uint32_t c) {
+    if (i == 0) return 0;
+    const uint64_t b = i >> 6;
+    uint64_t r = ix.wrank[b * kMaxSigma + c];
+    const uint32_t *w = reinterpret_cast<const uint32_t*>(ix.wW + (b << 6));
+    const int off = (int)(i & 63);                         // positions [0, off] of the block
+    for (int t = 0; 4 * t <= off; ++t) {
+        uint32_t m = bytes_eq(w[t], c);
+        const int rem = off - 4 * t;                       // bytes 0..rem of this word count
+        if (rem < 3) m &= (1u << (8 * rem + 1)) - 1u;
+        r += popc32(m);
+    }
+    return r;
+}
+MGB_HD uint64_t wide_rank_last(const IndexView &ix, uint64_t i) {
+    if (i == 0) return 0;
+    const uint32_t *l = ix.wl + (i >> 6) * 4;
+    int off = (int)(i & 63);
+    uint32_t r = l[2];
+    if (off < 32) return r + popc32(l[0] & (off == 31 ? 0xffffffffu : ((2u << off) - 1u)));
+    off -= 32;
+    return r + popc32(l[0]) + popc32(l[1] & (off == 31 ? 0xffffffffu : ((2u << off) - 1u)));
+}
+MGB_HD uint64_t wide_select_last(const IndexView &ix, uint64_t r) {
+    if (r == 0) return 0;
+    uint64_t j = (r - 1) / kSelLastRate;
+    uint32_t b = ix.sel_last[j], b1 = ix.sel_last[j + 1];
+    while (b < b1 && ix.blk_rank[b + 1] < r) ++b;          // largest block with blk_rank[b] < r
+    const uint32_t *l = ix.wl + (size_t)b * 4;
+    int t = (int)(r - l[2]);
+    int plo = popc32(l[0]);
+    int pos = t <= plo ? nth_set32(l[0], t) : 32 + nth_set32(l[1], t - plo);
+    return ((uint64_t)b << 6) + pos;
+}
+MGB_HD uint64_t wide_select_W(const IndexView &ix, uint32_t c, uint64_t r) {
+    uint64_t j = (r - 1) / kSelWRate;
+    const uint32_t *sel = ix.wsel + ix.wsel_off[c];
+    uint32_t b = sel[j], b1 = sel[j + 1];
+    while (b < b1 && ix.wrank[(size_t)(b + 1) * kMaxSigma + c] < r) ++b;
+    int t = (int)(r - ix.wrank[(size_t)b * kMaxSigma + c]);
+    const uint32_t *w = reinterpret_cast<const uint32_t*>(ix.wW + ((uint64_t)b << 6));
+    for (int q = 0; q < 16; ++q) {
+        uint32_t m = bytes_eq(w[q], c);
+        int pc = popc32(m);
+        if (t <= pc) return ((uint64_t)b << 6) + 4 * q + (nth_set32(m, t) >> 3);
+        t -= pc;
+    }
+    return 0;   // unreachable for r <= total_W[c]
+}
+MGB_HD uint64_t wide_pred_last(const IndexView &ix, uint64_t i) {
+    while (i) {
+        const uint32_t *l = ix.wl + (i >> 6) * 4;
+        int off = (int)(i & 63);
+        uint64_t bits = ((uint64_t)l[1] << 32) | l[0];
+        bits &= off == 63 ? ~0ull : ((2ull << off) - 1ull);
+        if (bits) {
+            uint32_t h = (uint32_t)(bits >> 32);
+            int p = h ? 63 - clz32(h) : 31 - clz32((uint32_t)bits);
+            return (i & ~63ull) + p;
+        }
+        if ((i >> 6) == 0) return 0;
+        i = (i & ~63ull) - 1;
+    }
+    return 0;
+}
+MGB_HD uint64_t wide_succ_last(const IndexView &ix, uint64_t i) {
+    while (i <= ix.n) {
+        const uint32_t *l = ix.wl + (i >> 6) * 4;
+        int off = (int)(i & 63);
+        uint64_t bits = ((((uint64_t)l[1] << 32) | l[0]) >> off) << off;
+        if (bits) {
+            uint32_t lo = (uint32_t)bits;
+            int p = lo ? ffs32(lo) - 1 : 32 + ffs32((uint32_t)(bits >> 32)) - 1;
+            return (i & ~63ull) + p;
+        }
+        i = (i & ~63ull) + 64;
+    }
+    return ix.n + 1;
+}
+MGB_HD uint64_t wide_succ_W2(const IndexView &ix, uint64_t i, uint32_t d, uint32_t *w) {
+    for (; i <= ix.n; ++i) {
+        // whole words ahead are skipped when they hold neither symbol
+        if ((i & 3) == 0) {
+            const uint32_t x = *reinterpret_cast<const uint32_t*>(ix.wW + i);
+            if (!(bytes_eq(x, d) | bytes_eq(x, d + ix.sigma))) { i += 3; continue; }
+        }
+        const uint32_t v = ix.wW[i];
+        if (v == d || v == d + ix.sigma) { *w = v; return i; }
+    }
+    *w = 0;
+    return ix.n + 1;
+}
+
 // A cached block: re-loaded only when another block is touched.
 struct LineCache {
     Line line;
@@ -152,18 +276,26 @@ struct LineCache {
         uint32_t b = (uint32_t)(edge >> 6);
         if (!valid_ || b != blk) { line = load_line(ix, b); blk = b; valid_ = true; }
     }
-    MGB_HD uint32_t get_W(const IndexView &ix, uint64_t e) { touch(ix, e); return line_get_W(line, (int)(e & 63)); }
-    MGB_HD bool get_last(const IndexView &ix, uint64_t e) { touch(ix, e); return line_get_last(line, (int)(e & 63)); }
+    MGB_HD uint32_t get_W(const IndexView &ix, uint64_t e) {
+        if (ix.wide) return wide_get_W(ix, e);
+        touch(ix, e); return line_get_W(line, (int)(e & 63));
+    }
+    MGB_HD bool get_last(const IndexView &ix, uint64_t e) {
+        if (ix.wide) return wide_get_last(ix, e);
+        touch(ix, e); return line_get_last(line, (int)(e & 63));
+    }
 };
 
 // boss.cpp:437-441; positions [1..i], un-flagged symbol c only
 MGB_HD uint64_t rank_W(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t c) {
+    if (ix.wide) return wide_rank_W(ix, i, c);
     if (i == 0) return 0;
     lc.touch(ix, i);
     return (uint64_t)line_word(lc.line, 11 + c) + line_count_W(lc.line, (int)(i & 63), c);
 }
 // boss.cpp:577-581
 MGB_HD uint64_t rank_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    if (ix.wide) return wide_rank_last(ix, i);
     if (i == 0) return 0;
     lc.touch(ix, i);
     return (uint64_t)line_word(lc.line, 10) + line_count_last(lc.line, (int)(i & 63));
@@ -171,6 +303,7 @@ MGB_HD uint64_t rank_last(const IndexView &ix, LineCache &lc, uint64_t i) {
 
 // boss.cpp:588-592: position of the r-th set bit of `last` (r >= 1); leaves its block in lc
 MGB_HD uint64_t select_last(const IndexView &ix, LineCache &lc, uint64_t r) {
+    if (ix.wide) return wide_select_last(ix, r);
     if (r == 0) return 0;
     uint64_t j = (r - 1) / kSelLastRate;
     uint32_t b = ldg32(ix.sel_last + j), b1 = ldg32(ix.sel_last + j + 1);
@@ -192,6 +325,7 @@ MGB_HD uint64_t select_last(const IndexView &ix, LineCache &lc, uint64_t r) {
 
 // wavelet_tree::select(c, r) (wavelet_tree.cpp:352-357) for un-flagged c, r >= 1
 MGB_HD uint64_t select_W(const IndexView &ix, LineCache &lc, uint32_t c, uint64_t r) {
+    if (ix.wide) return wide_select_W(ix, c, r);
     uint64_t j = (r - 1) / kSelWRate;
     uint32_t b = ldg32(ix.sel_W[c] + j), b1 = ldg32(ix.sel_W[c] + j + 1);
     for (uint32_t base = b + 1; base <= b1; base += kGroup) {
@@ -216,6 +350,7 @@ MGB_HD uint64_t select_W(const IndexView &ix, LineCache &lc, uint32_t c, uint64_
 
 // boss.cpp:598-607: last set bit of `last` in [1..i], 0 if none
 MGB_HD uint64_t pred_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    if (ix.wide) return wide_pred_last(ix, i);
     while (i) {
         lc.touch(ix, i);
         int off = (int)(i & 63);
@@ -235,6 +370,7 @@ MGB_HD uint64_t pred_last(const IndexView &ix, LineCache &lc, uint64_t i) {
 
 // boss.cpp:613-617: first set bit of `last` at a position >= i; n + 1 if none
 MGB_HD uint64_t succ_last(const IndexView &ix, LineCache &lc, uint64_t i) {
+    if (ix.wide) return wide_succ_last(ix, i);
     while (i <= ix.n) {
         lc.touch(ix, i);
         int off = (int)(i & 63);
@@ -282,6 +418,23 @@ MGB_HD uint64_t adj_child(uint2 a, uint32_t c) {   // edge with label c out of t
     uint64_t first = (uint64_t)a.x - popc32(all) + 1;
     return first + popc32(all & ((1u << c) - 1u));
 }
+// The record in decoded form, from either layout: `last` = last edge of the target node (0: none),
+// `all` / `ok` = label masks (bit c), as described above.
+struct Adj { uint32_t last, all, ok; };
+MGB_HD Adj adj_decode(uint2 a) { Adj r; r.last = a.x; r.all = a.y & 31u; r.ok = (a.y >> 8) & 31u; return r; }
+MGB_HD Adj load_adj_any(const IndexView &ix, uint64_t e) {
+    if (!ix.wide) return adj_decode(load_adj(ix, e));
+    const uint32_t *p = ix.wadj + e * 4;
+    Adj r; r.last = p[0]; r.all = p[1]; r.ok = p[2];
+    return r;
+}
+MGB_HD uint64_t adj_child(const Adj &a, uint32_t c) {
+    if (!a.last || !((a.all >> c) & 1u)) return 0;
+    return (uint64_t)a.last - popc32(a.all) + 1 + popc32(a.all & ((1u << c) - 1u));
+}
+// fields of the y word of a reverse adjacency record
+MGB_HD uint32_t radj_char(const IndexView &ix, uint32_t y) { return ix.wide ? (y & 127u) : (y & 7u); }
+MGB_HD bool radj_multi(const IndexView &ix, uint32_t y) { return ix.wide ? ((y >> 7) & 1u) : ((y >> 3) & 1u); }
 
 // Reverse adjacency record of edge e (backward extension through the RCDBG view, rc_dbg.hpp:86-97):
 //   x        bwd(e): first (un-flagged) edge entering the source node of e (boss.cpp:623-636)
@@ -316,6 +469,7 @@ MGB_HD uint64_t pick_edge(const IndexView &ix, LineCache &lc, uint64_t edge, uin
 // First position p >= i with W[p] in { d, d + sigma } (boss.cpp:515-570 succ_W with two
 // symbols); returns n + 1 and *w = 0 if none.
 MGB_HD uint64_t succ_W2(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t d, uint32_t *w) {
+    if (ix.wide) return wide_succ_W2(ix, i, d, w);
     while (i <= ix.n) {
         lc.touch(ix, i);
         int off = (int)(i & 63);

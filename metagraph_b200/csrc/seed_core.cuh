@@ -98,10 +98,16 @@ MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint6
                 break;
             }
             // fwd(edge, codes[i+K-2]) + pick_edge(.., codes[i+K-1]) through the adjacency record
-            const uint2 a = load_adj(ix, edge);
             const uint32_t c = codes[i + K - 1];
-            edge = adj_child(a, c);
-            if (writer) out[i] = (edge && ((a.y >> (8 + c)) & 1u)) ? edge : 0;
+            if (!ix.wide) {
+                const uint2 a = load_adj(ix, edge);
+                edge = adj_child(a, c);
+                if (writer) out[i] = (edge && ((a.y >> (8 + c)) & 1u)) ? edge : 0;
+            } else {
+                const Adj a = load_adj_any(ix, edge);
+                edge = adj_child(a, c);
+                if (writer) out[i] = (edge && ((a.ok >> c) & 1u)) ? edge : 0;
+            }
         }
     }
 }

@@ -101,6 +101,102 @@ def random_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=1):
     return stats
 
 
+def c1_case(lib, n_transcripts, max_len, seed=7, k=12):
+    """BASELINE configs[0] shape (k=12 graph of transcripts, the transcripts themselves as reads, CLI
+    defaults, ragged lengths from 59 bp up to max_len) on synthetic transcripts: related sequences
+    (shared segments) so the graph branches. Returns (#reads, #reads aligned end to end)."""
+    rng = np.random.default_rng(seed)
+    base = "".join(np.array(list("ACGT"))[rng.integers(0, 4, max_len)])
+    seqs = []
+    for i in range(n_transcripts):
+        L = 59 if i == 0 else (max_len if i == 1 else int(np.exp(rng.uniform(np.log(59), np.log(max_len)))))
+        p = int(rng.integers(0, max_len - L + 1))
+        t = base[p:p + L] if i % 3 else "".join(np.array(list("ACGT"))[rng.integers(0, 4, L)])
+        seqs.append(mutate(rng, t, 0.01) if i % 3 == 1 else t)
+    g = O.OracleGraph(k, seqs)
+    boss = BOSSTable.from_sequences(k, seqs, lib=lib)
+    W, last, F, _ = g.arrays()
+    assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
+    idx = DBGSuccinctIndex(boss, lib=lib)
+    cfg = cli_defaults(k)
+    exp = g.align_tsv(cfg, seqs, with_nodes=True, threads=8)
+    got, _ = run_lines(idx, cfg, seqs)
+    bad = [i for i in range(len(seqs)) if exp[i] != got[i]]
+    assert not bad, (bad[:3], len(seqs[bad[0]]), exp[bad[0]][:300], got[bad[0]][:300])
+    full = sum(1 for s_, l in zip(seqs, got) if l.split("\t")[6] == "%d=" % len(s_))
+    idx.close()
+    return len(seqs), full
+
+
+AA = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def mutate_aa(rng, r, rate, indel=0.0):
+    out = []
+    for c in r:
+        y = rng.random()
+        if y < rate:
+            out.append(AA[int(rng.integers(0, 20))])
+        elif y < rate + indel / 2:
+            out.append(c); out.append(AA[int(rng.integers(0, 20))])
+        elif y < rate + indel:
+            pass
+        else:
+            out.append(c)
+    return "".join(out)
+
+
+def protein_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=2, indel=0.0):
+    """BASELINE configs[3] shape: protein alphabet (sigma = 27, BLOSUM62, forward strand only) through the
+    alphabet-generic index layout; reads carry substitutions / indels, the odd 'X', 'B', 'Z', lower case
+    and characters outside the alphabet (encoded as 'X', kmer/alphabets.hpp:29-38)."""
+    rng = np.random.default_rng(seed)
+    seqs = ["".join(np.array(list(AA))[rng.integers(0, 20, G)])]
+    seqs += [mutate_aa(rng, seqs[0], 0.03) for _ in range(nseq - 1)]
+    seqs[-1] = seqs[-1][:G // 2] + "XBZ" + seqs[-1][G // 2:]
+    g = O.OracleGraph(k, seqs, alphabet="protein", mask=mask)
+    W, last, F, valid = g.arrays()
+    boss = BOSSTable.from_sequences(k, seqs, lib=lib, alphabet=1)
+    assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
+    if mask:
+        assert (boss.dummy_mask(lib=lib) == valid).all()
+    idx = DBGSuccinctIndex(boss, valid=valid if mask else None, lib=lib)
+    reads = []
+    for i in range(nreads):
+        s_ = seqs[int(rng.integers(0, len(seqs)))]
+        p = int(rng.integers(0, max(1, len(s_) - L)))
+        r = mutate_aa(rng, s_[p:p + L], rate, indel)
+        if i % 7 == 3 and len(r) > 4:
+            r = r[:len(r) // 2] + "X*" + r[len(r) // 2 + 2:]
+        if i % 5 == 1:
+            r = r.lower()
+        reads.append(r)
+    reads += ["", "A", "ACDE", "X" * 30, "**********"]
+    exp = g.align_tsv(cfg, reads, with_nodes=True)
+    got, stats = run_lines(idx, cfg, reads)
+    bad = [i for i in range(len(reads)) if exp[i] != got[i]]
+    assert not bad, (seed, bad[:3], exp[bad[0]], got[bad[0]])
+    nodes = idx.map_to_nodes_sequentially(reads)
+    for r, n in zip(reads, nodes):
+        assert list(n) == list(g.map_to_nodes(r)), r
+    idx.close()
+    n_aligned = sum(1 for l in got if l.split("\t")[3] != "*")
+    return n_aligned, len(reads)
+
+
+PROTEIN_CASES = [
+    # seed, k, G, nreads, L, subst rate, cfg, mask, nseq, indel rate
+    (21, 10, 3000, 40, 100, 0.05, lambda k: cli_defaults(k, alphabet="protein", min_exact_match=0.0), False, 2, 0.0),
+    (22, 10, 3000, 40, 100, 0.03, lambda k: cli_defaults(k, alphabet="protein"), False, 3, 0.02),
+    (23, 6, 1500, 30, 60, 0.08, lambda k: cli_defaults(k, alphabet="protein", min_exact_match=0.0,
+                                                         num_alternative_paths=2), True, 2, 0.02),
+    (24, 10, 4000, 30, 100, 0.0, lambda k: cli_defaults(k, alphabet="protein", min_seed_length=10,
+                                                         max_seed_length=10), False, 1, 0.0),
+    (25, 12, 3000, 30, 80, 0.05, lambda k: cli_defaults(k, alphabet="protein", min_exact_match=0.0,
+                                                         min_seed_length=5), False, 2, 0.01),
+]
+
+
 def sd(**kw):
     return struct_defaults(**kw)
 

@@ -32,6 +32,30 @@ def test_random_emu(case):
     P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+@pytest.mark.parametrize("case", P.PROTEIN_CASES, ids=[str(c[0]) for c in P.PROTEIN_CASES])
+def test_protein_emu(case):
+    seed, k, G, n, L, rate, cfgf, mask, nseq, indel = case
+    aligned, total = P.protein_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq, indel)
+    assert aligned >= total // 2
+
+
+def test_generic_layout_on_dna_emu(monkeypatch):
+    """The alphabet-generic index layout (used for protein) must reproduce every DNA golden too."""
+    monkeypatch.setenv("MGB_TEST_WIDE", "1")
+    P.check_goldens(EMU)
+    P.check_mt(EMU, True)
+    for case in P.RANDOM_CASES[:4] + P.RANDOM_CASES[6:8]:
+        seed, k, G, n, L, rate, cfgf, mask, nseq = case
+        P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
+def test_c1_shape_emu():
+    """configs[0] shape: transcripts aligned to their own k=12 graph, ragged lengths up to 2.5 kbp
+    (longer than the on-chip column buffers: the arena scratch and unstaged-query paths run)."""
+    n, full = P.c1_case(EMU, 10, 2500)
+    assert full >= n - 2
+
+
 def test_random_emu_in_pieces(monkeypatch):
     """mgb_align_batch splits big batches into pieces run by two host threads; force the split on a
     small batch (ragged piece boundaries, results merged in read order)."""

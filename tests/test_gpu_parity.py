@@ -25,6 +25,31 @@ def test_random_gpu(case):
     P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+@pytest.mark.parametrize("case", P.PROTEIN_CASES, ids=[str(c[0]) for c in P.PROTEIN_CASES])
+def test_protein_gpu(case):
+    """configs[3] shape: protein alphabet through the alphabet-generic kernel path."""
+    seed, k, G, n, L, rate, cfgf, mask, nseq, indel = case
+    aligned, total = P.protein_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq, indel)
+    assert aligned >= total // 2
+
+
+def test_generic_layout_on_dna_gpu(monkeypatch):
+    """The alphabet-generic index layout must reproduce the DNA goldens as well."""
+    monkeypatch.setenv("MGB_TEST_WIDE", "1")
+    P.check_goldens(LIB)
+    P.check_mt(LIB, True)
+    for case in P.RANDOM_CASES[:4] + P.RANDOM_CASES[6:8]:
+        seed, k, G, n, L, rate, cfgf, mask, nseq = case
+        P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
+def test_c1_shape_gpu():
+    """configs[0] shape: transcripts (59 bp .. 11 666 bp, the range of transcripts_1000.fa) aligned to
+    their own k=12 graph at CLI defaults."""
+    n, full = P.c1_case(LIB, 40, 11666)
+    assert full >= n - 4
+
+
 def test_random_gpu_in_pieces(monkeypatch):
     """Batch split into pieces on two streams / host threads (forced on small batches)."""
     monkeypatch.setenv("MGB_TEST_PIECES", "3")
