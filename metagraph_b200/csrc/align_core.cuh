@@ -355,7 +355,7 @@ struct ReadAligner {
     // as the extender does (extender.cpp:381-384). Returns the number of (node, char) pairs.
     MGB_HD int outgoing_fwd(uint64_t node, uint64_t *nodes, uint8_t *chars) {
         // the record of the most recently created column was requested while its DP was computed
-        const Adj a = (!ix.wide && node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, node);
+        const Adj a = (!MGB_WIDE(ix) && node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, node);
         if (!a.last) return 0;
         const uint32_t all = a.all, ok = a.ok;
         const uint64_t first = (uint64_t)a.last - popc32(all) + 1;
@@ -1224,7 +1224,7 @@ struct ReadAligner {
                         const score_t add = sm.out_scores[t];
                         {   // requests whose latency overlaps the DP below
                             const uint64_t cnode = sm.out_nodes[t];
-                            if (!rc && cnode && !ix.wide) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                            if (!rc && cnode && !MGB_WIDE(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
                             pf_key = cnode + (rc ? ix.n : 0);
                             pf_slot_idx = hash_node(pf_key);
                             pf_slot = cx[e].conv_slots[pf_slot_idx];

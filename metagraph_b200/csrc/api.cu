@@ -20,7 +20,11 @@
 #include <vector>
 
 #include "../../include/mgb.h"
-#include "align_core.cuh"
+#if !defined(MGB_HOST_EMU)
+#define MGB_NARROW_ONLY 1        // this translation unit's kernels: DNA block layout only (see kernels.cuh)
+#endif
+#define MGB_KERNEL_NS kern_dna
+#include "kernels.cuh"
 #include "host_common.hpp"
 #include "index_build.hpp"
 
@@ -36,230 +40,21 @@ thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
-struct ReadHdr {              // per read, written by the align kernel
-    uint32_t status, n_aln;
-    uint64_t heap_off;
-    ReadStats stats;
-};
-
-// ---------------------------------------------------------------------------------------
-// kernels (device) / loops (host emulation)
-// ---------------------------------------------------------------------------------------
-struct PrepArgs {
-    const char *seqs; const uint64_t *offsets; uint32_t n_reads;
-    char *qf, *qr; uint8_t *cf, *cr;
-    uint8_t code_of[256];     // KmerExtractorBOSS::encode of the index's alphabet
-};
-
-MGB_HD void prepare_read(const PrepArgs &a, uint32_t r) {
-    const uint64_t b = a.offsets[r];
-    const int L = (int)(a.offsets[r + 1] - b);
-    for (int i = wlane(); i < L; i += kWarp) {
-        uint8_t f = sanitize_char((uint8_t)a.seqs[b + i]);
-        uint8_t rc = complement_char(sanitize_char((uint8_t)a.seqs[b + L - 1 - i]));
-        a.qf[b + i] = (char)f; a.qr[b + i] = (char)rc;
-        a.cf[b + i] = a.code_of[f]; a.cr[b + i] = a.code_of[rc];
-    }
-}
-
-struct SeedArgs {
-    IndexView ix;
-    const uint8_t *cf, *cr; const uint64_t *offsets; const uint64_t *koff;
-    uint64_t *nodes_f, *nodes_r; uint32_t n_reads; uint32_t n_strands;
-};
-
-MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
-    uint32_t r = (uint32_t)(item / a.n_strands);
-    uint32_t s = (uint32_t)(item % a.n_strands);
-    const uint64_t b = a.offsets[r];
-    const int L = (int)(a.offsets[r + 1] - b);
-    map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r]);
-}
-
-struct AlignArgs {
-    IndexView ix; DevConfig cfg; Caps caps;
-    int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
-    int use_fast;               // 0 disables the register fast path (test knob)
-    unsigned long long *phase_out;   // MGB_PHASE_TIMERS builds: cycles per phase (setup, seeds, fwd, backtrack, align total)
-    const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
-    const uint64_t *nodes_f, *nodes_r;
-    const uint32_t *read_list; uint32_t n_list;
-    char *arena; size_t arena_stride;
-    ReadHdr *hdr; char *heap; uint64_t heap_cap; unsigned long long *heap_used;
-    unsigned int *next;
-};
-
-MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm) {
-    ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
-    al.use_fast = a.use_fast != 0;
-    const uint64_t b = a.offsets[r];
-    const int L = (int)(a.offsets[r + 1] - b);
-    int order[kMaxAlt];
-    const bool has_k = L >= (int)a.ix.k;
-    int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
-                   has_k ? a.nodes_f + a.koff[r] : nullptr,
-                   has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
-#if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
-    if (wlane() == 0 && a.phase_out) {
-        for (int p = 0; p < 5; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
-    }
-#endif
-    ReadHdr h;
-    h.status = al.overflow ? MGB_READ_OVERFLOW : MGB_READ_OK;
-    h.n_aln = 0; h.heap_off = 0; h.stats = al.stats;
-    if (!al.overflow && n) {
-        // bytes: per alignment OutAln + nodes*8 + cigar*4 + seq (padded to 8)
-        uint64_t bytes = 0;
-        for (int i = 0; i < n; ++i) {
-            const AlnHdr ah = *mem.slots[SLOT_AGG + order[i]].h;
-            bytes += sizeof(OutAln) + 8ull * ah.n_nodes + ((4ull * ah.n_cigar + 7) & ~7ull)
-                   + (((uint64_t)ah.seq_len + 7) & ~7ull);
-        }
-        unsigned long long off = 0;
-#if MGB_DEVICE_CODE
-        if (wlane() == 0) off = atomicAdd(a.heap_used, (unsigned long long)bytes);
-        off = wbcast64(off, 0);
-#else
-        off = *a.heap_used; *a.heap_used += bytes;
-#endif
-        if (off + bytes > a.heap_cap) {
-            h.status = MGB_READ_OVERFLOW;
-        } else {
-            h.n_aln = n; h.heap_off = off;
-            char *p = a.heap + off;
-            for (int i = 0; i < n; ++i) {
-                const AlnSlot &sl = mem.slots[SLOT_AGG + order[i]];
-                const AlnHdr ah = *sl.h;
-                OutAln o;
-                o.orientation = ah.orientation; o.score = ah.score; o.offset = ah.offset;
-                o.query_begin = al.aln_clipping(sl); o.query_len = ah.q_len;
-                o.n_nodes = ah.n_nodes; o.seq_len = ah.seq_len; o.n_cigar = ah.n_cigar;
-                if (wlane() == 0) *(OutAln*)p = o;
-                p += sizeof(OutAln);
-                uint64_t *pn = (uint64_t*)p;
-                for (int t = wlane(); t < ah.n_nodes; t += kWarp) pn[t] = sl.nodes[t];
-                p += 8ull * ah.n_nodes;
-                uint32_t *pc = (uint32_t*)p;
-                for (int t = wlane(); t < ah.n_cigar; t += kWarp) pc[t] = sl.cigar[t];
-                p += (4ull * ah.n_cigar + 7) & ~7ull;
-                for (int t = wlane(); t < ah.seq_len; t += kWarp) p[t] = sl.seq[t];
-                p += ((uint64_t)ah.seq_len + 7) & ~7ull;
-            }
-        }
-    }
-    if (wlane() == 0) {
-        a.hdr[r] = h;
-        mem.epoch_store[0] = sm.ctx[0].conv_epoch; mem.epoch_store[1] = sm.ctx[1].conv_epoch;
-    }
-    wsync();
-}
-
-// once per arena: convergence-table slots start with epoch 0 (never equal to a live epoch)
-MGB_HD void init_arena(const AlignArgs &a, char *arena) {
-    WarpMem mem;
-    mem.carve(arena, a.caps);
-    for (int e = 0; e < 2; ++e)
-        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv_slots[e][i].epoch = 0;
-    if (wlane() == 0) { mem.epoch_store[0] = 0; mem.epoch_store[1] = 0; }
-    wsync();
-}
-
-// One refinement level of the suffix-range table (boss.hpp:651-655 index order: the appended
-// character is the most significant digit): entry o = idx + (c-1)*cur_num of the new table is
-// tighten_range(cur[idx], c).
-struct SfxArgs { IndexView ix; const uint32_t *cur; uint32_t *nxt; uint64_t cur_num; };
-
-MGB_HD void sfx_extend_item(const SfxArgs &a, uint64_t o) {
-    const uint64_t idx = o % a.cur_num;
-    const uint32_t c = (uint32_t)(o / a.cur_num) + 1;
-    uint64_t rl = a.cur[2 * idx], ru = (uint64_t)a.cur[2 * idx + 1] - 1;
-    uint32_t b = 1, e = 1;
-    if (rl <= ru && tighten_range(a.ix, &rl, &ru, c)) { b = (uint32_t)rl; e = (uint32_t)(ru + 1); }
-    if (glane() == 0) { a.nxt[2 * o] = b; a.nxt[2 * o + 1] = e; }
-}
-
-// Reverse adjacency construction (index.cuh load_radj): per edge bwd(e) + "source node has several
-// incoming edges", then k-2 gather rounds c_{j+1}[e] = c_j[bwd(e)] that move the last node character
-// (boss.cpp:679-690) to the first position of the k-mer.
-struct RadjArgs { IndexView ix; uint32_t *bwd_arr; uint8_t *c_cur; uint8_t *c_nxt; uint8_t *multi; uint2 *radj; uint64_t n; };
-
-MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
-    LineCache lc;
-    uint64_t x = bwd(a.ix, lc, e);
-    uint32_t d = node_last_value(a.ix, e);
-    uint32_t multi = 0;
-    if (x + 1 <= a.ix.n) {
-        uint32_t w;
-        succ_W2(a.ix, lc, x + 1, d, &w);
-        multi = w == d + a.ix.sigma;
-    }
-    if (glane() == 0) { a.bwd_arr[e] = (uint32_t)x; a.c_cur[e] = (uint8_t)d; a.multi[e] = (uint8_t)multi; }
-}
 
 #if !defined(MGB_HOST_EMU)
-__global__ void __launch_bounds__(128) k_radj_bwd(RadjArgs a) {
-    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    for (uint64_t e = 1 + quad; e <= a.n; e += nquads) radj_bwd_item(a, e);
+} // namespace
+// the same kernels compiled for the alphabet-generic layout (api_generic.cu)
+namespace kern_any {
+cudaError_t launch_radj_bwd(unsigned grid, const mgb::RadjArgs &a);
+cudaError_t launch_sfx_extend(unsigned grid, const mgb::SfxArgs &a);
+cudaError_t launch_seed(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
+cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const mgb::AlignArgs &a);
+cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm);
 }
-__global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = 1 + t; e <= a.n; e += nt) a.c_nxt[e] = a.c_cur[a.bwd_arr[e]];
-}
-__global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = 1 + t; e <= a.n; e += nt)
-        a.radj[e] = make_uint2(a.bwd_arr[e], (uint32_t)a.c_cur[e] | ((uint32_t)a.multi[e] << (a.ix.wide ? 7 : 3)));
-}
+namespace {
 #endif
 
 #if !defined(MGB_HOST_EMU)
-__global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
-    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    const uint64_t total = a.cur_num * (a.ix.sigma - 1);
-    for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
-}
-
-__global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = warp; r < a.n_reads; r += nwarps) prepare_read(a, r);
-}
-
-__global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
-    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    uint64_t items = (uint64_t)a.n_reads * a.n_strands;
-    for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
-}
-
-#ifndef MGB_ALIGN_MIN_BLOCKS
-#define MGB_ALIGN_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    char *arena = a.arena + (size_t)warp * a.arena_stride;
-    extern __shared__ __align__(16) char smem_raw[];
-    WarpSmem probe;
-    const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
-    char *smem = smem_raw + (threadIdx.x >> 5) * smem_per_warp;
-    init_arena(a, arena);
-    WarpMem mem;                 // the warp's arena and on-chip working set are laid out once
-    mem.carve(arena, a.caps);
-    WarpSmem sm;
-    sm.carve(smem, a.bmax, a.lq, a.hcap);
-    while (true) {
-        unsigned int t = 0;
-        if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= a.n_list) break;
-        align_read(a, a.read_list[t], mem, sm);
-    }
-}
-
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
     return fail(MGB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 #endif
@@ -531,7 +326,7 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             std::swap(ra.c_cur, ra.c_nxt);
         }
         for (uint64_t e = 1; e <= n; ++e)
-            idx->radj_host[e] = uint2{ bwd_arr[e], (uint32_t)ra.c_cur[e] | ((uint32_t)multi[e] << (idx->view.wide ? 7 : 3)) };
+            idx->radj_host[e] = uint2{ bwd_arr[e], (uint32_t)ra.c_cur[e] | ((uint32_t)multi[e] << radj_multi_shift(idx->view)) };
         idx->view.radj = idx->radj_host.data();
     }
     idx->device_bytes = h.blocks.size() * 4 + h.wW.size();
@@ -608,8 +403,8 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             SfxArgs sa { idx->view, cur, nxt, cur_num };
             sa.ix.sfx = nullptr; sa.ix.sfx_len = 0;
             uint64_t blocks = std::min<uint64_t>((nxt_num + 31) / 32, (uint64_t)idx->num_sms * 32);
-            k_sfx_extend<<<(unsigned)blocks, 128>>>(sa);
-            e = cudaDeviceSynchronize();
+            e = idx->view.wide ? kern_any::launch_sfx_extend((unsigned)blocks, sa) : kern_dna::launch_sfx_extend((unsigned)blocks, sa);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { cudaFree(nxt); return fail(MGB_ERR_CUDA, std::string("k_sfx_extend: ") + cudaGetErrorString(e)); }
             // the previous level is no longer needed (the host-built one is freed with the index)
             if (len > sfx_host + 1) {
@@ -637,13 +432,13 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         cudaMemset(radj, 0, sizeof(uint2));
         RadjArgs ra { idx->view, bwd_arr, c0, c1, multi, radj, n };
         const unsigned grid = (unsigned)idx->num_sms * 16;
-        k_radj_bwd<<<grid, 128>>>(ra);
+        e = idx->view.wide ? kern_any::launch_radj_bwd(grid, ra) : kern_dna::launch_radj_bwd(grid, ra);
         for (uint32_t r = 0; r + 2 < k; ++r) {          // k - 2 bwd steps
-            k_radj_gather<<<grid, 256>>>(ra);
+            kern_dna::k_radj_gather<<<grid, 256>>>(ra);
             std::swap(ra.c_cur, ra.c_nxt);
         }
-        k_radj_pack<<<grid, 256>>>(ra);
-        e = cudaDeviceSynchronize();
+        kern_dna::k_radj_pack<<<grid, 256>>>(ra, radj_multi_shift(idx->view));
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         cudaFree(bwd_arr); cudaFree(c0); cudaFree(c1); cudaFree(multi);
         if (e != cudaSuccess) { cudaFree(radj); return fail(MGB_ERR_CUDA, std::string("radj build: ") + cudaGetErrorString(e)); }
         idx->bufs.push_back(radj);
@@ -756,7 +551,7 @@ int launch_prepare(const mgb_index_t *index, const Batch &b, Stream &st, int num
 #else
     if (!b.n_reads) return 0;
     int blocks = std::min<uint64_t>((b.n_reads + 7) / 8, (uint64_t)num_sms * 8);
-    k_prepare<<<blocks, 256, 0, st.s>>>(a);
+    kern_dna::k_prepare<<<blocks, 256, 0, st.s>>>(a);
     CUDA_TRY(cudaGetLastError());
 #endif
     return 0;
@@ -772,8 +567,7 @@ int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, St
     if (!items) return 0;
     // 32 quads per block; enough blocks to fill the machine, grid-stride beyond that
     uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
-    k_seed<<<(unsigned)blocks, 128, 0, st.s>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(index->view.wide ? kern_any::launch_seed((unsigned)blocks, st.s, a) : kern_dna::launch_seed((unsigned)blocks, st.s, a));
 #endif
     return 0;
 }
@@ -928,16 +722,15 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                 static std::mutex occ_mu;
                 static std::map<std::pair<int, size_t>, int> occ_cache;
                 std::lock_guard<std::mutex> lk(occ_mu);
-                auto key = std::make_pair(index->device, smem_block);
+                const bool wide = index->view.wide != 0;
+                auto key = std::make_pair(index->device * 2 + (wide ? 1 : 0), smem_block);
                 auto it = occ_cache.find(key);
                 if (it == occ_cache.end()) {
-                    CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_block));
-                    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_align, 128, smem_block));
-                    // the attribute is a high-water mark per device: re-assert the largest size seen
+                    // the shared memory limit is a high-water mark per device and kernel: keep the largest
                     size_t mx = smem_block;
-                    for (auto &kv : occ_cache) if (kv.first.first == index->device) mx = std::max(mx, kv.first.second);
-                    if (mx != smem_block)
-                        CUDA_TRY(cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+                    for (auto &kv : occ_cache) if (kv.first.first == key.first) mx = std::max(mx, kv.first.second);
+                    CUDA_TRY(wide ? kern_any::align_occupancy(mx, smem_block, &blocks_per_sm)
+                                  : kern_dna::align_occupancy(mx, smem_block, &blocks_per_sm));
                     occ_cache[key] = blocks_per_sm;
                 } else blocks_per_sm = it->second;
             }
@@ -992,8 +785,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             used = *d_used;
 #else
             cudaEventRecord(ev[3], st.s);
-            k_align<<<n_warps / 4, 128, smem_block, st.s>>>(a);
-            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(index->view.wide ? kern_any::launch_align(n_warps / 4, smem_block, st.s, a)
+                                      : kern_dna::launch_align(n_warps / 4, smem_block, st.s, a));
             cudaEventRecord(ev[4], st.s);
             if ((rc = d2h(&used, d_used, 8, st))) break;
             CUDA_TRY(cudaStreamSynchronize(st.s));

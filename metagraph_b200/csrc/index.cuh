@@ -23,7 +23,19 @@ struct uint2 { uint32_t x, y; };
 namespace mgb {
 
 static constexpr int kSigmaDNA = 5;
-static constexpr int kMaxSigma = 32;         // alphabet-generic ("wide") layout: sigma <= 32 (protein: 27)
+#ifndef MGB_MAX_SIGMA
+#define MGB_MAX_SIGMA 32
+#endif
+static constexpr int kMaxSigma = MGB_MAX_SIGMA;   // alphabet-generic ("wide") layout: sigma <= 32 (protein: 27)
+// MGB_WIDE(ix): is the index in the alphabet-generic layout? A translation unit built with
+// -DMGB_NARROW_ONLY / -DMGB_WIDE_ONLY serves one layout only and drops the branches (kernels.cuh).
+#if defined(MGB_NARROW_ONLY)
+#define MGB_WIDE(ix) false
+#elif defined(MGB_WIDE_ONLY)
+#define MGB_WIDE(ix) true
+#else
+#define MGB_WIDE(ix) ((ix).wide != 0)
+#endif
 static constexpr int kBlkEdges = 64;
 static constexpr int kBlkWords = 16;
 static constexpr int kSelLastRate = 64;
@@ -277,25 +289,25 @@ struct LineCache {
         if (!valid_ || b != blk) { line = load_line(ix, b); blk = b; valid_ = true; }
     }
     MGB_HD uint32_t get_W(const IndexView &ix, uint64_t e) {
-        if (ix.wide) return wide_get_W(ix, e);
+        if (MGB_WIDE(ix)) return wide_get_W(ix, e);
         touch(ix, e); return line_get_W(line, (int)(e & 63));
     }
     MGB_HD bool get_last(const IndexView &ix, uint64_t e) {
-        if (ix.wide) return wide_get_last(ix, e);
+        if (MGB_WIDE(ix)) return wide_get_last(ix, e);
         touch(ix, e); return line_get_last(line, (int)(e & 63));
     }
 };
 
 // boss.cpp:437-441; positions [1..i], un-flagged symbol c only
 MGB_HD uint64_t rank_W(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t c) {
-    if (ix.wide) return wide_rank_W(ix, i, c);
+    if (MGB_WIDE(ix)) return wide_rank_W(ix, i, c);
     if (i == 0) return 0;
     lc.touch(ix, i);
     return (uint64_t)line_word(lc.line, 11 + c) + line_count_W(lc.line, (int)(i & 63), c);
 }
 // boss.cpp:577-581
 MGB_HD uint64_t rank_last(const IndexView &ix, LineCache &lc, uint64_t i) {
-    if (ix.wide) return wide_rank_last(ix, i);
+    if (MGB_WIDE(ix)) return wide_rank_last(ix, i);
     if (i == 0) return 0;
     lc.touch(ix, i);
     return (uint64_t)line_word(lc.line, 10) + line_count_last(lc.line, (int)(i & 63));
@@ -303,7 +315,7 @@ MGB_HD uint64_t rank_last(const IndexView &ix, LineCache &lc, uint64_t i) {
 
 // boss.cpp:588-592: position of the r-th set bit of `last` (r >= 1); leaves its block in lc
 MGB_HD uint64_t select_last(const IndexView &ix, LineCache &lc, uint64_t r) {
-    if (ix.wide) return wide_select_last(ix, r);
+    if (MGB_WIDE(ix)) return wide_select_last(ix, r);
     if (r == 0) return 0;
     uint64_t j = (r - 1) / kSelLastRate;
     uint32_t b = ldg32(ix.sel_last + j), b1 = ldg32(ix.sel_last + j + 1);
@@ -325,7 +337,7 @@ MGB_HD uint64_t select_last(const IndexView &ix, LineCache &lc, uint64_t r) {
 
 // wavelet_tree::select(c, r) (wavelet_tree.cpp:352-357) for un-flagged c, r >= 1
 MGB_HD uint64_t select_W(const IndexView &ix, LineCache &lc, uint32_t c, uint64_t r) {
-    if (ix.wide) return wide_select_W(ix, c, r);
+    if (MGB_WIDE(ix)) return wide_select_W(ix, c, r);
     uint64_t j = (r - 1) / kSelWRate;
     uint32_t b = ldg32(ix.sel_W[c] + j), b1 = ldg32(ix.sel_W[c] + j + 1);
     for (uint32_t base = b + 1; base <= b1; base += kGroup) {
@@ -350,7 +362,7 @@ MGB_HD uint64_t select_W(const IndexView &ix, LineCache &lc, uint32_t c, uint64_
 
 // boss.cpp:598-607: last set bit of `last` in [1..i], 0 if none
 MGB_HD uint64_t pred_last(const IndexView &ix, LineCache &lc, uint64_t i) {
-    if (ix.wide) return wide_pred_last(ix, i);
+    if (MGB_WIDE(ix)) return wide_pred_last(ix, i);
     while (i) {
         lc.touch(ix, i);
         int off = (int)(i & 63);
@@ -370,7 +382,7 @@ MGB_HD uint64_t pred_last(const IndexView &ix, LineCache &lc, uint64_t i) {
 
 // boss.cpp:613-617: first set bit of `last` at a position >= i; n + 1 if none
 MGB_HD uint64_t succ_last(const IndexView &ix, LineCache &lc, uint64_t i) {
-    if (ix.wide) return wide_succ_last(ix, i);
+    if (MGB_WIDE(ix)) return wide_succ_last(ix, i);
     while (i <= ix.n) {
         lc.touch(ix, i);
         int off = (int)(i & 63);
@@ -423,7 +435,7 @@ MGB_HD uint64_t adj_child(uint2 a, uint32_t c) {   // edge with label c out of t
 struct Adj { uint32_t last, all, ok; };
 MGB_HD Adj adj_decode(uint2 a) { Adj r; r.last = a.x; r.all = a.y & 31u; r.ok = (a.y >> 8) & 31u; return r; }
 MGB_HD Adj load_adj_any(const IndexView &ix, uint64_t e) {
-    if (!ix.wide) return adj_decode(load_adj(ix, e));
+    if (!MGB_WIDE(ix)) return adj_decode(load_adj(ix, e));
     const uint32_t *p = ix.wadj + e * 4;
     Adj r; r.last = p[0]; r.all = p[1]; r.ok = p[2];
     return r;
@@ -433,8 +445,8 @@ MGB_HD uint64_t adj_child(const Adj &a, uint32_t c) {
     return (uint64_t)a.last - popc32(a.all) + 1 + popc32(a.all & ((1u << c) - 1u));
 }
 // fields of the y word of a reverse adjacency record
-MGB_HD uint32_t radj_char(const IndexView &ix, uint32_t y) { return ix.wide ? (y & 127u) : (y & 7u); }
-MGB_HD bool radj_multi(const IndexView &ix, uint32_t y) { return ix.wide ? ((y >> 7) & 1u) : ((y >> 3) & 1u); }
+MGB_HD uint32_t radj_char(const IndexView &ix, uint32_t y) { return MGB_WIDE(ix) ? (y & 127u) : (y & 7u); }
+MGB_HD bool radj_multi(const IndexView &ix, uint32_t y) { return MGB_WIDE(ix) ? ((y >> 7) & 1u) : ((y >> 3) & 1u); }
 
 // Reverse adjacency record of edge e (backward extension through the RCDBG view, rc_dbg.hpp:86-97):
 //   x        bwd(e): first (un-flagged) edge entering the source node of e (boss.cpp:623-636)
@@ -469,7 +481,7 @@ MGB_HD uint64_t pick_edge(const IndexView &ix, LineCache &lc, uint64_t edge, uin
 // First position p >= i with W[p] in { d, d + sigma } (boss.cpp:515-570 succ_W with two
 // symbols); returns n + 1 and *w = 0 if none.
 MGB_HD uint64_t succ_W2(const IndexView &ix, LineCache &lc, uint64_t i, uint32_t d, uint32_t *w) {
-    if (ix.wide) return wide_succ_W2(ix, i, d, w);
+    if (MGB_WIDE(ix)) return wide_succ_W2(ix, i, d, w);
     while (i <= ix.n) {
         lc.touch(ix, i);
         int off = (int)(i & 63);

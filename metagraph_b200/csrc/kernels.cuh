@@ -1,0 +1,269 @@
+// Kernel-side code of the C-ABI library: per-item device functions, the kernels and their launchers.
+//
+// The product library compiles this file twice (no relocatable device code, so the two sets of device
+// functions never meet):
+//   api.cu          -DMGB_NARROW_ONLY, MGB_KERNEL_NS = kern_dna : DNA block layout only; the branches
+//                   to the alphabet-generic index layout are compiled out of the hot kernels
+//   api_generic.cu  -DMGB_WIDE_ONLY,   MGB_KERNEL_NS = kern_any : alphabet-generic layout only (protein)
+// The host-emulation build (tests/emu) includes it once with the layout chosen at run time.
+#pragma once
+#include "align_core.cuh"
+#if !defined(MGB_HOST_EMU)
+#include <cuda_runtime.h>
+#endif
+
+#ifndef MGB_KERNEL_NS
+#define MGB_KERNEL_NS kern_dna
+#endif
+
+namespace mgb {
+
+struct ReadHdr {              // per read, written by the align kernel
+    uint32_t status, n_aln;
+    uint64_t heap_off;
+    ReadStats stats;
+};
+
+// ---------------------------------------------------------------------------------------
+// kernels (device) / loops (host emulation)
+// ---------------------------------------------------------------------------------------
+struct PrepArgs {
+    const char *seqs; const uint64_t *offsets; uint32_t n_reads;
+    char *qf, *qr; uint8_t *cf, *cr;
+    uint8_t code_of[256];     // KmerExtractorBOSS::encode of the index's alphabet
+};
+
+MGB_HD void prepare_read(const PrepArgs &a, uint32_t r) {
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    for (int i = wlane(); i < L; i += kWarp) {
+        uint8_t f = sanitize_char((uint8_t)a.seqs[b + i]);
+        uint8_t rc = complement_char(sanitize_char((uint8_t)a.seqs[b + L - 1 - i]));
+        a.qf[b + i] = (char)f; a.qr[b + i] = (char)rc;
+        a.cf[b + i] = a.code_of[f]; a.cr[b + i] = a.code_of[rc];
+    }
+}
+
+struct SeedArgs {
+    IndexView ix;
+    const uint8_t *cf, *cr; const uint64_t *offsets; const uint64_t *koff;
+    uint64_t *nodes_f, *nodes_r; uint32_t n_reads; uint32_t n_strands;
+};
+
+MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
+    uint32_t r = (uint32_t)(item / a.n_strands);
+    uint32_t s = (uint32_t)(item % a.n_strands);
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r]);
+}
+
+struct AlignArgs {
+    IndexView ix; DevConfig cfg; Caps caps;
+    int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
+    int use_fast;               // 0 disables the register fast path (test knob)
+    unsigned long long *phase_out;   // MGB_PHASE_TIMERS builds: cycles per phase (setup, seeds, fwd, backtrack, align total)
+    const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
+    const uint64_t *nodes_f, *nodes_r;
+    const uint32_t *read_list; uint32_t n_list;
+    char *arena; size_t arena_stride;
+    ReadHdr *hdr; char *heap; uint64_t heap_cap; unsigned long long *heap_used;
+    unsigned int *next;
+};
+
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm) {
+    ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
+    al.use_fast = a.use_fast != 0;
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    int order[kMaxAlt];
+    const bool has_k = L >= (int)a.ix.k;
+    int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
+                   has_k ? a.nodes_f + a.koff[r] : nullptr,
+                   has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
+#if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
+    if (wlane() == 0 && a.phase_out) {
+        for (int p = 0; p < 5; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
+    }
+#endif
+    ReadHdr h;
+    h.status = al.overflow ? MGB_READ_OVERFLOW : MGB_READ_OK;
+    h.n_aln = 0; h.heap_off = 0; h.stats = al.stats;
+    if (!al.overflow && n) {
+        // bytes: per alignment OutAln + nodes*8 + cigar*4 + seq (padded to 8)
+        uint64_t bytes = 0;
+        for (int i = 0; i < n; ++i) {
+            const AlnHdr ah = *mem.slots[SLOT_AGG + order[i]].h;
+            bytes += sizeof(OutAln) + 8ull * ah.n_nodes + ((4ull * ah.n_cigar + 7) & ~7ull)
+                   + (((uint64_t)ah.seq_len + 7) & ~7ull);
+        }
+        unsigned long long off = 0;
+#if MGB_DEVICE_CODE
+        if (wlane() == 0) off = atomicAdd(a.heap_used, (unsigned long long)bytes);
+        off = wbcast64(off, 0);
+#else
+        off = *a.heap_used; *a.heap_used += bytes;
+#endif
+        if (off + bytes > a.heap_cap) {
+            h.status = MGB_READ_OVERFLOW;
+        } else {
+            h.n_aln = n; h.heap_off = off;
+            char *p = a.heap + off;
+            for (int i = 0; i < n; ++i) {
+                const AlnSlot &sl = mem.slots[SLOT_AGG + order[i]];
+                const AlnHdr ah = *sl.h;
+                OutAln o;
+                o.orientation = ah.orientation; o.score = ah.score; o.offset = ah.offset;
+                o.query_begin = al.aln_clipping(sl); o.query_len = ah.q_len;
+                o.n_nodes = ah.n_nodes; o.seq_len = ah.seq_len; o.n_cigar = ah.n_cigar;
+                if (wlane() == 0) *(OutAln*)p = o;
+                p += sizeof(OutAln);
+                uint64_t *pn = (uint64_t*)p;
+                for (int t = wlane(); t < ah.n_nodes; t += kWarp) pn[t] = sl.nodes[t];
+                p += 8ull * ah.n_nodes;
+                uint32_t *pc = (uint32_t*)p;
+                for (int t = wlane(); t < ah.n_cigar; t += kWarp) pc[t] = sl.cigar[t];
+                p += (4ull * ah.n_cigar + 7) & ~7ull;
+                for (int t = wlane(); t < ah.seq_len; t += kWarp) p[t] = sl.seq[t];
+                p += ((uint64_t)ah.seq_len + 7) & ~7ull;
+            }
+        }
+    }
+    if (wlane() == 0) {
+        a.hdr[r] = h;
+        mem.epoch_store[0] = sm.ctx[0].conv_epoch; mem.epoch_store[1] = sm.ctx[1].conv_epoch;
+    }
+    wsync();
+}
+
+// once per arena: convergence-table slots start with epoch 0 (never equal to a live epoch)
+MGB_HD void init_arena(const AlignArgs &a, char *arena) {
+    WarpMem mem;
+    mem.carve(arena, a.caps);
+    for (int e = 0; e < 2; ++e)
+        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv_slots[e][i].epoch = 0;
+    if (wlane() == 0) { mem.epoch_store[0] = 0; mem.epoch_store[1] = 0; }
+    wsync();
+}
+
+// One refinement level of the suffix-range table (boss.hpp:651-655 index order: the appended
+// character is the most significant digit): entry o = idx + (c-1)*cur_num of the new table is
+// tighten_range(cur[idx], c).
+struct SfxArgs { IndexView ix; const uint32_t *cur; uint32_t *nxt; uint64_t cur_num; };
+
+MGB_HD void sfx_extend_item(const SfxArgs &a, uint64_t o) {
+    const uint64_t idx = o % a.cur_num;
+    const uint32_t c = (uint32_t)(o / a.cur_num) + 1;
+    uint64_t rl = a.cur[2 * idx], ru = (uint64_t)a.cur[2 * idx + 1] - 1;
+    uint32_t b = 1, e = 1;
+    if (rl <= ru && tighten_range(a.ix, &rl, &ru, c)) { b = (uint32_t)rl; e = (uint32_t)(ru + 1); }
+    if (glane() == 0) { a.nxt[2 * o] = b; a.nxt[2 * o + 1] = e; }
+}
+
+// Reverse adjacency construction (index.cuh load_radj): per edge bwd(e) + "source node has several
+// incoming edges", then k-2 gather rounds c_{j+1}[e] = c_j[bwd(e)] that move the last node character
+// (boss.cpp:679-690) to the first position of the k-mer.
+struct RadjArgs { IndexView ix; uint32_t *bwd_arr; uint8_t *c_cur; uint8_t *c_nxt; uint8_t *multi; uint2 *radj; uint64_t n; };
+inline uint32_t radj_multi_shift(const IndexView &ix) { return ix.wide ? 7u : 3u; }   // index.cuh radj_multi
+
+MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
+    LineCache lc;
+    uint64_t x = bwd(a.ix, lc, e);
+    uint32_t d = node_last_value(a.ix, e);
+    uint32_t multi = 0;
+    if (x + 1 <= a.ix.n) {
+        uint32_t w;
+        succ_W2(a.ix, lc, x + 1, d, &w);
+        multi = w == d + a.ix.sigma;
+    }
+    if (glane() == 0) { a.bwd_arr[e] = (uint32_t)x; a.c_cur[e] = (uint8_t)d; a.multi[e] = (uint8_t)multi; }
+}
+
+} // namespace mgb
+
+#if !defined(MGB_HOST_EMU)
+namespace MGB_KERNEL_NS {
+using namespace mgb;
+
+__global__ void __launch_bounds__(128) k_radj_bwd(RadjArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    for (uint64_t e = 1 + quad; e <= a.n; e += nquads) radj_bwd_item(a, e);
+}
+
+__global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    const uint64_t total = a.cur_num * (a.ix.sigma - 1);
+    for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
+}
+
+__global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    uint64_t items = (uint64_t)a.n_reads * a.n_strands;
+    for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
+}
+
+#ifndef MGB_ALIGN_MIN_BLOCKS
+#define MGB_ALIGN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    char *arena = a.arena + (size_t)warp * a.arena_stride;
+    extern __shared__ __align__(16) char smem_raw[];
+    WarpSmem probe;
+    const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
+    char *smem = smem_raw + (threadIdx.x >> 5) * smem_per_warp;
+    init_arena(a, arena);
+    WarpMem mem;                 // the warp's arena and on-chip working set are laid out once
+    mem.carve(arena, a.caps);
+    WarpSmem sm;
+    sm.carve(smem, a.bmax, a.lq, a.hcap);
+    while (true) {
+        unsigned int t = 0;
+        if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= a.n_list) break;
+        align_read(a, a.read_list[t], mem, sm);
+    }
+}
+
+// launchers (the only entry points the host code uses)
+cudaError_t launch_radj_bwd(unsigned grid, const RadjArgs &a) { k_radj_bwd<<<grid, 128>>>(a); return cudaGetLastError(); }
+cudaError_t launch_sfx_extend(unsigned grid, const SfxArgs &a) { k_sfx_extend<<<grid, 128>>>(a); return cudaGetLastError(); }
+cudaError_t launch_seed(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_seed<<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
+cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const AlignArgs &a) {
+    k_align<<<grid, 128, smem_block, s>>>(a);
+    return cudaGetLastError();
+}
+// raises the kernel's dynamic shared memory limit to `smem_limit` and reports the resident blocks per SM
+// for blocks of `smem_block` bytes
+cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_align, 128, smem_block);
+}
+
+#if !defined(MGB_WIDE_ONLY)
+// alphabet-independent kernels live in the first translation unit only
+__global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < a.n_reads; r += nwarps) prepare_read(a, r);
+}
+__global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = 1 + t; e <= a.n; e += nt) a.c_nxt[e] = a.c_cur[a.bwd_arr[e]];
+}
+__global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a, uint32_t multi_shift) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = 1 + t; e <= a.n; e += nt)
+        a.radj[e] = make_uint2(a.bwd_arr[e], (uint32_t)a.c_cur[e] | ((uint32_t)a.multi[e] << multi_shift));
+}
+#endif
+
+} // namespace MGB_KERNEL_NS
+#endif

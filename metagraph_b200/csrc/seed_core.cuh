@@ -99,7 +99,7 @@ MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint6
             }
             // fwd(edge, codes[i+K-2]) + pick_edge(.., codes[i+K-1]) through the adjacency record
             const uint32_t c = codes[i + K - 1];
-            if (!ix.wide) {
+            if (!MGB_WIDE(ix)) {
                 const uint2 a = load_adj(ix, edge);
                 edge = adj_child(a, c);
                 if (writer) out[i] = (edge && ((a.y >> (8 + c)) & 1u)) ? edge : 0;
