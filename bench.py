@@ -324,6 +324,18 @@ def main():
             kname, kms = "k_seed", seed_ms
             alg_bytes = N * 27520
         achieved = alg_bytes / (kms / 1e3) / 1e9
+        # DRAM traffic of the dominant kernel per launch: one ncu capture of this very workload
+        # (profiles/r1_traffic.json, made by scripts/profile_bench.py), scaled per read; null otherwise
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")))
+            w = tr["workload"]
+            if (w["read_len"], w["genome_bp"], w["k"]) == (150, G, K):
+                traffic = int((tr[kname]["dram_bytes_read"] + tr[kname]["dram_bytes_write"]) / w["reads"] * N)
+        except (OSError, KeyError, ValueError):
+            pass
+        seed_alg = N * 27520
+        seed_gbs = seed_alg / (seed_ms / 1e3) / 1e9
         # int-pipe view of the extension: 12 int32 ops per DP cell
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         gcups = cells / (align_ms / 1e3) / 1e9
@@ -338,9 +350,12 @@ def main():
                     "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]), "ms_per_step": wall_ms_max / args.steps},
             "gpu_launches": int(sum(s["kernel_launches"] for s, _, _ in stats + stats_e2e)),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": kms},
             "kernels_ms_per_step": {"prepare+seed": seed_ms, "align": align_ms},
+            # seeding against the HBM roofline (27 520 algorithmic bytes per read, both strands)
+            "seeding": {"bound": "hbm", "kernel": "k_prepare+k_seed", "achieved": seed_gbs, "peak": peak,
+                        "unit": "GB/s", "frac": seed_gbs / peak, "algorithmic_bytes_per_launch": int(seed_alg)},
             "extension": {"gcups": gcups, "gcups_int32_peak": gcups_peak, "frac": gcups / gcups_peak,
                           "dp_cells_per_step": int(cells), "dp_columns_per_step": int(cols)},
             "alignments_gathered": total_aln, "index_build_s": build_s,
