@@ -188,6 +188,15 @@ void mgb_boss_free(mgb_boss_t *boss);
  * valid must hold n_plus_1 bytes. */
 int mgb_boss_mask_dummy(const mgb_boss_t *boss, uint8_t *valid);
 
+/* Reads a graph file written by the reference (`.dbg`: DBGSuccinct::serialize, dbg_succinct.cpp:690-803 ->
+ * BOSS::serialize, boss.cpp:262-277) into plain BOSS arrays for mgb_index_create(). States SMALL and STAT
+ * (boss.hpp:325); DYN / FAST files are refused. *mode = DeBruijnGraph::Mode (0 BASIC, 1 CANONICAL,
+ * 2 PRIMARY; only BASIC graphs can be aligned against in this build), *state = BOSS::State. The suffix
+ * range index and the optional .edgemask file are not read. Free with mgb_boss_free(). On failure returns
+ * MGB_ERR_INVALID_ARGUMENT and mgb_dbg_last_error() describes why. */
+int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode, int *state);
+const char* mgb_dbg_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

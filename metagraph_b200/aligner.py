@@ -63,6 +63,27 @@ class BOSSTable:
             L.mgb_boss_free(ctypes.byref(b))
         return cls(k, W, last, F, alphabet=int(alphabet))
 
+    @classmethod
+    def from_dbg(cls, path, lib=None):
+        """Loads a graph written by the reference (`metagraph build` -> *.dbg; DBGSuccinct::load,
+        dbg_succinct.cpp:690-712). Returns the table; .mode / .state carry the file's graph mode and BOSS state."""
+        L = _lib.load_library(lib)
+        b = _lib.mgb_boss_t()
+        mode, state = ctypes.c_int(-1), ctypes.c_int(-1)
+        rc = L.mgb_dbg_load(str(path).encode(), ctypes.byref(b), ctypes.byref(mode), ctypes.byref(state))
+        if rc:
+            raise _lib.MgbError(rc, "mgb_dbg_load: " + L.mgb_dbg_last_error().decode())
+        try:
+            n1 = b.n_plus_1
+            W = np.ctypeslib.as_array(b.W, shape=(n1,)).copy()
+            last = np.ctypeslib.as_array(b.last, shape=(n1,)).copy()
+            F = np.array([b.F[i] for i in range(27 if b.alphabet == 1 else 5)], dtype=np.uint64)
+            t = cls(b.k, W, last, F, alphabet=int(b.alphabet))
+        finally:
+            L.mgb_boss_free(ctypes.byref(b))
+        t.mode, t.state = mode.value, state.value
+        return t
+
     def dummy_mask(self, lib=None):
         """valid-edge bytes as DBGSuccinct::mask_dummy_kmers computes them"""
         L = _lib.load_library(lib)
