@@ -29,6 +29,7 @@ struct DevConfig {
     double min_exact_match, max_nodes_per_seq_char, max_ram_per_alignment, rel_score_cutoff;
     int32_t gap_open, gap_ext, left_end_bonus, right_end_bonus;
     uint8_t forward_and_reverse_complement, allow_left_trim, no_backtrack, pad0;
+    int32_t ge_shift;              // log2(-gap_ext) if that is a power of two, else -1 (extend_ins_end's division)
     int8_t diag[128];              // score_matrix[c][c]
     int8_t prof[kMaxSigma + 1][128];   // score_matrix[decode(i)][q], row sigma = '\0'
     uint8_t opmatch[kMaxSigma + 1][128]; // kCharToOp[decode(i)][q] == MATCH (aligner_cigar.cpp:11-51)
@@ -1142,7 +1143,10 @@ struct ReadAligner {
 
             while (nn_n) {
                 const uint32_t i = np[--nn_n].idx;
-                const ColMeta par = (i == last_idx) ? last_col : m.cols[i];
+                // `last_col` is the register copy of column `last_idx`; the popped column takes it over
+                // (nothing below the child loop's start reads `par`, the children overwrite the copy)
+                if (i != last_idx) { last_col = m.cols[i]; last_idx = i; last_band_valid = false; }
+                const ColMeta &par = last_col;
                 const int next_offset = par.offset + 1;
                 const bool in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
                 // parent cells: on chip if it is one of the two most recent columns
@@ -1182,6 +1186,7 @@ struct ReadAligner {
 
                 // call_outgoing (:330-387)
                 int n_out = 0;
+                bool plain_out = false;                   // all added scores and trails are 0 (not stored)
                 {
                     uint32_t seed_pos = (uint32_t)(next_offset - (int)sh.offset);
                     if (in_seed && next_offset < K) {
@@ -1195,7 +1200,7 @@ struct ReadAligner {
                         n_out = 1;
                     } else if (!rc) {
                         n_out = outgoing_fwd(par.node, sm.out_nodes, sm.out_chars);
-                        for (int t = 0; t < n_out && t < kMaxOut; ++t) { sm.out_scores[t] = 0; sm.out_trails[t] = 0; }
+                        plain_out = true;
                     } else {
                         n_out = outgoing_rc(par.node, par.trail, sm.out_nodes, sm.out_chars, sm.out_trails);
                         for (int t = 0; t < n_out && t < kMaxOut; ++t) sm.out_scores[t] = 0;
@@ -1221,7 +1226,7 @@ struct ReadAligner {
                     if (use_fast && n <= 28 && size0 <= 27 && sm.bmax >= 40) {
                         const int j = wlane();
                         const score_t go = cfg.gap_open, ge = cfg.gap_ext;
-                        const score_t add = sm.out_scores[t];
+                        const score_t add = plain_out ? 0 : sm.out_scores[t];
                         {   // requests whose latency overlaps the DP below
                             const uint64_t cnode = sm.out_nodes[t];
                             if (!rc && cnode && !MGB_WIDE(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
@@ -1261,7 +1266,8 @@ struct ReadAligner {
                             const score_t ins = imax(s_last + go, e_last + ge);
                             if (ins >= cutoff) {
                                 const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;      // ins >= cutoff
-                                const uint32_t extra = ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu;
+                                const uint32_t extra = cfg.ge_shift >= 0 ? diff >> cfg.ge_shift
+                                                     : (ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu);
                                 const uint32_t room = (uint32_t)(max_size - size0 - 1);
                                 int cnt = 1 + (int)(extra < room ? extra : room);
                                 if (size0 + cnt > 27) fits = false;
@@ -1318,7 +1324,7 @@ struct ReadAligner {
                                 cb_S[j + 32] = kNinf; cb_S[sm.bmax + j + 32] = kNinf; cb_S[2 * sm.bmax + j + 32] = kNinf;
                             }
                             ColMeta col;
-                            col.node = sm.out_nodes[t]; col.trail = sm.out_trails[t]; col.parent = i; col.c = ch;
+                            col.node = sm.out_nodes[t]; col.trail = plain_out ? 0 : sm.out_trails[t]; col.parent = i; col.c = ch;
                             col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
                             col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size; col.cells_off = off;
                             const uint32_t idx = n_cols;
@@ -1354,7 +1360,7 @@ struct ReadAligner {
                     // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
                     for (int j = wlane(); j < size0 + 5; j += kWarp) { sc.S[j] = kNinf; sc.E[j] = kNinf; sc.F[j] = kNinf; }
                     wsync();
-                    const score_t add = sm.out_scores[t];
+                    const score_t add = plain_out ? 0 : sm.out_scores[t];
                     const uint32_t cap_before = cx[e].table_cap;
                     if (n_cols + 1 > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
                     const int code = encode_char(ch);
@@ -1403,7 +1409,7 @@ struct ReadAligner {
                         overflow = true; return 0;
                     }
                     ColMeta col;
-                    col.node = sm.out_nodes[t]; col.trail = sm.out_trails[t]; col.parent = i; col.c = ch;
+                    col.node = sm.out_nodes[t]; col.trail = plain_out ? 0 : sm.out_trails[t]; col.parent = i; col.c = ch;
                     col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
                     col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size;
                     col.cells_off = commit_column(sc, size);

@@ -85,6 +85,8 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConf
     d->min_exact_match = c.min_exact_match; d->max_nodes_per_seq_char = c.max_nodes_per_seq_char;
     d->max_ram_per_alignment = c.max_ram_per_alignment; d->rel_score_cutoff = c.rel_score_cutoff;
     d->gap_open = c.gap_opening_penalty; d->gap_ext = c.gap_extension_penalty;
+    d->ge_shift = -1;
+    for (int sh = 0; sh < 8; ++sh) if (-(int)c.gap_extension_penalty == (1 << sh)) d->ge_shift = sh;
     d->left_end_bonus = c.left_end_bonus; d->right_end_bonus = c.right_end_bonus;
     // protein builds compile the reverse-complement strand out (dbg_aligner.cpp:224-229, 289-293)
     d->forward_and_reverse_complement = c.forward_and_reverse_complement && at.has_complement;
