@@ -277,12 +277,16 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     HostIndex &h = hloc;
 #endif
     if (suffix_len == 0) {
-        // reference default 12 (cli/config/config.cpp:24-25), capped so the table stays
-        // well below the index size
+        // reference default 12 (cli/config/config.cpp:24-25). Here: as long as the table has at most
+        // ~12 entries per edge and 2^30 entries (8 GiB): a cold k-mer lookup that misses in the table
+        // costs one load instead of a chain of tighten_range steps, and on a strand that does not match
+        // every k-mer is a cold lookup (k_seed 7.6 -> 5.5 ms per 200 k reads going from s = 13 to 14 on a
+        // 20 M-node graph). HBM capacity is traded for latency.
         uint64_t n = n_plus_1 - 1;
         suffix_len = 1;
         uint64_t entries = sigma - 1;
-        while (suffix_len < 14 && suffix_len + 1 <= k - 1 && entries * (sigma - 1) <= 4 * n + 1024) {
+        while (suffix_len < 15 && suffix_len + 1 <= k - 1 && entries * (sigma - 1) <= 12 * n + 1024
+               && entries * (sigma - 1) <= (1ull << 30) + (1ull << 26)) {
             entries *= sigma - 1; ++suffix_len;
         }
     }
