@@ -105,6 +105,8 @@ struct StrandCtx {
     uint32_t rc;                 // set_graph(): 1 = RCDBG view
     uint32_t implicit_seeds;     // 1: seeds are the set bits of `mask` (one k-mer seed per matched k-mer)
     uint32_t *mask;              // alive bits of implicit seeds (shared memory)
+    // BOSS::index_range per query position from k_subk (nullptr: computed here); sub_len 0xFF = not computed
+    const uint32_t *sub_first, *sub_last; const uint8_t *sub_len;
 };
 
 // Per-read output record header; followed in the output heap by packed alignments.
@@ -118,7 +120,9 @@ struct ReadStats { uint32_t num_seeds, num_extensions, num_explored_nodes, dp_co
 #if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
 #define MGB_TIC(var) long long var = clock64()
 #define MGB_TOC(var, slot) phase_cycles[slot] += clock64() - var
+#define MGB_COUNT(slot) ++phase_cycles[slot]
 #else
+#define MGB_COUNT(slot)
 #define MGB_TIC(var)
 #define MGB_TOC(var, slot)
 #endif
@@ -615,13 +619,19 @@ struct ReadAligner {
             const int g = wlane() / kGroup;
             for (int base = 0; base < n_pos; base += groups) {
                 const int i = base + g;
-                if (i < n_pos && m.sfx_min[i] != k) {
+                if (i < n_pos && m.sfx_min[i] != k && cx[s].sub_len && cx[s].sub_len[i] != 0xFF) {
+                    if (glane() == 0) {                   // looked up by k_subk
+                        m.sfx_first[i] = cx[s].sub_first[i]; m.sfx_last[i] = cx[s].sub_last[i];
+                        m.sfx_len[i] = cx[s].sub_len[i];
+                    }
+                } else if (i < n_pos && m.sfx_min[i] != k) {
                     const int len = imin((int)msl_u, L - i);
                     uint64_t first = 0, lst = 0; int matched = 0;
                     bool ok = len >= (int)cfg.min_seed_length;
                     const uint8_t *cd = cx[s].codes + i;
                     for (int t = 0; t < len && ok; ++t) ok = cd[t] < ix.sigma;
-                    if (ok) boss_index_range(ix, cd, imin(len, k - 1), &first, &lst, &matched);
+                    // matches shorter than min_seed_length are never used below (sfx_min[i] >= min_seed_length)
+                    if (ok) boss_index_range(ix, cd, imin(len, k - 1), &first, &lst, &matched, (int)cfg.min_seed_length);
                     if (glane() == 0) {
                         m.sfx_first[i] = (uint32_t)first; m.sfx_last[i] = (uint32_t)lst; m.sfx_len[i] = (uint8_t)matched;
                     }
@@ -1282,6 +1292,7 @@ struct ReadAligner {
                             }
                         }
                         if (fits) {
+                            MGB_COUNT(5);
                             const uint32_t cap_before = cx[e].table_cap;
                             if (n_cols + 1 > cap_before) cx[e].table_cap = cap_before ? 2 * cap_before : 1;
                             stats.dp_cells += size; ++stats.dp_columns;
@@ -1354,6 +1365,7 @@ struct ReadAligner {
                         }
                     }
 #endif
+                    MGB_COUNT(6);
                     Scratch sc;
                     if (size0 + 8 <= sm.bmax) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
                     else if (!scratch_arena(wlen + 1 - begin, &sc)) return 0;
@@ -1942,6 +1954,9 @@ struct ReadAligner {
     }
 
     // whole pipeline for one read; returns the number of alignments left in SLOT_AGG.. (sorted)
+    // optional: per-position index_range results of both strands (k_subk), set before run()
+    const uint32_t *subk_first[2] = { nullptr, nullptr }, *subk_last[2] = { nullptr, nullptr };
+    const uint8_t *subk_len[2] = { nullptr, nullptr };
     MGB_HD int run(int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
                    const uint64_t *nf, const uint64_t *nr, int *order) {
         MGB_TIC(t_setup);
@@ -1962,6 +1977,8 @@ struct ReadAligner {
             c0.table_cap = c1.table_cap = 0; c0.num_ext = c1.num_ext = 0;
             c0.explored_prev = c1.explored_prev = 0; c0.rc = c1.rc = 0;
             c0.implicit_seeds = c1.implicit_seeds = 0; c0.mask = sm.mask0; c1.mask = sm.mask1;
+            c0.sub_first = subk_first[0]; c0.sub_last = subk_last[0]; c0.sub_len = subk_len[0];
+            c1.sub_first = subk_first[1]; c1.sub_last = subk_last[1]; c1.sub_len = subk_len[1];
             // stage the query strands (and their suffix sums) on chip when they fit
             if (L + 1 <= sm.lq) {
                 for (int i = wlane(); i < L; i += kWarp) { sm.q0[i] = qf[i]; sm.q1[i] = qr[i]; }

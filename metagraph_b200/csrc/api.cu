@@ -48,6 +48,7 @@ namespace kern_any {
 cudaError_t launch_radj_bwd(unsigned grid, const mgb::RadjArgs &a);
 cudaError_t launch_sfx_extend(unsigned grid, const mgb::SfxArgs &a);
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
+cudaError_t launch_subk(unsigned grid, cudaStream_t s, const mgb::SubkArgs &a, uint32_t chunks_per_strand);
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const mgb::AlignArgs &a);
 cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm);
 }
@@ -688,6 +689,38 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
         if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
         if (!rc && map_nodes) rc = launch_seed(index, b, both ? 2 : 1, st);
         res->stats.kernel_launches += 1 + (map_nodes ? 1 : 0);
+        // sub-k seeding (min_seed_length < k): the independent index_range lookups run GPU-wide first
+        SubkArgs sk;
+        std::memset(&sk, 0, sizeof(sk));
+        const bool subk = !rc && map_nodes && dcfg.min_seed_length < index->view.k && b.total_chars
+                          && !std::getenv("MGB_TEST_NOSUBK");
+        if (subk) {
+            sk.ix = index->view; sk.cf = b.cf; sk.cr = b.cr; sk.offsets = b.offsets; sk.koff = b.koff;
+            sk.nodes_f = b.nodes_f; sk.nodes_r = b.nodes_r; sk.n_reads = n_reads; sk.n_strands = both ? 2 : 1;
+            sk.min_seed_length = dcfg.min_seed_length;
+            sk.max_len = dcfg.max_seed_length < index->view.k - 1 ? dcfg.max_seed_length : index->view.k - 1;
+            const size_t nc = b.total_chars + 64;
+            if (!rc) rc = bufs.alloc(&sk.first_f, nc);
+            if (!rc) rc = bufs.alloc(&sk.last_f, nc);
+            if (!rc) rc = bufs.alloc(&sk.len_f, nc);
+            if (!rc && both) rc = bufs.alloc(&sk.first_r, nc);
+            if (!rc && both) rc = bufs.alloc(&sk.last_r, nc);
+            if (!rc && both) rc = bufs.alloc(&sk.len_r, nc);
+            const uint32_t chunks = (b.L_max + kSubkChunk - 1) / kSubkChunk;
+#if defined(MGB_HOST_EMU)
+            for (uint32_t r = 0; r < n_reads && !rc; ++r)
+                for (uint32_t s2 = 0; s2 < sk.n_strands; ++s2)
+                    for (uint32_t c = 0; c < chunks; ++c) subk_item(sk, r, s2, c);
+#else
+            if (!rc) {
+                const uint64_t items = (uint64_t)n_reads * sk.n_strands * chunks;
+                const uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
+                CUDA_TRY(index->view.wide ? kern_any::launch_subk((unsigned)blocks, st.s, sk, chunks)
+                                          : kern_dna::launch_subk((unsigned)blocks, st.s, sk, chunks));
+            }
+#endif
+            res->stats.kernel_launches += 1;
+        }
 #if !defined(MGB_HOST_EMU)
         cudaEventRecord(ev[2], st.s);
 #endif
@@ -776,6 +809,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #endif
             a.qf = b.qf; a.qr = b.qr; a.cf = b.cf; a.cr = b.cr; a.offsets = b.offsets; a.koff = b.koff;
             a.nodes_f = b.nodes_f; a.nodes_r = b.nodes_r;
+            a.sub_first_f = subk ? sk.first_f : nullptr; a.sub_last_f = sk.last_f; a.sub_len_f = subk ? sk.len_f : nullptr;
+            a.sub_first_r = sk.first_r; a.sub_last_r = sk.last_r; a.sub_len_r = subk && both ? sk.len_r : nullptr;
             a.read_list = d_list; a.n_list = (uint32_t)list.size();
             a.arena = d_arena; a.arena_stride = stride;
             a.hdr = d_hdr; a.heap = d_heap; a.heap_cap = heap_cap; a.heap_used = d_used; a.next = d_next;
@@ -803,9 +838,10 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             {
                 unsigned long long ph[8];
                 cudaMemcpy(ph, a.phase_out, 64, cudaMemcpyDeviceToHost);
-                std::fprintf(stderr, "[phase cycles/read] setup %.0f seeds %.0f fwd %.0f backtrack %.0f align_total %.0f (reads %u)\n",
+                std::fprintf(stderr, "[phase cycles/read] setup %.0f seeds %.0f fwd %.0f backtrack %.0f align_total %.0f; columns/read: register path %.1f, general path %.1f (reads %u)\n",
                              (double)ph[0] / a.n_list, (double)ph[1] / a.n_list, (double)ph[2] / a.n_list,
-                             (double)ph[3] / a.n_list, (double)ph[4] / a.n_list, a.n_list);
+                             (double)ph[3] / a.n_list, (double)ph[4] / a.n_list, (double)ph[5] / a.n_list,
+                             (double)ph[6] / a.n_list, a.n_list);
             }
 #endif
             if (used > heap_cap) used = heap_cap;

@@ -584,14 +584,17 @@ MGB_HD uint64_t boss_index_slot(const IndexView &ix, const uint8_t *codes, int l
 
 // boss.hpp:720-764: longest matching prefix of codes[0..len) (len <= k - 1) and its edge
 // range; *matched = number of matched characters (0 -> (0, 0)).
+// min_len > 0: the caller discards matches shorter than min_len, so a miss in a suffix table of
+// length <= min_len is final (*matched = 0) and the walk from the first character is skipped.
 MGB_HD void boss_index_range(const IndexView &ix, const uint8_t *codes, int len,
-                             uint64_t *first, uint64_t *lst, int *matched) {
+                             uint64_t *first, uint64_t *lst, int *matched, int min_len = 0) {
     if (len == 0) { *first = 1; *lst = 1; *matched = 0; return; }
     for (int i = 0; i < len; ++i)
         if (codes[i] >= ix.sigma) { *first = 0; *lst = 0; *matched = 0; return; }
     uint64_t rl, ru; int off;
     initial_range(ix, codes, len, &rl, &ru, &off);
     if (rl > ru) {
+        if (off > 1 && off <= min_len) { *first = 0; *lst = 0; *matched = 0; return; }
         uint32_t s = codes[0];
         rl = ix.F[s] + 1 < ix.n + 1 ? ix.F[s] + 1 : ix.n + 1;
         ru = s + 1 < ix.sigma ? ix.F[s + 1] : ix.n;

@@ -58,6 +58,43 @@ MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
     map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r]);
 }
 
+// Sub-k seeding, lookup part (SuffixSeeder::generate_seeds, aligner_seeder_methods.cpp:215-238 ->
+// dbg_succinct.cpp:307-330 -> BOSS::index_range, boss.hpp:720-764): the longest prefix of the query at
+// every position without a full k-mer hit and its edge range. The lookups are independent of each other,
+// so they run GPU-wide, one quad per 16 positions of a strand, before the per-read kernel; k_align
+// keeps the order-dependent part (enumeration, per-locus rules, merging with the MEM seeds).
+struct SubkArgs {
+    IndexView ix;
+    const uint8_t *cf, *cr; const uint64_t *offsets, *koff; const uint64_t *nodes_f, *nodes_r;
+    uint32_t n_reads, n_strands, min_seed_length, max_len;     // max_len = min(max_seed_length, k - 1)
+    uint32_t *first_f, *last_f, *first_r, *last_r; uint8_t *len_f, *len_r;
+};
+static constexpr int kSubkChunk = 16;
+MGB_HD void subk_item(const SubkArgs &a, uint32_t r, uint32_t s, uint32_t chunk) {
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    const int K = (int)a.ix.k;
+    if (L < (int)a.min_seed_length) return;
+    const int n_pos = L - (int)a.min_seed_length + 1;
+    const uint8_t *codes = (s ? a.cr : a.cf) + b;
+    const uint64_t *nodes = L >= K ? (s ? a.nodes_r : a.nodes_f) + a.koff[r] : nullptr;
+    uint32_t *of = (s ? a.first_r : a.first_f) + b, *ol = (s ? a.last_r : a.last_f) + b;
+    uint8_t *on = (s ? a.len_r : a.len_f) + b;
+    const int nk = L >= K ? L - K + 1 : 0;
+    for (int i = (int)chunk * kSubkChunk; i < n_pos && i < (int)(chunk + 1) * kSubkChunk; ++i) {
+        uint64_t first = 0, lst = 0; int matched = 0;
+        uint8_t code = 0xFF;                              // not computed: a full k-mer matches here
+        if (!(i < nk && nodes && nodes[i] != 0)) {
+            const int len = (int)a.max_len < L - i ? (int)a.max_len : L - i;
+            bool ok = len >= (int)a.min_seed_length;
+            for (int t = 0; t < len && ok; ++t) ok = codes[i + t] < a.ix.sigma;
+            if (ok) boss_index_range(a.ix, codes + i, len < K - 1 ? len : K - 1, &first, &lst, &matched, (int)a.min_seed_length);
+            code = (uint8_t)matched;
+        }
+        if (glane() == 0) { of[i] = (uint32_t)first; ol[i] = (uint32_t)lst; on[i] = code; }
+    }
+}
+
 struct AlignArgs {
     IndexView ix; DevConfig cfg; Caps caps;
     int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
@@ -65,6 +102,8 @@ struct AlignArgs {
     unsigned long long *phase_out;   // MGB_PHASE_TIMERS builds: cycles per phase (setup, seeds, fwd, backtrack, align total)
     const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
     const uint64_t *nodes_f, *nodes_r;
+    const uint32_t *sub_first_f, *sub_last_f, *sub_first_r, *sub_last_r;    // k_subk results or nullptr
+    const uint8_t *sub_len_f, *sub_len_r;
     const uint32_t *read_list; uint32_t n_list;
     char *arena; size_t arena_stride;
     ReadHdr *hdr; char *heap; uint64_t heap_cap; unsigned long long *heap_used;
@@ -78,12 +117,16 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &s
     const int L = (int)(a.offsets[r + 1] - b);
     int order[kMaxAlt];
     const bool has_k = L >= (int)a.ix.k;
+    if (a.sub_len_f) {
+        al.subk_first[0] = a.sub_first_f + b; al.subk_last[0] = a.sub_last_f + b; al.subk_len[0] = a.sub_len_f + b;
+        if (a.sub_len_r) { al.subk_first[1] = a.sub_first_r + b; al.subk_last[1] = a.sub_last_r + b; al.subk_len[1] = a.sub_len_r + b; }
+    }
     int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
                    has_k ? a.nodes_f + a.koff[r] : nullptr,
                    has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
 #if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
     if (wlane() == 0 && a.phase_out) {
-        for (int p = 0; p < 5; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
+        for (int p = 0; p < 8; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
     }
 #endif
     ReadHdr h;
@@ -198,6 +241,17 @@ __global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
     for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
 }
 
+__global__ void __launch_bounds__(128) k_subk(SubkArgs a, uint32_t chunks_per_strand) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    const uint64_t per_read = (uint64_t)a.n_strands * chunks_per_strand;
+    const uint64_t items = (uint64_t)a.n_reads * per_read;
+    for (uint64_t it = quad; it < items; it += nquads) {
+        const uint32_t r = (uint32_t)(it / per_read), rem = (uint32_t)(it % per_read);
+        subk_item(a, r, rem / chunks_per_strand, rem % chunks_per_strand);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
     uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
@@ -232,6 +286,10 @@ __global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const Align
 // launchers (the only entry points the host code uses)
 cudaError_t launch_radj_bwd(unsigned grid, const RadjArgs &a) { k_radj_bwd<<<grid, 128>>>(a); return cudaGetLastError(); }
 cudaError_t launch_sfx_extend(unsigned grid, const SfxArgs &a) { k_sfx_extend<<<grid, 128>>>(a); return cudaGetLastError(); }
+cudaError_t launch_subk(unsigned grid, cudaStream_t s, const SubkArgs &a, uint32_t chunks_per_strand) {
+    k_subk<<<grid, 128, 0, s>>>(a, chunks_per_strand);
+    return cudaGetLastError();
+}
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_seed<<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const AlignArgs &a) {
     k_align<<<grid, 128, smem_block, s>>>(a);

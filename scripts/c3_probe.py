@@ -23,3 +23,18 @@ al = B200Aligner(index, cli_defaults(K, min_exact_match=0.0))
 for i in range(2):
     res = al.align_batch_raw(buf, off); st = al.stats_of(res); al.free_raw(res)
     print("c3 probe: seed_ms %.2f align_ms %.2f seeds %d ext %d cols %d" % (st["seed_kernel_ms"], st["align_kernel_ms"], st["num_seeds"], st["num_extensions"], st["dp_columns"]), flush=True)
+# CPU restatement on a bounded sample of the same reads (test infrastructure, timing only)
+if os.environ.get("C3_CPU", "1") == "1":
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    g = O.OracleGraph(K, arrays=(boss.W, boss.last, boss.F))
+    ns = int(os.environ.get("C3_CPU_READS", 4000))
+    sample = ["".join(map(chr, reads[i])) for i in range(ns)]
+    cfg = cli_defaults(K, min_exact_match=0.0)
+    for th in (32, 64):
+        t0 = time.time(); exp = g.align_tsv(cfg, sample, threads=th); dt = time.time() - t0
+        print("c3 cpu restatement: %d reads, %d threads, %.2f s -> %.0f reads/s" % (ns, th, dt, ns / dt), flush=True)
+    got = al.align_batch([("", r) for r in sample])
+    from metagraph_b200.aligner import format_alignment
+    same = sum(format_alignment("", r, 0) == e for r, e in zip(got, exp))
+    print("c3 parity on the sample: %d / %d lines identical" % (same, ns), flush=True)
