@@ -590,13 +590,14 @@ struct ReadAligner {
         }
         cx[s].num_matching = num_exact_matching(s, nk);
         if (L < (int)cfg.min_seed_length) return;
-        if ((int)cfg.min_seed_length >= k) { mem_seeds(s, nk); return; }
+        const bool mem_only = (int)cfg.min_seed_length >= k;
 
         // base (MEM) seeds first; they are merged with the sub-k seeds in query order below
         const int n_pos = L - (int)cfg.min_seed_length + 1;
-        for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
+        if (!mem_only) for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
         wsync();
         mem_seeds(s, nk);
+        if (mem_only) return;
         const int n_base = cx[s].n_seeds;
         if (overflow) return;
         if (2 * n_base > (int)caps.max_seeds) { overflow = true; return; }
@@ -802,23 +803,16 @@ struct ReadAligner {
             wsync();
             return mx;
         }
-        if (query_start + size <= en.start) {
-            if (!conv_grow(e, slot, &en, query_start, en.start + en.size)) return kNinf;
-            score_t *c = cells + en.seg_off;
-            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
-            wsync();
-            return mx;
-        }
-        if (query_start >= en.start + en.size) {
-            if (!conv_grow(e, slot, &en, en.start, query_start + size)) return kNinf;
-            score_t *c = cells + en.seg_off;
-            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
-            wsync();
-            return mx;
-        }
+        const bool disjoint = query_start + size <= en.start || query_start >= en.start + en.size;
         int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
         if (ns != en.start || ne != en.start + en.size)
             if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
+        if (disjoint) {                                  // before / after the stored range: stored as is
+            score_t *c = cells + en.seg_off;
+            for (int j = wlane(); j < size; j += kWarp) c[query_start + j - en.seg_start] = sv[j];
+            wsync();
+            return mx;
+        }
         score_t *v = cells + en.seg_off + (query_start - en.seg_start);
         score_t max_changed = kNinf;
         for (int j = wlane(); j < size; j += kWarp) {
@@ -855,21 +849,17 @@ struct ReadAligner {
             wsync();
             return mx;
         }
-        if (query_start + size <= en.start) {
-            if (!conv_grow(e, slot, &en, query_start, en.start + en.size)) return kNinf;
-            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
-            wsync();
-            return mx;
-        }
-        if (query_start >= en.start + en.size) {
-            if (!conv_grow(e, slot, &en, en.start, query_start + size)) return kNinf;
-            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
-            wsync();
-            return mx;
-        }
+        // disjoint from the stored range (before / after it): the values are stored as they are (:118-131);
+        // one conv_grow call site serves all three cases
+        const bool disjoint = query_start + size <= en.start || query_start >= en.start + en.size;
         int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
         if (ns != en.start || ne != en.start + en.size)
             if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
+        if (disjoint) {
+            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
+            wsync();
+            return mx;
+        }
         score_t max_changed = kNinf;
         if (has) {
             score_t *v = cells + en.seg_off + (query_start + vi - en.seg_start);
@@ -1855,28 +1845,35 @@ struct ReadAligner {
             seed_to_slot(SLOT_SEED, s, sd);
             seed_is_query = true;
             const score_t mps_fwd = both ? cfg.min_cell_score : get_min_path_score();
-            set_seed(fe);
-            int n_res = extend(fe, SLOT_SEED, mps_fwd, false, SLOT_EXT);
-            if (overflow) return;
+            // One call site for both kinds of extension (the forward one, then the backward ones it
+            // spawns): the extender is by far the largest piece of code and must exist once.
             int n_rc = 0;
-            for (int r = 0; r < n_res; ++r) {
-                const int slot = SLOT_EXT + r;
-                if (!both) { agg_add(slot); continue; }
-                if (sm.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
-                if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
-                if (!reverse_complement_slot(slot)) continue;
-                if (n_rc != r) copy_slot(SLOT_EXT + n_rc, slot);
-                ++n_rc;
-            }
-            // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
-            for (int r = 0; r < n_rc && !overflow; ++r) {
-                if (!sm.slots[SLOT_EXT + r].h->used) continue;
-                score_t mps = get_min_path_score();
-                set_seed(be);
-                seed_is_query = false;
-                int nb = extend(be, SLOT_EXT + r, mps, true, SLOT_BWD);
+            for (int it = 0; it <= n_rc && !overflow; ++it) {
+                if (it == 0) {
+                    set_seed(fe);
+                } else {
+                    // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
+                    if (!sm.slots[SLOT_EXT + it - 1].h->used) continue;
+                    set_seed(be);
+                    seed_is_query = false;
+                }
+                const int r = it - 1;
+                const int n_ext = extend(it ? be : fe, it ? SLOT_EXT + r : SLOT_SEED,
+                                         it ? get_min_path_score() : mps_fwd, it != 0, it ? SLOT_BWD : SLOT_EXT);
                 if (overflow) return;
-                for (int b = 0; b < nb; ++b) {
+                if (it == 0) {
+                    for (int r0 = 0; r0 < n_ext; ++r0) {
+                        const int slot = SLOT_EXT + r0;
+                        if (!both || sm.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
+                        if (!both) continue;
+                        if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
+                        if (!reverse_complement_slot(slot)) continue;
+                        if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
+                        ++n_rc;
+                    }
+                    continue;
+                }
+                for (int b = 0; b < n_ext; ++b) {
                     const int slot = SLOT_BWD + b;
                     if (!reverse_complement_slot(slot)) continue;
                     const AlnHdr h = *sm.slots[slot].h;
@@ -1894,6 +1891,7 @@ struct ReadAligner {
                         a.h->used = 0;
                 }
             }
+            if (overflow) return;
             // later seeds already covered by this extension are dropped (:731-734, :379-382);
             // independent probes, one seed per lane
             wsync();
@@ -1998,14 +1996,14 @@ struct ReadAligner {
         if (both) build_psum(1);
         MGB_TOC(t_setup, 0);
         MGB_TIC(t_seeds);
-        build_seeds(0);
-        if (overflow) return 0;
-        if ((double)L * cfg.min_exact_match > (double)cx[0].num_matching) { cx[0].n_seeds = 0; cx[0].num_matching = 0; }
+        #pragma unroll 1
+        for (int s = 0; s < (both ? 2 : 1); ++s) {           // one call site: the seeder is large
+            build_seeds(s);
+            if (overflow) return 0;
+            if ((double)L * cfg.min_exact_match > (double)cx[s].num_matching) { cx[s].n_seeds = 0; cx[s].num_matching = 0; }
+        }
         int first = 0, n_pass = 1;
         if (both) {
-            build_seeds(1);
-            if (overflow) return 0;
-            if ((double)L * cfg.min_exact_match > (double)cx[1].num_matching) { cx[1].n_seeds = 0; cx[1].num_matching = 0; }
             // the strand with more exact-match bases first; the other only if it is close (:738-755)
             uint32_t fm = cx[0].num_matching, bm = cx[1].num_matching;
             first = fm >= bm ? 0 : 1;
