@@ -75,7 +75,7 @@ typedef struct mgb_config {
     uint8_t global_xdrop;
     uint8_t allow_left_trim;
     uint8_t no_backtrack;
-    uint8_t seed_complexity_filter; /* must be 0: sdust is not vendored */
+    uint8_t seed_complexity_filter; /* sdust(T=20, W=64) on seed windows, restated from its definition (library not vendored) */
     uint8_t reserved1[7];
     int8_t score_matrix[128][128];
 } mgb_config_t;

@@ -124,7 +124,8 @@ class DBGAlignerConfig:
     global_xdrop: bool = True
     allow_left_trim: bool = True
     no_backtrack: bool = False
-    # sdust is not vendored in the reference tree; the filter is rejected when set
+    # sdust is not vendored in the reference tree: the filter is restated from the symmetric-DUST definition
+    # (parity with the library unpinned, tests/test_sdust.py); parity / bench runs keep it off
     seed_complexity_filter: bool = False
     score_matrix: list = field(default_factory=lambda: dna_scoring_matrix(2, -1, -2))
 
@@ -148,7 +149,8 @@ def struct_defaults(**kw):
 def cli_defaults(k, alphabet="dna", **kw):
     """`metagraph align` defaults: match 2, mismatch -3/-3, gaps -6/-2, end bonus 5, xdrop 27,
     rel_score_cutoff 0.95, min_seed 19 (capped at k), max_seed inf, 1000 seeds/locus,
-    5 nodes/char, 200 MB, min_exact_match 0.7; seed complexity filter off (no sdust).
+    5 nodes/char, 200 MB, min_exact_match 0.7; seed complexity filter off here (the CLI default is on; pass
+    seed_complexity_filter=True for `metagraph align` without --align-no-seed-complexity-filter).
     alphabet="protein": BLOSUM62 (DBGAlignerConfig::set_scoring_matrix, aligner_config.cpp:164-205);
     the reverse-complement strand does not exist there (dbg_aligner.cpp:224-229)."""
     d = dict(num_alternative_paths=1, min_seed_length=min(19, k), max_seed_length=SIZE_MAX,

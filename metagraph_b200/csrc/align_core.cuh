@@ -28,7 +28,8 @@ struct DevConfig {
     score_t min_cell_score, min_path_score, xdrop;
     double min_exact_match, max_nodes_per_seq_char, max_ram_per_alignment, rel_score_cutoff;
     int32_t gap_open, gap_ext, left_end_bonus, right_end_bonus;
-    uint8_t forward_and_reverse_complement, allow_left_trim, no_backtrack, pad0;
+    uint8_t forward_and_reverse_complement, allow_left_trim, no_backtrack;
+    uint8_t seed_complexity_filter;   // sdust on seed windows (aligner_seeder_methods.cpp:21-29), DNA only
     int32_t ge_shift;              // log2(-gap_ext) if that is a power of two, else -1 (extend_ins_end's division)
     int8_t diag[128];              // score_matrix[c][c]
     int8_t prof[kMaxSigma + 1][128];   // score_matrix[decode(i)][q], row sigma = '\0'
@@ -142,6 +143,9 @@ struct WarpMem {
     uint32_t *bt_ops; uint64_t *bt_path; char *bt_seq;
     uint8_t *sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
     uint32_t *sfx_first, *sfx_last; uint8_t *sfx_len;   // index_range result per query position
+    // seed complexity filter: 3-mer codes / equal-3-mer masks (scratch) and, per strand, the largest start of a
+    // low-complexity 3-mer interval ending at or before each 3-mer (see build_lowcx)
+    uint8_t *lc_word; uint64_t *lc_eq; int16_t *lc_max[2];
     uint32_t *epoch_store;  // conv-table epochs survive across the reads a warp processes
 
     MGB_HOSTDEV size_t carve(char *base, const Caps &c) {
@@ -171,6 +175,8 @@ struct WarpMem {
         sfx_min = (uint8_t*)take(c.L_max + 8);
         sfx_first = (uint32_t*)take(4 * ((size_t)c.L_max + 8)); sfx_last = (uint32_t*)take(4 * ((size_t)c.L_max + 8));
         sfx_len = (uint8_t*)take(c.L_max + 8);
+        lc_word = (uint8_t*)take(c.L_max + 8); lc_eq = (uint64_t*)take(8 * ((size_t)c.L_max + 8));
+        lc_max[0] = (int16_t*)take(2 * ((size_t)c.L_max + 8)); lc_max[1] = (int16_t*)take(2 * ((size_t)c.L_max + 8));
         return o;
     }
 };
@@ -467,6 +473,75 @@ struct ReadAligner {
         return nm;
     }
 
+    // --------------------------------------------------------------------------------
+    // Seed complexity filter: is_low_complexity(window) = sdust(window, T = 20, W = 64) reports an interval
+    // (aligner_seeder_methods.cpp:21-29). sdust is not vendored; restated from its definition (oracle:
+    // is_low_complexity, parity unpinned): some interval of l + 1 <= 62 consecutive valid 3-mers has
+    // 10 * sum_t c_t (c_t - 1) / 2 > 20 * l. Computed once per strand: lc_max[b] = the largest start a such
+    // that (a .. b') qualifies for some b' <= b; a window of words [i, i + nt) is low-complexity iff
+    // lc_max[i + nt - 1] >= i.
+    // --------------------------------------------------------------------------------
+    MGB_HD void build_lowcx(int s) {
+        const uint8_t *cd = cx[s].codes;
+        const int n_w = L - 2;
+        if (n_w <= 0) return;
+        uint8_t *wd = m.lc_word; uint64_t *eq = m.lc_eq; int16_t *mx = m.lc_max[s];
+        for (int j = wlane(); j < n_w; j += kWarp) {
+            const uint32_t a = cd[j], b = cd[j + 1], c = cd[j + 2];
+            const bool ok = a >= 1 && a <= 4 && b >= 1 && b <= 4 && c >= 1 && c <= 4;
+            wd[j] = ok ? (uint8_t)(((a - 1) << 4) | ((b - 1) << 2) | (c - 1)) : (uint8_t)0xFF;
+        }
+        wsync();
+        // eq[a] bit d-1: 3-mer a + d equals 3-mer a (d = 1..61, inside the same run of valid 3-mers)
+        for (int a = wlane(); a < n_w; a += kWarp) {
+            uint64_t e = 0;
+            const uint8_t w = wd[a];
+            if (w != 0xFF)
+                for (int d = 1; d <= 61 && a + d < n_w; ++d) {
+                    const uint8_t x = wd[a + d];
+                    if (x == 0xFF) break;
+                    if (x == w) e |= 1ull << (d - 1);
+                }
+            eq[a] = e;
+        }
+        wsync();
+        // largest qualifying start per end: growing the interval to the left by 3-mer a adds the number of its
+        // occurrences in (a, b] to the score
+        for (int base = 0; base < n_w; base += kWarp) {
+            const int b = base + wlane();
+            int best = -1;
+            if (b < n_w && wd[b] != 0xFF) {
+                int r = 0;
+                for (int a = b - 1; a >= 0 && b - a <= 61; --a) {
+                    if (wd[a] == 0xFF) break;
+                    const int span = b - a;
+                    const uint64_t mk = eq[a] & ((1ull << span) - 1ull);
+                    r += popc32((uint32_t)mk) + popc32((uint32_t)(mk >> 32));
+                    if (r * 10 > 20 * span) { best = a; break; }
+                }
+            }
+            if (b < n_w) mx[b] = (int16_t)best;
+        }
+        wsync();
+        // running maximum over the ends
+        int carry = -1;
+        for (int base = 0; base < n_w; base += kWarp) {
+            const int b = base + wlane();
+            int v = b < n_w ? (int)mx[b] : -1;
+            v = imax(wscan_max(v), carry);
+            if (b < n_w) mx[b] = (int16_t)v;
+            carry = wbcast(v, kWarp - 1);
+        }
+        wsync();
+    }
+    // window = characters [i, i + len) of strand s (clamped to the read as substr() does); lane-divergent i allowed
+    MGB_HD bool low_complexity(int s, int i, int len) const {
+        if (len > L - i) len = L - i;
+        const int nt = len - 2;
+        if (nt < 2) return false;
+        return (int)m.lc_max[s][i + nt - 1] >= i;
+    }
+
     // ExactSeeder::get_seeds (:67-93)
     MGB_HD void exact_seeds(int s, int nk) {
         const int k = ix.k;
@@ -474,7 +549,7 @@ struct ReadAligner {
         if (cfg.max_seed_length < (uint32_t)k) return;
         for (int i = 0; i < nk; ++i) {
             uint64_t nd = qnode(s, i);
-            if (nd) push_seed(s, i, k, 0, 1, nd);
+            if (nd && !(cfg.seed_complexity_filter && low_complexity(s, i, k))) push_seed(s, i, k, 0, 1, nd);
         }
     }
 
@@ -582,6 +657,19 @@ struct ReadAligner {
             }
             cx[s].num_matching = nm;
             cx[s].implicit_seeds = 1;
+            if (cfg.seed_complexity_filter) {            // low-complexity k-mers give no seed (:84)
+                total = 0;
+                for (int w = 0; w < nw; ++w) {
+                    unsigned drop = 0;
+                    for (int b = 0; b < 32; b += kWarp) {
+                        int i = 32 * w + b + wlane();
+                        drop |= wballot(i < nk && low_complexity(s, i, k)) << b;
+                    }
+                    mask[w] &= ~drop;
+                    total += popc32(mask[w]);
+                }
+                wsync();
+            }
             // ExactSeeder::get_seeds (:67-93)
             if (L < (int)cfg.min_seed_length || (double)nm < cfg.min_exact_match * L || cfg.max_seed_length < (uint32_t)k)
                 total = 0;
@@ -657,8 +745,10 @@ struct ReadAligner {
             } else if (m.sfx_min[i] != k) {
                 const int min_here = m.sfx_min[i];
                 const int matched = m.sfx_len[i];
-                // call_nodes_with_suffix_matching_longest_prefix (:231-238): nothing below min_match_length
-                if (matched >= min_here && matched > 0) {
+                // call_nodes_with_suffix_matching_longest_prefix (:231-238): nothing below min_match_length;
+                // a low-complexity window of the current minimum length is skipped altogether (:226-229)
+                if (matched >= min_here && matched > 0
+                        && !(cfg.seed_complexity_filter && low_complexity(s, i, min_here))) {
                     uint64_t first_node = 0;
                     // capacity: the scratch copy of the base seeds lives at the end of the array
                     int cnt = suffix_enumerate(s, i, matched, m.sfx_first[i], m.sfx_last[i], &first_node);
@@ -1994,6 +2084,7 @@ struct ReadAligner {
         const bool both = cfg.forward_and_reverse_complement;
         build_psum(0);
         if (both) build_psum(1);
+        if (cfg.seed_complexity_filter) { build_lowcx(0); if (both) build_lowcx(1); }
         MGB_TOC(t_setup, 0);
         MGB_TIC(t_seeds);
         #pragma unroll 1

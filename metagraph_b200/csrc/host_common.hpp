@@ -58,11 +58,6 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConf
     AlphabetTables at;
     if (!alphabet_tables(alphabet, &at)) { *err = "unknown alphabet"; return MGB_ERR_UNSUPPORTED; }
 
-    if (c.seed_complexity_filter) {
-        *err = "seed_complexity_filter requires sdust, which the reference does not vendor; "
-               "run with --align-no-seed-complexity-filter semantics (set it to 0)";
-        return MGB_ERR_UNSUPPORTED;
-    }
     if (!c.global_xdrop) { *err = "global_xdrop = false is not supported"; return MGB_ERR_UNSUPPORTED; }
     if (c.num_alternative_paths < 1 || c.num_alternative_paths > (uint64_t)kMaxAlt) {
         *err = "num_alternative_paths must be in [1, " + std::to_string(kMaxAlt) + "]";
@@ -91,6 +86,8 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConf
     // protein builds compile the reverse-complement strand out (dbg_aligner.cpp:224-229, 289-293)
     d->forward_and_reverse_complement = c.forward_and_reverse_complement && at.has_complement;
     d->allow_left_trim = c.allow_left_trim; d->no_backtrack = c.no_backtrack;
+    // is_low_complexity() is compiled to `false` in protein builds (aligner_seeder_methods.cpp:30-34)
+    d->seed_complexity_filter = c.seed_complexity_filter && at.has_complement;
     d->sigma = at.sigma; d->has_complement = at.has_complement ? 1 : 0;
     std::memcpy(d->letters, at.letters, sizeof(d->letters));
     std::memcpy(d->code_of, at.code_of, sizeof(d->code_of));

@@ -82,6 +82,45 @@ void DBGAlignerConfig::set_blosum62() {
             score_matrix[(int)order[i]][(int)order[j]] = b62[i][j];
 }
 
+// is_low_complexity (aligner_seeder_methods.cpp:21-35) = sdust(seq, T = 20, W = 64) finds at least one
+// interval. sdust (hmusta/sdust, a fork of lh3/sdust = symmetric DUST, Morgulis et al. 2006) is NOT vendored
+// in the reference tree; this restates its published definition — PARITY UNPINNED against the library:
+// over the 3-mers of every maximal A/C/G/T run, an interval of l + 1 consecutive 3-mers (at most W - 2 of
+// them) is low-complexity when 10 * sum_t c_t (c_t - 1) / 2 > T * l, c_t = occurrences of 3-mer t in it;
+// some interval is "perfect" (reported) iff some interval exceeds the threshold.
+bool is_low_complexity(std::string_view s, int T, int W) {
+    auto nt4 = [](char c) -> int {
+        switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+                     case 'T': case 't': case 'U': case 'u': return 3; default: return 4; }
+    };
+    const int max_words = W - 2;
+    std::vector<int> words;          // 3-mer at every position of the current run
+    size_t i = 0;
+    auto scan_run = [&]() -> bool {
+        const int n = (int)words.size();
+        for (int a = 0; a < n; ++a) {
+            int cnt[64] = { 0 };
+            int r = 0;
+            for (int b = a; b < n && b - a < max_words; ++b) {
+                r += cnt[words[b]]++;
+                if (b > a && r * 10 > T * (b - a)) return true;
+            }
+        }
+        return false;
+    };
+    while (i <= s.size()) {
+        int run = 0, w = 0;
+        words.clear();
+        for (; i < s.size() && nt4(s[i]) < 4; ++i) {
+            w = ((w << 2) | nt4(s[i])) & 63;
+            if (++run >= 3) words.push_back(w);
+        }
+        if (scan_run()) return true;
+        ++i;                         // skip the non-ACGT character (or step past the end)
+    }
+    return false;
+}
+
 // aligner_cigar.cpp:11-51: kCharToOp
 static Cigar::Operator char_to_op(const Alphabet &a, char ref, char q) {
     // MATCH iff both are the same valid letter, case-insensitively
@@ -340,7 +379,7 @@ struct SeederBase {
         return nm;
     }
 
-    // ExactSeeder::get_seeds :67-93 (seed complexity filter unsupported: sdust absent)
+    // ExactSeeder::get_seeds :67-93
     std::vector<Seed> exact_seeds() const {
         size_t k = graph.get_k();
         if (num_matching < config.min_exact_match * query.size())
@@ -351,6 +390,9 @@ struct SeederBase {
         size_t end_clipping = query.size() - k;
         for (size_t i = 0; i < query_nodes.size(); ++i, --end_clipping) {
             if (query_nodes[i] != npos) {
+                if (config.seed_complexity_filter && config.alphabet->sigma == 5
+                        && is_low_complexity(query.substr(i, k)))
+                    continue;                                              // :84
                 Seed s;
                 s.query_view = query.substr(i, k);
                 s.nodes = { query_nodes[i] };
@@ -446,6 +488,9 @@ struct SeederBase {
             size_t max_seed_length = std::min({ config.max_seed_length, k - 1, query.size() - i });
             size_t seed_length = 0;
             std::vector<node_index> alt_nodes;
+            if (config.seed_complexity_filter && config.alphabet->sigma == 5
+                    && is_low_complexity(query.substr(i, min_seed_length[i])))
+                continue;                                                  // :226-229
             graph.call_nodes_with_suffix_matching_longest_prefix(
                 query.substr(i, max_seed_length),
                 [&](node_index alt, uint64_t len) { seed_length = len; alt_nodes.push_back(alt); },

@@ -19,6 +19,9 @@ namespace mgo {
 typedef int32_t score_t;
 
 // graph/alignment/aligner_config.hpp:18-94
+// aligner_seeder_methods.cpp:21-35 (protein builds: always false)
+bool is_low_complexity(std::string_view s, int T = 20, int W = 64);
+
 struct DBGAlignerConfig {
     size_t num_alternative_paths = 1;
     size_t min_seed_length = 0;
@@ -40,7 +43,7 @@ struct DBGAlignerConfig {
     bool global_xdrop = true;
     bool allow_left_trim = true;
     bool no_backtrack = false;
-    bool seed_complexity_filter = false; // sdust is un-vendored; parity runs disable it
+    bool seed_complexity_filter = false; // sdust is un-vendored: restated from its definition, parity unpinned (mgo_align.cpp)
     int8_t score_matrix[128][128];
     const Alphabet *alphabet = &Alphabet::dna();
 

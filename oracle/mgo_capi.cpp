@@ -153,6 +153,9 @@ void mgo_node_sequence(void *g, uint64_t node, char *out) {
 }
 
 // Seeds of one strand: returns count; each seed -> (clipping, length, offset, first node, num nodes)
+// is_low_complexity (aligner_seeder_methods.cpp:21-29) on a raw character string
+int mgo_is_low_complexity(const char *seq, uint64_t len) { return is_low_complexity(std::string_view(seq, len)) ? 1 : 0; }
+
 uint64_t mgo_seeds(void *gp, const char *alphabet, const mgo_config_t *cfg, const char *seq,
                    uint64_t len, int orientation, uint64_t *out, uint64_t max_out,
                    uint64_t *num_matching) {

@@ -160,6 +160,12 @@ class OracleGraph:
         return lines[:-1]
 
 
+def is_low_complexity(seq):
+    """oracle restatement of sdust(seq, T=20, W=64) finding at least one interval"""
+    b = seq.encode() if isinstance(seq, str) else seq
+    return bool(lib().mgo_is_low_complexity(b, len(b)))
+
+
 def parse_tsv_line(line, with_nodes=False):
     """-> (header, query, [alignments]) each alignment = dict(strand, seq, score, nm, cigar, offset[, nodes])"""
     f = line.split("\t")

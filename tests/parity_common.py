@@ -128,6 +128,54 @@ def c1_case(lib, n_transcripts, max_len, seed=7, k=12):
     return len(seqs), full
 
 
+def lowcx_genome(rng, n):
+    """random sequence interleaved with homopolymers, di-/tri-nucleotide repeats and the odd N"""
+    out = []
+    while sum(len(x) for x in out) < n:
+        y = rng.random()
+        if y < 0.5:
+            out.append("".join(np.array(list("ACGT"))[rng.integers(0, 4, int(rng.integers(20, 120)))]))
+        elif y < 0.65:
+            out.append("ACGT"[int(rng.integers(0, 4))] * int(rng.integers(5, 40)))
+        elif y < 0.85:
+            u = "".join(np.array(list("ACGT"))[rng.integers(0, 4, int(rng.integers(2, 5)))])
+            out.append(u * int(rng.integers(3, 15)))
+        else:
+            out.append("".join(np.array(list("ACGT"))[rng.integers(0, 4, 12)]))
+    return "".join(out)[:n]
+
+
+def lowcx_case(lib, seed, k, exact):
+    rng = np.random.default_rng(seed)
+    seqs = [lowcx_genome(rng, 6000), lowcx_genome(rng, 3000)]
+    g = O.OracleGraph(k, seqs)
+    boss = BOSSTable.from_sequences(k, seqs, lib=lib)
+    idx = DBGSuccinctIndex(boss, lib=lib)
+    kw = dict(min_exact_match=0.0, seed_complexity_filter=True)
+    if exact:
+        kw.update(min_seed_length=k, max_seed_length=k)
+    cfg = cli_defaults(k, **kw)
+    reads = []
+    for i in range(60):
+        s_ = seqs[i % 2]
+        p = int(rng.integers(0, len(s_) - 150))
+        r = mutate(rng, s_[p:p + 150], 0.03)
+        if i % 3 == 0:
+            r = r.translate(COMP)[::-1]
+        if i % 11 == 5:
+            r = r[:70] + "N" + r[71:]
+        reads.append(r)
+    reads += ["A" * 150, "CA" * 60, "ACG" * 40, "", "AC"]
+    exp_on = g.align_tsv(cfg, reads, with_nodes=True)
+    got, _ = run_lines(idx, cfg, reads)
+    bad = [i for i in range(len(reads)) if exp_on[i] != got[i]]
+    assert not bad, (seed, bad[:3], exp_on[bad[0]][:200], got[bad[0]][:200])
+    cfg.seed_complexity_filter = False
+    exp_off = g.align_tsv(cfg, reads, with_nodes=True)
+    idx.close()
+    return sum(a != b for a, b in zip(exp_on, exp_off))      # reads whose result the filter changes
+
+
 AA = "ACDEFGHIKLMNPQRSTVWY"
 
 

@@ -49,6 +49,13 @@ def test_generic_layout_on_dna_emu(monkeypatch):
         P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_seed_complexity_filter_emu():
+    """CLI default `seed_complexity_filter` (sdust restated from its definition, parity with the library
+    unpinned): kernels vs oracle on reads and graphs full of homopolymers / short tandem repeats."""
+    for seed, k, exact in ((31, 15, False), (32, 21, True), (33, 31, False)):
+        P.lowcx_case(EMU, seed, k, exact)
+
+
 def test_c1_shape_emu():
     """configs[0] shape: transcripts aligned to their own k=12 graph, ragged lengths up to 2.5 kbp
     (longer than the on-chip column buffers: the arena scratch and unstaged-query paths run)."""
@@ -72,7 +79,7 @@ def test_unsupported_configs_fail_loudly():
     from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex, B200Aligner
     from metagraph_b200.config import struct_defaults
     idx = DBGSuccinctIndex(BOSSTable.from_sequences(4, ["AGCTTCGAGGCCAA"], lib=EMU), lib=EMU)
-    for kw, code in ((dict(seed_complexity_filter=True), -4), (dict(global_xdrop=False), -4),
+    for kw, code in ((dict(global_xdrop=False), -4),
                      (dict(num_alternative_paths=99), -4), (dict(min_cell_score=-2**31), -3)):
         with pytest.raises(_lib.MgbError) as e:
             B200Aligner(idx, struct_defaults(**kw)).align("AGCTTCGAGG")

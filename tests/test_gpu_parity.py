@@ -43,6 +43,12 @@ def test_generic_layout_on_dna_gpu(monkeypatch):
         P.random_case(LIB, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_seed_complexity_filter_gpu():
+    """seed complexity filter on (CLI default): kernels vs oracle on low-complexity inputs."""
+    for seed, k, exact in ((31, 15, False), (32, 21, True), (33, 31, False)):
+        P.lowcx_case(LIB, seed, k, exact)
+
+
 def test_c1_shape_gpu():
     """configs[0] shape: transcripts (59 bp .. 11 666 bp, the range of transcripts_1000.fa) aligned to
     their own k=12 graph at CLI defaults."""
