@@ -48,6 +48,7 @@ namespace kern_any {
 cudaError_t launch_radj_bwd(unsigned grid, const mgb::RadjArgs &a);
 cudaError_t launch_sfx_extend(unsigned grid, const mgb::SfxArgs &a);
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
+cudaError_t launch_premap(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
 cudaError_t launch_subk(unsigned grid, cudaStream_t s, const mgb::SubkArgs &a, uint32_t chunks_per_strand);
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const mgb::AlignArgs &a);
 cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm);
@@ -562,14 +563,33 @@ int launch_prepare(const mgb_index_t *index, const Batch &b, Stream &st, int num
     return 0;
 }
 
-int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, Stream &st) {
-    SeedArgs a { index->view, b.cf, b.cr, b.offsets, b.koff, b.nodes_f, b.nodes_r, b.n_reads, n_strands };
+int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, Stream &st, DevBufs &bufs,
+                uint64_t *n_launches = nullptr) {
+    SeedArgs a { index->view, b.cf, b.cr, b.offsets, b.koff, b.nodes_f, b.nodes_r, b.n_reads, n_strands, 0, nullptr, nullptr };
     uint64_t items = (uint64_t)b.n_reads * n_strands;
+    // first pass (k_premap): rules out the k-mers the suffix-range table has no node for; the node arrays
+    // are zero-filled, so the second pass only visits what is left
+    const bool premap = index->view.sfx_len && index->view.sfx_len <= index->view.k - 1 && b.total_kmers
+                        && !std::getenv("MGB_TEST_NOPREMAP");
+    if (premap) {
+        const size_t words = (size_t)(b.total_kmers >> 5) + b.n_reads + 2;
+        int rc;
+        if ((rc = bufs.alloc(&a.hint_f, words))) return rc;
+        if (n_strands > 1 && (rc = bufs.alloc(&a.hint_r, words))) return rc;
+        a.hinted = 1;
+    }
+    if (n_launches) *n_launches += premap ? 2 : 1;
 #if defined(MGB_HOST_EMU)
     (void)st;
+    if (premap)
+        for (uint64_t it = 0; it < items; ++it) premap_item(a, (uint32_t)(it / n_strands), (uint32_t)(it % n_strands));
     for (uint64_t it = 0; it < items; ++it) seed_item(a, it);
 #else
     if (!items) return 0;
+    if (premap) {
+        const uint64_t pb = std::min<uint64_t>((items + 7) / 8, (uint64_t)index->num_sms * 16);
+        CUDA_TRY(index->view.wide ? kern_any::launch_premap((unsigned)pb, st.s, a) : kern_dna::launch_premap((unsigned)pb, st.s, a));
+    }
     // 32 quads per block; enough blocks to fill the machine, grid-stride beyond that
     uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
     CUDA_TRY(index->view.wide ? kern_any::launch_seed((unsigned)blocks, st.s, a) : kern_dna::launch_seed((unsigned)blocks, st.s, a));
@@ -598,7 +618,7 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
         rc = upload_batch(index, seqs, offsets, n_seqs, false, st, bufs, &b, &koff, &stats);
         if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
         if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
-        if (!rc) rc = launch_seed(index, b, 1, st);
+        if (!rc) rc = launch_seed(index, b, 1, st, bufs);
         if (!rc) rc = d2h(out_nodes, b.nodes_f, b.total_kmers * 8, st);
 #if !defined(MGB_HOST_EMU)
         if (!rc) { cudaError_t e = cudaStreamSynchronize(st.s); if (e != cudaSuccess) rc = fail(MGB_ERR_CUDA, cudaGetErrorString(e)); }
@@ -687,8 +707,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
         cudaEventRecord(ev[1], st.s);
 #endif
         if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
-        if (!rc && map_nodes) rc = launch_seed(index, b, both ? 2 : 1, st);
-        res->stats.kernel_launches += 1 + (map_nodes ? 1 : 0);
+        res->stats.kernel_launches += 1;
+        if (!rc && map_nodes) rc = launch_seed(index, b, both ? 2 : 1, st, bufs, &res->stats.kernel_launches);
         // sub-k seeding (min_seed_length < k): the independent index_range lookups run GPU-wide first
         SubkArgs sk;
         std::memset(&sk, 0, sizeof(sk));

@@ -48,6 +48,8 @@ struct SeedArgs {
     IndexView ix;
     const uint8_t *cf, *cr; const uint64_t *offsets; const uint64_t *koff;
     uint64_t *nodes_f, *nodes_r; uint32_t n_reads; uint32_t n_strands;
+    uint32_t hinted;           // 1: k_premap ran, hint_f / hint_r hold its verdicts
+    uint32_t *hint_f, *hint_r;
 };
 
 MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
@@ -55,7 +57,26 @@ MGB_HD void seed_item(const SeedArgs &a, uint64_t item) {
     uint32_t s = (uint32_t)(item % a.n_strands);
     const uint64_t b = a.offsets[r];
     const int L = (int)(a.offsets[r + 1] - b);
-    map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r]);
+    const uint32_t *hints = a.hinted ? (s ? a.hint_r : a.hint_f) + (a.koff[r] >> 5) + r : nullptr;
+    map_to_edges(a.ix, (s ? a.cr : a.cf) + b, L, (s ? a.nodes_r : a.nodes_f) + a.koff[r], hints);
+}
+// first pass (premap_kmer) for strand s of read r: one k-mer per lane, one hint word per 32 k-mers
+// (the words of read r start at word koff[r] / 32 + r of the strand's hint array)
+MGB_HD void premap_item(const SeedArgs &a, uint32_t r, uint32_t s) {
+    const uint64_t b = a.offsets[r];
+    const int L = (int)(a.offsets[r + 1] - b);
+    const int nk = L - (int)a.ix.k + 1;
+    if (nk <= 0) return;
+    const uint8_t *codes = (s ? a.cr : a.cf) + b;
+    uint32_t *hw = (s ? a.hint_r : a.hint_f) + (a.koff[r] >> 5) + r;
+    for (int base = 0; base < nk; base += 32) {
+        unsigned word = 0;
+        for (int o = 0; o < 32; o += kWarp) {                 // one pass on the device
+            const int i = base + o + wlane();
+            word |= wballot(i < nk && premap_kmer(a.ix, codes, i) != 0) << o;
+        }
+        if (wlane() == 0) hw[base >> 5] = word;
+    }
 }
 
 // Sub-k seeding, lookup part (SuffixSeeder::generate_seeds, aligner_seeder_methods.cpp:215-238 ->
@@ -252,6 +273,14 @@ __global__ void __launch_bounds__(128) k_subk(SubkArgs a, uint32_t chunks_per_st
     }
 }
 
+// one warp per read strand
+__global__ void __launch_bounds__(256) k_premap(SeedArgs a) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t items = (uint64_t)a.n_reads * a.n_strands;
+    for (uint64_t it = warp; it < items; it += nwarps) premap_item(a, (uint32_t)(it / a.n_strands), (uint32_t)(it % a.n_strands));
+}
+
 __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
     uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
@@ -290,6 +319,7 @@ cudaError_t launch_subk(unsigned grid, cudaStream_t s, const SubkArgs &a, uint32
     k_subk<<<grid, 128, 0, s>>>(a, chunks_per_strand);
     return cudaGetLastError();
 }
+cudaError_t launch_premap(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_premap<<<grid, 256, 0, s>>>(a); return cudaGetLastError(); }
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_seed<<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const AlignArgs &a) {
     k_align<<<grid, 128, smem_block, s>>>(a);

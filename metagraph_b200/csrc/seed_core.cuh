@@ -40,12 +40,45 @@ MGB_HD uint8_t sanitize_char(uint8_t ch) {
     return (ch >= 'a' && ch <= 'z') ? ch - 32 : ch;
 }
 
+// First pass of the exact seeding, one k-mer per thread: can the k-mer at codes[i..i+K) exist at all?
+// 0 = no (an invalid character in it, or the suffix-range table has no node for its first sfx_len
+// characters -> BOSS::index returns 0, boss.hpp:695-718), 1 = maybe. On a strand that does not match the
+// graph nearly every k-mer ends here, with one table load and no dependent chain; map_to_edges() below
+// only resolves the rest. Results are unchanged: a k-mer's node does not depend on how it is looked up.
+MGB_HD uint64_t premap_kmer(const IndexView &ix, const uint8_t *codes, int i) {
+    const int K = (int)ix.k;
+    const int S = (ix.sfx_len && (int)ix.sfx_len <= K - 1) ? (int)ix.sfx_len : 0;
+    bool zero = false;
+    for (int j = 0; j < K; ++j) {
+        const uint32_t c = codes[i + j];
+        if (c >= ix.sigma) return 0;
+        zero |= c == 0;
+    }
+    if (!S || zero) return 1;
+    const uint64_t base = ix.sigma - 1;
+    uint64_t slot = 0;
+    for (int j = S - 1; j >= 0; --j) slot = slot * base + (codes[i + j] - 1);
+    const uint32_t rl = ldg32(ix.sfx + 2 * slot), ru1 = ldg32(ix.sfx + 2 * slot + 1);
+    return rl < ru1 ? 1 : 0;                             // [rl, ru1) non-empty
+}
+
 // map_to_edges for codes[0..L). Writes L - K + 1 node ids (validate_edge applied) to `out`
 // and, if `flags` != nullptr, per k-mer bit0 = "BOSS fwd() of this edge lands on a node with
 // more than one outgoing edge" when the walk continued from it (used for the UniMEM
 // terminator, dbg_succinct.cpp:617-630 has_multiple_outgoing).
 // All lanes of the group execute this with identical arguments; lane 0 of the group stores.
-MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint64_t *out) {
+// hints (optional): bit i = premap_kmer() of k-mer i (first pass); k-mers whose bit is clear are known to
+// be absent, `out` is zero-filled beforehand, and the cold search jumps from set bit to set bit.
+MGB_HD int next_hint(const uint32_t *hints, int n, int pos) {
+    while (pos < n) {
+        const uint32_t w = hints[pos >> 5] >> (pos & 31);
+        if (w) return pos + ffs32(w) - 1;
+        pos = (pos | 31) + 1;
+    }
+    return n;
+}
+MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint64_t *out,
+                         const uint32_t *hints = nullptr) {
     const int K = (int)ix.k;
     if (L < K) return;
     const bool writer = glane() == 0;
@@ -63,12 +96,22 @@ MGB_HD void map_to_edges(const IndexView &ix, const uint8_t *codes, int L, uint6
     uint64_t top = 1;                                  // base^(S-1)
     for (int j = 1; j < S; ++j) top *= base;
     uint64_t slot = 0; int slot_at = -1 - S;           // window start the slot belongs to
+    const int nk = L - K + 1;
     for (int i = 0; i + K <= L; ++i) {
-        if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
-        if (codes[i + K - 1] == 0) last_zero = i + K - 1;
-        if (last_inv >= i) {              // invalid[i + k_]
-            if (writer) out[i] = 0;
-            continue;
+        if (hints) {
+            // jump to the next k-mer the first pass left open: it has no invalid character, so the
+            // trackers (only ever compared with the current position) need no update for the gap
+            i = next_hint(hints, nk, i);
+            if (i >= nk) break;
+            last_zero = -1;
+            for (int j = 0; j < K; ++j) if (codes[i + j] == 0) last_zero = i + j;
+        } else {
+            if (codes[i + K - 1] >= ix.sigma) last_inv = i + K - 1;
+            if (codes[i + K - 1] == 0) last_zero = i + K - 1;
+            if (last_inv >= i) {              // invalid[i + k_]
+                if (writer) out[i] = 0;
+                continue;
+            }
         }
         // map_to_edge (boss.hpp:766-777); all K codes are valid here
         uint64_t edge;
