@@ -176,6 +176,41 @@ def lowcx_case(lib, seed, k, exact):
     return sum(a != b for a, b in zip(exp_on, exp_off))      # reads whose result the filter changes
 
 
+def concurrent_case(lib):
+    """cli/align.cpp:440-475 runs align_batch from several worker threads on one shared graph: mgb_align_batch
+    must be re-entrant (per-call workspaces, thread-local error state)."""
+    import threading
+    rng = np.random.default_rng(3)
+    genome = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 8000)])
+    k = 21
+    g = O.OracleGraph(k, [genome])
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(k, [genome], lib=lib), lib=lib)
+    cfg = cli_defaults(k, min_exact_match=0.0)
+    batches = []
+    for t in range(6):
+        reads = []
+        for i in range(25):
+            p = int(rng.integers(0, len(genome) - 120))
+            r = mutate(rng, genome[p:p + 120], 0.04)
+            reads.append(r.translate(COMP)[::-1] if i % 2 else r)
+        batches.append(reads)
+    exp = [g.align_tsv(cfg, b) for b in batches]
+    got = [None] * len(batches)
+
+    def work(t):
+        al = B200Aligner(idx, cfg)
+        got[t] = [format_alignment("", r, cfg.min_path_score) for r in al.align_batch([("", x) for x in batches[t]])]
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(len(batches))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert got == exp
+    idx.close()
+
+
+
 AA = "ACDEFGHIKLMNPQRSTVWY"
 
 

@@ -74,6 +74,12 @@ def test_random_emu_in_pieces(monkeypatch):
     P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_concurrent_callers_emu():
+    """cli/align.cpp:440-475 runs align_batch from several worker threads on one shared graph: mgb_align_batch
+    must be re-entrant (per-call workspaces, thread-local error state)."""
+    P.concurrent_case(EMU)
+
+
 def test_unsupported_configs_fail_loudly():
     from metagraph_b200 import _lib
     from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex, B200Aligner

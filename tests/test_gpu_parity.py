@@ -49,6 +49,11 @@ def test_seed_complexity_filter_gpu():
         P.lowcx_case(LIB, seed, k, exact)
 
 
+def test_concurrent_callers_gpu():
+    """several host threads call mgb_align_batch on one index at the same time (cli/align.cpp:440-475)"""
+    P.concurrent_case(LIB)
+
+
 def test_c1_shape_gpu():
     """configs[0] shape: transcripts (59 bp .. 11 666 bp, the range of transcripts_1000.fa) aligned to
     their own k=12 graph at CLI defaults."""
