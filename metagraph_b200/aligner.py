@@ -167,6 +167,161 @@ class Alignment:
                                            self.get_num_matches(), self.get_cigar_string(), self.offset)
 
 
+_COMP = {}
+for _f, _t in zip("ABCDGHKMRTUVY", "TVGHCDMKYAABR"):      # COMPL_TAB (seq_tools/reverse_complement.hpp:31-48)
+    _COMP[_f] = _t
+    _COMP[_f.lower()] = _t.lower()
+_COMP["`"] = "@"
+
+
+def reverse_complement(seq):
+    return "".join(_COMP.get(c, c) for c in reversed(seq))
+
+
+def _json_value(v):
+    """Json::StreamWriterBuilder with indentation "" (jsoncpp): sorted keys, no blanks, doubles as %.17g"""
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, int):
+        return str(v)
+    if isinstance(v, float):
+        t = "%.17g" % v
+        return t if any(c in t for c in ".en") else t + ".0"
+    if isinstance(v, str):
+        out = ['"']
+        for ch in v:
+            if ch in '"\\':
+                out.append("\\" + ch)
+            elif ch == "\n":
+                out.append("\\n")
+            elif ch == "\t":
+                out.append("\\t")
+            elif ord(ch) < 0x20:
+                out.append("\\u%04x" % ord(ch))
+            else:
+                out.append(ch)
+        out.append('"')
+        return "".join(out)
+    if isinstance(v, list):
+        return "[" + ",".join(_json_value(x) for x in v) + "]"
+    return "{" + ",".join(_json_value(k) + ":" + _json_value(v[k]) for k in sorted(v)) + "}"
+
+
+def _path_json(nodes, cigar, node_size, query_view, offset, label):
+    """path_json (alignment.cpp:704-880), derived there from GraphAligner's vg.proto"""
+    ops = [(int(x) & 7, int(x) >> 3) for x in cigar]          # (Cigar::Operator, length); 0 = CLIPPED
+    it = 1 if ops and ops[0][0] == 0 else 0
+    cigar_offset = 0
+    qpos = 0
+    path = {"mapping": []}
+    cur_pos = offset
+    position = {"node_id": int(nodes[0])}
+    if cur_pos:
+        position["offset"] = cur_pos
+    mapping = {"position": position, "edit": []}
+    while cur_pos < node_size and it < len(ops):                # the first node
+        op, n = ops[it]
+        if op == 0:                                             # trailing clipping
+            it += 1
+            cigar_offset = 0
+            continue
+        next_pos = min(node_size, cur_pos + (n - cigar_offset))
+        next_size = next_pos - cur_pos
+        edit = {}
+        if op == 1:                                             # MISMATCH
+            edit = {"from_length": next_size, "to_length": next_size, "sequence": query_view[qpos:qpos + next_size]}
+            qpos += next_size
+        elif op == 4:                                           # INSERTION
+            edit = {"to_length": next_size, "sequence": query_view[qpos:qpos + next_size]}
+            qpos += next_size
+            next_pos = cur_pos
+        elif op == 3:                                           # DELETION
+            edit = {"from_length": next_size}
+        elif op == 2:                                           # MATCH
+            edit = {"from_length": next_size, "to_length": next_size}
+            qpos += next_size
+        cigar_offset += next_size
+        cur_pos = next_pos
+        mapping["edit"].append(edit)
+        if cigar_offset == n:
+            it += 1
+            cigar_offset = 0
+    rank = 1
+    mapping["rank"] = rank
+    if not mapping["edit"]:
+        del mapping["edit"]
+    path["mapping"].append(mapping)
+    for node in nodes[1:]:                                      # one character per further node
+        rank += 1
+        mapping = {"position": {"node_id": int(node), "offset": node_size - 1}, "edit": []}
+        op, n = ops[it]
+        if op in (4, 0):
+            length = n - cigar_offset
+            mapping["edit"].append({"to_length": length, "sequence": query_view[qpos:qpos + length]})
+            qpos += length
+            it += 1
+            cigar_offset = 0
+            op, n = ops[it]
+        if op == 1:
+            edit = {"from_length": 1, "to_length": 1, "sequence": query_view[qpos:qpos + 1]}
+            qpos += 1
+        elif op == 3:
+            edit = {"from_length": 1}
+        else:
+            edit = {"from_length": 1, "to_length": 1}
+            qpos += 1
+        cigar_offset += 1
+        if cigar_offset == n:
+            cigar_offset = 0
+            it += 1
+        mapping["edit"].append(edit)
+        mapping["rank"] = rank
+        path["mapping"].append(mapping)
+    path["length"] = len(nodes)
+    if int(nodes[0]) == int(nodes[-1]):
+        path["is_circular"] = True
+    path["name"] = label
+    return path
+
+
+def alignment_to_json(a, strand_query, node_size, is_secondary, read_name, label=""):
+    """Alignment::to_json (alignment.cpp:882-963). strand_query = the query strand `a` was aligned to
+    (a None alignment gives the record of an unaligned read)."""
+    out = {"name": read_name, "sequence": strand_query}
+    if a is None:
+        return out
+    if a.sequence:
+        out.setdefault("annotation", {})["ref_sequence"] = a.sequence
+    if not a.query_len:
+        return out
+    out.setdefault("annotation", {})["cigar"] = a.get_cigar_string()
+    view = strand_query[a.query_begin:a.query_begin + a.query_len]
+    if len(a.nodes):
+        out["path"] = _path_json(a.nodes, a.cigar, node_size, view, a.offset, label)
+    out["score"] = int(a.score)
+    if a.query_begin:
+        out["query_position"] = int(a.query_begin)
+        out["soft_clipped"] = True
+    if is_secondary:
+        out["is_secondary"] = True
+    out["identity"] = a.get_num_matches() / a.query_len if a.query_len else 0.0
+    out["read_mapped"] = bool(a.query_len)
+    if a.orientation:
+        out["read_on_reverse_strand"] = True
+    return out
+
+
+def format_alignment_json(header, paths, k):
+    """cli/align.cpp:289-304, JSON branch: one line per alignment (without the trailing newline)"""
+    lines = []
+    for i, a in enumerate(paths):
+        q = reverse_complement(paths.get_query()) if a.orientation else paths.get_query()
+        lines.append(_json_value(alignment_to_json(a, q, k, i > 0, header)))
+    if not paths:
+        lines.append(_json_value(alignment_to_json(None, "", k, False, header)))
+    return "\n".join(lines)
+
+
 class AlignmentResults(list):
     """Alignments of one read (alignment.hpp:366-406)."""
 

@@ -146,7 +146,7 @@ def struct_defaults(**kw):
     return DBGAlignerConfig(**kw)
 
 
-def cli_defaults(k, alphabet="dna", **kw):
+def cli_defaults(k, alphabet="dna", edit_distance=False, **kw):
     """`metagraph align` defaults: match 2, mismatch -3/-3, gaps -6/-2, end bonus 5, xdrop 27,
     rel_score_cutoff 0.95, min_seed 19 (capped at k), max_seed inf, 1000 seeds/locus,
     5 nodes/char, 200 MB, min_exact_match 0.7; seed complexity filter off here (the CLI default is on; pass
@@ -162,5 +162,8 @@ def cli_defaults(k, alphabet="dna", **kw):
     if alphabet == "protein":
         d["score_matrix"] = blosum62_scoring_matrix()
         d["forward_and_reverse_complement"] = False
+    if edit_distance:        # --align-edit-distance (DBGAlignerConfig::set_scoring_matrix, aligner_config.cpp:128-148)
+        d["score_matrix"] = unit_scoring_matrix(1, "ABCDEFGHIJKLMNOPQRSTUVWYZ" if alphabet == "protein" else "ACGT")
+        d["left_end_bonus"] = d["right_end_bonus"] = 0
     d.update(kw)
     return DBGAlignerConfig(**d)
