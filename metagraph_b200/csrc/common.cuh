@@ -17,13 +17,11 @@
 #define MGB_HD __device__ __forceinline__
 #define MGB_D __device__ __forceinline__
 #define MGB_HOSTDEV __host__ __device__ __forceinline__
-#define MGB_COLD __device__ __noinline__
 #define MGB_DEVICE_CODE 1
 #else
 #define MGB_HD inline
 #define MGB_D inline
 #define MGB_HOSTDEV inline
-#define MGB_COLD inline
 #define MGB_DEVICE_CODE 0
 #endif
 
