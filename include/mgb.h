@@ -140,7 +140,9 @@ uint32_t mgb_index_k(const mgb_index_t *index);
 
 /* Default configs. mgb_config_init = DBGAlignerConfig{} + dna_scoring_matrix(2,-1,-2)
  * (what the reference unit tests use); mgb_config_init_cli = `metagraph align` defaults
- * (cli/config/config.hpp:114-145) for a graph with k-mer length k. */
+ * (cli/config/config.hpp:114-145) for a graph with k-mer length k: DNA match 2 / mismatch -3, protein
+ * BLOSUM62 and forward strand only. seed_complexity_filter is left 0 (the CLI turns it on; its sdust
+ * dependency is restated here) — set it to 1 for flag-free `metagraph align` behaviour. */
 void mgb_config_init(mgb_config_t *config);
 void mgb_config_init_cli(mgb_config_t *config, uint32_t k, int alphabet);
 

@@ -489,7 +489,6 @@ void mgb_config_init(mgb_config_t *c) {
 }
 
 void mgb_config_init_cli(mgb_config_t *c, uint32_t k, int alphabet) {
-    (void)alphabet;
     mgb_config_init(c);
     c->min_seed_length = k < 19 ? k : 19;           // cli/align.cpp:42-43
     c->max_seed_length = UINT64_MAX;
@@ -503,6 +502,10 @@ void mgb_config_init_cli(mgb_config_t *c, uint32_t k, int alphabet) {
     c->left_end_bonus = 5; c->right_end_bonus = 5;
     std::memset(c->score_matrix, -3, sizeof(c->score_matrix));
     for (const char *p = "ACGT"; *p; ++p) c->score_matrix[(int)*p][(int)*p] = 2;
+    if (alphabet == MGB_ALPHABET_PROTEIN) {              // set_scoring_matrix (aligner_config.cpp:128-163)
+        blosum62_matrix(c->score_matrix);
+        c->forward_and_reverse_complement = 0;           // no reverse complement (dbg_aligner.cpp:224-229)
+    }
 }
 
 } // extern "C"

@@ -44,6 +44,8 @@ def test_config_defaults_match_library():
     assert bytes(c) == bytes(cli_defaults(31).to_c())
     L.mgb_config_init_cli(ctypes.byref(c), 11, 0)
     assert bytes(c) == bytes(cli_defaults(11).to_c())
+    L.mgb_config_init_cli(ctypes.byref(c), 10, 1)                     # protein: BLOSUM62, forward strand only
+    assert bytes(c) == bytes(cli_defaults(10, alphabet="protein").to_c())
 
 
 def test_missing_library_fails_loudly():
