@@ -1951,27 +1951,30 @@ struct ReadAligner {
                 const int n_ext = extend(it ? be : fe, it ? SLOT_EXT + r : SLOT_SEED,
                                          it ? get_min_path_score() : mps_fwd, it != 0, it ? SLOT_BWD : SLOT_EXT);
                 if (overflow) return;
-                if (it == 0) {
-                    for (int r0 = 0; r0 < n_ext; ++r0) {
-                        const int slot = SLOT_EXT + r0;
-                        if (!both || sm.slots[slot].h->score >= get_min_path_score()) agg_add(slot);
-                        if (!both) continue;
-                        if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
+                // results of this extension: one loop (and one agg_add site: the aggregator's comparison
+                // code is large) for the forward case (aggregate, then reverse-complement the clipped
+                // ones for the backward pass) and the backward case (reverse-complement back, then aggregate)
+                for (int r0 = 0; r0 < n_ext; ++r0) {
+                    const int slot = (it ? SLOT_BWD : SLOT_EXT) + r0;
+                    bool add;
+                    if (it == 0) {
+                        add = !both || sm.slots[slot].h->score >= get_min_path_score();
+                    } else {
                         if (!reverse_complement_slot(slot)) continue;
-                        if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
-                        ++n_rc;
+                        const AlnHdr h = *sm.slots[slot].h;
+                        int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
+                        for (int t = 0; t < h.n_nodes && !overflow; ++t)
+                            filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                        add = true;
                     }
-                    continue;
-                }
-                for (int b = 0; b < n_ext; ++b) {
-                    const int slot = SLOT_BWD + b;
+                    if (add) agg_add(slot);
+                    if (it != 0 || !both) continue;
+                    if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
                     if (!reverse_complement_slot(slot)) continue;
-                    const AlnHdr h = *sm.slots[slot].h;
-                    int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
-                    for (int t = 0; t < h.n_nodes && !overflow; ++t)
-                        filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
-                    agg_add(slot);
+                    if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
+                    ++n_rc;
                 }
+                if (it == 0) continue;
                 for (int r2 = r + 1; r2 < n_rc; ++r2) {
                     AlnSlot &a = sm.slots[SLOT_EXT + r2];
                     if (!a.h->used) continue;
