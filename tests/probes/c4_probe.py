@@ -2,7 +2,7 @@
 vs a graph of a uniform random protein sequence; alphabet-generic kernels. Prints device times and the CPU
 restatement's rate on a bounded sample (parity of the sample is checked too)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex, format_alignment

@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe: synthetic graph + reads, parity on a sample vs the oracle, timings."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from metagraph_b200.aligner import *
