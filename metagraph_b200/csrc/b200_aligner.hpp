@@ -32,9 +32,23 @@ class B200Graph {
     // W / last / F exactly as boss::BOSS holds them (boss.hpp:499-525); valid = dummy mask or
     // nullptr (`metagraph align` drops it, cli/align.cpp:335-339)
     B200Graph(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, const uint64_t *F,
-              const uint8_t *valid, uint32_t k, int device = 0) : k_(k) {
-        if (mgb_index_create(W, last, n_plus_1, F, valid, k, MGB_ALPHABET_DNA, 0, device, &index_) != MGB_OK)
+              const uint8_t *valid, uint32_t k, int device = 0, int alphabet = MGB_ALPHABET_DNA) : k_(k) {
+        if (mgb_index_create(W, last, n_plus_1, F, valid, k, alphabet, 0, device, &index_) != MGB_OK)
             throw std::runtime_error(mgb_last_error());
+    }
+    // A graph file written by `metagraph build` (DBGSuccinct::load, dbg_succinct.cpp:690-712), for callers
+    // that do not link MetaGraph. BASIC-mode graphs only.
+    explicit B200Graph(const std::string &dbg_path, int device = 0) {
+        mgb_boss_t boss;
+        int mode = -1, state = -1;
+        if (mgb_dbg_load(dbg_path.c_str(), &boss, &mode, &state) != MGB_OK)
+            throw std::runtime_error(std::string("cannot load ") + dbg_path + ": " + mgb_dbg_last_error());
+        k_ = boss.k;
+        int rc = mode == 0 ? mgb_index_create(boss.W, boss.last, boss.n_plus_1, boss.F, nullptr, boss.k,
+                                              boss.alphabet, 0, device, &index_) : MGB_ERR_UNSUPPORTED;
+        mgb_boss_free(&boss);
+        if (mode != 0) throw std::runtime_error("only BASIC-mode graphs are supported (CANONICAL / PRIMARY: not yet)");
+        if (rc != MGB_OK) throw std::runtime_error(mgb_last_error());
     }
 #ifdef MGB_WITH_METAGRAPH
     // Flatten a loaded DBGSuccinct (get_W / get_last / get_F are public on boss::BOSS).
@@ -50,7 +64,8 @@ class B200Graph {
             for (uint64_t i = 1; i < n1; ++i) valid[i] = (*dbg.get_mask())[i];
         }
         if (mgb_index_create(W.data(), last.data(), n1, F.data(), valid.empty() ? nullptr : valid.data(),
-                             k_, MGB_ALPHABET_DNA, 0, device, &index_) != MGB_OK)
+                             k_, boss.alph_size == 27 ? MGB_ALPHABET_PROTEIN : MGB_ALPHABET_DNA, 0, device,
+                             &index_) != MGB_OK)
             throw std::runtime_error(mgb_last_error());
     }
 #endif

@@ -7,7 +7,7 @@
 
 #include "../../metagraph_b200/csrc/b200_aligner.hpp"
 
-int main() {
+int main(int argc, char **argv) {
     const std::string ref = "AGCTTCGAGGCCAA";
     uint64_t offsets[2] = { 0, ref.size() };
     mgb_boss_t boss;
@@ -36,5 +36,16 @@ int main() {
     cfg.min_cell_score = INT32_MIN;
     bool thrown = false;
     try { mgb_shim::B200Aligner(graph, cfg).align("AGCTTCGAGG"); } catch (const std::runtime_error&) { thrown = true; }
-    return (n == 2 && bad == 0 && thrown) ? 0 : 1;
+    // a graph file written by the reference (examples/data/graphs/test_DNA_graph.dbg, k = 20): every
+    // query of examples/data/test_DNA_query.fa is a path of the graph
+    int dbg_bad = 0;
+    if (argc > 1) {
+        mgb_shim::B200Graph g2(std::string(argv[1]));
+        mgb_config_t c2;
+        mgb_config_init_cli(&c2, g2.get_k(), MGB_ALPHABET_DNA);
+        auto res = mgb_shim::B200Aligner(g2, c2).align("ACGTACGTACGTACGTACGTACGTACGTACGTACGT");
+        if (res.alignments.size() != 1 || res.alignments[0].cigar_string() != "36=") ++dbg_bad;
+        std::printf("dbg\t%s\n", res.alignments.empty() ? "*" : res.alignments[0].cigar_string().c_str());
+    }
+    return (n == 2 && bad == 0 && thrown && dbg_bad == 0) ? 0 : 1;
 }

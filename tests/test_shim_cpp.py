@@ -12,6 +12,8 @@ def test_cpp_shim_roundtrip(tmp_path):
     exe = str(tmp_path / "test_shim")
     subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
                            "-o", exe, "-L" + emu_dir, "-lmgb_emu", "-Wl,-rpath," + emu_dir, "-fopenmp"])
-    out = subprocess.run([exe], capture_output=True, text=True)
+    dbg = os.path.join(ROOT, "tests", "golden", "example_graphs", "test_DNA_graph.dbg")
+    out = subprocess.run([exe, dbg], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "q1\tAGCTNCGAGGCCAA\t4=1X9=\t24" in out.stdout
+    assert "dbg\t36=" in out.stdout
