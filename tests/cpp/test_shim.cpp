@@ -40,7 +40,8 @@ int main(int argc, char **argv) {
     // query of examples/data/test_DNA_query.fa is a path of the graph
     int dbg_bad = 0;
     if (argc > 1) {
-        mgb_shim::B200Graph g2(std::string(argv[1]));
+        const std::string dbg_path = argv[1];
+        mgb_shim::B200Graph g2(dbg_path);
         mgb_config_t c2;
         mgb_config_init_cli(&c2, g2.get_k(), MGB_ALPHABET_DNA);
         auto res = mgb_shim::B200Aligner(g2, c2).align("ACGTACGTACGTACGTACGTACGTACGTACGTACGT");
