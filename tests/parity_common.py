@@ -8,7 +8,7 @@ import numpy as np
 
 import oracle_lib as O
 from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex, format_alignment
-from metagraph_b200.config import SIZE_MAX, cli_defaults, struct_defaults
+from metagraph_b200.config import SIZE_MAX, cli_defaults, dna_scoring_matrix, struct_defaults
 from test_oracle_golden import GOLD, make_cfg, read_fasta, read_fastq, revcomp
 
 COMP = str.maketrans("ACGT", "TGCA")
@@ -210,6 +210,64 @@ def concurrent_case(lib):
     idx.close()
 
 
+
+def fuzz_case(lib, seed):
+    """One randomized (graph, reads, config) triple: k, graph shape (variants, repeats, dummy mask), scoring
+    matrix, gap penalties, xdrop, seed lengths (exact / MEM / sub-k), seeds per locus, alternative paths,
+    strands, end bonuses, cut-offs, node budget, left trim, complexity filter. Returns the mismatching reads."""
+    rng = np.random.default_rng(1000 + seed)
+    k = int(rng.integers(4, 34))
+    G = int(rng.integers(300, 4000))
+    nseq = int(rng.integers(1, 4))
+    base = "".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])
+    seqs = [base] + [mutate(rng, base, 0.03) for _ in range(nseq - 1)]
+    if rng.random() < 0.3:      # repeats -> branching / cycles
+        u = base[:int(rng.integers(k, 3 * k))]
+        seqs.append(u * int(rng.integers(2, 5)) + base[50:120])
+    match = int(rng.integers(1, 4)); mm1 = -int(rng.integers(1, 5)); mm2 = -int(rng.integers(1, 5))
+    go = -int(rng.integers(2, 9)); ge = -int(rng.integers(1, min(-go, 4) + 1))
+    kw = dict(score_matrix=dna_scoring_matrix(match, mm1, mm2), gap_opening_penalty=go, gap_extension_penalty=ge,
+              xdrop=int(rng.integers(5, 60)), min_exact_match=float(rng.choice([0.0, 0.0, 0.3, 0.7])),
+              rel_score_cutoff=float(rng.choice([0.0, 0.5, 0.8, 0.95])),
+              num_alternative_paths=int(rng.integers(1, 4)),
+              forward_and_reverse_complement=bool(rng.random() < 0.7),
+              left_end_bonus=int(rng.integers(0, 7)), right_end_bonus=int(rng.integers(0, 7)),
+              max_nodes_per_seq_char=float(rng.choice([5.0, 2.0, 12.0])),
+              allow_left_trim=bool(rng.random() < 0.8),
+              seed_complexity_filter=bool(rng.random() < 0.3))
+    msl = int(rng.integers(2, k + 1)); kw["min_seed_length"] = msl
+    kw["max_seed_length"] = int(rng.choice([k, SIZE_MAX, max(msl, k - 1), k + 5]))
+    if kw["max_seed_length"] < msl: kw["max_seed_length"] = msl
+    kw["max_num_seeds_per_locus"] = int(rng.choice([1000, 2, SIZE_MAX]))
+    cfg = cli_defaults(k, **kw)
+    mask = bool(rng.random() < 0.3)
+    g = O.OracleGraph(k, seqs, mask=mask)
+    W, last, F, valid = g.arrays()
+    idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if mask else None, lib=lib)
+    reads = []
+    for i in range(25):
+        s_ = seqs[int(rng.integers(0, len(seqs)))]
+        L = int(rng.integers(max(3, k - 3), 160))
+        p = int(rng.integers(0, max(1, len(s_) - L)))
+        r = mutate(rng, s_[p:p + L], float(rng.choice([0.0, 0.02, 0.08])))
+        if rng.random() < 0.5: r = r.translate(COMP)[::-1]
+        if rng.random() < 0.1 and len(r) > 5: r = r[:len(r)//2] + "N" + r[len(r)//2+1:]
+        reads.append(r)
+    try:
+        exp = g.align_tsv(cfg, reads, with_nodes=True)
+    except RuntimeError as err:                         # DBGAligner ctor: check_config_scores failed
+        assert "too low" in str(err)
+        import pytest
+        from metagraph_b200 import _lib
+        with pytest.raises(_lib.MgbError) as e2:
+            run_lines(idx, cfg, reads)
+        assert e2.value.code == -3                      # MGB_ERR_BAD_CONFIG
+        idx.close()
+        return [], None
+    got, _ = run_lines(idx, cfg, reads)
+    bad = [i for i in range(len(reads)) if exp[i] != got[i]]
+    idx.close()
+    return bad, (k, kw, mask, reads[bad[0]] if bad else None, exp[bad[0]] if bad else None, got[bad[0]] if bad else None)
 
 AA = "ACDEFGHIKLMNPQRSTVWY"
 

@@ -1,0 +1,25 @@
+"""Randomized parity: many (graph, reads, config) triples through the kernels and the oracle
+(400 further seeds were swept once by hand with zero mismatches; these run every time)."""
+import os
+import subprocess
+
+import pytest
+
+import parity_common as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu", "build", "libmgb_emu.so")
+
+
+def test_fuzz_emu():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    for seed in range(40):
+        bad, info = P.fuzz_case(EMU, seed)
+        assert not bad, (seed, info)
+
+
+@pytest.mark.gpu
+def test_fuzz_gpu():
+    for seed in range(100, 160):
+        bad, info = P.fuzz_case(None, seed)
+        assert not bad, (seed, info)
