@@ -145,7 +145,7 @@ struct WarpMem {
     uint32_t *sfx_first, *sfx_last; uint8_t *sfx_len;   // index_range result per query position
     // seed complexity filter: 3-mer codes / equal-3-mer masks (scratch) and, per strand, the largest start of a
     // low-complexity 3-mer interval ending at or before each 3-mer (see build_lowcx)
-    uint8_t *lc_word; uint64_t *lc_eq; int16_t *lc_max[2];
+    uint8_t *lc_word; uint64_t *lc_eq; int32_t *lc_max[2];
     uint32_t *epoch_store;  // conv-table epochs survive across the reads a warp processes
 
     MGB_HOSTDEV size_t carve(char *base, const Caps &c) {
@@ -176,7 +176,7 @@ struct WarpMem {
         sfx_first = (uint32_t*)take(4 * ((size_t)c.L_max + 8)); sfx_last = (uint32_t*)take(4 * ((size_t)c.L_max + 8));
         sfx_len = (uint8_t*)take(c.L_max + 8);
         lc_word = (uint8_t*)take(c.L_max + 8); lc_eq = (uint64_t*)take(8 * ((size_t)c.L_max + 8));
-        lc_max[0] = (int16_t*)take(2 * ((size_t)c.L_max + 8)); lc_max[1] = (int16_t*)take(2 * ((size_t)c.L_max + 8));
+        lc_max[0] = (int32_t*)take(4 * ((size_t)c.L_max + 8)); lc_max[1] = (int32_t*)take(4 * ((size_t)c.L_max + 8));
         return o;
     }
 };
@@ -485,7 +485,7 @@ struct ReadAligner {
         const uint8_t *cd = cx[s].codes;
         const int n_w = L - 2;
         if (n_w <= 0) return;
-        uint8_t *wd = m.lc_word; uint64_t *eq = m.lc_eq; int16_t *mx = m.lc_max[s];
+        uint8_t *wd = m.lc_word; uint64_t *eq = m.lc_eq; int32_t *mx = m.lc_max[s];
         for (int j = wlane(); j < n_w; j += kWarp) {
             const uint32_t a = cd[j], b = cd[j + 1], c = cd[j + 2];
             const bool ok = a >= 1 && a <= 4 && b >= 1 && b <= 4 && c >= 1 && c <= 4;
@@ -520,7 +520,7 @@ struct ReadAligner {
                     if (r * 10 > 20 * span) { best = a; break; }
                 }
             }
-            if (b < n_w) mx[b] = (int16_t)best;
+            if (b < n_w) mx[b] = best;
         }
         wsync();
         // running maximum over the ends
@@ -529,7 +529,7 @@ struct ReadAligner {
             const int b = base + wlane();
             int v = b < n_w ? (int)mx[b] : -1;
             v = imax(wscan_max(v), carry);
-            if (b < n_w) mx[b] = (int16_t)v;
+            if (b < n_w) mx[b] = v;
             carry = wbcast(v, kWarp - 1);
         }
         wsync();
