@@ -175,7 +175,8 @@ def main():
         if rank != 0:
             return
         genome = make_genome(G)
-        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
+        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)),
+                                        threads=min(host_threads, 32))   # torchrun pins OMP_NUM_THREADS=1
         buf, offsets = make_reads(genome, min(N, 400_000), 42)
         per_step = []
         sample_n = 0
@@ -210,7 +211,8 @@ def main():
     genome = make_genome(G)
     if rank == 0:
         t0 = time.time()
-        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)))
+        boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)),
+                                        threads=min(host_threads, 32))   # torchrun pins OMP_NUM_THREADS=1
         build_s = time.time() - t0
         meta = torch.tensor([len(boss.W)] + [int(x) for x in boss.F], dtype=torch.int64, device=dev)
     else:
