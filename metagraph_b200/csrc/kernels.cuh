@@ -90,7 +90,10 @@ struct SubkArgs {
     uint32_t n_reads, n_strands, min_seed_length, max_len;     // max_len = min(max_seed_length, k - 1)
     uint32_t *first_f, *last_f, *first_r, *last_r; uint8_t *len_f, *len_r;
 };
-static constexpr int kSubkChunk = 16;
+#ifndef MGB_SUBK_CHUNK
+#define MGB_SUBK_CHUNK 1
+#endif
+static constexpr int kSubkChunk = MGB_SUBK_CHUNK;
 MGB_HD void subk_item(const SubkArgs &a, uint32_t r, uint32_t s, uint32_t chunk) {
     const uint64_t b = a.offsets[r];
     const int L = (int)(a.offsets[r + 1] - b);
