@@ -131,6 +131,10 @@ int mgb_device_count(void);
 int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1,
                      const uint64_t *F, const uint8_t *valid, uint32_t k, int alphabet,
                      uint32_t suffix_len, int device, mgb_index_t **out);
+/* DeBruijnGraph::get_mode() of the graph (sequence_graph.hpp:160): 0 = BASIC (default), 1 = CANONICAL (built with
+ * --mode canonical: the graph holds the reverse complement of every k-mer; dbg_aligner.cpp:224-226, 646-722).
+ * 2 = PRIMARY is refused: it needs the CanonicalDBG wrapper (canonical_dbg.cpp), not implemented. */
+int mgb_index_set_mode(mgb_index_t *index, int mode);
 void mgb_index_destroy(mgb_index_t *index);
 uint64_t mgb_index_num_edges(const mgb_index_t *index);
 uint64_t mgb_index_device_bytes(const mgb_index_t *index);

@@ -92,6 +92,8 @@ def load_library(path=None):
     L.mgb_boss_free.argtypes = [ctypes.POINTER(mgb_boss_t)]
     L.mgb_boss_mask_dummy.restype = i
     L.mgb_boss_mask_dummy.argtypes = [ctypes.POINTER(mgb_boss_t), vp]
+    L.mgb_index_set_mode.restype = i
+    L.mgb_index_set_mode.argtypes = [vp, i]
     L.mgb_dbg_load.restype = i
     L.mgb_dbg_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(mgb_boss_t), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.mgb_dbg_last_error.restype = ctypes.c_char_p
@@ -111,5 +113,5 @@ REQUIRED_SYMBOLS = [
     "mgb_index_device_bytes", "mgb_index_k", "mgb_config_init", "mgb_config_init_cli", "mgb_map_to_nodes",
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
     "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_boss_build", "mgb_boss_free",
-    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_dbg_load", "mgb_dbg_last_error",
+    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_index_set_mode",
 ]

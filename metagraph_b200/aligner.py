@@ -103,9 +103,11 @@ class BOSSTable:
 class DBGSuccinctIndex:
     """BOSS index resident in one GPU's HBM (DBGSuccinct's role for the aligner)."""
 
-    def __init__(self, boss, valid=None, device=0, suffix_len=0, lib=None):
+    def __init__(self, boss, valid=None, device=0, suffix_len=0, lib=None, mode=None):
         self._L = _lib.load_library(lib)
         self.k = boss.k
+        if mode is None:        # a table read from a .dbg file carries the file's mode
+            mode = getattr(boss, "mode", 0)
         h = ctypes.c_void_p()
         v = None
         if valid is not None:
@@ -115,6 +117,13 @@ class DBGSuccinctIndex:
             v.ctypes.data if v is not None else None, boss.k, boss.alphabet, suffix_len, device,
             ctypes.byref(h)))
         self.handle = h
+        if mode:     # DeBruijnGraph::Mode: 1 = CANONICAL (graph built from the sequences and their reverse complements)
+            try:
+                _lib.check(self._L, self._L.mgb_index_set_mode(h, int(mode)))
+            except Exception:
+                self.close()
+                raise
+        self.mode = mode
 
     def close(self):
         if self.handle:

@@ -38,6 +38,7 @@ struct DevConfig {
     char letters[kMaxSigma + 1];       // alphabet, "$ACGT" / "$ABCDEFGHIJKLMNOPQRSTUVWYZX"
     uint32_t sigma;
     uint32_t has_complement;           // DNA: reverse complement defined
+    uint32_t canonical;                // graph in CANONICAL mode (holds both strands): dbg_aligner.cpp:224-226, 646-656
 };
 
 static constexpr int kMaxAlt = 4;            // supported num_alternative_paths
@@ -357,6 +358,138 @@ struct ReadAligner {
         *a.h = h;
         wsync();
         return true;
+    }
+
+    // alignment.cpp:563-702 on a plain DBGSuccinct (CANONICAL-mode graph, no RCDBG view): the path of the
+    // reverse complement is looked up in the graph itself. Returns false if the alignment became empty.
+    MGB_HD bool reverse_complement_slot_plain(int slot) {
+        trim_offset(slot);
+        AlnSlot &a = sm.slots[slot];
+        AlnHdr h = *a.h;
+        const int K = ix.k;
+        uint8_t *codes = (uint8_t*)m.bt_seq;                    // scratch (not in use outside backtrack)
+        auto kill = [&]() { h.used = 0; h.n_nodes = 0; *a.h = h; wsync(); return false; };
+        // reverse_complement_seq_path (sequence_graph.cpp:563-573) of a.seq[0..len): complement in place, map
+        auto rc_seq_path = [&](int len) {
+            wsync();
+            for (int base = 0; base < (len + 1) / 2; base += kWarp) {
+                int i = base + wlane();
+                if (i < (len + 1) / 2) {
+                    int jj = len - 1 - i;
+                    char x = complement_char(a.seq[i]), y = complement_char(a.seq[jj]);
+                    a.seq[i] = y; a.seq[jj] = x;
+                }
+            }
+            wsync();
+            for (int i = wlane(); i < len; i += kWarp) codes[i] = (uint8_t)encode_char((uint8_t)a.seq[i]);
+            for (int i = wlane(); i < len - K + 1; i += kWarp) a.nodes[i] = 0;
+            wsync();
+            map_to_edges(ix, codes, len, a.nodes);
+            wsync();
+        };
+        if ((int)caps.aln_seq < K + 8 || (int)caps.aln_nodes < 2) { overflow = true; return false; }
+        if (!h.offset) {
+            if (h.seq_len < K) return kill();
+            rc_seq_path(h.seq_len);
+            h.n_nodes = h.seq_len - K + 1;
+        } else {
+            // one node, its first `offset` characters are not part of the alignment: rebuild the whole k-mer
+            const int off = (int)h.offset;
+            const uint64_t node = a.nodes[0];
+            wsync();
+            for (int i = wlane(); i < h.seq_len; i += kWarp) codes[K + i] = (uint8_t)a.seq[i];   // stash
+            wsync();
+            {   // BOSS::get_node_str + edge label: last characters first (boss.cpp:663-690)
+                uint64_t e = node;
+                for (int i = K - 2; i >= 0; --i) {
+                    const uint32_t c = node_last_value(ix, e);
+                    if (i < off) a.seq[i] = cfg.letters[c];
+                    e = (uint64_t)load_radj(ix, e).x;         // bwd(e)
+                }
+            }
+            wsync();
+            for (int i = wlane(); i < h.seq_len; i += kWarp) a.seq[off + i] = (char)codes[K + i];
+            wsync();
+            if (a.seq[0] == '$') {
+                // starts in a source dummy k-mer: walk forward along the last outgoing edge until the k-mer is
+                // real (:572-640), then take the reverse complement of that k-mer
+                LineCache lc;
+                uint64_t edge = node;
+                uint32_t label = lc.get_W(ix, edge) % ix.sigma;
+                int len = off + h.seq_len;                       // == K
+                for (int i = 0; i < off; ++i) {
+                    edge = fwd(ix, lc, edge, label);
+                    label = lc.get_W(ix, edge) % ix.sigma;
+                    if (label == 0) return kill();
+                    if (len >= (int)caps.aln_seq) { overflow = true; return false; }
+                    a.seq[len++] = cfg.letters[label];
+                }
+                wsync();
+                for (int base = 0; base < K; base += kWarp) {     // seq = seq.substr(off)
+                    int i = base + wlane();
+                    char v = i < K ? a.seq[off + i] : 0;
+                    wsync();
+                    if (i < K) a.seq[i] = v;
+                    wsync();
+                }
+                rc_seq_path(K);
+                if (a.nodes[0] == 0) return kill();
+                wsync();
+                for (int base = 0; base < K - off; base += kWarp) {     // keep the last K - off characters
+                    int i = base + wlane();
+                    char v = i < K - off ? a.seq[off + i] : 0;
+                    wsync();
+                    if (i < K - off) a.seq[i] = v;
+                    wsync();
+                }
+            } else {
+                rc_seq_path(K);
+                if (a.nodes[0] == 0) return kill();
+                // drop the ending that corresponds to the added prefix: first incoming node each time
+                // (adjacent_incoming_nodes, dbg_succinct.cpp:176-193)
+                uint64_t cur = a.nodes[0];
+                for (int i = 0; i < off; ++i) {
+                    const uint2 r = load_radj(ix, cur);
+                    const uint32_t d = node_last_value(ix, cur);
+                    uint64_t edge = r.x, found = 0;
+                    LineCache lc;
+                    while (true) {
+                        if (in_graph(ix, edge)) { found = edge; break; }
+                        if (!radj_multi(ix, r.y)) break;
+                        if (++edge > ix.n) break;
+                        uint32_t w;
+                        edge = succ_W2(ix, lc, edge, d, &w);
+                        if (w != d + ix.sigma) break;
+                    }
+                    if (!found) return kill();
+                    cur = found;
+                }
+                wsync();
+                a.nodes[0] = cur;
+                wsync();
+            }
+            h.n_nodes = 1;
+            h.seq_len = K - off;
+        }
+        wsync();
+        for (int base = 0; base < (h.n_cigar + 1) / 2; base += kWarp) {
+            int i = base + wlane();
+            if (i < h.n_cigar / 2) {
+                uint32_t x = a.cigar[i], y = a.cigar[h.n_cigar - 1 - i];
+                a.cigar[i] = y; a.cigar[h.n_cigar - 1 - i] = x;
+            }
+        }
+        h.orientation ^= 1u;
+        *a.h = h;
+        wsync();
+        h.q_len = L - aln_clipping(a) - aln_end_clipping(a);
+        *a.h = h;
+        wsync();
+        return true;
+    }
+    // Alignment::reverse_complement against the graph view the backward extender works on
+    MGB_HD bool reverse_complement_for_bwd(int slot) {
+        return cfg.canonical ? reverse_complement_slot_plain(slot) : reverse_complement_slot(slot);
     }
 
     // --------------------------------------------------------------------------------
@@ -1914,7 +2047,7 @@ struct ReadAligner {
     MGB_HD void align_strand(int s, bool both) {
         const int fe = s, be = 1 - s;
         cx[fe].rc = 0;
-        if (both) cx[be].rc = 1;
+        if (both) cx[be].rc = cfg.canonical ? 0 : 1;     // use_rcdbg (dbg_aligner.cpp:646-650)
         const int n_seeds_s = cx[s].n_seeds;
         SeedRec *seeds_s = cx[s].seeds;
         const bool implicit = cx[s].implicit_seeds != 0;
@@ -1957,20 +2090,32 @@ struct ReadAligner {
                 for (int r0 = 0; r0 < n_ext; ++r0) {
                     const int slot = (it ? SLOT_BWD : SLOT_EXT) + r0;
                     bool add;
+                    int add_slot = slot;
+                    // is_reversible (:652-656): on a CANONICAL-mode graph an alignment to the reverse strand
+                    // with no offset is reported as its reverse complement
+                    const bool reversible = cfg.canonical && sm.slots[slot].h->orientation && !sm.slots[slot].h->offset;
                     if (it == 0) {
                         add = !both || sm.slots[slot].h->score >= get_min_path_score();
+                        if (add && reversible) {                  // :680-684
+                            copy_slot(SLOT_TMP, slot);
+                            add = reverse_complement_slot_plain(SLOT_TMP);
+                            if (overflow) return;
+                            add_slot = SLOT_TMP;
+                        }
                     } else {
-                        if (!reverse_complement_slot(slot)) continue;
-                        const AlnHdr h = *sm.slots[slot].h;
-                        int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
-                        for (int t = 0; t < h.n_nodes && !overflow; ++t)
-                            filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                        if (!cfg.canonical || reversible) {       // use_rcdbg || is_reversible (:710-722)
+                            if (!reverse_complement_for_bwd(slot)) { if (overflow) return; continue; }
+                            const AlnHdr h = *sm.slots[slot].h;
+                            int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
+                            for (int t = 0; t < h.n_nodes && !overflow; ++t)
+                                filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                        }
                         add = true;
                     }
-                    if (add) agg_add(slot);
+                    if (add) agg_add(add_slot);
                     if (it != 0 || !both) continue;
                     if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
-                    if (!reverse_complement_slot(slot)) continue;
+                    if (!reverse_complement_for_bwd(slot)) { if (overflow) return; continue; }
                     if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
                     ++n_rc;
                 }
@@ -1979,7 +2124,7 @@ struct ReadAligner {
                     AlnSlot &a = sm.slots[SLOT_EXT + r2];
                     if (!a.h->used) continue;
                     const AlnHdr h = *a.h;
-                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, true,
+                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, cx[be].rc != 0,
                                          a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
                         a.h->used = 0;
                 }

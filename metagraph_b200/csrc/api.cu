@@ -456,6 +456,15 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     return MGB_OK;
 }
 
+int mgb_index_set_mode(mgb_index_t *index, int mode) {
+    if (!index) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode != 0 && mode != 1)
+        return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs need the CanonicalDBG wrapper, which is not implemented");
+    if (mode == 1 && !index->at.has_complement) return fail(MGB_ERR_BAD_CONFIG, "CANONICAL mode needs a DNA graph");
+    index->view.mode = (uint32_t)mode;
+    return MGB_OK;
+}
+
 void mgb_index_destroy(mgb_index_t *index) {
     if (!index) return;
 #if !defined(MGB_HOST_EMU)
@@ -957,6 +966,10 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     std::string err;
     int rc = lower_config(*config, index->view.k, index->alphabet, &dcfg, &err);
     if (rc) return fail(rc, err);
+    if (index->view.mode == 1) {                 // CANONICAL-mode graph: both strands, no RCDBG view (dbg_aligner.cpp:224-226)
+        dcfg.canonical = 1;
+        dcfg.forward_and_reverse_complement = 1;
+    }
 
     // pieces of >= 64k reads, at most 8; two host threads keep two pieces in flight
     const uint32_t kMinPiece = 65536, kMaxPieces = 8;

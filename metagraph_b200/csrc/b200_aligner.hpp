@@ -37,18 +37,18 @@ class B200Graph {
             throw std::runtime_error(mgb_last_error());
     }
     // A graph file written by `metagraph build` (DBGSuccinct::load, dbg_succinct.cpp:690-712), for callers
-    // that do not link MetaGraph. BASIC-mode graphs only.
+    // that do not link MetaGraph. BASIC and CANONICAL graphs; PRIMARY ones need the CanonicalDBG wrapper and are refused.
     explicit B200Graph(const std::string &dbg_path, int device = 0) {
         mgb_boss_t boss;
         int mode = -1, state = -1;
         if (mgb_dbg_load(dbg_path.c_str(), &boss, &mode, &state) != MGB_OK)
             throw std::runtime_error(std::string("cannot load ") + dbg_path + ": " + mgb_dbg_last_error());
         k_ = boss.k;
-        int rc = mode == 0 ? mgb_index_create(boss.W, boss.last, boss.n_plus_1, boss.F, nullptr, boss.k,
-                                              boss.alphabet, 0, device, &index_) : MGB_ERR_UNSUPPORTED;
+        int rc = mgb_index_create(boss.W, boss.last, boss.n_plus_1, boss.F, nullptr, boss.k,
+                                  boss.alphabet, 0, device, &index_);
         mgb_boss_free(&boss);
-        if (mode != 0) throw std::runtime_error("only BASIC-mode graphs are supported (CANONICAL / PRIMARY: not yet)");
         if (rc != MGB_OK) throw std::runtime_error(mgb_last_error());
+        set_mode(mode);
     }
 #ifdef MGB_WITH_METAGRAPH
     // Flatten a loaded DBGSuccinct (get_W / get_last / get_F are public on boss::BOSS).
@@ -67,8 +67,18 @@ class B200Graph {
                              k_, boss.alph_size == 27 ? MGB_ALPHABET_PROTEIN : MGB_ALPHABET_DNA, 0, device,
                              &index_) != MGB_OK)
             throw std::runtime_error(mgb_last_error());
+        set_mode(static_cast<int>(dbg.get_mode()));
     }
 #endif
+    // DeBruijnGraph::Mode of the graph (sequence_graph.hpp:160): 0 BASIC, 1 CANONICAL; PRIMARY is refused
+    void set_mode(int mode) {
+        if (mgb_index_set_mode(index_, mode) != MGB_OK) {
+            std::string err = mgb_last_error();
+            mgb_index_destroy(index_);
+            index_ = nullptr;
+            throw std::runtime_error(err);
+        }
+    }
     ~B200Graph() { mgb_index_destroy(index_); }
     B200Graph(const B200Graph&) = delete;
     B200Graph& operator=(const B200Graph&) = delete;

@@ -69,6 +69,7 @@ struct IndexView {
     //          DBG nodes), 0 -- the adj record with sigma-bit masks
     // radj is shared; its y word holds the first character in bits 0..6 and the multi-incoming flag in
     // bit 7 here (bits 0..2 / bit 3 in the DNA layout).
+    uint32_t mode;              // DeBruijnGraph::Mode: 0 BASIC, 1 CANONICAL (graph holds both strands)
     uint32_t wide;
     const uint8_t *wW;
     const uint32_t *wl;

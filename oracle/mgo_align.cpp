@@ -295,20 +295,68 @@ size_t Alignment::trim_offset() {
 
 void Alignment::reverse_complement(const GraphView &graph, std::string_view query_rev_comp) {
     trim_offset();
-    if (!graph.rc)
-        throw std::runtime_error("oracle: Alignment::reverse_complement only restated for RCDBG "
-                                 "(BASIC-mode graphs); CanonicalDBG is out of scope");
-    // alignment.cpp:547-561
-    if (offset_) {
-        *this = Alignment();
-    } else {
-        std::reverse(cigar_.data().begin(), cigar_.data().end());
-        std::reverse(nodes_.begin(), nodes_.end());
-        reverse_complement_inplace(sequence_);
-        orientation_ = !orientation_;
-        query_view_ = { query_rev_comp.data() + get_clipping(),
-                        query_rev_comp.size() - get_clipping() - get_end_clipping() };
+    if (graph.rc) {
+        // alignment.cpp:547-561
+        if (offset_) {
+            *this = Alignment();
+        } else {
+            std::reverse(cigar_.data().begin(), cigar_.data().end());
+            std::reverse(nodes_.begin(), nodes_.end());
+            reverse_complement_inplace(sequence_);
+            orientation_ = !orientation_;
+            query_view_ = { query_rev_comp.data() + get_clipping(),
+                            query_rev_comp.size() - get_clipping() - get_end_clipping() };
+        }
+        return;
     }
+    // alignment.cpp:563-702 for a plain DBGSuccinct in CANONICAL mode (no CanonicalDBG wrapper): the path of
+    // the reverse complement is looked up in the graph itself
+    const DBGSuccinct &dbg = *graph.g;
+    auto rc_seq_path = [&]() {                                // reverse_complement_seq_path, sequence_graph.cpp:563-573
+        reverse_complement_inplace(sequence_);
+        nodes_ = dbg.map_to_nodes_sequentially(sequence_);
+    };
+    if (!offset_) {
+        rc_seq_path();
+    } else {
+        sequence_ = dbg.get_node_sequence(nodes_[0]).substr(0, offset_) + sequence_;
+        if (sequence_[0] == '$') {
+            // starts in a source dummy k-mer: walk forward (always the last outgoing edge) until the k-mer is
+            // real, then take its reverse complement (:572-640)
+            size_t num_sentinels = sequence_.find_last_of('$') + 1;
+            const BOSS &boss = dbg.boss;
+            edge_index edge = nodes_[0];
+            TAlphabet edge_label = boss.get_W(edge) % boss.alph_size;
+            for (size_t i = 0; i < offset_; ++i) {
+                edge = boss.fwd(edge, edge_label);
+                edge_label = boss.get_W(edge) % boss.alph_size;
+                if (edge_label == 0) { *this = Alignment(); return; }
+                nodes_[0] = dbg.validate_edge(edge);
+                sequence_.push_back(boss.alph->decode(edge_label));
+            }
+            (void)num_sentinels;
+            sequence_ = sequence_.substr(offset_);
+            rc_seq_path();
+            if (std::find(nodes_.begin(), nodes_.end(), npos) != nodes_.end()) { *this = Alignment(); return; }
+            sequence_.assign(sequence_.data() + offset_, dbg.get_k() - offset_);
+        } else {
+            rc_seq_path();
+            if (std::find(nodes_.begin(), nodes_.end(), npos) != nodes_.end()) { *this = Alignment(); return; }
+            // trim the ending that corresponds to the added prefix (:667-690): first incoming node each time
+            for (size_t i = 0; i < offset_; ++i) {
+                size_t indegree = 0;
+                node_index first_prev = npos;
+                graph.adjacent_incoming_nodes(nodes_[0], [&](node_index prev) { if (++indegree == 1) first_prev = prev; });
+                if (!indegree) { *this = Alignment(); return; }
+                nodes_[0] = first_prev;
+                sequence_.pop_back();
+            }
+        }
+    }
+    std::reverse(cigar_.data().begin(), cigar_.data().end());
+    orientation_ = !orientation_;
+    query_view_ = { query_rev_comp.data() + get_clipping(),
+                    query_rev_comp.size() - get_clipping() - get_end_clipping() };
 }
 
 // alignment.cpp:1239-1314 (no npos nodes: chaining is out of scope)
@@ -1373,9 +1421,13 @@ AlignmentResults DBGAligner::align(std::string_view query) const {
 void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::string>> &batch,
                              const std::function<void(const std::string&, AlignmentResults&&)> &callback,
                              AlignStats *stats) const {
-    const bool both = config_.forward_and_reverse_complement && config_.alphabet->sigma == 5;
+    // dbg_aligner.cpp:224-226, 646-656
+    const bool canonical = graph_.mode == 1;
+    const bool both = (canonical || config_.forward_and_reverse_complement) && config_.alphabet->sigma == 5;
+    const bool use_rcdbg = !canonical && config_.forward_and_reverse_complement;
     GraphView fwd_graph { &graph_, false };
-    GraphView rc_graph { &graph_, true };
+    GraphView rc_graph { &graph_, use_rcdbg };
+    auto is_reversible = [&](const Alignment &a) { return canonical && a.get_orientation() && !a.get_offset(); };
 
     for (const auto &[header, query] : batch) {
         AlignmentResults paths(query);
@@ -1436,8 +1488,15 @@ void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::strin
                     auto extensions = fwd_extender.get_extensions(seeds[i], min_path_score, false);
                     std::vector<Alignment> rc_of_alignments;
                     for (Alignment &path : extensions) {
-                        if (path.get_score() >= get_min_path_score(path))
-                            add_alignment(Alignment(path));
+                        if (path.get_score() >= get_min_path_score(path)) {
+                            if (is_reversible(path)) {                        // :680-684
+                                Alignment out_path = path;
+                                out_path.reverse_complement(fwd_graph, q_rc);
+                                add_alignment(std::move(out_path));
+                            } else {
+                                add_alignment(Alignment(path));
+                            }
+                        }
                         if (!path.get_clipping() || path.get_offset())
                             continue;
                         path.reverse_complement(rc_graph, q_rc);
@@ -1447,12 +1506,14 @@ void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::strin
                     }
                     align_core(std::move(rc_of_alignments), bwd_extender,
                         [&](Alignment &&path) {
-                            path.reverse_complement(rc_graph, q);
-                            if (path.empty())
-                                return;
-                            for (node_index node : path.get_nodes()) {
-                                fwd_extender.filter_nodes(node, path.get_clipping(),
-                                                          q.size() - path.get_end_clipping());
+                            if (use_rcdbg || is_reversible(path)) {           // :710-722
+                                path.reverse_complement(rc_graph, q);
+                                if (path.empty())
+                                    return;
+                                for (node_index node : path.get_nodes()) {
+                                    fwd_extender.filter_nodes(node, path.get_clipping(),
+                                                              q.size() - path.get_end_clipping());
+                                }
                             }
                             add_alignment(std::move(path));
                         },

@@ -86,6 +86,10 @@ void* mgo_graph_build(const char *alphabet, int K, const char **seqs, int n,
     } catch (...) { return nullptr; }
 }
 
+// DeBruijnGraph::Mode of the graph: 0 BASIC, 1 CANONICAL (the caller built it from the sequences and their
+// reverse complements, as `metagraph build --mode canonical` does)
+void mgo_graph_set_mode(void *gp, int mode) { static_cast<DBGSuccinct*>(gp)->mode = mode; }
+
 void* mgo_graph_from_arrays(const char *alphabet, int K, const uint8_t *W, const uint8_t *last,
                             uint64_t n_plus_1, const uint64_t *F, int suffix_index_len) {
     try {

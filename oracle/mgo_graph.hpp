@@ -178,6 +178,9 @@ class DBGSuccinct {
   public:
     BOSS boss;
     std::vector<uint8_t> valid_edges;
+    // DeBruijnGraph::Mode (sequence_graph.hpp:160): 0 BASIC, 1 CANONICAL (the graph holds the reverse
+    // complement of every k-mer). PRIMARY graphs need the CanonicalDBG wrapper, which is not restated.
+    int mode = 0;
 
     size_t get_k() const { return boss.k_ + 1; }
     uint64_t max_index() const { return boss.num_edges(); }
@@ -229,6 +232,10 @@ void DBGSuccinct::call_incoming_kmers(node_index node, CB &&cb) const {
 struct GraphView {
     const DBGSuccinct *g = nullptr;
     bool rc = false;
+    // DBGSuccinct::adjacent_incoming_nodes (dbg_succinct.cpp:176-193), plain view only
+    template <class CB> void adjacent_incoming_nodes(node_index node, CB &&cb) const {
+        g->call_incoming_kmers(node, [&](node_index prev, char) { cb(prev); });
+    }
     size_t get_k() const { return g->get_k(); }
     uint64_t max_index() const { return g->max_index(); }
     template <class CB> void call_outgoing_kmers(node_index node, CB &&cb) const {

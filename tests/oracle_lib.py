@@ -31,6 +31,7 @@ def lib():
         L.mgo_graph_from_arrays.restype = vp
         L.mgo_graph_from_arrays.argtypes = [cp, i, vp, vp, u64, vp, i]
         L.mgo_graph_free.argtypes = [vp]
+        L.mgo_graph_set_mode.argtypes = [vp, ctypes.c_int]
         for f in ("mgo_graph_num_edges", "mgo_graph_num_nodes"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [vp]
@@ -85,6 +86,10 @@ class OracleGraph:
                                        int(dynamic))
         if not self.h:
             raise RuntimeError("oracle graph construction failed")
+
+    def set_mode(self, mode):
+        """0 = BASIC, 1 = CANONICAL (graph built from the sequences plus their reverse complements)"""
+        lib().mgo_graph_set_mode(self.h, int(mode))
 
     def __del__(self):
         if getattr(self, "h", None):

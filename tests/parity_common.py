@@ -211,7 +211,24 @@ def concurrent_case(lib):
 
 
 
-def fuzz_case(lib, seed):
+def check_mt_canonical(lib, **kw):
+    """CANONICAL-mode graph (sequences + their reverse complements, mode flag set): integration_tests/test_align.py:207-268."""
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    names, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    seqs = seqs + [revcomp(s) for s in seqs]
+    g = O.OracleGraph(11, seqs, mask=False)
+    g.set_mode(1)
+    W, last, F, _ = g.arrays()
+    idx = DBGSuccinctIndex(BOSSTable(11, W, last, F), lib=lib, mode=1)
+    cfg = cli_defaults(11, min_exact_match=0.0, **kw)
+    got, _ = run_lines(idx, cfg, reads, names)
+    exp = g.align_tsv(cfg, reads, headers=names, with_nodes=True)
+    idx.close()
+    assert got == exp
+    return got
+
+
+def fuzz_case(lib, seed, canonical=False):
     """One randomized (graph, reads, config) triple: k, graph shape (variants, repeats, dummy mask), scoring
     matrix, gap penalties, xdrop, seed lengths (exact / MEM / sub-k), seeds per locus, alternative paths,
     strands, end bonuses, cut-offs, node budget, left trim, complexity filter. Returns the mismatching reads."""
@@ -241,9 +258,14 @@ def fuzz_case(lib, seed):
     kw["max_num_seeds_per_locus"] = int(rng.choice([1000, 2, SIZE_MAX]))
     cfg = cli_defaults(k, **kw)
     mask = bool(rng.random() < 0.3)
+    if canonical:               # `build --mode canonical`: every sequence and its reverse complement
+        seqs = seqs + [revcomp(s_) for s_ in seqs]
     g = O.OracleGraph(k, seqs, mask=mask)
+    if canonical:
+        g.set_mode(1)
     W, last, F, valid = g.arrays()
-    idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if mask else None, lib=lib)
+    idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if mask else None, lib=lib,
+                           mode=1 if canonical else 0)
     reads = []
     for i in range(25):
         s_ = seqs[int(rng.integers(0, len(seqs)))]

@@ -26,6 +26,15 @@ def test_mt_integration_emu(both):
     P.check_mt(EMU, both)
 
 
+@pytest.mark.parametrize("subk", [False, True])
+def test_mt_canonical_emu(subk, _emu_built):
+    # integration_tests/test_align.py:207-268 (graph built with --mode canonical)
+    got = P.check_mt_canonical(EMU, **({"min_seed_length": 10} if subk else {}))
+    from test_oracle_canonical import CANONICAL, CANONICAL_SUBK
+    for i, exp in (CANONICAL_SUBK if subk else CANONICAL):
+        assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
+
+
 @pytest.mark.parametrize("case", P.RANDOM_CASES, ids=[str(c[0]) for c in P.RANDOM_CASES])
 def test_random_emu(case):
     seed, k, G, n, L, rate, cfgf, mask, nseq = case

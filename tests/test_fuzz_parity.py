@@ -23,3 +23,19 @@ def test_fuzz_gpu():
     for seed in range(100, 160):
         bad, info = P.fuzz_case(None, seed)
         assert not bad, (seed, info)
+
+
+def test_fuzz_canonical_emu():
+    """CANONICAL-mode graphs (sequences + reverse complements, mode flag set): dbg_aligner.cpp:646-722,
+    alignment.cpp:563-702 (Alignment::reverse_complement without the RCDBG view)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    for seed in range(25):
+        bad, info = P.fuzz_case(EMU, seed, canonical=True)
+        assert not bad, (seed, info)
+
+
+@pytest.mark.gpu
+def test_fuzz_canonical_gpu():
+    for seed in range(100, 140):
+        bad, info = P.fuzz_case(None, seed, canonical=True)
+        assert not bad, (seed, info)

@@ -19,6 +19,15 @@ def test_mt_integration_gpu(both):
     P.check_mt(LIB, both)
 
 
+@pytest.mark.parametrize("subk", [False, True])
+def test_mt_canonical_gpu(subk):
+    # integration_tests/test_align.py:207-268 (graph built with --mode canonical)
+    got = P.check_mt_canonical(LIB, **({"min_seed_length": 10} if subk else {}))
+    from test_oracle_canonical import CANONICAL, CANONICAL_SUBK
+    for i, exp in (CANONICAL_SUBK if subk else CANONICAL):
+        assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
+
+
 @pytest.mark.parametrize("case", P.RANDOM_CASES, ids=[str(c[0]) for c in P.RANDOM_CASES])
 def test_random_gpu(case):
     seed, k, G, n, L, rate, cfgf, mask, nseq = case
