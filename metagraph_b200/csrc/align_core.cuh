@@ -15,6 +15,16 @@
 #include "index.cuh"
 #include "seed_core.cuh"
 
+// Graph mode seen by the aligner (DeBruijnGraph::Mode): the product library compiles k_align per mode
+// (kernels.cuh); the host-emulation build decides at run time.
+#if defined(MGB_CANONICAL_ONLY)
+#define MGB_CANONICAL(cfg) true
+#elif defined(MGB_BASIC_ONLY)
+#define MGB_CANONICAL(cfg) false
+#else
+#define MGB_CANONICAL(cfg) ((cfg).canonical != 0)
+#endif
+
 namespace mgb {
 
 // ------------------------------------------------------------------------------------
@@ -489,7 +499,7 @@ struct ReadAligner {
     }
     // Alignment::reverse_complement against the graph view the backward extender works on
     MGB_HD bool reverse_complement_for_bwd(int slot) {
-        return cfg.canonical ? reverse_complement_slot_plain(slot) : reverse_complement_slot(slot);
+        return MGB_CANONICAL(cfg) ? reverse_complement_slot_plain(slot) : reverse_complement_slot(slot);
     }
 
     // --------------------------------------------------------------------------------
@@ -2047,7 +2057,7 @@ struct ReadAligner {
     MGB_HD void align_strand(int s, bool both) {
         const int fe = s, be = 1 - s;
         cx[fe].rc = 0;
-        if (both) cx[be].rc = cfg.canonical ? 0 : 1;     // use_rcdbg (dbg_aligner.cpp:646-650)
+        if (both) cx[be].rc = MGB_CANONICAL(cfg) ? 0 : 1;     // use_rcdbg (dbg_aligner.cpp:646-650)
         const int n_seeds_s = cx[s].n_seeds;
         SeedRec *seeds_s = cx[s].seeds;
         const bool implicit = cx[s].implicit_seeds != 0;
@@ -2089,35 +2099,46 @@ struct ReadAligner {
                 // ones for the backward pass) and the backward case (reverse-complement back, then aggregate)
                 for (int r0 = 0; r0 < n_ext; ++r0) {
                     const int slot = (it ? SLOT_BWD : SLOT_EXT) + r0;
-                    bool add;
-                    int add_slot = slot;
                     // is_reversible (:652-656): on a CANONICAL-mode graph an alignment to the reverse strand
                     // with no offset is reported as its reverse complement
-                    const bool reversible = cfg.canonical && sm.slots[slot].h->orientation && !sm.slots[slot].h->offset;
-                    if (it == 0) {
-                        add = !both || sm.slots[slot].h->score >= get_min_path_score();
-                        if (add && reversible) {                  // :680-684
-                            copy_slot(SLOT_TMP, slot);
-                            add = reverse_complement_slot_plain(SLOT_TMP);
-                            if (overflow) return;
-                            add_slot = SLOT_TMP;
+                    const bool reversible = MGB_CANONICAL(cfg) && sm.slots[slot].h->orientation && !sm.slots[slot].h->offset;
+                    // pass 0 reports the result, pass 1 (forward case only) turns a left-clipped result into
+                    // a seed of the backward extension; both go through the one reverse-complement call site
+                    #pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        bool add = false, need_rc;
+                        int target = slot;
+                        if (pass == 0) {
+                            if (it == 0) {
+                                add = !both || sm.slots[slot].h->score >= get_min_path_score();
+                                need_rc = add && reversible;              // :680-684
+                                if (need_rc) { copy_slot(SLOT_TMP, slot); target = SLOT_TMP; }
+                            } else {
+                                need_rc = !MGB_CANONICAL(cfg) || reversible;   // use_rcdbg || is_reversible (:710-722)
+                                add = true;
+                            }
+                        } else {
+                            if (it != 0 || !both) break;
+                            if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) break;
+                            need_rc = true;
                         }
-                    } else {
-                        if (!cfg.canonical || reversible) {       // use_rcdbg || is_reversible (:710-722)
-                            if (!reverse_complement_for_bwd(slot)) { if (overflow) return; continue; }
-                            const AlnHdr h = *sm.slots[slot].h;
-                            int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
-                            for (int t = 0; t < h.n_nodes && !overflow; ++t)
-                                filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                        bool ok = true;
+                        if (need_rc) ok = reverse_complement_for_bwd(target);
+                        if (overflow) return;
+                        if (!ok) break;                                   // the alignment cannot be reversed
+                        if (pass == 0) {
+                            if (it != 0 && need_rc) {
+                                const AlnHdr h = *sm.slots[slot].h;
+                                int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
+                                for (int t = 0; t < h.n_nodes && !overflow; ++t)
+                                    filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                            }
+                            if (add) agg_add(target);
+                        } else {
+                            if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
+                            ++n_rc;
                         }
-                        add = true;
                     }
-                    if (add) agg_add(add_slot);
-                    if (it != 0 || !both) continue;
-                    if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) continue;
-                    if (!reverse_complement_for_bwd(slot)) { if (overflow) return; continue; }
-                    if (n_rc != r0) copy_slot(SLOT_EXT + n_rc, slot);
-                    ++n_rc;
                 }
                 if (it == 0) continue;
                 for (int r2 = r + 1; r2 < n_rc; ++r2) {

@@ -22,6 +22,7 @@
 #include "../../include/mgb.h"
 #if !defined(MGB_HOST_EMU)
 #define MGB_NARROW_ONLY 1        // this translation unit's kernels: DNA block layout only (see kernels.cuh)
+#define MGB_BASIC_ONLY 1         // ... and BASIC-mode graphs only (api_canonical.cu holds the CANONICAL-mode k_align)
 #endif
 #define MGB_KERNEL_NS kern_dna
 #include "kernels.cuh"
@@ -50,6 +51,11 @@ cudaError_t launch_sfx_extend(unsigned grid, const mgb::SfxArgs &a);
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
 cudaError_t launch_premap(unsigned grid, cudaStream_t s, const mgb::SeedArgs &a);
 cudaError_t launch_subk(unsigned grid, cudaStream_t s, const mgb::SubkArgs &a, uint32_t chunks_per_strand);
+cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const mgb::AlignArgs &a);
+cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm);
+}
+// k_align for CANONICAL-mode DNA graphs (api_canonical.cu)
+namespace kern_canon {
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const mgb::AlignArgs &a);
 cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm);
 }
@@ -461,6 +467,8 @@ int mgb_index_set_mode(mgb_index_t *index, int mode) {
     if (mode != 0 && mode != 1)
         return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs need the CanonicalDBG wrapper, which is not implemented");
     if (mode == 1 && !index->at.has_complement) return fail(MGB_ERR_BAD_CONFIG, "CANONICAL mode needs a DNA graph");
+    if (mode == 1 && index->view.wide)
+        return fail(MGB_ERR_UNSUPPORTED, "CANONICAL mode is served on the DNA block layout only");
     index->view.mode = (uint32_t)mode;
     return MGB_OK;
 }
@@ -791,15 +799,16 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                 static std::mutex occ_mu;
                 static std::map<std::pair<int, size_t>, int> occ_cache;
                 std::lock_guard<std::mutex> lk(occ_mu);
-                const bool wide = index->view.wide != 0;
-                auto key = std::make_pair(index->device * 2 + (wide ? 1 : 0), smem_block);
+                const int variant = index->view.wide ? 1 : index->view.mode == 1 ? 2 : 0;    // which k_align
+                auto key = std::make_pair(index->device * 4 + variant, smem_block);
                 auto it = occ_cache.find(key);
                 if (it == occ_cache.end()) {
                     // the shared memory limit is a high-water mark per device and kernel: keep the largest
                     size_t mx = smem_block;
                     for (auto &kv : occ_cache) if (kv.first.first == key.first) mx = std::max(mx, kv.first.second);
-                    CUDA_TRY(wide ? kern_any::align_occupancy(mx, smem_block, &blocks_per_sm)
-                                  : kern_dna::align_occupancy(mx, smem_block, &blocks_per_sm));
+                    CUDA_TRY(variant == 1 ? kern_any::align_occupancy(mx, smem_block, &blocks_per_sm)
+                           : variant == 2 ? kern_canon::align_occupancy(mx, smem_block, &blocks_per_sm)
+                                          : kern_dna::align_occupancy(mx, smem_block, &blocks_per_sm));
                     occ_cache[key] = blocks_per_sm;
                 } else blocks_per_sm = it->second;
             }
@@ -857,7 +866,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #else
             cudaEventRecord(ev[3], st.s);
             CUDA_TRY(index->view.wide ? kern_any::launch_align(n_warps / 4, smem_block, st.s, a)
-                                      : kern_dna::launch_align(n_warps / 4, smem_block, st.s, a));
+                   : index->view.mode == 1 ? kern_canon::launch_align(n_warps / 4, smem_block, st.s, a)
+                                           : kern_dna::launch_align(n_warps / 4, smem_block, st.s, a));
             cudaEventRecord(ev[4], st.s);
             if ((rc = d2h(&used, d_used, 8, st))) break;
             CUDA_TRY(cudaStreamSynchronize(st.s));

@@ -5,6 +5,8 @@
 //   api.cu          -DMGB_NARROW_ONLY, MGB_KERNEL_NS = kern_dna : DNA block layout only; the branches
 //                   to the alphabet-generic index layout are compiled out of the hot kernels
 //   api_generic.cu  -DMGB_WIDE_ONLY,   MGB_KERNEL_NS = kern_any : alphabet-generic layout only (protein)
+//   api_canonical.cu -DMGB_NARROW_ONLY -DMGB_CANONICAL_ONLY -DMGB_ALIGN_KERNEL_ONLY, MGB_KERNEL_NS = kern_canon :
+//                   k_align for CANONICAL-mode DNA graphs; the other two sets compile that mode's branches out
 // The host-emulation build (tests/emu) includes it once with the layout chosen at run time.
 #pragma once
 #include "align_core.cuh"
@@ -252,6 +254,7 @@ MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
 namespace MGB_KERNEL_NS {
 using namespace mgb;
 
+#if !defined(MGB_ALIGN_KERNEL_ONLY)
 __global__ void __launch_bounds__(128) k_radj_bwd(RadjArgs a) {
     uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
@@ -291,6 +294,8 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
     for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
 }
 
+#endif // MGB_ALIGN_KERNEL_ONLY
+
 #ifndef MGB_ALIGN_MIN_BLOCKS
 #define MGB_ALIGN_MIN_BLOCKS 4
 #endif
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const Align
 }
 
 // launchers (the only entry points the host code uses)
+#if !defined(MGB_ALIGN_KERNEL_ONLY)
 cudaError_t launch_radj_bwd(unsigned grid, const RadjArgs &a) { k_radj_bwd<<<grid, 128>>>(a); return cudaGetLastError(); }
 cudaError_t launch_sfx_extend(unsigned grid, const SfxArgs &a) { k_sfx_extend<<<grid, 128>>>(a); return cudaGetLastError(); }
 cudaError_t launch_subk(unsigned grid, cudaStream_t s, const SubkArgs &a, uint32_t chunks_per_strand) {
@@ -324,6 +330,7 @@ cudaError_t launch_subk(unsigned grid, cudaStream_t s, const SubkArgs &a, uint32
 }
 cudaError_t launch_premap(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_premap<<<grid, 256, 0, s>>>(a); return cudaGetLastError(); }
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_seed<<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
+#endif
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const AlignArgs &a) {
     k_align<<<grid, 128, smem_block, s>>>(a);
     return cudaGetLastError();
@@ -336,7 +343,7 @@ cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_pe
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_align, 128, smem_block);
 }
 
-#if !defined(MGB_WIDE_ONLY)
+#if !defined(MGB_WIDE_ONLY) && !defined(MGB_ALIGN_KERNEL_ONLY)
 // alphabet-independent kernels live in the first translation unit only
 __global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
