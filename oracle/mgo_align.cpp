@@ -309,32 +309,54 @@ void Alignment::reverse_complement(const GraphView &graph, std::string_view quer
         }
         return;
     }
-    // alignment.cpp:563-702 for a plain DBGSuccinct in CANONICAL mode (no CanonicalDBG wrapper): the path of
-    // the reverse complement is looked up in the graph itself
+    // alignment.cpp:563-702 on a CANONICAL-mode DBGSuccinct (the path of the reverse complement is looked up in
+    // the graph itself) or on a PRIMARY graph behind CanonicalDBG (the node ids are flipped)
     const DBGSuccinct &dbg = *graph.g;
+    const CanonicalDBG *canonical = graph.canon;
     auto rc_seq_path = [&]() {                                // reverse_complement_seq_path, sequence_graph.cpp:563-573
+        if (canonical) {
+            canonical->reverse_complement(sequence_, nodes_);
+            return;
+        }
         reverse_complement_inplace(sequence_);
         nodes_ = dbg.map_to_nodes_sequentially(sequence_);
     };
     if (!offset_) {
         rc_seq_path();
     } else {
-        sequence_ = dbg.get_node_sequence(nodes_[0]).substr(0, offset_) + sequence_;
+        sequence_ = graph.get_node_sequence(nodes_[0]).substr(0, offset_) + sequence_;
         if (sequence_[0] == '$') {
             // starts in a source dummy k-mer: walk forward (always the last outgoing edge) until the k-mer is
             // real, then take its reverse complement (:572-640)
             size_t num_sentinels = sequence_.find_last_of('$') + 1;
+            if (canonical && nodes_[0] != canonical->get_base_node(nodes_[0])) {
+                *this = Alignment();                          // reverse complement of a sink dummy k-mer
+                return;
+            }
+            size_t num_first_steps = canonical ? std::min(offset_, num_sentinels) : offset_;
             const BOSS &boss = dbg.boss;
             edge_index edge = nodes_[0];
             TAlphabet edge_label = boss.get_W(edge) % boss.alph_size;
-            for (size_t i = 0; i < offset_; ++i) {
+            for (size_t i = 0; i < num_first_steps; ++i) {
                 edge = boss.fwd(edge, edge_label);
                 edge_label = boss.get_W(edge) % boss.alph_size;
                 if (edge_label == 0) { *this = Alignment(); return; }
                 nodes_[0] = dbg.validate_edge(edge);
                 sequence_.push_back(boss.alph->decode(edge_label));
             }
-            (void)num_sentinels;
+            for (size_t i = num_first_steps; i < offset_; ++i) {
+                node_index next_node = 0;
+                char last_char = 0;
+                canonical->call_outgoing_kmers(nodes_[0], [&](node_index next, char c) {
+                    if (c == '$')
+                        return;
+                    next_node = next;
+                    last_char = c;
+                });
+                if (!next_node) { *this = Alignment(); return; }
+                nodes_[0] = next_node;
+                sequence_.push_back(last_char);
+            }
             sequence_ = sequence_.substr(offset_);
             rc_seq_path();
             if (std::find(nodes_.begin(), nodes_.end(), npos) != nodes_.end()) { *this = Alignment(); return; }
@@ -409,6 +431,14 @@ struct SeederBase {
     std::vector<node_index> query_nodes;
     const DBGAlignerConfig &config;
     size_t num_matching = 0;
+    const CanonicalDBG *canon = nullptr;       // set when the aligner's graph is a PRIMARY graph behind CanonicalDBG
+
+    bool has_multiple_outgoing(node_index n) const {
+        return canon ? canon->has_multiple_outgoing(n) : graph.has_multiple_outgoing(n);
+    }
+    bool has_single_incoming(node_index n) const {
+        return canon ? canon->has_single_incoming(n) : graph.has_single_incoming(n);
+    }
 
     // :49-65
     size_t num_exact_matching() const {
@@ -464,8 +494,8 @@ struct SeederBase {
             if (query_nodes[i] != npos) {
                 flags[i] = 2 | (i + 1 == query_nodes.size()
                                 || query_nodes[i + 1] == npos
-                                || graph.has_multiple_outgoing(query_nodes[i])
-                                || !graph.has_single_incoming(query_nodes[i]));
+                                || has_multiple_outgoing(query_nodes[i])
+                                || !has_single_incoming(query_nodes[i]));
             }
         }
         std::vector<Seed> seeds;
@@ -490,7 +520,7 @@ struct SeederBase {
         return seeds;
     }
 
-    // SuffixSeeder<UniMEMSeeder>::generate_seeds :153-358 (non-canonical part)
+    // SuffixSeeder<UniMEMSeeder>::generate_seeds :153-358
     std::vector<Seed> suffix_seeds() {
         std::vector<Seed> seeds_;
         size_t k = graph.get_k();
@@ -552,6 +582,62 @@ struct SeederBase {
                 append_suffix_seed(i, alt, seed_length);
         }
 
+        if (canon) {
+            // sub-k matches of the reverse complement (:251-314): a prefix of query_rc[i..] that is the suffix
+            // of nodes, turned into nodes whose reverse complement starts with the match (suffix_to_prefix :95-139)
+            const BOSS &boss = graph.boss;
+            std::string query_rc(query);
+            reverse_complement_inplace(query_rc);
+            for (size_t i = 0; i + config.min_seed_length <= query_rc.size(); ++i) {
+                size_t max_seed_length = std::min({ config.max_seed_length, k - 1, query.size() - i });
+                size_t j_min = query_rc.size() - i - max_seed_length;
+                size_t j_max = query_rc.size() - i - config.min_seed_length;
+                while (j_min <= j_max && min_seed_length[j_min] > max_seed_length) {
+                    ++j_min;
+                    --max_seed_length;
+                }
+                if (j_min > j_max)
+                    continue;
+                std::vector<TAlphabet> encoded = boss.alph->encode(std::string_view(query_rc.data() + i, max_seed_length));
+                auto [first, last, end] = boss.index_range(encoded.data(), encoded.data() + encoded.size());
+                size_t seed_length = end - encoded.data();
+                size_t j = query_rc.size() - i - seed_length;
+                if (seed_length < config.min_seed_length
+                        || seed_length < min_seed_length[j]
+                        || (config.seed_complexity_filter && config.alphabet->sigma == 5
+                                && is_low_complexity(query.substr(j, seed_length))))
+                    continue;
+                typedef std::tuple<edge_index, edge_index, size_t> Range;
+                auto call_nodes_in_range = [&](const Range &r) {
+                    for (edge_index e = std::get<0>(r); e <= std::get<1>(r); ++e) {
+                        node_index node = graph.validate_edge(e);
+                        if (node)
+                            append_suffix_seed(j, canon->reverse_complement(node), seed_length);
+                    }
+                };
+                Range start { boss.pred_last(first - 1) + 1, last, seed_length };
+                if (std::get<2>(start) == boss.k_) {
+                    call_nodes_in_range(start);
+                    continue;
+                }
+                std::vector<Range> range_stack { start };
+                while (range_stack.size()) {
+                    Range cur = range_stack.back();
+                    range_stack.pop_back();
+                    ++std::get<2>(cur);
+                    for (TAlphabet c = 1; c < boss.alph_size; ++c) {
+                        Range next = cur;
+                        if (boss.tighten_range(&std::get<0>(next), &std::get<1>(next), c)) {
+                            if (std::get<2>(next) == boss.k_)
+                                call_nodes_in_range(next);
+                            else
+                                range_stack.push_back(next);
+                        }
+                    }
+                }
+            }
+        }
+
         num_matching = 0;
         size_t last_end = 0;
         for (size_t i = 0; i < suffix_seeds.size(); ++i) {
@@ -581,8 +667,8 @@ struct SeederBase {
 
 SeederOutput run_seeder(const DBGSuccinct &graph, const DBGAlignerConfig &config,
                         std::string_view query, bool orientation,
-                        std::vector<node_index> &&nodes) {
-    SeederBase s { graph, query, orientation, std::move(nodes), config };
+                        std::vector<node_index> &&nodes, const CanonicalDBG *canon) {
+    SeederBase s { graph, query, orientation, std::move(nodes), config, 0, canon };
     s.num_matching = s.num_exact_matching();
     SeederOutput out;
     out.seeds = s.suffix_seeds();
@@ -1400,6 +1486,8 @@ void align_core(std::vector<Alignment> seeds, Extender &extender, Callback &&cal
 // ---------------------------------------------------------------------------
 DBGAligner::DBGAligner(const DBGSuccinct &graph, const DBGAlignerConfig &config)
       : graph_(graph), config_(config) {
+    if (graph_.mode == 2)
+        canonical_ = std::make_unique<CanonicalDBG>(graph_);
     if (!config_.min_seed_length)
         config_.min_seed_length = graph_.get_k();
     if (!config_.max_seed_length)
@@ -1422,11 +1510,15 @@ void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::strin
                              const std::function<void(const std::string&, AlignmentResults&&)> &callback,
                              AlignStats *stats) const {
     // dbg_aligner.cpp:224-226, 646-656
-    const bool canonical = graph_.mode == 1;
+    const CanonicalDBG *canon = canonical_.get();         // CanonicalDBG::get_mode() == CANONICAL (canonical_dbg.hpp:83)
+    const bool canonical = graph_.mode == 1 || canon;
     const bool both = (canonical || config_.forward_and_reverse_complement) && config_.alphabet->sigma == 5;
     const bool use_rcdbg = !canonical && config_.forward_and_reverse_complement;
-    GraphView fwd_graph { &graph_, false };
-    GraphView rc_graph { &graph_, use_rcdbg };
+    GraphView fwd_graph { &graph_, false, canon };
+    GraphView rc_graph { &graph_, use_rcdbg, canon };
+    auto map_nodes = [&](std::string_view seq) {
+        return canon ? canon->map_to_nodes_sequentially(seq) : graph_.map_to_nodes_sequentially(seq);
+    };
     auto is_reversible = [&](const Alignment &a) { return canonical && a.get_orientation() && !a.get_offset(); };
 
     for (const auto &[header, query] : batch) {
@@ -1437,7 +1529,7 @@ void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::strin
         // build_seeders (:193-248)
         std::vector<node_index> nodes;
         if (config_.max_seed_length >= graph_.get_k()) {
-            nodes = graph_.map_to_nodes_sequentially(query);
+            nodes = map_nodes(query);
         } else if (this_query.size() >= graph_.get_k()) {
             nodes.resize(this_query.size() - graph_.get_k() + 1);
         }
@@ -1447,15 +1539,16 @@ void DBGAligner::align_batch(const std::vector<std::pair<std::string, std::strin
             if (config_.max_seed_length >= graph_.get_k()) {
                 std::string dummy(query);
                 reverse_complement_inplace(dummy);
-                nodes_rc = graph_.map_to_nodes_sequentially(dummy); // sequence_graph.cpp:563-573
+                if (canon) canon->reverse_complement(dummy, nodes_rc);   // reverse_complement_seq_path,
+                else nodes_rc = map_nodes(dummy);                        // sequence_graph.cpp:563-573
             }
         }
-        SeederOutput seeder = run_seeder(graph_, config_, this_query, false, std::move(nodes));
+        SeederOutput seeder = run_seeder(graph_, config_, this_query, false, std::move(nodes), canon);
         if (this_query.size() * config_.min_exact_match > seeder.num_matching)
             seeder = SeederOutput();
         SeederOutput seeder_rc;
         if (both) {
-            seeder_rc = run_seeder(graph_, config_, reverse, true, std::move(nodes_rc));
+            seeder_rc = run_seeder(graph_, config_, reverse, true, std::move(nodes_rc), canon);
             if (reverse.size() * config_.min_exact_match > seeder_rc.num_matching)
                 seeder_rc = SeederOutput();
         }

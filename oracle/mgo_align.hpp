@@ -192,6 +192,9 @@ class DBGAligner {
     AlignmentResults align(std::string_view query) const;
   private:
     const DBGSuccinct &graph_;
+    // PRIMARY graphs are aligned to through the CanonicalDBG wrapper, as `metagraph align` does
+    // (cli/align.cpp primary_to_canonical; dbg_aligner.cpp:52-53 asserts it)
+    std::unique_ptr<CanonicalDBG> canonical_;
     DBGAlignerConfig config_;
 };
 
@@ -206,6 +209,6 @@ struct SeederOutput {
 };
 SeederOutput run_seeder(const DBGSuccinct &graph, const DBGAlignerConfig &config,
                         std::string_view query, bool orientation,
-                        std::vector<node_index> &&nodes);
+                        std::vector<node_index> &&nodes, const CanonicalDBG *canon = nullptr);
 
 } // namespace mgo

@@ -87,7 +87,8 @@ void* mgo_graph_build(const char *alphabet, int K, const char **seqs, int n,
 }
 
 // DeBruijnGraph::Mode of the graph: 0 BASIC, 1 CANONICAL (the caller built it from the sequences and their
-// reverse complements, as `metagraph build --mode canonical` does)
+// reverse complements, as `metagraph build --mode canonical` does), 2 PRIMARY (the caller built it from contigs
+// that hold one k-mer of every reverse-complement pair; the aligner wraps it into CanonicalDBG as the CLI does)
 void mgo_graph_set_mode(void *gp, int mode) { static_cast<DBGSuccinct*>(gp)->mode = mode; }
 
 void* mgo_graph_from_arrays(const char *alphabet, int K, const uint8_t *W, const uint8_t *last,

@@ -640,4 +640,222 @@ void DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix(
     }
 }
 
+// ---------------------------------------------------------------------------
+// CanonicalDBG (graph/representation/canonical_dbg.cpp)
+// ---------------------------------------------------------------------------
+node_index CanonicalDBG::reverse_complement(node_index node) const {   // :521-553
+    if (node > offset_)
+        return node - offset_;
+    if (k_odd_)
+        return node + offset_;
+    std::string seq = get_node_sequence(node);
+    std::string rev_seq = seq;
+    reverse_complement_inplace(rev_seq);
+    return rev_seq == seq ? node : node + offset_;
+}
+
+void CanonicalDBG::reverse_complement(std::string &seq, std::vector<node_index> &path) const {   // :555-565
+    reverse_complement_inplace(seq);
+    std::vector<node_index> rev_path(path.size());
+    std::transform(path.begin(), path.end(), rev_path.rbegin(),
+                   [&](node_index i) { return i ? reverse_complement(i) : i; });
+    std::swap(path, rev_path);
+}
+
+std::string CanonicalDBG::get_node_sequence(node_index index) const {   // :423-432
+    node_index node = get_base_node(index);
+    std::string seq = g.get_node_sequence(node);
+    if (node != index)
+        reverse_complement_inplace(seq);
+    return seq;
+}
+
+// :55-146. The forward strand is mapped up to its first miss; from there on every k-mer is looked up on both
+// strands. For odd k (no palindromes) the reference skips the forward lookup of k-mers whose reverse
+// complement was found (and of the k-mer the first pass stopped on), for even k the forward hit wins.
+std::vector<node_index> CanonicalDBG::map_to_nodes_sequentially(std::string_view sequence) const {
+    std::vector<node_index> out;
+    if (sequence.size() < get_k())
+        return out;
+    std::vector<node_index> fwd_all = g.map_to_nodes_sequentially(sequence);
+    size_t prefix = 0;
+    while (prefix < fwd_all.size() && fwd_all[prefix])
+        ++prefix;
+    out.assign(fwd_all.begin(), fwd_all.begin() + prefix);
+    sequence = sequence.substr(prefix);
+    if (sequence.size() < get_k())
+        return out;
+    std::string rev_seq(sequence);
+    reverse_complement_inplace(rev_seq);
+    std::vector<node_index> rev_path = g.map_to_nodes_sequentially(rev_seq);
+    std::vector<node_index> path(fwd_all.begin() + prefix, fwd_all.end());
+    auto it = rev_path.rbegin();
+    for (size_t j = 0; j < path.size(); ++j, ++it) {
+        if (k_odd_ && (j == 0 || *it))
+            path[j] = npos;
+        if (path[j] != npos) out.push_back(path[j]);
+        else if (*it != npos) out.push_back(*it + offset_);
+        else out.push_back(npos);
+    }
+    return out;
+}
+
+// node_first_cache.cpp:122-148 get_prefix_rc / :150-176 get_suffix_rc, uncached
+static edge_index rc_range_edge(const BOSS &boss, std::string rev_seq, bool upper) {
+    if (rev_seq[0] == '$')
+        return 0;
+    reverse_complement_inplace(rev_seq);
+    std::vector<TAlphabet> encoded = boss.alph->encode(rev_seq);
+    auto [e1, e2, end] = boss.index_range(encoded.data(), encoded.data() + encoded.size());
+    if (end != encoded.data() + encoded.size())
+        return 0;
+    return upper ? e2 : e1;
+}
+
+void CanonicalDBG::adjacent_incoming_rc_strand(node_index, const std::string &spelling,
+                                               const std::function<void(node_index, char)> &cb) const {
+    const BOSS &boss = g.boss;
+    edge_index rc_edge = rc_range_edge(boss, spelling.substr(0, spelling.size() - 1), true);
+    if (!rc_edge)
+        return;
+    // BOSS::call_outgoing (boss.hpp:779-784): the edges of the node, last one first
+    edge_index edge = rc_edge;
+    do {
+        node_index prev = edge;
+        if (g.in_graph(prev)) {
+            char c = boss.alph->decode(boss.get_W(edge) % boss.alph_size);
+            if (!(spelling.back() == '$' && c == '$'))
+                cb(prev, c);
+        }
+    } while (--edge && !boss.get_last(edge));
+}
+
+void CanonicalDBG::adjacent_outgoing_rc_strand(node_index, const std::string &spelling,
+                                               const std::function<void(node_index, char)> &cb) const {
+    const BOSS &boss = g.boss;
+    edge_index rc_edge = rc_range_edge(boss, spelling.substr(1), false);
+    if (!rc_edge)
+        return;
+    // NodeFirstCache::call_incoming_edges + get_first_char (node_first_cache.cpp:9-36)
+    boss.call_incoming_to_target(boss.bwd(rc_edge), boss.get_node_last_value(rc_edge),
+        [&](edge_index prev_edge) {
+            node_index prev = prev_edge;
+            if (!g.in_graph(prev))
+                return;
+            char c = boss.alph->decode(boss.get_minus_k_value(prev_edge, boss.k_ - 1).first);
+            if (spelling[0] == '$' && c == '$')
+                return;
+            cb(prev, c);
+        });
+}
+
+// alphabet_encoder_ (canonical_dbg.cpp:31-38): position in the graph's alphabet string, '$' included
+static inline TAlphabet alphabet_pos(const Alphabet &alph, char c) { return c == '$' ? 0 : alph.encode(c); }
+
+void CanonicalDBG::call_outgoing_kmers(node_index node, const std::function<void(node_index, char)> &cb) const {
+    if (node > offset_) {
+        call_incoming_kmers(node - offset_, [&](node_index next, char c) {
+            cb(reverse_complement(next), complement_char(c));
+        });
+        return;
+    }
+    const std::string spelling = get_node_sequence(node);
+    const Alphabet &alph = *g.boss.alph;
+    std::vector<node_index> children(alph.sigma, npos);
+    size_t max_num_edges_left = children.size() - has_sentinel_;
+    g.call_outgoing_kmers(node, [&](node_index next, char c) {
+        if (c != '$') {
+            cb(next, c);
+            --max_num_edges_left;
+        }
+        children[alphabet_pos(alph, c)] = next;
+    });
+    if (!max_num_edges_left)
+        return;
+    adjacent_outgoing_rc_strand(node, spelling, [&](node_index next, char c) {
+        c = complement_char(c);
+        TAlphabet s = alphabet_pos(alph, c);
+        if (children[s] != npos && c != '$') {
+            if (k_odd_)
+                throw std::runtime_error("Forward traversal: Primary graph contains both forward and reverse complement");
+            return;                                   // `next` is a palindrome
+        }
+        next = reverse_complement(next);
+        if (c != '$') {
+            cb(next, c);
+            children[s] = next;
+            --max_num_edges_left;
+        }
+    });
+    if (has_sentinel_ && children[alphabet_pos(alph, '$')] && max_num_edges_left + 1 == (size_t)alph.sigma)
+        cb(children[alphabet_pos(alph, '$')], '$');
+}
+
+void CanonicalDBG::call_incoming_kmers(node_index node, const std::function<void(node_index, char)> &cb) const {
+    if (node > offset_) {
+        call_outgoing_kmers(node - offset_, [&](node_index prev, char c) {
+            cb(reverse_complement(prev), complement_char(c));
+        });
+        return;
+    }
+    const std::string spelling = get_node_sequence(node);
+    const Alphabet &alph = *g.boss.alph;
+    std::vector<node_index> parents(alph.sigma, npos);
+    size_t max_num_edges_left = parents.size() - has_sentinel_;
+    g.call_incoming_kmers(node, [&](node_index prev, char c) {
+        if (c != '$') {
+            cb(prev, c);
+            --max_num_edges_left;
+        }
+        parents[alphabet_pos(alph, c)] = prev;
+    });
+    if (!max_num_edges_left)
+        return;
+    adjacent_incoming_rc_strand(node, spelling, [&](node_index prev, char c) {
+        c = complement_char(c);
+        TAlphabet s = alphabet_pos(alph, c);
+        if (parents[s] != npos && c != '$') {
+            if (k_odd_)
+                throw std::runtime_error("Backward traversal: Primary graph contains both forward and reverse complement");
+            return;
+        }
+        prev = reverse_complement(prev);
+        if (c != '$') {
+            cb(prev, c);
+            parents[s] = prev;
+            --max_num_edges_left;
+        }
+    });
+    if (has_sentinel_ && parents[alphabet_pos(alph, '$')] && max_num_edges_left + 1 == (size_t)alph.sigma)
+        cb(parents[alphabet_pos(alph, '$')], '$');
+}
+
+void CanonicalDBG::adjacent_incoming_nodes(node_index node, const std::function<void(node_index)> &cb) const {
+    if (node > offset_) {
+        adjacent_outgoing_nodes(node - offset_, [&](node_index prev) { cb(reverse_complement(prev)); });
+    } else {
+        call_incoming_kmers(node, [&](node_index prev, char) { cb(prev); });
+    }
+}
+
+void CanonicalDBG::adjacent_outgoing_nodes(node_index node, const std::function<void(node_index)> &cb) const {
+    if (node > offset_) {
+        adjacent_incoming_nodes(node - offset_, [&](node_index next) { cb(reverse_complement(next)); });
+    } else {
+        call_outgoing_kmers(node, [&](node_index next, char) { cb(next); });
+    }
+}
+
+bool CanonicalDBG::has_multiple_outgoing(node_index node) const {
+    size_t n = 0;
+    adjacent_outgoing_nodes(node, [&](node_index) { ++n; });
+    return n > 1;
+}
+
+bool CanonicalDBG::has_single_incoming(node_index node) const {
+    size_t n = 0;
+    adjacent_incoming_nodes(node, [&](node_index) { ++n; });
+    return n == 1;
+}
+
 } // namespace mgo

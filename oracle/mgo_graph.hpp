@@ -179,7 +179,8 @@ class DBGSuccinct {
     BOSS boss;
     std::vector<uint8_t> valid_edges;
     // DeBruijnGraph::Mode (sequence_graph.hpp:160): 0 BASIC, 1 CANONICAL (the graph holds the reverse
-    // complement of every k-mer). PRIMARY graphs need the CanonicalDBG wrapper, which is not restated.
+    // complement of every k-mer), 2 PRIMARY (one k-mer of every reverse-complement pair; aligned to through
+    // the CanonicalDBG wrapper below).
     int mode = 0;
 
     size_t get_k() const { return boss.k_ + 1; }
@@ -227,25 +228,66 @@ void DBGSuccinct::call_incoming_kmers(node_index node, CB &&cb) const {
         });
 }
 
-// Graph view used by the aligner: either the graph itself or its reverse
-// complement (graph/representation/rc_dbg.hpp:17-178).
+// ---------------------------------------------------------------------------
+// CanonicalDBG (graph/representation/canonical_dbg.{hpp,cpp}): wraps a PRIMARY-mode DBGSuccinct (one k-mer of
+// every reverse-complement pair) and behaves like a CANONICAL-mode graph. Node ids above `offset_` denote the
+// reverse complements of base-graph nodes. The caches of the reference (NodeFirstCache, palindrome cache)
+// only memoise: the values they would hold are recomputed here (graph_extensions/node_first_cache.cpp).
+// ---------------------------------------------------------------------------
+class CanonicalDBG {
+  public:
+    explicit CanonicalDBG(const DBGSuccinct &graph)
+        : g(graph), offset_(graph.max_index()), k_odd_(graph.get_k() % 2),
+          has_sentinel_(graph.valid_edges.empty()) {}              // canonical_dbg.cpp:23-44
+    const DBGSuccinct &g;
+
+    size_t get_k() const { return g.get_k(); }
+    uint64_t max_index() const { return offset_ * 2; }
+    node_index get_base_node(node_index node) const { return node > offset_ ? node - offset_ : node; }
+    node_index reverse_complement(node_index node) const;                              // :521-553
+    void reverse_complement(std::string &seq, std::vector<node_index> &path) const;    // :555-565
+    std::vector<node_index> map_to_nodes_sequentially(std::string_view seq) const;     // :55-146
+    std::string get_node_sequence(node_index node) const;                              // :423-432
+    // :158-243 and :245-336; cb(node, char); the spelling hint of the reference is the node's sequence
+    void call_outgoing_kmers(node_index node, const std::function<void(node_index, char)> &cb) const;
+    void call_incoming_kmers(node_index node, const std::function<void(node_index, char)> &cb) const;
+    void adjacent_outgoing_nodes(node_index node, const std::function<void(node_index)> &cb) const; // :352-364
+    void adjacent_incoming_nodes(node_index node, const std::function<void(node_index)> &cb) const; // :338-350
+    bool has_multiple_outgoing(node_index node) const;                                 // :366-380
+    bool has_single_incoming(node_index node) const;                                   // :382-392
+  private:
+    uint64_t offset_;
+    bool k_odd_, has_sentinel_;
+    void adjacent_incoming_rc_strand(node_index node, const std::string &spelling,
+                                     const std::function<void(node_index, char)> &cb) const;  // :579-625
+    void adjacent_outgoing_rc_strand(node_index node, const std::string &spelling,
+                                     const std::function<void(node_index, char)> &cb) const;  // :640-680
+};
+
+// Graph view used by the aligner: the graph itself, its reverse complement
+// (graph/representation/rc_dbg.hpp:17-178), or a PRIMARY graph behind the CanonicalDBG wrapper.
 struct GraphView {
     const DBGSuccinct *g = nullptr;
     bool rc = false;
+    const CanonicalDBG *canon = nullptr;
     // DBGSuccinct::adjacent_incoming_nodes (dbg_succinct.cpp:176-193), plain view only
     template <class CB> void adjacent_incoming_nodes(node_index node, CB &&cb) const {
+        if (canon) { canon->adjacent_incoming_nodes(node, cb); return; }
         g->call_incoming_kmers(node, [&](node_index prev, char) { cb(prev); });
     }
     size_t get_k() const { return g->get_k(); }
-    uint64_t max_index() const { return g->max_index(); }
+    uint64_t max_index() const { return canon ? canon->max_index() : g->max_index(); }
     template <class CB> void call_outgoing_kmers(node_index node, CB &&cb) const {
-        if (!rc) {
+        if (canon) {
+            canon->call_outgoing_kmers(node, cb);
+        } else if (!rc) {
             g->call_outgoing_kmers(node, cb);
         } else {   // rc_dbg.hpp:86-97
             g->call_incoming_kmers(node, [&](node_index prev, char c) { cb(prev, complement_char(c)); });
         }
     }
     std::string get_node_sequence(node_index node) const {
+        if (canon) return canon->get_node_sequence(node);
         std::string s = g->get_node_sequence(node);
         if (rc) reverse_complement_inplace(s);
         return s;

@@ -88,7 +88,8 @@ class OracleGraph:
             raise RuntimeError("oracle graph construction failed")
 
     def set_mode(self, mode):
-        """0 = BASIC, 1 = CANONICAL (graph built from the sequences plus their reverse complements)"""
+        """0 = BASIC, 1 = CANONICAL (graph built from the sequences plus their reverse complements),
+        2 = PRIMARY (graph built from primary contigs; the aligner wraps it into CanonicalDBG)"""
         lib().mgo_graph_set_mode(self.h, int(mode))
 
     def __del__(self):

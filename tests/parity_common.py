@@ -211,6 +211,30 @@ def concurrent_case(lib):
 
 
 
+def primary_contigs(seqs, k):
+    """Stand-in for `metagraph build --mode primary` (primary contigs of the canonical graph): one k-mer of every
+    reverse-complement pair, emitted as maximal runs of consecutive k-mers not seen before on either strand.
+    Which strand of a pair is kept depends on the reference's traversal order; alignments do not depend on it
+    beyond node ids and tie order."""
+    seen, out = set(), []
+    for s in seqs:
+        start = None
+        for i in range(len(s) - k + 1):
+            km = s[i:i + k]
+            key = min(km, revcomp(km))
+            if key in seen:
+                if start is not None:
+                    out.append(s[start:i + k - 1])
+                    start = None
+            else:
+                seen.add(key)
+                if start is None:
+                    start = i
+        if start is not None:
+            out.append(s[start:])
+    return out
+
+
 def check_mt_canonical(lib, **kw):
     """CANONICAL-mode graph (sequences + their reverse complements, mode flag set): integration_tests/test_align.py:207-268."""
     _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
