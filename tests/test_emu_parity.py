@@ -99,3 +99,19 @@ def test_unsupported_configs_fail_loudly():
         with pytest.raises(_lib.MgbError) as e:
             B200Aligner(idx, struct_defaults(**kw)).align("AGCTTCGAGG")
         assert e.value.code == code
+
+
+def test_graph_modes_fail_loudly():
+    """DeBruijnGraph::Mode at the boundary: BASIC and CANONICAL are served, PRIMARY (CanonicalDBG wrapper) and
+    CANONICAL on a protein graph are refused with an error code, never silently aligned as BASIC."""
+    from metagraph_b200 import _lib
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex
+    boss = BOSSTable.from_sequences(4, ["AGCTTCGAGGCCAA"], lib=EMU)
+    assert DBGSuccinctIndex(boss, lib=EMU, mode=1).mode == 1
+    with pytest.raises(_lib.MgbError) as e:
+        DBGSuccinctIndex(boss, lib=EMU, mode=2)
+    assert e.value.code == -4 and "PRIMARY" in str(e.value)            # MGB_ERR_UNSUPPORTED
+    prot = BOSSTable.from_sequences(3, ["MKVLAAGIVGLLLAQ"], alphabet=1, lib=EMU)
+    with pytest.raises(_lib.MgbError) as e:
+        DBGSuccinctIndex(prot, lib=EMU, mode=1)
+    assert e.value.code == -3                                           # MGB_ERR_BAD_CONFIG
