@@ -24,6 +24,13 @@
 #else
 #define MGB_CANONICAL(cfg) ((cfg).canonical != 0)
 #endif
+// PRIMARY graph behind CanonicalDBG semantics (node ids above ix.n denote reverse complements): only ever true
+// in the CANONICAL-mode compilation
+#if defined(MGB_BASIC_ONLY)
+#define MGB_PRIMARY(ix) false
+#else
+#define MGB_PRIMARY(ix) ((ix).mode == 2)
+#endif
 
 namespace mgb {
 
@@ -497,8 +504,148 @@ struct ReadAligner {
         wsync();
         return true;
     }
+    // alignment.cpp:563-702 on a PRIMARY graph behind CanonicalDBG: reverse_complement_seq_path flips the node ids
+    // (canonical_dbg.cpp:555-565) instead of mapping the sequence. Returns false if the alignment became empty.
+    MGB_HD bool reverse_complement_slot_primary(int slot) {
+        trim_offset(slot);
+        AlnSlot &a = sm.slots[slot];
+        AlnHdr h = *a.h;
+        const int K = ix.k;
+        auto kill = [&]() { h.used = 0; h.n_nodes = 0; *a.h = h; wsync(); return false; };
+        auto rc_seq = [&](int len) {
+            wsync();
+            for (int base = 0; base < (len + 1) / 2; base += kWarp) {
+                int i = base + wlane();
+                if (i < (len + 1) / 2) {
+                    int jj = len - 1 - i;
+                    char x = complement_char(a.seq[i]), y = complement_char(a.seq[jj]);
+                    a.seq[i] = y; a.seq[jj] = x;
+                }
+            }
+            wsync();
+        };
+        if ((int)caps.aln_seq < 2 * K + 8) { overflow = true; return false; }
+        if (!h.offset) {
+            rc_seq(h.seq_len);
+            for (int base = 0; base < (h.n_nodes + 1) / 2; base += kWarp) {
+                int i = base + wlane();
+                if (i < (h.n_nodes + 1) / 2) {
+                    uint64_t x = canon_flip(a.nodes[i]), y = canon_flip(a.nodes[h.n_nodes - 1 - i]);
+                    a.nodes[i] = y; a.nodes[h.n_nodes - 1 - i] = x;
+                }
+            }
+            wsync();
+        } else {
+            const int off = (int)h.offset;
+            uint64_t node = a.nodes[0];
+            const uint64_t base_node = node > ix.n ? node - ix.n : node;
+            uint8_t *stash = (uint8_t*)m.bt_seq;                 // scratch (not in use outside backtrack)
+            wsync();
+            for (int i = wlane(); i < h.seq_len; i += kWarp) stash[i] = (uint8_t)a.seq[i];
+            wsync();
+            // the first `off` characters of CanonicalDBG::get_node_sequence(node) (:423-432)
+            if (node == base_node) {
+                uint64_t e = node;
+                for (int i = K - 2; i >= 0; --i) {
+                    const uint32_t c = node_last_value(ix, e);
+                    if (i < off) a.seq[i] = cfg.letters[c];
+                    e = (uint64_t)load_radj(ix, e).x;
+                }
+            } else {                                             // reverse complement of the stored k-mer
+                LineCache lc;
+                uint64_t e = base_node;
+                for (int t = 0; t < off; ++t) {
+                    const uint32_t c = t == 0 ? lc.get_W(ix, base_node) % ix.sigma : node_last_value(ix, e);
+                    a.seq[t] = (char)complement_char((uint8_t)cfg.letters[c]);
+                    if (t > 0) e = (uint64_t)load_radj(ix, e).x;
+                }
+            }
+            wsync();
+            for (int i = wlane(); i < h.seq_len; i += kWarp) a.seq[off + i] = (char)stash[i];
+            wsync();
+            if (a.seq[0] == '$') {
+                if (node != base_node) return kill();            // reverse complement of a sink dummy k-mer (:592-597)
+                int num_sentinels = 0;
+                for (int i = 0; i < off + h.seq_len; ++i) if (a.seq[i] == '$') num_sentinels = i + 1;
+                const int num_first_steps = imin(off, num_sentinels);
+                LineCache lc;
+                uint64_t edge = node;
+                uint32_t label = lc.get_W(ix, edge) % ix.sigma;
+                int len = off + h.seq_len;                       // == K
+                for (int i = 0; i < num_first_steps; ++i) {
+                    edge = fwd(ix, lc, edge, label);
+                    label = lc.get_W(ix, edge) % ix.sigma;
+                    if (label == 0) return kill();
+                    if (len >= (int)caps.aln_seq) { overflow = true; return false; }
+                    node = edge;
+                    wsync();
+                    a.seq[len++] = cfg.letters[label];
+                }
+                for (int i = num_first_steps; i < off; ++i) {    // last non-'$' child through the wrapper (:624-646)
+                    const int n = canon_out(node, sm.out_nodes, sm.out_chars);
+                    wsync();
+                    if (n > kMaxOut) { overflow = true; return false; }
+                    if (!n) return kill();
+                    if (len >= (int)caps.aln_seq) { overflow = true; return false; }
+                    node = sm.out_nodes[n - 1];
+                    a.seq[len++] = (char)sm.out_chars[n - 1];
+                    wsync();
+                }
+                wsync();
+                for (int base = 0; base < K; base += kWarp) {     // seq = seq.substr(off)
+                    int i = base + wlane();
+                    char v = i < K ? a.seq[off + i] : 0;
+                    wsync();
+                    if (i < K) a.seq[i] = v;
+                    wsync();
+                }
+                rc_seq(K);
+                node = canon_flip(node);
+                for (int base = 0; base < K - off; base += kWarp) {     // keep the last K - off characters
+                    int i = base + wlane();
+                    char v = i < K - off ? a.seq[off + i] : 0;
+                    wsync();
+                    if (i < K - off) a.seq[i] = v;
+                    wsync();
+                }
+            } else {
+                rc_seq(K);
+                node = canon_flip(node);
+                // drop the ending that corresponds to the added prefix: first incoming node each time (:667-690)
+                for (int i = 0; i < off; ++i) {
+                    uint64_t sent = 0;
+                    const int n = canon_in(node, sm.out_nodes, sm.out_chars, &sent);
+                    wsync();
+                    if (n > kMaxOut) { overflow = true; return false; }
+                    if (!n && !sent) return kill();
+                    node = n ? sm.out_nodes[0] : sent;
+                    wsync();
+                }
+            }
+            wsync();
+            a.nodes[0] = node;
+            h.n_nodes = 1;
+            h.seq_len = K - off;
+        }
+        wsync();
+        for (int base = 0; base < (h.n_cigar + 1) / 2; base += kWarp) {
+            int i = base + wlane();
+            if (i < h.n_cigar / 2) {
+                uint32_t x = a.cigar[i], y = a.cigar[h.n_cigar - 1 - i];
+                a.cigar[i] = y; a.cigar[h.n_cigar - 1 - i] = x;
+            }
+        }
+        h.orientation ^= 1u;
+        *a.h = h;
+        wsync();
+        h.q_len = L - aln_clipping(a) - aln_end_clipping(a);
+        *a.h = h;
+        wsync();
+        return true;
+    }
     // Alignment::reverse_complement against the graph view the backward extender works on
     MGB_HD bool reverse_complement_for_bwd(int slot) {
+        if (MGB_CANONICAL(cfg) && MGB_PRIMARY(ix)) return reverse_complement_slot_primary(slot);
         return MGB_CANONICAL(cfg) ? reverse_complement_slot_plain(slot) : reverse_complement_slot(slot);
     }
 
@@ -551,14 +698,153 @@ struct ReadAligner {
         return n;
     }
 
+    // --------------------------------------------------------------------------------
+    // CanonicalDBG over a PRIMARY graph (canonical_dbg.cpp): nodes 1..n are the stored k-mers, n+1..2n their
+    // reverse complements. The rc-strand jumps that the reference answers with k-1 bwd steps and an index
+    // lookup behind LRU caches (NodeFirstCache) are one load from IndexView::rcs / rcp here.
+    // --------------------------------------------------------------------------------
+    MGB_HD uint64_t canon_flip(uint64_t node) const {            // CanonicalDBG::reverse_complement(node), :521-553
+        if (node > ix.n) return node - ix.n;
+        if ((ix.k & 1u) || !ix.palin) return node + ix.n;
+        return ((ix.palin[node >> 5] >> (node & 31)) & 1u) ? node : node + ix.n;
+    }
+    MGB_HD static bool has_char(const uint8_t *chars, int n, uint8_t ch) {
+        bool f = false;
+        for (int t = 0; t < n && t < kMaxOut; ++t) f = f || chars[t] == ch;
+        return f;
+    }
+    // call_outgoing_kmers (:158-243) of a stored node: its children in the base graph, then the parents of its
+    // reverse complement that no base child covers. Non-'$' children in callback order; *sentinel receives the
+    // '$' child the reference reports when there is no other (has_sentinel_, :238-242), 0 if none.
+    MGB_HD int canon_base_out(uint64_t base, uint64_t *nodes, uint8_t *chars, uint64_t *sentinel) {
+        const Adj a = load_adj_any(ix, base);
+        int n = 0;
+        uint64_t dollar = 0;
+        if (a.last) {
+            const uint64_t first = (uint64_t)a.last - popc32(a.all) + 1;
+            if ((a.all & 1u) && in_graph(ix, first)) dollar = first;
+            for (uint32_t c = 1; c < ix.sigma; ++c) {
+                if (!((a.ok >> c) & 1u)) continue;
+                if (n < kMaxOut) { nodes[n] = first + popc32(a.all & ((1u << c) - 1u)); chars[n] = cfg.letters[c]; }
+                ++n;
+            }
+        }
+        const int max_children = (int)ix.sigma - (ix.valid ? 0 : 1);
+        if (n < max_children) {
+            const uint64_t rc_edge = ix.rcs[base];
+            if (rc_edge) {
+                // NodeFirstCache::call_incoming_edges (node_first_cache.cpp:26-38) of the rc node
+                const uint2 r = load_radj(ix, rc_edge);
+                const uint32_t d = node_last_value(ix, rc_edge);
+                uint64_t edge = r.x;
+                LineCache lc;
+                while (true) {
+                    if (in_graph(ix, edge)) {
+                        const uint32_t c = radj_char(ix, load_radj(ix, edge).y);
+                        if (c != 0) {
+                            const uint8_t ch = (uint8_t)cfg.letters[ix.sigma - c];
+                            if (!has_char(chars, n, ch)) {
+                                if (n < kMaxOut) { nodes[n] = canon_flip(edge); chars[n] = ch; }
+                                ++n;
+                            }
+                        }                               // a '$' seen through the rc strand is never reported (:209-233)
+                    }
+                    if (!radj_multi(ix, r.y)) break;
+                    if (++edge > ix.n) break;
+                    uint32_t w;
+                    edge = succ_W2(ix, lc, edge, d, &w);
+                    if (w != d + ix.sigma) break;
+                }
+            }
+        }
+        if (sentinel) *sentinel = (!ix.valid && dollar && n == 0) ? dollar : 0;
+        return n;
+    }
+    // call_incoming_kmers (:245-336) of a stored node, same conventions
+    MGB_HD int canon_base_in(uint64_t base, uint64_t *nodes, uint8_t *chars, uint64_t *sentinel) {
+        int n = 0;
+        uint64_t dollar = 0;
+        {   // DBGSuccinct::call_incoming_kmers through the reverse adjacency records
+            const uint2 r = load_radj(ix, base);
+            const uint32_t d = node_last_value(ix, base);
+            uint64_t edge = r.x;
+            LineCache lc;
+            while (true) {
+                if (in_graph(ix, edge)) {
+                    const uint32_t c = radj_char(ix, load_radj(ix, edge).y);
+                    if (c != 0) {
+                        if (n < kMaxOut) { nodes[n] = edge; chars[n] = (uint8_t)cfg.letters[c]; }
+                        ++n;
+                    } else {
+                        dollar = edge;
+                    }
+                }
+                if (!radj_multi(ix, r.y)) break;
+                if (++edge > ix.n) break;
+                uint32_t w;
+                edge = succ_W2(ix, lc, edge, d, &w);
+                if (w != d + ix.sigma) break;
+            }
+        }
+        const int max_parents = (int)ix.sigma - (ix.valid ? 0 : 1);
+        if (n < max_parents) {
+            const uint64_t rc_edge = ix.rcp[base];
+            if (rc_edge) {
+                LineCache lc;
+                // BOSS::call_outgoing (boss.hpp:779-784): the edges of the rc node, last one first
+                uint64_t edge = rc_edge;
+                do {
+                    if (in_graph(ix, edge)) {
+                        const uint32_t c = lc.get_W(ix, edge) % ix.sigma;
+                        if (c != 0) {
+                            const uint8_t ch = (uint8_t)cfg.letters[ix.sigma - c];
+                            if (!has_char(chars, n, ch)) {
+                                if (n < kMaxOut) { nodes[n] = canon_flip(edge); chars[n] = ch; }
+                                ++n;
+                            }
+                        }
+                    }
+                } while (--edge && !lc.get_last(ix, edge));
+            }
+        }
+        if (sentinel) *sentinel = (!ix.valid && dollar && n == 0) ? dollar : 0;
+        return n;
+    }
+    // flips a neighbour list onto the other strand (:163-172, :250-259)
+    MGB_HD void canon_flip_list(int n, uint64_t *nodes, uint8_t *chars, uint64_t *sentinel) {
+        for (int t = 0; t < n && t < kMaxOut; ++t) { nodes[t] = canon_flip(nodes[t]); chars[t] = complement_char(chars[t]); }
+        if (sentinel && *sentinel) *sentinel = canon_flip(*sentinel);
+    }
+    MGB_HD int canon_out(uint64_t node, uint64_t *nodes, uint8_t *chars, uint64_t *sentinel = nullptr) {
+        if (node <= ix.n) return canon_base_out(node, nodes, chars, sentinel);
+        int n = canon_base_in(node - ix.n, nodes, chars, sentinel);
+        canon_flip_list(n, nodes, chars, sentinel);
+        return n;
+    }
+    MGB_HD int canon_in(uint64_t node, uint64_t *nodes, uint8_t *chars, uint64_t *sentinel = nullptr) {
+        if (node <= ix.n) return canon_base_in(node, nodes, chars, sentinel);
+        int n = canon_base_out(node - ix.n, nodes, chars, sentinel);
+        canon_flip_list(n, nodes, chars, sentinel);
+        return n;
+    }
+
     // dbg_succinct.cpp:617-630
     MGB_HD bool has_multiple_outgoing(uint64_t node) {
+        if (MGB_PRIMARY(ix)) {                               // canonical_dbg.cpp:366-380
+            uint64_t sent;
+            return canon_out(node, sm.out_nodes, sm.out_chars, &sent) > 1;
+        }
         // !get_last(fwd(node, d) - 1): the target node has more than one edge
         const Adj a = load_adj_any(ix, node);
         return a.last && popc32(a.all) > 1;
     }
     // dbg_succinct.cpp:662-680
     MGB_HD bool has_single_incoming(uint64_t node) {
+        if (MGB_PRIMARY(ix)) {                               // canonical_dbg.cpp:382-392
+            uint64_t sent;
+            int n = canon_in(node, sm.out_nodes, sm.out_chars, &sent);
+            return n + (sent ? 1 : 0) == 1;
+        }
         if (node == 1) return false;
         if (!ix.valid) return !radj_multi(ix, load_radj(ix, node).y);   // mask dropped: !multi-incoming
         LineCache lc;
@@ -1431,6 +1717,9 @@ struct ReadAligner {
                         sm.out_nodes[0] = next_node; sm.out_chars[0] = seed_seq[seed_pos]; sm.out_trails[0] = 0;
                         sm.out_scores[0] = next_node ? 0 : (!par.node ? cfg.gap_ext : cfg.gap_open);
                         n_out = 1;
+                    } else if (MGB_PRIMARY(ix)) {          // extender.cpp:361-380 (the hint equals the node's sequence)
+                        n_out = canon_out(par.node, sm.out_nodes, sm.out_chars);
+                        plain_out = true;
                     } else if (!rc) {
                         n_out = outgoing_fwd(par.node, sm.out_nodes, sm.out_chars);
                         plain_out = true;
@@ -1462,7 +1751,7 @@ struct ReadAligner {
                         const score_t add = plain_out ? 0 : sm.out_scores[t];
                         {   // requests whose latency overlaps the DP below
                             const uint64_t cnode = sm.out_nodes[t];
-                            if (!rc && cnode && !MGB_WIDE(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                            if (!rc && cnode && !MGB_WIDE(ix) && !MGB_PRIMARY(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
                             pf_key = cnode + (rc ? ix.n : 0);
                             pf_slot_idx = hash_node(pf_key);
                             pf_slot = cx[e].conv_slots[pf_slot_idx];
@@ -2251,6 +2540,21 @@ struct ReadAligner {
         stats.num_seeds = stats.num_extensions = stats.num_explored_nodes = stats.dp_columns = 0;
         stats.dp_cells = 0;
         const bool both = cfg.forward_and_reverse_complement;
+        if (MGB_CANONICAL(cfg) && MGB_PRIMARY(ix) && L >= (int)ix.k) {
+            // CanonicalDBG::map_to_nodes_sequentially (:55-146) from the two per-strand maps of the stored k-mers: a
+            // k-mer missing on its own strand takes the id of its reverse complement + n; the other strand's path is
+            // the flipped one (reverse_complement_seq_path, dbg_aligner.cpp:224-230). Idempotent (overflow retries).
+            uint64_t *nf_w = const_cast<uint64_t*>(cx[0].qnodes), *nr_w = const_cast<uint64_t*>(cx[1].qnodes);
+            const int nk = L - (int)ix.k + 1;
+            wsync();
+            for (int i = wlane(); i < nk; i += kWarp) {
+                const uint64_t f = nf_w[i], r = nr_w[nk - 1 - i];
+                const uint64_t mf = f ? f : (r ? (r > ix.n ? r : r + ix.n) : 0);
+                nf_w[i] = mf;
+                nr_w[nk - 1 - i] = mf ? canon_flip(mf) : 0;
+            }
+            wsync();
+        }
         build_psum(0);
         if (both) build_psum(1);
         if (cfg.seed_complexity_filter) { build_lowcx(0); if (both) build_lowcx(1); }

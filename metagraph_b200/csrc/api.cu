@@ -223,6 +223,9 @@ struct mgb_index {
     uint64_t device_bytes = 0;
     int num_sms = 1;
     std::vector<void*> bufs;
+#if defined(MGB_HOST_EMU)
+    std::vector<uint32_t> rc_host;   // PRIMARY graphs: rcs / rcp / palin (mgb_index_set_mode)
+#endif
     int alphabet = MGB_ALPHABET_DNA;
     AlphabetTables at;
     // working memory recycled between calls (at most 3 sets are kept)
@@ -464,11 +467,40 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
 
 int mgb_index_set_mode(mgb_index_t *index, int mode) {
     if (!index) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
-    if (mode != 0 && mode != 1)
-        return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs need the CanonicalDBG wrapper, which is not implemented");
-    if (mode == 1 && !index->at.has_complement) return fail(MGB_ERR_BAD_CONFIG, "CANONICAL mode needs a DNA graph");
-    if (mode == 1 && index->view.wide)
-        return fail(MGB_ERR_UNSUPPORTED, "CANONICAL mode is served on the DNA block layout only");
+    if (mode < 0 || mode > 2) return fail(MGB_ERR_INVALID_ARGUMENT, "mode must be 0 (BASIC), 1 (CANONICAL) or 2 (PRIMARY)");
+    if (mode != 0 && !index->at.has_complement)
+        return fail(MGB_ERR_BAD_CONFIG, "CANONICAL / PRIMARY modes need a DNA graph");
+    if (mode != 0 && index->view.wide)
+        return fail(MGB_ERR_UNSUPPORTED, "CANONICAL / PRIMARY modes are served on the DNA block layout only");
+    if (mode == 2 && !index->view.rcs) {
+        // PRIMARY graph: the rc-strand jump tables of the CanonicalDBG semantics (IndexView::rcs / rcp / palin)
+        if (index->view.k > (uint32_t)kMaxPrimaryK)
+            return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs: k above 128 is not supported");
+        const uint64_t n = index->view.n;
+        const bool even_k = index->view.k % 2 == 0;
+        const size_t pal_words = (n >> 5) + 1;
+#if defined(MGB_HOST_EMU)
+        index->rc_host.assign(2 * (n + 1) + (even_k ? pal_words : 0), 0);
+        RcArgs ra { index->view, index->rc_host.data(), index->rc_host.data() + (n + 1),
+                    even_k ? index->rc_host.data() + 2 * (n + 1) : nullptr, n };
+        for (uint64_t e = 1; e <= n; ++e) rc_tables_item(ra, e);
+#else
+        CUDA_TRY(cudaSetDevice(index->device));
+        uint32_t *buf = nullptr;
+        const size_t words = 2 * (n + 1) + (even_k ? pal_words : 0);
+        cudaError_t e = cudaMalloc((void**)&buf, words * 4);
+        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(rc tables): ") + cudaGetErrorString(e));
+        cudaMemset(buf, 0, words * 4);
+        RcArgs ra { index->view, buf, buf + (n + 1), even_k ? buf + 2 * (n + 1) : nullptr, n };
+        kern_dna::k_rc_tables<<<(unsigned)index->num_sms * 16, 128>>>(ra);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { cudaFree(buf); return fail(MGB_ERR_CUDA, std::string("rc tables: ") + cudaGetErrorString(e)); }
+        index->bufs.push_back(buf);
+        index->device_bytes += words * 4;
+#endif
+        index->view.rcs = ra.rcs; index->view.rcp = ra.rcp; index->view.palin = ra.palin;
+    }
     index->view.mode = (uint32_t)mode;
     return MGB_OK;
 }
@@ -624,6 +656,9 @@ extern "C" {
 int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t *offsets,
                      uint32_t n_seqs, uint64_t *out_nodes) {
     if (!index || !seqs || !offsets || !out_nodes) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    if (index->view.mode == 2)
+        return fail(MGB_ERR_UNSUPPORTED, "mgb_map_to_nodes maps in the stored graph; CanonicalDBG::map_to_nodes_sequentially "
+                                         "of a PRIMARY graph is only available inside mgb_align_batch");
     Stream st;
     int rc = 0;
     struct WsGuard { const mgb_index_t *ix; Workspace *w; ~WsGuard() { ix->ws_release(w); } } wsg{ index, index->ws_acquire() };
@@ -799,7 +834,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                 static std::mutex occ_mu;
                 static std::map<std::pair<int, size_t>, int> occ_cache;
                 std::lock_guard<std::mutex> lk(occ_mu);
-                const int variant = index->view.wide ? 1 : index->view.mode == 1 ? 2 : 0;    // which k_align
+                const int variant = index->view.wide ? 1 : index->view.mode != 0 ? 2 : 0;    // which k_align
                 auto key = std::make_pair(index->device * 4 + variant, smem_block);
                 auto it = occ_cache.find(key);
                 if (it == occ_cache.end()) {
@@ -866,7 +901,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #else
             cudaEventRecord(ev[3], st.s);
             CUDA_TRY(index->view.wide ? kern_any::launch_align(n_warps / 4, smem_block, st.s, a)
-                   : index->view.mode == 1 ? kern_canon::launch_align(n_warps / 4, smem_block, st.s, a)
+                   : index->view.mode != 0 ? kern_canon::launch_align(n_warps / 4, smem_block, st.s, a)
                                            : kern_dna::launch_align(n_warps / 4, smem_block, st.s, a));
             cudaEventRecord(ev[4], st.s);
             if ((rc = d2h(&used, d_used, 8, st))) break;
@@ -976,10 +1011,13 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     std::string err;
     int rc = lower_config(*config, index->view.k, index->alphabet, &dcfg, &err);
     if (rc) return fail(rc, err);
-    if (index->view.mode == 1) {                 // CANONICAL-mode graph: both strands, no RCDBG view (dbg_aligner.cpp:224-226)
-        dcfg.canonical = 1;
-        dcfg.forward_and_reverse_complement = 1;
+    if (index->view.mode != 0) {                 // CANONICAL-mode graph, or a PRIMARY one with CanonicalDBG semantics
+        dcfg.canonical = 1;                      // (get_mode() == CANONICAL): both strands, no RCDBG view
+        dcfg.forward_and_reverse_complement = 1; // (dbg_aligner.cpp:224-226)
     }
+    if (index->view.mode == 2 && dcfg.min_seed_length < index->view.k)
+        return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs: seeds shorter than k (the reverse-complement sub-k seeding of "
+                                         "aligner_seeder_methods.cpp:251-314) are not implemented; set min_seed_length >= k");
 
     // pieces of >= 64k reads, at most 8; two host threads keep two pieces in flight
     const uint32_t kMinPiece = 65536, kMaxPieces = 8;

@@ -69,7 +69,15 @@ struct IndexView {
     //          DBG nodes), 0 -- the adj record with sigma-bit masks
     // radj is shared; its y word holds the first character in bits 0..6 and the multi-incoming flag in
     // bit 7 here (bits 0..2 / bit 3 in the DNA layout).
-    uint32_t mode;              // DeBruijnGraph::Mode: 0 BASIC, 1 CANONICAL (graph holds both strands)
+    uint32_t mode;              // DeBruijnGraph::Mode: 0 BASIC, 1 CANONICAL (graph holds both strands),
+                                // 2 PRIMARY (one k-mer of every reverse-complement pair; CanonicalDBG semantics)
+    // PRIMARY graphs only (canonical_dbg.cpp, node_first_cache.cpp:122-176, one u32 per edge e with k-mer x):
+    //   rcs[e]  last edge of the BOSS node rc(x[1..k)) or 0   (get_suffix_rc: where children of x enter on the rc strand)
+    //   rcp[e]  last edge of the BOSS node rc(x[0..k-1)) or 0 (get_prefix_rc: where parents of x leave on the rc strand)
+    //   palin   bit per edge: x is its own reverse complement (even k only, else nullptr)
+    const uint32_t *rcs;
+    const uint32_t *rcp;
+    const uint32_t *palin;
     uint32_t wide;
     const uint8_t *wW;
     const uint32_t *wl;

@@ -248,6 +248,54 @@ MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
     if (glane() == 0) { a.bwd_arr[e] = (uint32_t)x; a.c_cur[e] = (uint8_t)d; a.multi[e] = (uint8_t)multi; }
 }
 
+// PRIMARY graphs: the rc-strand jump tables of IndexView (rcs / rcp / palin) for edge e. The k-mer is spelled
+// through the reverse adjacency records (BOSS::get_node_seq, boss.cpp:953-973), its two (k-1)-mers are reverse
+// complemented and looked up (NodeFirstCache::get_suffix_rc / get_prefix_rc, node_first_cache.cpp:122-176).
+constexpr int kMaxPrimaryK = 128;
+struct RcArgs { IndexView ix; uint32_t *rcs; uint32_t *rcp; uint32_t *palin; uint64_t n; };
+MGB_HD void rc_tables_item(const RcArgs &a, uint64_t e) {
+    const IndexView &ix = a.ix;
+    const int K = (int)ix.k;
+    uint8_t km[kMaxPrimaryK];
+    {
+        LineCache lc;
+        km[K - 1] = (uint8_t)(lc.get_W(ix, e) % ix.sigma);
+        uint64_t cur = e;
+        for (int i = K - 2; i >= 0; --i) {
+            km[i] = (uint8_t)node_last_value(ix, cur);
+            cur = load_radj(ix, cur).x;
+        }
+    }
+    uint8_t rc[kMaxPrimaryK];
+    uint32_t r_s = 0, r_p = 0;
+    bool clean = true;                                   // no '$' in x[1..k)
+    for (int i = 1; i < K; ++i) clean = clean && km[i] != 0;
+    if (clean) {
+        for (int t = 0; t < K - 1; ++t) rc[t] = (uint8_t)(ix.sigma - km[K - 1 - t]);
+        uint64_t first, lst; int matched;
+        boss_index_range(ix, rc, K - 1, &first, &lst, &matched);
+        if (matched == K - 1) r_s = (uint32_t)lst;
+    }
+    if (km[0] != 0) {                                    // then x[0..k-1) holds no '$' at all
+        for (int t = 0; t < K - 1; ++t) rc[t] = (uint8_t)(ix.sigma - km[K - 2 - t]);
+        uint64_t first, lst; int matched;
+        boss_index_range(ix, rc, K - 1, &first, &lst, &matched);
+        if (matched == K - 1) r_p = (uint32_t)lst;
+    }
+    bool pal = a.palin != nullptr && clean && km[0] != 0;
+    for (int t = 0; t < K && pal; ++t) pal = km[t] == ix.sigma - km[K - 1 - t];
+    if (glane() == 0) {
+        a.rcs[e] = r_s; a.rcp[e] = r_p;
+        if (pal) {
+#if MGB_DEVICE_CODE
+            atomicOr(a.palin + (e >> 5), 1u << (e & 31));
+#else
+            a.palin[e >> 5] |= 1u << (e & 31);
+#endif
+        }
+    }
+}
+
 } // namespace mgb
 
 #if !defined(MGB_HOST_EMU)
@@ -344,6 +392,12 @@ cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_pe
 }
 
 #if !defined(MGB_WIDE_ONLY) && !defined(MGB_ALIGN_KERNEL_ONLY)
+// PRIMARY graphs are DNA graphs in the block layout: first translation unit only
+__global__ void __launch_bounds__(128) k_rc_tables(RcArgs a) {
+    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+    for (uint64_t e = 1 + quad; e <= a.n; e += nquads) rc_tables_item(a, e);
+}
 // alphabet-independent kernels live in the first translation unit only
 __global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

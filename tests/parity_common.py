@@ -252,7 +252,24 @@ def check_mt_canonical(lib, **kw):
     return got
 
 
-def fuzz_case(lib, seed, canonical=False):
+def check_mt_primary(lib, **kw):
+    """PRIMARY-mode graph behind CanonicalDBG semantics: integration_tests/test_align.py:270-300."""
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    names, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    contigs = primary_contigs(seqs, 11)
+    g = O.OracleGraph(11, contigs, mask=False)
+    g.set_mode(2)
+    W, last, F, _ = g.arrays()
+    idx = DBGSuccinctIndex(BOSSTable(11, W, last, F), lib=lib, mode=2)
+    cfg = cli_defaults(11, min_exact_match=0.0, **kw)
+    got, _ = run_lines(idx, cfg, reads, names)
+    exp = g.align_tsv(cfg, reads, headers=names, with_nodes=True)
+    idx.close()
+    assert got == exp
+    return got
+
+
+def fuzz_case(lib, seed, canonical=False, primary=False):
     """One randomized (graph, reads, config) triple: k, graph shape (variants, repeats, dummy mask), scoring
     matrix, gap penalties, xdrop, seed lengths (exact / MEM / sub-k), seeds per locus, alternative paths,
     strands, end bonuses, cut-offs, node budget, left trim, complexity filter. Returns the mismatching reads."""
@@ -279,17 +296,25 @@ def fuzz_case(lib, seed, canonical=False):
     msl = int(rng.integers(2, k + 1)); kw["min_seed_length"] = msl
     kw["max_seed_length"] = int(rng.choice([k, SIZE_MAX, max(msl, k - 1), k + 5]))
     if kw["max_seed_length"] < msl: kw["max_seed_length"] = msl
+    if primary:                 # the kernels serve exact / MEM seeds on PRIMARY graphs (no sub-k seeds yet)
+        kw["min_seed_length"] = k
+        kw["max_seed_length"] = int(rng.choice([k, SIZE_MAX, k + 5]))
     kw["max_num_seeds_per_locus"] = int(rng.choice([1000, 2, SIZE_MAX]))
     cfg = cli_defaults(k, **kw)
     mask = bool(rng.random() < 0.3)
+    read_src = seqs
     if canonical:               # `build --mode canonical`: every sequence and its reverse complement
         seqs = seqs + [revcomp(s_) for s_ in seqs]
+        read_src = seqs
+    if primary:                 # `build --mode primary`: one k-mer of every reverse-complement pair
+        seqs = primary_contigs(seqs, k)
     g = O.OracleGraph(k, seqs, mask=mask)
-    if canonical:
-        g.set_mode(1)
+    if canonical or primary:
+        g.set_mode(2 if primary else 1)
     W, last, F, valid = g.arrays()
     idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if mask else None, lib=lib,
-                           mode=1 if canonical else 0)
+                           mode=2 if primary else 1 if canonical else 0)
+    seqs = read_src
     reads = []
     for i in range(25):
         s_ = seqs[int(rng.integers(0, len(seqs)))]
