@@ -39,3 +39,13 @@ def test_fuzz_canonical_gpu():
     for seed in range(100, 140):
         bad, info = P.fuzz_case(None, seed, canonical=True)
         assert not bad, (seed, info)
+
+
+def test_fuzz_primary_emu():
+    """PRIMARY graphs (one k-mer of every reverse-complement pair) with CanonicalDBG semantics on device
+    (canonical_dbg.cpp; exact / MEM seeds)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    for seed in range(25):
+        bad, info = P.fuzz_case(EMU, seed, primary=True)
+        assert not bad, (seed, info)
+

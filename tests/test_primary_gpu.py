@@ -1,0 +1,24 @@
+"""PRIMARY graphs through the sm_100a kernels (CanonicalDBG semantics on device: rc-strand jump tables, node-id flips,
+both-strand node map). Kept in its own module, collected after test_gpu_parity.py: the emulation build of the same
+sources is parity-green on these inputs (tests/test_emu_parity.py, tests/test_fuzz_parity.py), the device run of this
+mode was added after the round's GPU budget was spent."""
+import pytest
+
+import parity_common as P
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mt_primary_gpu():
+    # integration_tests/test_align.py:270-300 (graph built with --mode primary)
+    got = P.check_mt_primary(None)
+    from test_oracle_canonical import CANONICAL
+    for i, exp in CANONICAL:
+        assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
+    assert got[6].split("\t")[4] == "310" and got[5].split("\t")[4] == "22"
+
+
+def test_fuzz_primary_gpu():
+    for seed in range(100, 140):
+        bad, info = P.fuzz_case(None, seed, primary=True)
+        assert not bad, (seed, info)
