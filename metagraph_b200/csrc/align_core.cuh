@@ -1051,6 +1051,159 @@ struct ReadAligner {
         return count;
     }
 
+    // suffix_to_prefix (aligner_seeder_methods.cpp:95-139): the nodes whose k-mer starts with the `len0` characters
+    // that select the BOSS range [rl0, ru0] (a set of nodes ending in them), found by extending the range one
+    // character at a time, last pushed first. Counts the valid nodes; with `emit` each becomes a seed of the
+    // reverse-complement node at query position `pos`. `stack`: scratch of 3 words per entry.
+    MGB_HD int suffix_to_prefix(int s, int pos, uint64_t rl0, uint64_t ru0, int len0, bool emit,
+                                uint32_t *stack, int stack_cap) {
+        const int bk = (int)ix.k - 1;                         // boss.get_k()
+        int count = 0;
+        if (len0 == bk) {
+            for (uint64_t e = rl0; e <= ru0 && !overflow; ++e)
+                if (in_graph(ix, e)) { ++count; if (emit) push_seed(s, pos, len0, ix.k - len0, 1, canon_flip(e)); }
+            return count;
+        }
+        int sp = 0;
+        wsync();
+        stack[0] = (uint32_t)rl0; stack[1] = (uint32_t)ru0; stack[2] = (uint32_t)len0; sp = 1;
+        wsync();
+        while (sp && !overflow) {
+            --sp;
+            const uint64_t rl = stack[3 * sp], ru = stack[3 * sp + 1];
+            const int len = (int)stack[3 * sp + 2] + 1;
+            wsync();
+            for (uint32_t c = 1; c < ix.sigma && !overflow; ++c) {
+                uint64_t nrl = rl, nru = ru;
+                if (!tighten_range(ix, &nrl, &nru, c)) continue;
+                if (len == bk) {
+                    for (uint64_t e = nrl; e <= nru && !overflow; ++e)
+                        if (in_graph(ix, e)) { ++count; if (emit) push_seed(s, pos, len0, ix.k - len0, 1, canon_flip(e)); }
+                } else {
+                    if (sp >= stack_cap) { overflow = true; break; }
+                    stack[3 * sp] = (uint32_t)nrl; stack[3 * sp + 1] = (uint32_t)nru; stack[3 * sp + 2] = (uint32_t)len;
+                    ++sp;
+                }
+            }
+            wsync();
+        }
+        return count;
+    }
+
+    // Second half of SuffixSeeder::generate_seeds on a PRIMARY graph (CanonicalDBG): sub-k matches of the query
+    // (:216-249) AND of its reverse complement (:251-314) compete per query position, so the seeds of a position are
+    // only known after both passes. Pass A replays the reference's bookkeeping (min_seed_length per position, which
+    // source holds the current seeds) while only counting nodes; pass B emits the survivors in position order with
+    // the aggregation rules (:316-357). m.sfx_* hold the forward lookups; scratch lives in the (idle) DP cell arena.
+    MGB_HD void build_seeds_subk_primary(int s, int n_base, const SeedRec *base_seeds, int n_pos) {
+        const int k = ix.k;
+        const int min_len = (int)cfg.min_seed_length;
+        const int stack_cap = 4 * k + 8;
+        if ((uint64_t)3 * n_pos + 3 * (uint64_t)stack_cap > 3ull * caps.max_cells) { overflow = true; return; }
+        uint32_t *rc_first = (uint32_t*)m.cells, *rc_last = rc_first + n_pos;
+        uint32_t *meta = rc_last + n_pos;                         // fwd length | rc length << 8
+        uint32_t *stack = meta + n_pos;
+        for (int i = wlane(); i < n_pos; i += kWarp) meta[i] = 0;
+        wsync();
+        // ---- pass A, forward matches (:216-249) ----
+        {
+            int b_next = 0;
+            const int last_full_id = L >= k ? L - k + 1 : n_pos;
+            int lf_count = 0; uint64_t lf_node = 0;
+            for (int i = 0; i < n_pos; ++i) {
+                int n_here = 0; uint64_t node_here = 0;
+                if (b_next < n_base && (int)base_seeds[b_next].clip == i) {
+                    node_here = base_seeds[b_next].node0; ++b_next; n_here = 1;
+                } else if (m.sfx_min[i] != k) {
+                    const int min_here = m.sfx_min[i];
+                    const int matched = m.sfx_len[i];
+                    if (matched >= min_here && matched > 0
+                            && !(cfg.seed_complexity_filter && low_complexity(s, i, min_here))) {
+                        uint64_t first_node = 0;
+                        const int keep = cx[s].n_seeds;
+                        int cnt = suffix_enumerate(s, i, matched, m.sfx_first[i], m.sfx_last[i], &first_node);
+                        if (overflow) return;
+                        cx[s].n_seeds = keep;                     // counted only
+                        const bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
+                                    && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
+                        if (cnt != 0 && !skip) {
+                            wsync();
+                            m.sfx_min[i] = (uint8_t)matched;
+                            meta[i] = (uint32_t)matched;
+                            int sl = matched;
+                            for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j) m.sfx_min[j] = (uint8_t)(sl--);
+                            wsync();
+                            n_here = cnt; node_here = first_node;
+                        }
+                    }
+                }
+                if (i == last_full_id - 1) { lf_count = n_here; lf_node = n_here ? node_here : 0; }
+            }
+        }
+        // ---- pass A, matches of the reverse complement (:251-314) ----
+        const uint8_t *rc_codes = cx[1 - s].codes;
+        for (int i = 0; i + min_len <= L && !overflow; ++i) {
+            int max_len = imin(imin((int)(cfg.max_seed_length < 0x7fffffffu ? cfg.max_seed_length : 0x7fffffffu), k - 1), L - i);
+            int j_min = L - i - max_len;
+            const int j_max = L - i - min_len;
+            while (j_min <= j_max && (int)m.sfx_min[j_min] > max_len) { ++j_min; --max_len; }
+            if (j_min > j_max) continue;
+            uint64_t first = 0, lst = 0; int matched = 0;
+            boss_index_range(ix, rc_codes + i, max_len, &first, &lst, &matched, min_len);
+            const int seed_length = matched;
+            if (seed_length < min_len) continue;
+            const int j = L - i - seed_length;
+            if (seed_length < (int)m.sfx_min[j]
+                    || (cfg.seed_complexity_filter && low_complexity(s, j, seed_length)))
+                continue;
+            LineCache lc;
+            const uint64_t lo = pred_last(ix, lc, first - 1) + 1;
+            const int cnt = suffix_to_prefix(s, j, lo, lst, seed_length, false, stack, stack_cap);
+            if (overflow) return;
+            if (!cnt) continue;
+            wsync();
+            // append_suffix_seed (:195-213): longer than what the position holds -> replaces it
+            m.sfx_min[j] = (uint8_t)seed_length;
+            rc_first[j] = (uint32_t)lo; rc_last[j] = (uint32_t)lst;
+            meta[j] = (meta[j] & 0xffu) | ((uint32_t)seed_length << 8);
+            int sl = seed_length;
+            for (int jj = j + 1; jj < n_pos && sl > (int)m.sfx_min[jj]; ++jj) m.sfx_min[jj] = (uint8_t)(sl--);
+            wsync();
+        }
+        if (overflow) return;
+        // ---- pass B: aggregation in query order (:316-357) ----
+        int b_next = 0;
+        uint32_t nm = 0; int last_end = 0;
+        for (int i = 0; i < n_pos; ++i) {
+            const int pos_first = cx[s].n_seeds;
+            if (b_next < n_base && (int)base_seeds[b_next].clip == i) {
+                if (cx[s].n_seeds >= (int)caps.max_seeds - n_base) { overflow = true; return; }
+                cx[s].seeds[cx[s].n_seeds++] = base_seeds[b_next++];
+            } else {
+                const int cur = m.sfx_min[i];
+                const int fl = (int)(meta[i] & 0xffu), rl_ = (int)((meta[i] >> 8) & 0xffu);
+                uint64_t cnt = 0;
+                if (fl && fl == cur) {
+                    uint64_t fn = 0;
+                    cnt += (uint64_t)suffix_enumerate(s, i, fl, m.sfx_first[i], m.sfx_last[i], &fn);
+                }
+                if (!overflow && rl_ && rl_ == cur)
+                    cnt += (uint64_t)suffix_to_prefix(s, i, rc_first[i], rc_last[i], rl_, true, stack, stack_cap);
+                if (overflow) return;
+                if (cx[s].n_seeds > (int)caps.max_seeds - n_base) { overflow = true; return; }
+                if (cnt > cfg.max_num_seeds_per_locus) cx[s].n_seeds = pos_first;
+            }
+            if (cx[s].n_seeds > pos_first) {
+                const SeedRec &bk = cx[s].seeds[cx[s].n_seeds - 1];
+                int begin = bk.clip, end = begin + (int)bk.len;
+                if (begin < last_end) nm += end - begin - (last_end - begin);
+                else nm += end - begin;
+                last_end = end;
+            }
+        }
+        cx[s].num_matching = nm;
+    }
+
     // SuffixSeeder<UniMEMSeeder>::generate_seeds (:153-358), non-canonical part
     MGB_HD void build_seeds(int s) {
         const int k = ix.k;
@@ -1157,6 +1310,8 @@ struct ReadAligner {
             }
         }
         wsync();
+
+        if (MGB_CANONICAL(cfg) && MGB_PRIMARY(ix)) { build_seeds_subk_primary(s, n_base, base_seeds, n_pos); return; }
 
         int b_next = 0;
         const int last_full_id = L >= k ? L - k + 1 : n_pos;

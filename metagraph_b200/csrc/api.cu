@@ -1015,9 +1015,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
         dcfg.canonical = 1;                      // (get_mode() == CANONICAL): both strands, no RCDBG view
         dcfg.forward_and_reverse_complement = 1; // (dbg_aligner.cpp:224-226)
     }
-    if (index->view.mode == 2 && dcfg.min_seed_length < index->view.k)
-        return fail(MGB_ERR_UNSUPPORTED, "PRIMARY graphs: seeds shorter than k (the reverse-complement sub-k seeding of "
-                                         "aligner_seeder_methods.cpp:251-314) are not implemented; set min_seed_length >= k");
+
 
     // pieces of >= 64k reads, at most 8; two host threads keep two pieces in flight
     const uint32_t kMinPiece = 65536, kMaxPieces = 8;

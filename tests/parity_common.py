@@ -296,9 +296,6 @@ def fuzz_case(lib, seed, canonical=False, primary=False):
     msl = int(rng.integers(2, k + 1)); kw["min_seed_length"] = msl
     kw["max_seed_length"] = int(rng.choice([k, SIZE_MAX, max(msl, k - 1), k + 5]))
     if kw["max_seed_length"] < msl: kw["max_seed_length"] = msl
-    if primary:                 # the kernels serve exact / MEM seeds on PRIMARY graphs (no sub-k seeds yet)
-        kw["min_seed_length"] = k
-        kw["max_seed_length"] = int(rng.choice([k, SIZE_MAX, k + 5]))
     kw["max_num_seeds_per_locus"] = int(rng.choice([1000, 2, SIZE_MAX]))
     cfg = cli_defaults(k, **kw)
     mask = bool(rng.random() < 0.3)

@@ -35,13 +35,14 @@ def test_mt_canonical_emu(subk, _emu_built):
         assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
 
 
-def test_mt_primary_emu():
-    # integration_tests/test_align.py:270-300 (graph built with --mode primary), CanonicalDBG semantics on device
-    got = P.check_mt_primary(EMU)
-    from test_oracle_canonical import CANONICAL
-    for i, exp in CANONICAL:
+@pytest.mark.parametrize("subk", [False, True])
+def test_mt_primary_emu(subk):
+    # integration_tests/test_align.py:270-330 (graph built with --mode primary), CanonicalDBG semantics on device
+    got = P.check_mt_primary(EMU, **({"min_seed_length": 10} if subk else {}))
+    from test_oracle_canonical import CANONICAL, CANONICAL_SUBK
+    for i, exp in (CANONICAL_SUBK if subk else CANONICAL):
         assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
-    assert got[6].split("\t")[4] == "310" and got[5].split("\t")[4] == "22"
+    assert got[6].split("\t")[4] == "310" and (subk or got[5].split("\t")[4] == "22")
 
 
 @pytest.mark.parametrize("case", P.RANDOM_CASES, ids=[str(c[0]) for c in P.RANDOM_CASES])
@@ -111,9 +112,9 @@ def test_unsupported_configs_fail_loudly():
 
 
 def test_graph_modes_fail_loudly():
-    """DeBruijnGraph::Mode at the boundary: BASIC, CANONICAL and PRIMARY (CanonicalDBG semantics, exact / MEM seeds) are
-    served; what is not (sub-k seeds on a PRIMARY graph, a strand mode on a protein graph) is refused with an error
-    code, never silently aligned as BASIC."""
+    """DeBruijnGraph::Mode at the boundary: BASIC, CANONICAL and PRIMARY (CanonicalDBG semantics) are served; what is
+    not (an unknown mode, mgb_map_to_nodes on a PRIMARY graph, a strand mode on a protein graph) is refused with an
+    error code, never silently treated as BASIC."""
     from metagraph_b200 import _lib
     from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex
     from metagraph_b200.config import cli_defaults
@@ -123,11 +124,9 @@ def test_graph_modes_fail_loudly():
         DBGSuccinctIndex(boss, lib=EMU, mode=3)
     assert e.value.code == -1                                           # MGB_ERR_INVALID_ARGUMENT
     idx = DBGSuccinctIndex(boss, lib=EMU, mode=2)
-    B200Aligner(idx, cli_defaults(5)).align("AGCTTCGAGG")              # min_seed_length clamps to k: served
-    with pytest.raises(_lib.MgbError) as e:
-        B200Aligner(idx, cli_defaults(5, min_seed_length=3)).align("AGCTTCGAGG")
-    assert e.value.code == -4 and "PRIMARY" in str(e.value)            # MGB_ERR_UNSUPPORTED
-    with pytest.raises(_lib.MgbError) as e:
+    B200Aligner(idx, cli_defaults(5)).align("AGCTTCGAGG")
+    B200Aligner(idx, cli_defaults(5, min_seed_length=3)).align("AGCTTCGAGG")
+    with pytest.raises(_lib.MgbError) as e:                             # the wrapper's both-strand map: align only
         idx.map_to_nodes_sequentially(["AGCTTCGAGG"])
     assert e.value.code == -4
     prot = BOSSTable.from_sequences(3, ["MKVLAAGIVGLLLAQ"], alphabet=1, lib=EMU)

@@ -43,7 +43,7 @@ def test_fuzz_canonical_gpu():
 
 def test_fuzz_primary_emu():
     """PRIMARY graphs (one k-mer of every reverse-complement pair) with CanonicalDBG semantics on device
-    (canonical_dbg.cpp; exact / MEM seeds)."""
+    (canonical_dbg.cpp; all seeders, incl. the reverse-complement sub-k seeds of aligner_seeder_methods.cpp:251-314)."""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
     for seed in range(25):
         bad, info = P.fuzz_case(EMU, seed, primary=True)

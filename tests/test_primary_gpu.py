@@ -1,5 +1,5 @@
 """PRIMARY graphs through the sm_100a kernels (CanonicalDBG semantics on device: rc-strand jump tables, node-id flips,
-both-strand node map). Kept in its own module, collected after test_gpu_parity.py: the emulation build of the same
+both-strand node map, sub-k seeding of both strands). Kept in its own module, collected after test_gpu_parity.py: the emulation build of the same
 sources is parity-green on these inputs (tests/test_emu_parity.py, tests/test_fuzz_parity.py), the device run of this
 mode was added after the round's GPU budget was spent."""
 import pytest
@@ -9,13 +9,14 @@ import parity_common as P
 pytestmark = pytest.mark.gpu
 
 
-def test_mt_primary_gpu():
-    # integration_tests/test_align.py:270-300 (graph built with --mode primary)
-    got = P.check_mt_primary(None)
-    from test_oracle_canonical import CANONICAL
-    for i, exp in CANONICAL:
+@pytest.mark.parametrize("subk", [False, True])
+def test_mt_primary_gpu(subk):
+    # integration_tests/test_align.py:270-330 (graph built with --mode primary)
+    got = P.check_mt_primary(None, **({"min_seed_length": 10} if subk else {}))
+    from test_oracle_canonical import CANONICAL, CANONICAL_SUBK
+    for i, exp in (CANONICAL_SUBK if subk else CANONICAL):
         assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
-    assert got[6].split("\t")[4] == "310" and got[5].split("\t")[4] == "22"
+    assert got[6].split("\t")[4] == "310" and (subk or got[5].split("\t")[4] == "22")
 
 
 def test_fuzz_primary_gpu():
