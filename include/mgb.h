@@ -133,7 +133,10 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1,
                      uint32_t suffix_len, int device, mgb_index_t **out);
 /* DeBruijnGraph::get_mode() of the graph (sequence_graph.hpp:160): 0 = BASIC (default), 1 = CANONICAL (built with
  * --mode canonical: the graph holds the reverse complement of every k-mer; dbg_aligner.cpp:224-226, 646-722).
- * 2 = PRIMARY is refused: it needs the CanonicalDBG wrapper (canonical_dbg.cpp), not implemented. */
+ * 2 = PRIMARY (built with --mode primary: one k-mer of every reverse-complement pair): the index answers with the
+ * semantics of the CanonicalDBG wrapper `metagraph align` puts around such graphs (canonical_dbg.cpp): node ids
+ * above mgb_index_num_edges() denote reverse complements. The first call builds two 4-byte-per-edge tables on the
+ * device. mgb_map_to_nodes is not available on a PRIMARY index (MGB_ERR_UNSUPPORTED). */
 int mgb_index_set_mode(mgb_index_t *index, int mode);
 void mgb_index_destroy(mgb_index_t *index);
 uint64_t mgb_index_num_edges(const mgb_index_t *index);

@@ -37,7 +37,7 @@ class B200Graph {
             throw std::runtime_error(mgb_last_error());
     }
     // A graph file written by `metagraph build` (DBGSuccinct::load, dbg_succinct.cpp:690-712), for callers
-    // that do not link MetaGraph. BASIC and CANONICAL graphs; PRIMARY ones need the CanonicalDBG wrapper and are refused.
+    // that do not link MetaGraph. BASIC, CANONICAL and PRIMARY graphs (the latter answer with CanonicalDBG semantics, as under `metagraph align`).
     explicit B200Graph(const std::string &dbg_path, int device = 0) {
         mgb_boss_t boss;
         int mode = -1, state = -1;
@@ -70,7 +70,7 @@ class B200Graph {
         set_mode(static_cast<int>(dbg.get_mode()));
     }
 #endif
-    // DeBruijnGraph::Mode of the graph (sequence_graph.hpp:160): 0 BASIC, 1 CANONICAL; PRIMARY is refused
+    // DeBruijnGraph::Mode of the graph (sequence_graph.hpp:160): 0 BASIC, 1 CANONICAL, 2 PRIMARY
     void set_mode(int mode) {
         if (mgb_index_set_mode(index_, mode) != MGB_OK) {
             std::string err = mgb_last_error();

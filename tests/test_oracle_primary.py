@@ -2,8 +2,8 @@
 (graph/representation/canonical_dbg.cpp, graph_extensions/node_first_cache.cpp:122-176), the sub-k seeding of the
 reverse complement (aligner_seeder_methods.cpp:95-139, 251-314) and the CanonicalDBG branches of
 Alignment::reverse_complement (alignment.cpp:583-640) and is pinned here on the reference's integration goldens
-(integration_tests/test_align.py:270-330). The kernels do not serve this mode yet (`mgb_index_set_mode(…, 2)` fails
-with MGB_ERR_UNSUPPORTED; DESIGN.md section 7 has the plan)."""
+(integration_tests/test_align.py:270-330). The kernels are checked against it in tests/test_emu_parity.py,
+tests/test_fuzz_parity.py and tests/test_primary_gpu.py."""
 import os
 
 import oracle_lib as O
