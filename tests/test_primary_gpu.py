@@ -1,7 +1,6 @@
 """PRIMARY graphs through the sm_100a kernels (CanonicalDBG semantics on device: rc-strand jump tables, node-id flips,
-both-strand node map, sub-k seeding of both strands). Kept in its own module, collected after test_gpu_parity.py: the emulation build of the same
-sources is parity-green on these inputs (tests/test_emu_parity.py, tests/test_fuzz_parity.py), the device run of this
-mode was added after the round's GPU budget was spent."""
+both-strand node map, sub-k seeding of both strands) against the oracle's CanonicalDBG restatement, which is pinned on the
+reference's primary-mode goldens (tests/test_oracle_primary.py)."""
 import pytest
 
 import parity_common as P
