@@ -1464,7 +1464,7 @@ struct ReadAligner {
         mx = wreduce_max(mx);
         if (node == 0) return mx;
         StrandCtx &t = cx[e];
-        uint64_t key = node + (t.rc ? ix.n : 0);
+        uint64_t key = node + ((!MGB_CANONICAL(cfg) && t.rc) ? ix.n : 0);
         score_t *cells = t.conv_cells;
         ConvSlot en;
         int free_at;
@@ -1511,7 +1511,7 @@ struct ReadAligner {
         const score_t mx = wreduce_max(has ? val : kNinf);
         if (node == 0) return mx;
         StrandCtx &t = cx[e];
-        uint64_t key = node + (t.rc ? ix.n : 0);
+        uint64_t key = node + ((!MGB_CANONICAL(cfg) && t.rc) ? ix.n : 0);
         score_t *cells = t.conv_cells;
         ConvSlot en;
         int free_at;
@@ -1754,7 +1754,7 @@ struct ReadAligner {
         const int s = e;                                 // query strand of this extender
         const AlnSlot &seed = sm.slots[seed_slot];
         const AlnHdr sh = *seed.h;
-        const bool rc = cx[e].rc;
+        const bool rc = !MGB_CANONICAL(cfg) && cx[e].rc;      // the RCDBG view is never used on CANONICAL / PRIMARY graphs
         const int K = ix.k;
         ++cx[e].num_ext;
         min_path_score = imax(0, min_path_score);
@@ -2589,7 +2589,7 @@ struct ReadAligner {
                     AlnSlot &a = sm.slots[SLOT_EXT + r2];
                     if (!a.h->used) continue;
                     const AlnHdr h = *a.h;
-                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, cx[be].rc != 0,
+                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, !MGB_CANONICAL(cfg) && cx[be].rc != 0,
                                          a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
                         a.h->used = 0;
                 }
