@@ -656,9 +656,6 @@ extern "C" {
 int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t *offsets,
                      uint32_t n_seqs, uint64_t *out_nodes) {
     if (!index || !seqs || !offsets || !out_nodes) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
-    if (index->view.mode == 2)
-        return fail(MGB_ERR_UNSUPPORTED, "mgb_map_to_nodes maps in the stored graph; CanonicalDBG::map_to_nodes_sequentially "
-                                         "of a PRIMARY graph is only available inside mgb_align_batch");
     Stream st;
     int rc = 0;
     struct WsGuard { const mgb_index_t *ix; Workspace *w; ~WsGuard() { ix->ws_release(w); } } wsg{ index, index->ws_acquire() };
@@ -670,14 +667,30 @@ int mgb_map_to_nodes(const mgb_index_t *index, const char *seqs, const uint64_t 
     {
         DevBufs bufs(st, wsg.w, 0);
         Batch b; std::vector<uint64_t> koff; mgb_stats_t stats; std::memset(&stats, 0, sizeof(stats));
-        rc = upload_batch(index, seqs, offsets, n_seqs, false, st, bufs, &b, &koff, &stats);
+        // PRIMARY graph: CanonicalDBG::map_to_nodes_sequentially (canonical_dbg.cpp:55-146) = both strands mapped in
+        // the stored graph; a k-mer missing on its own strand takes the id of its reverse complement + n
+        const bool primary = index->view.mode == 2;
+        std::vector<uint64_t> rev;
+        rc = upload_batch(index, seqs, offsets, n_seqs, primary, st, bufs, &b, &koff, &stats);
         if (!rc) rc = dev_zero(b.nodes_f, (b.total_kmers + 1) * 8, st);
+        if (!rc && primary) rc = dev_zero(b.nodes_r, (b.total_kmers + 1) * 8, st);
         if (!rc) rc = launch_prepare(index, b, st, index->num_sms);
-        if (!rc) rc = launch_seed(index, b, 1, st, bufs);
+        if (!rc) rc = launch_seed(index, b, primary ? 2 : 1, st, bufs);
         if (!rc) rc = d2h(out_nodes, b.nodes_f, b.total_kmers * 8, st);
+        if (!rc && primary) { rev.resize(b.total_kmers + 1); rc = d2h(rev.data(), b.nodes_r, b.total_kmers * 8, st); }
 #if !defined(MGB_HOST_EMU)
         if (!rc) { cudaError_t e = cudaStreamSynchronize(st.s); if (e != cudaSuccess) rc = fail(MGB_ERR_CUDA, cudaGetErrorString(e)); }
 #endif
+        if (!rc && primary) {
+            const uint64_t n = index->view.n;
+            for (uint32_t r = 0; r < n_seqs; ++r) {
+                const uint64_t lo = koff[r], nk = koff[r + 1] - koff[r];
+                for (uint64_t i = 0; i < nk; ++i) {
+                    const uint64_t rv = rev[lo + nk - 1 - i];
+                    if (!out_nodes[lo + i] && rv) out_nodes[lo + i] = rv + n;
+                }
+            }
+        }
     }
 #if !defined(MGB_HOST_EMU)
     cudaStreamSynchronize(st.s);

@@ -124,7 +124,10 @@ void mgo_graph_get_arrays(void *g, uint8_t *W, uint8_t *last, uint64_t *F, uint8
 }
 
 uint64_t mgo_map_to_nodes(void *g, const char *seq, uint64_t len, uint64_t *out) {
-    auto nodes = static_cast<DBGSuccinct*>(g)->map_to_nodes_sequentially(std::string_view(seq, len));
+    const DBGSuccinct *dbg = static_cast<DBGSuccinct*>(g);
+    // a PRIMARY graph is seen through the CanonicalDBG wrapper, as under `metagraph align`
+    auto nodes = dbg->mode == 2 ? CanonicalDBG(*dbg).map_to_nodes_sequentially(std::string_view(seq, len))
+                                : dbg->map_to_nodes_sequentially(std::string_view(seq, len));
     std::copy(nodes.begin(), nodes.end(), out);
     return nodes.size();
 }

@@ -264,6 +264,10 @@ def check_mt_primary(lib, **kw):
     cfg = cli_defaults(11, min_exact_match=0.0, **kw)
     got, _ = run_lines(idx, cfg, reads, names)
     exp = g.align_tsv(cfg, reads, headers=names, with_nodes=True)
+    # CanonicalDBG::map_to_nodes_sequentially (canonical_dbg.cpp:55-146) at the boundary
+    probes = reads + [revcomp(r) for r in reads] + ["ACGT", "N" * 30]
+    for r, nodes in zip(probes, idx.map_to_nodes_sequentially(probes)):
+        assert list(nodes) == list(g.map_to_nodes(r)), r
     idx.close()
     assert got == exp
     return got

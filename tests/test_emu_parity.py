@@ -113,7 +113,7 @@ def test_unsupported_configs_fail_loudly():
 
 def test_graph_modes_fail_loudly():
     """DeBruijnGraph::Mode at the boundary: BASIC, CANONICAL and PRIMARY (CanonicalDBG semantics) are served; what is
-    not (an unknown mode, mgb_map_to_nodes on a PRIMARY graph, a strand mode on a protein graph) is refused with an
+    not (an unknown mode, a strand mode on a protein graph) is refused with an
     error code, never silently treated as BASIC."""
     from metagraph_b200 import _lib
     from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex
@@ -126,9 +126,6 @@ def test_graph_modes_fail_loudly():
     idx = DBGSuccinctIndex(boss, lib=EMU, mode=2)
     B200Aligner(idx, cli_defaults(5)).align("AGCTTCGAGG")
     B200Aligner(idx, cli_defaults(5, min_seed_length=3)).align("AGCTTCGAGG")
-    with pytest.raises(_lib.MgbError) as e:                             # the wrapper's both-strand map: align only
-        idx.map_to_nodes_sequentially(["AGCTTCGAGG"])
-    assert e.value.code == -4
     prot = BOSSTable.from_sequences(3, ["MKVLAAGIVGLLLAQ"], alphabet=1, lib=EMU)
     with pytest.raises(_lib.MgbError) as e:
         DBGSuccinctIndex(prot, lib=EMU, mode=1)
