@@ -34,7 +34,7 @@ extern "C" {
 #define MGB_ERR_INVALID_ARGUMENT (-1)
 #define MGB_ERR_CUDA (-2)
 #define MGB_ERR_BAD_CONFIG (-3)   /* reference: std::runtime_error in DBGAligner ctor (dbg_aligner.cpp:55-56) */
-#define MGB_ERR_UNSUPPORTED (-4)  /* chaining, labels, seed complexity filter, CanonicalDBG */
+#define MGB_ERR_UNSUPPORTED (-4)  /* a configuration or graph the kernels do not serve (chaining, labels, ...) */
 #define MGB_ERR_OVERFLOW (-5)     /* a read exceeded the largest per-read work arena */
 #define MGB_ERR_NO_DEVICE (-6)
 
