@@ -235,6 +235,79 @@ def primary_contigs(seqs, k):
     return out
 
 
+# Known-answer tests of the reference's unit tests for the strand modes (tests/graph/test_aligner.cpp). Every entry:
+# (name, k, graph sequences, mode, masked batch construction or dynamic add_sequence, config, query, check(fields)).
+def mode_kats():
+    from metagraph_b200.config import INT32_MIN
+    lo = INT32_MIN + 100
+    ref, query = "AAAAACTTTCGAGGCCAA", "GGGGGCTTTCGAGGCCAA"
+    ref_rc = revcomp(ref)
+    snp = dict(max_num_seeds_per_locus=SIZE_MAX, min_cell_score=lo, min_path_score=lo, min_seed_length=13)
+
+    def check_snp(f):                                  # :1483-1539 align_suffix_seed_snp_canonical
+        assert len(f) == 6
+        strand, seq, score, _, cigar, off = f
+        assert off == "5"
+        assert (seq, cigar) in ((ref[5:], "5S13="), (ref_rc[:13], "13=5S"))
+        assert int(score) == 26
+
+    ref2, query2 = "AAAAGCTTTCGAGGCCAA", "AAAAGTTTTCGAGGCCAA"
+
+    def check_both(f):                                 # :1541-1577 align_both_directions
+        assert len(f) == 6
+        strand, seq, score, _, cigar, off = f
+        assert off == "0" and (seq, cigar) in ((ref2, "5=1X12="), (revcomp(ref2), "12=1X5="))
+        assert int(score) == 2 * 17 - 1
+
+    ref3 = "CTGCTGCGCCATCGCAACCCACGGTTGCTTTTTGAGTCGCTGCTCACGTTAGCCATCACACTGACGTTAAGCTGGCTTTCGATGCTGTATC"
+    query3 = ("CTTACTGCTGCGCTCTTCGCAAACCCCACGGTTTCTTGTTTTGAGCTCGCCTGCTCACGATACCCATACACACTGACGTTCAAGCTGGCTTTCGATGTTGTATC")
+
+    def one_path(f):                                   # :1773-1800 align_suffix_seed_no_full_seeds
+        assert len(f) == 6
+
+    _, transcripts = read_fasta(os.path.join(GOLD, "transcripts_100.fa"))
+    query4 = ("TCGATCGATCGATCGATCGATCGACGATCGATCGATCGATCGATCGACGATCGAT"
+              "CGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA"
+              "TCGATCGATCGATCGACGATCGATCGATCGATCGATCGACGATCGATCGATCGAT"
+              "CGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA"
+              "TCGATCGACGATCGATCGATCGATCGATCGACGATCGATCGATCGATCGATCGAT"
+              "CGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA"
+              "CGATCGATCGATCGATCGATCGACGATCGATCGATCGATCGATCGATCGATCGAT"
+              "CGATCGATCGATCGATCGATCGA")
+
+    def three_paths(f):                                # :1600-1631 align_low_similarity4_rep_primary
+        assert len(f) == 18
+
+    rep = dict(score_matrix=dna_scoring_matrix(2, -3, -3), gap_opening_penalty=-5, gap_extension_penalty=-2, xdrop=27,
+               min_exact_match=0.0, max_nodes_per_seq_char=10.0, num_alternative_paths=3)
+    return [
+        ("snp_canonical", 18, [ref_rc, ref], 1, False, snp, query, check_snp),
+        ("snp_primary", 18, [ref_rc], 2, False, snp, query, check_snp),
+        ("both_directions", 7, [ref2, revcomp(ref2)], 1, True, {}, query2, check_both),
+        ("no_full_seeds_0", 31, [ref3], 2, False, dict(snp, max_seed_length=0), query3, one_path),
+        ("no_full_seeds_k100", 31, [ref3], 2, False, dict(snp, max_seed_length=131), query3, one_path),
+        ("low_similarity4_rep_primary", 6, primary_contigs(transcripts, 6), 2, True, rep, query4, three_paths),
+    ]
+
+
+def check_mode_kats(lib=None, oracle_only=False):
+    """The oracle must satisfy the reference's expectations; with a library, its lines must equal the oracle's."""
+    for name, k, seqs, mode, masked, kw, query, check in mode_kats():
+        g = O.OracleGraph(k, seqs, mask=masked, dynamic=not masked)
+        g.set_mode(mode)
+        cfg = struct_defaults(**kw)
+        exp = g.align_tsv(cfg, [query], with_nodes=True)
+        n_aln = (len(exp[0].split("\t")) - 2) // 7
+        check(exp[0].split("\t")[2:2 + 6 * n_aln])
+        if oracle_only:
+            continue
+        W, last, F, valid = g.arrays()
+        idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if masked else None, lib=lib, mode=mode)
+        got, _ = run_lines(idx, cfg, [query])
+        idx.close()
+        assert got == exp, (name, exp, got)
+
+
 def check_mt_canonical(lib, **kw):
     """CANONICAL-mode graph (sequences + their reverse complements, mode flag set): integration_tests/test_align.py:207-268."""
     _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))

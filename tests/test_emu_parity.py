@@ -35,6 +35,11 @@ def test_mt_canonical_emu(subk, _emu_built):
         assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
 
 
+def test_mode_known_answers_emu():
+    # the reference's unit tests for CANONICAL / PRIMARY graphs (tests/graph/test_aligner.cpp:1483-1631, 1773-1800)
+    P.check_mode_kats(EMU)
+
+
 @pytest.mark.parametrize("subk", [False, True])
 def test_mt_primary_emu(subk):
     # integration_tests/test_align.py:270-330 (graph built with --mode primary), CanonicalDBG semantics on device

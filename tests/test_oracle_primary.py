@@ -42,3 +42,11 @@ def test_primary_mode_subk():
     assert len(got) == 7
     for i, exp in CANONICAL_SUBK:
         assert got[int(i)] == exp.encode().decode("unicode_escape")
+
+
+def test_mode_known_answers():
+    """tests/graph/test_aligner.cpp: align_suffix_seed_snp_canonical (:1483-1539, PRIMARY behind CanonicalDBG and
+    CANONICAL), align_both_directions (:1541-1577), align_low_similarity4_rep_primary (:1600-1631),
+    align_suffix_seed_no_full_seeds (:1773-1800): the oracle satisfies the reference's expectations."""
+    from parity_common import check_mode_kats
+    check_mode_kats(oracle_only=True)

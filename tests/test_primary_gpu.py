@@ -22,3 +22,8 @@ def test_fuzz_primary_gpu():
     for seed in range(100, 140):
         bad, info = P.fuzz_case(None, seed, primary=True)
         assert not bad, (seed, info)
+
+
+def test_mode_known_answers_gpu():
+    # the reference's unit tests for CANONICAL / PRIMARY graphs (tests/graph/test_aligner.cpp:1483-1631, 1773-1800)
+    P.check_mode_kats(None)
