@@ -35,6 +35,18 @@ def test_mt_canonical_emu(subk, _emu_built):
         assert got[int(i)].split("\t")[:8] == exp.encode().decode("unicode_escape").split("\t")[:8]
 
 
+def test_map_count_kmers_golden_emu():
+    # `metagraph align --map --count-kmers` (integration_tests/test_align.py:58-87) through mgb_map_to_nodes
+    from test_oracle_golden import GOLD, MAP_COUNTS, _map_counts, read_fasta, read_fastq
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    _, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    boss = BOSSTable.from_sequences(11, seqs, lib=EMU)
+    idx = DBGSuccinctIndex(boss, valid=boss.dummy_mask(lib=EMU), lib=EMU)
+    assert [_map_counts(n) for n in idx.map_to_nodes_sequentially(reads)] == MAP_COUNTS
+    idx.close()
+
+
 def test_mode_known_answers_emu():
     # the reference's unit tests for CANONICAL / PRIMARY graphs (tests/graph/test_aligner.cpp:1483-1631, 1773-1800)
     P.check_mode_kats(EMU)

@@ -211,3 +211,20 @@ def test_integration_mt_cli_defaults(both):
         assert got == exp
     f = lines[5].split("\t")
     assert f[0] == "MT-11/1" and f[4] == "22"
+
+
+MAP_COUNTS = ["1/140/1", "140/140/140", "140/140/140", "0/140/0", "140/140/140", "1/140/1", "1/140/1"]
+
+
+def _map_counts(nodes):
+    nodes = [int(x) for x in nodes]
+    return "%d/%d/%d" % (sum(1 for x in nodes if x), len(nodes), len(set(x for x in nodes if x)))
+
+
+def test_map_count_kmers_golden():
+    """`metagraph align --map --count-kmers` on the masked MT graph (integration_tests/test_align.py:58-87,
+    cli/align.cpp:108-165): discovered / total / unique k-mers per read pin map_to_nodes_sequentially."""
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    _, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    g = O.OracleGraph(11, seqs, mask=True)
+    assert [_map_counts(g.map_to_nodes(r)) for r in reads] == MAP_COUNTS
