@@ -136,7 +136,8 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1,
  * 2 = PRIMARY (built with --mode primary: one k-mer of every reverse-complement pair): the index answers with the
  * semantics of the CanonicalDBG wrapper `metagraph align` puts around such graphs (canonical_dbg.cpp): node ids
  * above mgb_index_num_edges() denote reverse complements. The first call builds two 4-byte-per-edge tables on the
- * device; mgb_map_to_nodes then follows CanonicalDBG::map_to_nodes_sequentially (both strands, canonical_dbg.cpp:55-146). */
+ * device; mgb_map_to_nodes then follows CanonicalDBG::map_to_nodes_sequentially (both strands, canonical_dbg.cpp:55-146).
+ * Set the mode once, right after mgb_index_create and before the index is shared between threads. */
 int mgb_index_set_mode(mgb_index_t *index, int mode);
 void mgb_index_destroy(mgb_index_t *index);
 uint64_t mgb_index_num_edges(const mgb_index_t *index);
