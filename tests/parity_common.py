@@ -280,7 +280,51 @@ def mode_kats():
 
     rep = dict(score_matrix=dna_scoring_matrix(2, -3, -3), gap_opening_penalty=-5, gap_extension_penalty=-2, xdrop=27,
                min_exact_match=0.0, max_nodes_per_seq_char=10.0, num_alternative_paths=3)
-    return [
+    # BASIC-mode tests of the same file that need the transcripts fixture or the complexity filter
+    ref5 = "AGCTTCGAGGCCAA"
+
+    def check_straight(f):                             # :338-381 align_straight_forward_and_reverse_complement_batch
+        assert f == ["-", ref5, "28", "14", "14=", "0"]
+
+    ref6 = ("AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAGTGCTGGGATTATAGGTGTGAACCACCACACCTGGCTAATTTTTTTTGTGTGTGTGTGTGTTTTTTC")
+    query6 = ("AAAAAAAAAAAAAAAAAAAAAAAAAAACGCCAAAAAGGGGGAATAGGGGGGGGGGAACCCCAACACCGGTATGTTTTTTTGTGTGTGGGGGATTTTTTTC")
+    sim3 = dict(score_matrix=dna_scoring_matrix(2, -3, -3))
+
+    def non_empty(f):                                  # :1345-1363 align_low_similarity3
+        assert len(f) >= 6
+
+    def empty(f):
+        assert f == []
+
+    match4 = ("TCGATCAATCGATCAATCGATCAACGATCAATCGATCAATCGATCAACGATCAAT"
+              "CGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAA"
+              "TCGATCAATCGATCAACGATCAATCGATCAATCGATCAACGATCAATCGATCAAT"
+              "CGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAA"
+              "TCGATCAACGATCAATCGATCAATCGATCAACGATCAATCGATCAATCGATCAAT"
+              "CGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAATCGATCAA"
+              "CGATCAATCGATCAATCGATCAACGATCAATCGATCAATCGATCAATCGATCAAT"
+              "CGATCAATCGATCAATCGATC")
+
+    def two_paths(f):                                  # :1365-1424 align_low_similarity4
+        assert len(f) == 12 and f[:6] != f[6:] and int(f[2]) >= int(f[8])
+
+    def exact(f):
+        assert len(f) >= 6 and f[1] == match4 and f[4] == "%d=" % len(match4)
+
+    sim4 = []
+    for npc in (10.0, 50.0):
+        for xd in (27, 30):
+            for disc in (0.0, 1.0):
+                c4 = dict(score_matrix=dna_scoring_matrix(2, -3, -3), gap_opening_penalty=-5, gap_extension_penalty=-2,
+                          xdrop=xd, min_exact_match=disc, max_nodes_per_seq_char=npc, num_alternative_paths=2,
+                          min_path_score=0, min_cell_score=0, min_seed_length=6)
+                tag = "low_similarity4_%g_%d_%g" % (npc, xd, disc)
+                sim4.append((tag, 6, transcripts, 0, True, c4, query4, two_paths if disc == 0.0 else empty))
+                sim4.append((tag + "_match", 6, transcripts, 0, True, c4, match4, exact))
+    return sim4 + [
+        ("straight_fwd_rc_batch", 4, [ref5], 0, True, {}, revcomp(ref5), check_straight),
+        ("low_similarity3", 27, [ref6], 0, True, sim3, query6, non_empty),
+        ("low_similarity3_filter", 27, [ref6], 0, True, dict(sim3, seed_complexity_filter=True), query6, empty),
         ("snp_canonical", 18, [ref_rc, ref], 1, False, snp, query, check_snp),
         ("snp_primary", 18, [ref_rc], 2, False, snp, query, check_snp),
         ("both_directions", 7, [ref2, revcomp(ref2)], 1, True, {}, query2, check_both),
@@ -292,20 +336,29 @@ def mode_kats():
 
 def check_mode_kats(lib=None, oracle_only=False):
     """The oracle must satisfy the reference's expectations; with a library, its lines must equal the oracle's."""
+    graphs = {}
     for name, k, seqs, mode, masked, kw, query, check in mode_kats():
-        g = O.OracleGraph(k, seqs, mask=masked, dynamic=not masked)
-        g.set_mode(mode)
+        key = (k, len(seqs), seqs[0][:64], mode, masked)
+        if key not in graphs:
+            g = O.OracleGraph(k, seqs, mask=masked, dynamic=not masked)
+            g.set_mode(mode)
+            idx = None
+            if not oracle_only:
+                W, last, F, valid = g.arrays()
+                idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if masked else None, lib=lib, mode=mode)
+            graphs[key] = (g, idx)
+        g, idx = graphs[key]
         cfg = struct_defaults(**kw)
         exp = g.align_tsv(cfg, [query], with_nodes=True)
         n_aln = (len(exp[0].split("\t")) - 2) // 7
         check(exp[0].split("\t")[2:2 + 6 * n_aln])
         if oracle_only:
             continue
-        W, last, F, valid = g.arrays()
-        idx = DBGSuccinctIndex(BOSSTable(k, W, last, F), valid=valid if masked else None, lib=lib, mode=mode)
         got, _ = run_lines(idx, cfg, [query])
-        idx.close()
         assert got == exp, (name, exp, got)
+    for g, idx in graphs.values():
+        if idx is not None:
+            idx.close()
 
 
 def check_mt_canonical(lib, **kw):

@@ -47,6 +47,9 @@ def test_primary_mode_subk():
 def test_mode_known_answers():
     """tests/graph/test_aligner.cpp: align_suffix_seed_snp_canonical (:1483-1539, PRIMARY behind CanonicalDBG and
     CANONICAL), align_both_directions (:1541-1577), align_low_similarity4_rep_primary (:1600-1631),
-    align_suffix_seed_no_full_seeds (:1773-1800): the oracle satisfies the reference's expectations."""
+    align_suffix_seed_no_full_seeds (:1773-1800), and the BASIC-mode tests that need the transcripts fixture or the
+    seed complexity filter: align_straight_forward_and_reverse_complement_batch (:338-381), align_low_similarity3
+    (:1345-1363: with the filter on the read must stay unaligned, the one known answer of the reference that depends
+    on sdust), align_low_similarity4 (:1365-1424). The oracle satisfies the reference's expectations."""
     from parity_common import check_mode_kats
     check_mode_kats(oracle_only=True)
