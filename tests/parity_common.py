@@ -399,12 +399,13 @@ def check_mt_primary(lib, **kw):
     return got
 
 
-def fuzz_case(lib, seed, canonical=False, primary=False):
+def fuzz_case(lib, seed, canonical=False, primary=False, k=None):
     """One randomized (graph, reads, config) triple: k, graph shape (variants, repeats, dummy mask), scoring
     matrix, gap penalties, xdrop, seed lengths (exact / MEM / sub-k), seeds per locus, alternative paths,
     strands, end bonuses, cut-offs, node budget, left trim, complexity filter. Returns the mismatching reads."""
     rng = np.random.default_rng(1000 + seed)
-    k = int(rng.integers(4, 34))
+    k_drawn = int(rng.integers(4, 34))
+    k = k_drawn if k is None else k
     G = int(rng.integers(300, 4000))
     nseq = int(rng.integers(1, 4))
     base = "".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])
