@@ -1,5 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see mgo_graph.hpp header).
 #include "mgo_graph.hpp"
+#include <cstdlib>
 
 #include <cctype>
 #include <stdexcept>
@@ -132,37 +133,83 @@ uint64_t SampledSeq::select(uint8_t c, uint64_t r) const {
 namespace {
 typedef unsigned __int128 u128;
 
+// 256-bit key for (k+1)-mers beyond 128 bits (the reference switches to KMer<sdsl::uint256_t>, kmer_boss.hpp):
+// only the operations BOSS construction needs
+struct U256 {
+    uint64_t w[4];
+    U256() : w{0, 0, 0, 0} {}
+    U256(uint64_t x) : w{x, 0, 0, 0} {}
+    explicit operator uint64_t() const { return w[0]; }
+    friend U256 operator<<(const U256 &a, int n) {
+        U256 r;
+        if (n >= 256) return r;
+        const int ws = n / 64, bs = n % 64;
+        for (int i = 3; i >= ws; --i) {
+            r.w[i] = a.w[i - ws] << bs;
+            if (bs && i - ws - 1 >= 0) r.w[i] |= a.w[i - ws - 1] >> (64 - bs);
+        }
+        return r;
+    }
+    friend U256 operator>>(const U256 &a, int n) {
+        U256 r;
+        if (n >= 256) return r;
+        const int ws = n / 64, bs = n % 64;
+        for (int i = 0; i + ws < 4; ++i) {
+            r.w[i] = a.w[i + ws] >> bs;
+            if (bs && i + ws + 1 < 4) r.w[i] |= a.w[i + ws + 1] << (64 - bs);
+        }
+        return r;
+    }
+    friend U256 operator|(const U256 &a, const U256 &b) { U256 r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] | b.w[i]; return r; }
+    friend U256 operator&(const U256 &a, const U256 &b) { U256 r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] & b.w[i]; return r; }
+    friend U256 operator-(const U256 &a, const U256 &b) {
+        U256 r; unsigned __int128 borrow = 0;
+        for (int i = 0; i < 4; ++i) {
+            unsigned __int128 d = (unsigned __int128)a.w[i] - b.w[i] - borrow;
+            r.w[i] = (uint64_t)d; borrow = (d >> 64) & 1;
+        }
+        return r;
+    }
+    U256 operator~() const { U256 r; for (int i = 0; i < 4; ++i) r.w[i] = ~w[i]; return r; }
+    friend bool operator==(const U256 &a, const U256 &b) { return a.w[0] == b.w[0] && a.w[1] == b.w[1] && a.w[2] == b.w[2] && a.w[3] == b.w[3]; }
+    friend bool operator!=(const U256 &a, const U256 &b) { return !(a == b); }
+    friend bool operator<(const U256 &a, const U256 &b) {
+        for (int i = 3; i >= 0; --i) if (a.w[i] != b.w[i]) return a.w[i] < b.w[i];
+        return false;
+    }
+};
+
 // Packed (k+1)-mer in KMerBOSS order (kmer/kmer_boss.hpp:58-64, 125-140):
 // most significant = last node char a_k ... a_1, least significant = edge label.
+template <class Key>
 struct Packer {
     int bits; size_t k; // node length
-    u128 pack(const TAlphabet *x) const { // x[0..k] = a_1..a_k, label
-        u128 key = 0;
+    Key pack(const TAlphabet *x) const { // x[0..k] = a_1..a_k, label
+        Key key = 0;
         for (size_t i = k; i-- > 0; )
             key = (key << bits) | x[i];
         return (key << bits) | x[k];
     }
-    TAlphabet label(u128 key) const { return (TAlphabet)(key & ((1u << bits) - 1)); }
-    u128 node(u128 key) const { return key >> bits; } // a_k..a_1 (a_1 least significant)
-    TAlphabet node_char(u128 key, size_t i /*1-based a_i*/) const {
-        return (TAlphabet)((key >> (bits * i)) & ((1u << bits) - 1));
+    TAlphabet label(Key key) const { return (TAlphabet)(uint64_t)(key & Key((1u << bits) - 1)); }
+    Key node(Key key) const { return key >> bits; } // a_k..a_1 (a_1 least significant)
+    TAlphabet node_char(Key key, size_t i /*1-based a_i*/) const {
+        return (TAlphabet)(uint64_t)((key >> (bits * i)) & Key((1u << bits) - 1));
     }
 };
 } // namespace
 
-BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> &seqs,
-                 bool force_source_dummies) {
-    if ((k + 1) * alph.bits_per_char > 128)
-        throw std::runtime_error("oracle BOSS::build: k too large for packed k-mers");
+template <class Key>
+static BOSS build_impl(const Alphabet &alph, size_t k, const std::vector<std::string> &seqs,
+                       bool force_source_dummies) {
     const size_t K = k + 1;
     const int sigma = alph.sigma;
-    Packer pk { alph.bits_per_char, k };
+    Packer<Key> pk { alph.bits_per_char, k };
     const unsigned mask = (1u << pk.bits) - 1;
 
     // real (k+1)-mers; segments are split at invalid characters
     // (kmer/kmer_extractor.cpp:320-372)
-    std::vector<u128> real;
-    std::vector<u128> forced;
+    std::vector<Key> real;
+    std::vector<Key> forced;
     for (const std::string &s : seqs) {
         std::vector<TAlphabet> enc = alph.encode(s);
         size_t i = 0;
@@ -188,30 +235,30 @@ BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> 
     real.erase(std::unique(real.begin(), real.end()), real.end());
 
     // node sets for redundancy checks
-    std::vector<u128> src_nodes(real.size()), tgt_nodes(real.size());
+    std::vector<Key> src_nodes(real.size()), tgt_nodes(real.size());
     for (size_t i = 0; i < real.size(); ++i) {
         src_nodes[i] = pk.node(real[i]);
         // target node a_2..a_{k+1}: drop a_1, append the label as the new last char
-        u128 n = pk.node(real[i]) >> pk.bits;
-        tgt_nodes[i] = n | ((u128)pk.label(real[i]) << (pk.bits * (k - 1)));
+        Key n = pk.node(real[i]) >> pk.bits;
+        tgt_nodes[i] = n | ((Key)pk.label(real[i]) << (pk.bits * (k - 1)));
     }
     // src_nodes is already sorted (node is the major key)
     src_nodes.erase(std::unique(src_nodes.begin(), src_nodes.end()), src_nodes.end());
     std::sort(tgt_nodes.begin(), tgt_nodes.end());
     tgt_nodes.erase(std::unique(tgt_nodes.begin(), tgt_nodes.end()), tgt_nodes.end());
 
-    std::vector<u128> dummy;
+    std::vector<Key> dummy;
     // dummy sink edges a_2..a_{k+1} -> $ (boss_chunk_construct.cpp:57-100)
-    for (u128 t : tgt_nodes) {
+    for (Key t : tgt_nodes) {
         if (!std::binary_search(src_nodes.begin(), src_nodes.end(), t))
             dummy.push_back(t << pk.bits);
     }
     // dummy source edges with one sentinel: $a_1..a_{k-1} -> a_k (:124-170)
-    std::vector<u128> level;
-    for (u128 n : src_nodes) {
+    std::vector<Key> level;
+    for (Key n : src_nodes) {
         if (!std::binary_search(tgt_nodes.begin(), tgt_nodes.end(), n)) {
-            TAlphabet lbl = (TAlphabet)((n >> (pk.bits * (k - 1))) & mask); // a_k
-            u128 prev_node = (n << pk.bits) & (((u128)1 << (pk.bits * k)) - 1); // $a_1..a_{k-1}
+            TAlphabet lbl = (TAlphabet)(uint64_t)((n >> (pk.bits * (k - 1))) & Key(mask)); // a_k
+            Key prev_node = (n << pk.bits) & (((Key)1 << (pk.bits * k)) - 1); // $a_1..a_{k-1}
             level.push_back((prev_node << pk.bits) | lbl);
         }
     }
@@ -220,14 +267,14 @@ BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> 
     // longer sentinel prefixes (:380-397)
     for (size_t c = 2; c < k + 1; ++c) {
         dummy.insert(dummy.end(), level.begin(), level.end());
-        std::vector<u128> next;
-        u128 prev_n = ~(u128)0;
-        for (u128 key : level) {
-            u128 n = pk.node(key);
+        std::vector<Key> next;
+        Key prev_n = ~(Key)0;
+        for (Key key : level) {
+            Key n = pk.node(key);
             if (n == prev_n) continue;
             prev_n = n;
-            TAlphabet lbl = (TAlphabet)((n >> (pk.bits * (k - 1))) & mask);
-            u128 pn = (n << pk.bits) & (((u128)1 << (pk.bits * k)) - 1);
+            TAlphabet lbl = (TAlphabet)(uint64_t)((n >> (pk.bits * (k - 1))) & Key(mask));
+            Key pn = (n << pk.bits) & (((Key)1 << (pk.bits * k)) - 1);
             next.push_back((pn << pk.bits) | lbl);
         }
         std::sort(next.begin(), next.end());
@@ -237,7 +284,7 @@ BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> 
     dummy.insert(dummy.end(), level.begin(), level.end());
     dummy.insert(dummy.end(), forced.begin(), forced.end());
 
-    std::vector<u128> all;
+    std::vector<Key> all;
     all.reserve(real.size() + dummy.size() + 1);
     all.push_back(0); // main dummy source $..$ -> $ (:404-409)
     all.insert(all.end(), real.begin(), real.end());
@@ -252,11 +299,11 @@ BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> 
     b.F.assign(sigma, 0);
     uint64_t curpos = 1;
     TAlphabet lastF = 0;
-    std::vector<u128> last_kmer(sigma, 0);
+    std::vector<Key> last_kmer(sigma, 0);
     std::vector<bool> last_kmer_set(sigma, false);
-    const u128 minus1_mask = ~(((u128)1 << (2 * pk.bits)) - 1); // node chars a_2..a_k
+    const Key minus1_mask = ~(((Key)1 << (2 * pk.bits)) - 1); // node chars a_2..a_k
     for (size_t it = 0; it < all.size(); ) {
-        u128 kmer = all[it];
+        Key kmer = all[it];
         TAlphabet curW = pk.label(kmer);
         TAlphabet curF = pk.node_char(kmer, k);
         ++it;
@@ -286,6 +333,16 @@ BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> 
         b.F[lastF] = curpos - 1;
     b.finalize();
     return b;
+}
+
+BOSS BOSS::build(const Alphabet &alph, size_t k, const std::vector<std::string> &seqs,
+                 bool force_source_dummies) {
+    // MGO_FORCE_U256=1 sends every graph through the wide-key instantiation (cross-check of the two)
+    if ((k + 1) * alph.bits_per_char <= 128 && !std::getenv("MGO_FORCE_U256"))
+        return build_impl<u128>(alph, k, seqs, force_source_dummies);
+    if ((k + 1) * alph.bits_per_char <= 256)
+        return build_impl<U256>(alph, k, seqs, force_source_dummies);
+    throw std::runtime_error("oracle BOSS::build: k too large for packed k-mers");
 }
 
 BOSS BOSS::from_arrays(const Alphabet &alph, size_t k, std::vector<uint8_t> &&W,

@@ -151,9 +151,9 @@ class BOSS {
     std::vector<TAlphabet> get_node_seq(edge_index i) const;  // boss.cpp:953-973
     std::string get_node_str(edge_index i) const;
 
+    void finalize();   // builds the rank/select structures once W / last / F are set
   private:
     SampledSeq W_rs_, last_rs_;
-    void finalize();
 };
 
 template <class CB>

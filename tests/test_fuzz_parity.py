@@ -49,3 +49,13 @@ def test_fuzz_primary_emu():
         bad, info = P.fuzz_case(EMU, seed, primary=True)
         assert not bad, (seed, info)
 
+
+
+@pytest.mark.parametrize("k", [47, 64, 84])
+def test_fuzz_large_k_emu(k):
+    """k beyond one 128-bit packed k-mer (the reference switches to 256-bit k-mers, k <= 84 for DNA): the graphs come from the
+    oracle's wide-key constructor (cross-checked against the narrow one: MGO_FORCE_U256=1 reproduces every golden)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL)
+    for seed, mode in ((k, "basic"), (k + 1, "canonical"), (k + 2, "primary")):
+        bad, info = P.fuzz_case(EMU, seed, canonical=mode == "canonical", primary=mode == "primary", k=k)
+        assert not bad, (k, seed, mode, info)
