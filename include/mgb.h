@@ -182,7 +182,8 @@ void mgb_results_free(mgb_results_t *results);
 /* ---- host-side construction (index build, untimed) ------------------------------------ */
 
 /* Builds BOSS arrays from sequences (batch construction incl. dummy edges). Caller frees
- * with mgb_boss_free. force_source_dummies mimics BOSS::add_sequence leftovers. */
+ * with mgb_boss_free. force_source_dummies mimics BOSS::add_sequence leftovers. (k+1)-mers are packed into 128-bit
+ * keys, 256-bit ones beyond (DNA: k <= 85, protein: k <= 51; larger k: MGB_ERR_UNSUPPORTED). */
 typedef struct mgb_boss {
     uint64_t n_plus_1;
     uint8_t *W;

@@ -20,6 +20,56 @@ namespace {
 typedef unsigned __int128 u128;
 thread_local std::string g_build_err;
 
+// Key of a (k+1)-mer that does not fit 128 bits (DNA k > 42; the reference moves to 256-bit k-mers there,
+// kmer_boss.hpp / boss_construct.cpp): four little-endian words with the handful of operations the construction uses.
+struct Wide256 {
+    uint64_t q[4] = { 0, 0, 0, 0 };
+    Wide256() {}
+    Wide256(uint64_t lo) { q[0] = lo; }
+    explicit operator uint32_t() const { return (uint32_t)q[0]; }
+};
+inline Wide256 operator<<(const Wide256 &a, int n) {
+    Wide256 r;
+    const int wq = n >> 6, bq = n & 63;
+    for (int i = 3; i >= 0; --i) {
+        uint64_t v = 0;
+        if (i - wq >= 0) v = a.q[i - wq] << bq;
+        if (bq && i - wq - 1 >= 0) v |= a.q[i - wq - 1] >> (64 - bq);
+        r.q[i] = v;
+    }
+    return r;
+}
+inline Wide256 operator>>(const Wide256 &a, int n) {
+    Wide256 r;
+    const int wq = n >> 6, bq = n & 63;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t v = 0;
+        if (i + wq < 4) v = a.q[i + wq] >> bq;
+        if (bq && i + wq + 1 < 4) v |= a.q[i + wq + 1] << (64 - bq);
+        r.q[i] = v;
+    }
+    return r;
+}
+inline Wide256 operator|(Wide256 a, const Wide256 &b) { for (int i = 0; i < 4; ++i) a.q[i] |= b.q[i]; return a; }
+inline Wide256 operator&(Wide256 a, const Wide256 &b) { for (int i = 0; i < 4; ++i) a.q[i] &= b.q[i]; return a; }
+inline Wide256& operator|=(Wide256 &a, const Wide256 &b) { a = a | b; return a; }
+inline Wide256 operator~(Wide256 a) { for (int i = 0; i < 4; ++i) a.q[i] = ~a.q[i]; return a; }
+inline Wide256 operator-(const Wide256 &a, const Wide256 &b) {
+    Wide256 r; uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t x = a.q[i], y = b.q[i];
+        r.q[i] = x - y - borrow;
+        borrow = (x < y) || (x == y && borrow);
+    }
+    return r;
+}
+inline bool operator==(const Wide256 &a, const Wide256 &b) { return !std::memcmp(a.q, b.q, sizeof(a.q)); }
+inline bool operator!=(const Wide256 &a, const Wide256 &b) { return !(a == b); }
+inline bool operator<(const Wide256 &a, const Wide256 &b) {
+    for (int i = 3; i > 0; --i) if (a.q[i] != b.q[i]) return a.q[i] < b.q[i];
+    return a.q[0] < b.q[0];
+}
+
 struct Alpha { int sigma, bits; uint8_t code[256]; };
 
 Alpha make_dna() {
@@ -45,27 +95,17 @@ template <class It> void psort(It b, It e, int threads) {
     else std::sort(b, e);
 }
 
-} // namespace
-
-extern "C" {
-
-int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t K,
+template <class Key>
+int build_with_key(const Alpha &al, const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t K,
                    int alphabet, int force_source_dummies, int num_threads, mgb_boss_t *out) {
-    if (!offsets || !out || (n_seqs && !seqs)) return MGB_ERR_INVALID_ARGUMENT;
-    if (alphabet != MGB_ALPHABET_DNA && alphabet != MGB_ALPHABET_PROTEIN) return MGB_ERR_UNSUPPORTED;
-    if (K < 2) return MGB_ERR_INVALID_ARGUMENT;
-    const Alpha al = alphabet == MGB_ALPHABET_PROTEIN ? make_protein() : make_dna();
-    if ((uint64_t)K * al.bits > 128) return MGB_ERR_UNSUPPORTED;
-    if (num_threads < 1) num_threads = omp_get_max_threads();
-    omp_set_num_threads(num_threads);
     const uint32_t k = K - 1;                       // node length
     const int bits = al.bits;
-    const u128 cmask = ((u128)1 << bits) - 1;
-    const u128 node_mask = ((u128)1 << (bits * k)) - 1;
+    const Key cmask = ((Key)1 << bits) - 1;
+    const Key node_mask = ((Key)1 << (bits * k)) - 1;
 
     // key: [a_k ... a_1 | label], a_k most significant (KMerBOSS order, kmer_boss.hpp:58-64)
-    std::vector<u128> real;
-    std::vector<u128> forced;
+    std::vector<Key> real;
+    std::vector<Key> forced;
     for (uint32_t s = 0; s < n_seqs; ++s) {
         const uint8_t *p = (const uint8_t*)seqs + offsets[s];
         const uint64_t len = offsets[s + 1] - offsets[s];
@@ -77,17 +117,17 @@ int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, u
                 const size_t base = real.size();
                 real.resize(base + (j - i - K + 1));
                 // rolling pack: node part shifts down by one char, new last char enters on top
-                u128 node = 0;                     // a_k..a_1 of the current window's node
-                for (uint32_t t = 0; t < k; ++t) node |= (u128)al.code[p[i + t]] << (bits * t);
+                Key node = 0;                     // a_k..a_1 of the current window's node
+                for (uint32_t t = 0; t < k; ++t) node |= (Key)al.code[p[i + t]] << (bits * t);
                 for (uint64_t w = i; w + K <= j; ++w) {
-                    u128 lbl = al.code[p[w + k]];
+                    Key lbl = al.code[p[w + k]];
                     real[base + (w - i)] = (node << bits) | lbl;
                     node = (node >> bits) | (lbl << (bits * (k - 1)));
                 }
                 if (force_source_dummies) {
                     for (uint32_t d = 1; d <= k; ++d) {   // d leading sentinels
-                        u128 nd = 0;
-                        for (uint32_t t = d; t < k; ++t) nd |= (u128)al.code[p[i + t - d]] << (bits * t);
+                        Key nd = 0;
+                        for (uint32_t t = d; t < k; ++t) nd |= (Key)al.code[p[i + t - d]] << (bits * t);
                         forced.push_back((nd << bits) | al.code[p[i + k - d]]);
                     }
                 }
@@ -99,54 +139,54 @@ int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, u
     real.erase(std::unique(real.begin(), real.end()), real.end());
 
     // source nodes (sorted, unique) and target nodes of the real edges
-    std::vector<u128> src, tgt(real.size());
+    std::vector<Key> src, tgt(real.size());
     src.reserve(real.size());
     for (size_t i = 0; i < real.size(); ++i) {
-        u128 n = real[i] >> bits;
+        Key n = real[i] >> bits;
         if (src.empty() || src.back() != n) src.push_back(n);
     }
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < real.size(); ++i) {
-        u128 n = real[i] >> bits;
+        Key n = real[i] >> bits;
         tgt[i] = (n >> bits) | ((real[i] & cmask) << (bits * (k - 1)));
     }
     psort(tgt.begin(), tgt.end(), num_threads);
     tgt.erase(std::unique(tgt.begin(), tgt.end()), tgt.end());
 
-    std::vector<u128> dummy;
+    std::vector<Key> dummy;
     // sinks: target nodes without a real outgoing edge (boss_chunk_construct.cpp:57-100)
     {
         size_t si = 0;
-        for (u128 t : tgt) {
+        for (Key t : tgt) {
             while (si < src.size() && src[si] < t) ++si;
             if (si == src.size() || src[si] != t) dummy.push_back(t << bits);
         }
     }
     // sources with one sentinel: nodes without a real incoming edge (:124-170)
-    std::vector<u128> level;
+    std::vector<Key> level;
     {
         size_t ti = 0;
-        for (u128 n : src) {
+        for (Key n : src) {
             while (ti < tgt.size() && tgt[ti] < n) ++ti;
             if (ti == tgt.size() || tgt[ti] != n) {
-                u128 lbl = (n >> (bits * (k - 1))) & cmask;
+                Key lbl = (n >> (bits * (k - 1))) & cmask;
                 level.push_back((((n << bits) & node_mask) << bits) | lbl);
             }
         }
     }
-    std::vector<u128>().swap(src);
-    std::vector<u128>().swap(tgt);
+    std::vector<Key>().swap(src);
+    std::vector<Key>().swap(tgt);
     std::sort(level.begin(), level.end());
     level.erase(std::unique(level.begin(), level.end()), level.end());
     for (uint32_t c = 2; c < k + 1; ++c) {          // longer sentinel prefixes (:380-397)
         dummy.insert(dummy.end(), level.begin(), level.end());
-        std::vector<u128> next;
-        u128 prev = ~(u128)0;
-        for (u128 key : level) {
-            u128 n = key >> bits;
+        std::vector<Key> next;
+        Key prev = ~(Key)0;
+        for (Key key : level) {
+            Key n = key >> bits;
             if (n == prev) continue;
             prev = n;
-            u128 lbl = (n >> (bits * (k - 1))) & cmask;
+            Key lbl = (n >> (bits * (k - 1))) & cmask;
             next.push_back((((n << bits) & node_mask) << bits) | lbl);
         }
         std::sort(next.begin(), next.end());
@@ -168,11 +208,11 @@ int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, u
     std::memset(out->F, 0, sizeof(out->F));
     uint64_t curpos = 1;
     uint32_t lastF = 0;
-    std::vector<u128> last_kmer(al.sigma, 0);
+    std::vector<Key> last_kmer(al.sigma, 0);
     std::vector<char> last_set(al.sigma, 0);
-    const u128 minus1 = ~(((u128)1 << (2 * bits)) - 1);
+    const Key minus1 = ~(((Key)1 << (2 * bits)) - 1);
     size_t ri = 0, di = 0;
-    auto peek = [&](bool *ok) -> u128 {
+    auto peek = [&](bool *ok) -> Key {
         if (ri < real.size() && (di >= dummy.size() || real[ri] < dummy[di])) { *ok = true; return real[ri]; }
         if (di < dummy.size()) { *ok = true; return dummy[di]; }
         *ok = false; return 0;
@@ -181,11 +221,11 @@ int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, u
         if (ri < real.size() && (di >= dummy.size() || real[ri] < dummy[di])) ++ri; else ++di;
     };
     bool ok;
-    u128 kmer = peek(&ok);
+    Key kmer = peek(&ok);
     while (ok) {
         pop();
         bool ok2;
-        u128 nxt = peek(&ok2);
+        Key nxt = peek(&ok2);
         uint32_t curW = (uint32_t)(kmer & cmask);
         uint32_t curF = (uint32_t)((kmer >> (bits * k)) & cmask);
         bool same_node = ok2 && (nxt >> bits) == (kmer >> bits);
@@ -208,6 +248,25 @@ int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, u
     out->n_plus_1 = curpos;
     out->W = W; out->last = last; out->k = K; out->alphabet = alphabet;
     return MGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t K,
+                   int alphabet, int force_source_dummies, int num_threads, mgb_boss_t *out) {
+    if (!offsets || !out || (n_seqs && !seqs)) return MGB_ERR_INVALID_ARGUMENT;
+    if (alphabet != MGB_ALPHABET_DNA && alphabet != MGB_ALPHABET_PROTEIN) return MGB_ERR_UNSUPPORTED;
+    if (K < 2) return MGB_ERR_INVALID_ARGUMENT;
+    const Alpha al = alphabet == MGB_ALPHABET_PROTEIN ? make_protein() : make_dna();
+    if ((uint64_t)K * al.bits > 256) return MGB_ERR_UNSUPPORTED;      // DNA: k <= 85, protein: k <= 51
+    if (num_threads < 1) num_threads = omp_get_max_threads();
+    omp_set_num_threads(num_threads);
+    // MGB_TEST_WIDE_KEYS=1 (tests): every graph through the 256-bit instantiation
+    if ((uint64_t)K * al.bits <= 128 && !std::getenv("MGB_TEST_WIDE_KEYS"))
+        return build_with_key<u128>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
+    return build_with_key<Wide256>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
 }
 
 void mgb_boss_free(mgb_boss_t *b) {

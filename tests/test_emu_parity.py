@@ -147,3 +147,19 @@ def test_graph_modes_fail_loudly():
     with pytest.raises(_lib.MgbError) as e:
         DBGSuccinctIndex(prot, lib=EMU, mode=1)
     assert e.value.code == -3                                           # MGB_ERR_BAD_CONFIG
+
+
+@pytest.mark.parametrize("k", [43, 64, 85])
+def test_boss_build_large_k(k):
+    """mgb_boss_build beyond 128-bit packed k-mers (256-bit keys): same W / last / F as the oracle's constructor,
+    which reproduces the reference-built graph files with either key width (MGO_FORCE_U256, MGB_TEST_WIDE_KEYS)."""
+    import numpy as np
+    import oracle_lib as O
+    from metagraph_b200.aligner import BOSSTable
+    rng = np.random.default_rng(k)
+    seqs = ["".join(np.array(list("ACGT"))[rng.integers(0, 4, 700)]) for _ in range(3)]
+    seqs.append(seqs[0][100:300] + "N" + seqs[1][50:250])
+    boss = BOSSTable.from_sequences(k, seqs, lib=EMU)
+    W, last, F, valid = O.OracleGraph(k, seqs, mask=True).arrays()
+    assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
+    assert (boss.dummy_mask(lib=EMU) == valid).all()
