@@ -33,6 +33,7 @@ import numpy as np  # noqa: E402
 
 K = 31
 READ_LEN = 150
+CPU_SUFFIX_INDEX = 12      # BOSS::index_suffix_ranges length of the CPU arm's graph (reference default)
 
 
 def env_int(name, default):
@@ -125,7 +126,9 @@ def cpu_reference(boss, reads_buf, offsets, cfg, target_seconds, threads, n_max)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     if "g" not in _ORACLE_CACHE:
-        _ORACLE_CACHE["g"] = O.OracleGraph(K, arrays=(boss.W, boss.last, boss.F))
+        # the reference builds its graphs with a suffix-range index of length 12 (`metagraph build
+        # --index-ranges 12`, cli/config/config.cpp:24-25): the CPU arm runs with it
+        _ORACLE_CACHE["g"] = O.OracleGraph(K, arrays=(boss.W, boss.last, boss.F), suffix_index=CPU_SUFFIX_INDEX)
     g = _ORACLE_CACHE["g"]
     def reads_of(a, b):
         return [bytes(reads_buf[int(offsets[i]):int(offsets[i + 1])]) for i in range(a, b)]
@@ -144,6 +147,14 @@ def cpu_reference(boss, reads_buf, offsets, cfg, target_seconds, threads, n_max)
     rs = reads_of(0, n)
     t = time.time(); g.align_tsv(cfg, rs, threads=th); dt = time.time() - t
     return n / dt, n, dt, th
+
+
+def cpu_single_thread(boss, reads_buf, offsets, cfg, n=1500):
+    """single-thread rate of the same CPU arm (BASELINE.md asks for the 1-thread row); cpu_reference() first"""
+    g = _ORACLE_CACHE["g"]
+    rs = [bytes(reads_buf[int(offsets[i]):int(offsets[i + 1])]) for i in range(n)]
+    t = time.time(); g.align_tsv(cfg, rs, threads=1); dt = time.time() - t
+    return n / dt
 
 
 def main():
@@ -167,7 +178,7 @@ def main():
     workload = ("%d synthetic %d bp DNA reads/GPU (50%% rc, error-free) vs k=%d BOSS graph of a %d bp random "
                 "genome, exact-match seeder, CLI-default scoring" % (N, READ_LEN, K, G))
     config = {"workload": workload, "reads_per_gpu": N, "read_len": READ_LEN, "k": K, "genome_bp": G,
-              "seeder": "exact (min=max seed length = k)", "l2_policy": "inputs larger than L2 "
+              "seeder": "exact (min=max seed length = k)", "cpu_arm_suffix_index": CPU_SUFFIX_INDEX, "l2_policy": "inputs larger than L2 "
               "(index + node arrays + per-warp arenas >> 126 MB)", "parallelism": "reads sharded x%d" % world}
 
     # ---------------------------------------------------------------- reference arm (CPU) ----
@@ -191,10 +202,12 @@ def main():
                 "ms_per_step": float(np.mean([d for _, d in per_step]) * 1e3), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": "reads/s", "cores": used_threads, "kind": "port",
+                                 "single_thread": cpu_single_thread(boss, buf, offsets, cfg),
                                  "sample": "%d reads of the same workload per step (CPU restatement of the "
-                                           "reference algorithm, oracle/, best of %d/%d/%d threads = %d)"
-                                           % (sample_n, max(1, host_threads // 4), max(1, host_threads // 2),
-                                              host_threads, used_threads)},
+                                           "reference algorithm, oracle/, graph with suffix-range index %d, best of "
+                                           "%d/%d/%d threads = %d)"
+                                           % (sample_n, CPU_SUFFIX_INDEX, max(1, host_threads // 4),
+                                              max(1, host_threads // 2), host_threads, used_threads)},
                 "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -367,10 +380,12 @@ def main():
             # CPU baseline: oracle (port of the reference algorithm) on all host cores, bounded sample
             rate, n, dt, used_threads = cpu_reference(boss, buf_np, off_np, cfg, 10.0, host_threads, min(N, 400_000))
             line["cpu_baseline"] = {"value": rate, "unit": "reads/s", "cores": used_threads, "kind": "port",
+                                    "single_thread": cpu_single_thread(boss, buf_np, off_np, cfg),
                                     "sample": "first %d reads of the same workload, %.1f s wall, CPU restatement "
-                                              "of the reference algorithm (oracle/), best of %d/%d/%d threads = %d"
-                                              % (n, dt, max(1, host_threads // 4), max(1, host_threads // 2),
-                                                 host_threads, used_threads)}
+                                              "of the reference algorithm (oracle/), graph with suffix-range index "
+                                              "%d, best of %d/%d/%d threads = %d"
+                                              % (n, dt, CPU_SUFFIX_INDEX, max(1, host_threads // 4),
+                                                 max(1, host_threads // 2), host_threads, used_threads)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
