@@ -51,7 +51,8 @@ _libs = {}
 
 
 def load_library(path=None):
-    path = os.path.abspath(path or DEFAULT_LIB)
+    # MGB_LIB: another build of the same library (e.g. a different lane-group width), for probes
+    path = os.path.abspath(path or os.environ.get("MGB_LIB") or DEFAULT_LIB)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

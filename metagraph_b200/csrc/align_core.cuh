@@ -75,9 +75,20 @@ struct Caps {
     uint32_t aln_nodes, aln_seq, aln_cigar;   // per alignment slot
 };
 
+// Cells of a column in the DP table arena (ColMeta::fmt):
+//   FMT_FULL     S[size+5] | E[size+5] | F[size+5]                       (general path, any width)
+//   FMT_COMPACT  S[capr] | 32 flag bytes | F[capr] reserved, not written  (register path, size + 5 <= 32;
+//   FMT_COMPACT_F  ... F written                                           capr = size + 5 rounded up to 8)
+// A compact column keeps, instead of E and F, the four comparisons the backtrack makes with them (one byte
+// per cell, see CF_*); F is only written when a later column may have to read it (the column waits in the
+// queue, or a general-path child is created from it).
+enum : uint8_t { FMT_FULL = 0, FMT_COMPACT = 1, FMT_COMPACT_F = 2 };
+enum : uint8_t { CF_INS = 1,      // S == E                          (extender.cpp:943, insertion start)
+                 CF_INS_EXT = 2,  // E[j] == E[j-1] + gap_ext        (:947-957, insertion run)
+                 CF_DEL = 4,      // S == F                          (:972, deletion start)
+                 CF_DEL_EXT = 8 };// F[j] == F_parent[row] + score + gap_ext  (:976-997, deletion run)
 struct ColMeta {              // DefaultColumnExtender::DPTColumn (extender.hpp:129-147)
     uint64_t node;
-    uint64_t trail;           // rc graph only: bwd^{k-2}(node) if known, else 0 (NodeFirstCache role)
     uint32_t parent;
     uint32_t cells_off;       // index of the first cell in the cells arena
     int32_t size;             // S.size()
@@ -88,7 +99,8 @@ struct ColMeta {              // DefaultColumnExtender::DPTColumn (extender.hpp:
     uint8_t c;                // upper-cased character
     uint8_t is_tip;
     uint8_t started;          // prev_starts membership
-    uint8_t pad;
+    uint8_t fmt;              // FMT_*
+    uint32_t pad0, pad1;      // 48 bytes: three 16-byte stores
 };
 
 struct HeapItem { int32_t score, neg_off_diag; uint32_t idx; int32_t max_score; };
@@ -211,7 +223,7 @@ struct WarpSmem {
     AlnSlot *slots;           // [kNumSlots]
     MGB_HOSTDEV score_t* buf(int b) const { return buf0 + (size_t)b * 3 * bmax; }
     HeapItem *heap, *nn; int hcap;
-    uint64_t *out_nodes, *out_trails; int32_t *out_scores; uint8_t *out_chars;
+    uint64_t *out_nodes; int32_t *out_scores; uint8_t *out_chars;
 
     MGB_HOSTDEV size_t carve(char *base, int bmax_, int lq_, int hcap_) {
         size_t o = 0;
@@ -225,7 +237,7 @@ struct WarpSmem {
         slots = (AlnSlot*)take(sizeof(AlnSlot) * kNumSlots);
         heap = (HeapItem*)take(sizeof(HeapItem) * hcap);
         nn = (HeapItem*)take(sizeof(HeapItem) * hcap);
-        out_nodes = (uint64_t*)take(8 * kMaxOut); out_trails = (uint64_t*)take(8 * kMaxOut);
+        out_nodes = (uint64_t*)take(8 * kMaxOut);
         out_scores = (int32_t*)take(4 * kMaxOut); out_chars = (uint8_t*)take(kMaxOut);
         return o;
     }
@@ -266,10 +278,30 @@ struct ReadAligner {
     // --------------------------------------------------------------------------------
     // small helpers
     // --------------------------------------------------------------------------------
-    // committed columns: S[size+5] | E[size+5] | F[size+5] starting at cells_off
+    // committed columns (layouts: see ColMeta); S always starts at cells_off
+    MGB_HD static int capr_of(int size) { return (size + 5 + 7) & ~7; }
     MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + j]; }
-    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + (c.size + 5) + j]; }
-    MGB_HD score_t& cellF(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + 2 * (c.size + 5) + j]; }
+    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + (c.size + 5) + j]; }    // FMT_FULL
+    MGB_HD score_t& cellF(const ColMeta &c, int j) {
+        return m.cells[(size_t)c.cells_off + (c.fmt == FMT_FULL ? 2 * (c.size + 5) : capr_of(c.size) + 8) + j];
+    }
+    MGB_HD uint32_t cell_flags(const ColMeta &c, int j) {                                                          // compact
+        return reinterpret_cast<const uint8_t*>(m.cells + (size_t)c.cells_off + capr_of(c.size))[j];
+    }
+    // the backtrack's comparisons with E and F (extender.cpp:943-999), from the cells or from the flag bytes
+    MGB_HD bool bt_is_ins(const ColMeta &c, int j, score_t sv) {
+        return c.fmt == FMT_FULL ? sv == cellE(c, j) : (cell_flags(c, j) & CF_INS) != 0;
+    }
+    MGB_HD bool bt_ins_ext(const ColMeta &c, int j) {
+        return c.fmt == FMT_FULL ? cellE(c, j) == cellE(c, j - 1) + cfg.gap_ext : (cell_flags(c, j) & CF_INS_EXT) != 0;
+    }
+    MGB_HD bool bt_is_del(const ColMeta &c, int j, score_t sv) {
+        return c.fmt == FMT_FULL ? sv == cellF(c, j) : (cell_flags(c, j) & CF_DEL) != 0;
+    }
+    MGB_HD bool bt_del_ext(const ColMeta &c, const ColMeta &p, int pos) {
+        return c.fmt == FMT_FULL ? cellF(c, pos - c.trim) == cellF(p, pos - p.trim) + c.score + cfg.gap_ext
+                                 : (cell_flags(c, pos - c.trim) & CF_DEL_EXT) != 0;
+    }
 
     MGB_HD int prof_score(int s, int x, int code) const {   // profile_score_[code][x]
         return (x >= 1 && x <= L) ? cfg.prof[code][(uint8_t)cx[s].q[x - 1]] : 0;
@@ -673,8 +705,7 @@ struct ReadAligner {
     // (node_first_cache.cpp:40-50): incoming nodes in call_incoming_to_target order
     // (boss.cpp:766-786) with the complement of their first character, through the reverse
     // adjacency records.
-    MGB_HD int outgoing_rc(uint64_t node, uint64_t /*node_trail*/, uint64_t *nodes, uint8_t *chars,
-                           uint64_t *trails) {
+    MGB_HD int outgoing_rc(uint64_t node, uint64_t *nodes, uint8_t *chars) {
         const uint2 r = load_radj(ix, node);
         const uint32_t d = node_last_value(ix, node);
         int n = 0;
@@ -685,7 +716,7 @@ struct ReadAligner {
                 const uint32_t c = radj_char(ix, load_radj(ix, edge).y);
                 uint8_t ch = complement_char((uint8_t)cfg.letters[c]);
                 if (ch != '$') {
-                    if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; trails[n] = 0; }
+                    if (n < kMaxOut) { nodes[n] = edge; chars[n] = ch; }
                     ++n;
                 }
             }
@@ -1503,52 +1534,44 @@ struct ReadAligner {
         return max_changed;
     }
 
+    // update_seed_filter for a column of the register path: lane l holds S[l * kCPL + c] in S[c]; the passed
+    // range is cells [s_first, size). sm_S: the same column in the on-chip child buffer.
+    MGB_HD score_t update_seed_filter_regs(int e, uint64_t node, int query_start, const score_t (&S)[kCPL],
+                                           int s_first, int size, const score_t *sm_S) {
+        const int j0 = wlane() * kCPL;
+        score_t mx = kNinf;
 #if MGB_DEVICE_CODE
-    // update_seed_filter with the passed range held one value per lane: lane holds s[vi] if
-    // 0 <= vi < size (size <= 32)
-    MGB_HD score_t update_seed_filter_reg(int e, uint64_t node, int query_start, score_t val, int vi, int size) {
-        const bool has = vi >= 0 && vi < size;
-        const score_t mx = wreduce_max(has ? val : kNinf);
+#pragma unroll
+#endif
+        for (int c = 0; c < kCPL; ++c) {
+            const int j = j0 + c;
+            if (j >= s_first && j < size) mx = imax(mx, S[c]);
+        }
+        mx = wreduce_max(mx);
         if (node == 0) return mx;
         StrandCtx &t = cx[e];
-        uint64_t key = node + ((!MGB_CANONICAL(cfg) && t.rc) ? ix.n : 0);
-        score_t *cells = t.conv_cells;
+        const uint64_t key = node + ((!MGB_CANONICAL(cfg) && t.rc) ? ix.n : 0);
         ConvSlot en;
         int free_at;
         int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, true, &free_at);
         if (slot < 0) {
-            slot = conv_insert(e, key, query_start, size, &en, free_at);
+            slot = conv_insert(e, key, query_start, size - s_first, &en, free_at);
             if (slot < 0) return kNinf;
-            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
-            wsync();
-            return mx;
-        }
-        // disjoint from the stored range (before / after it): the values are stored as they are (:118-131);
-        // one conv_grow call site serves all three cases
-        const bool disjoint = query_start + size <= en.start || query_start >= en.start + en.size;
-        int ns = imin(query_start, en.start), ne = imax(query_start + size, en.start + en.size);
-        if (ns != en.start || ne != en.start + en.size)
-            if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
-        if (disjoint) {
-            if (has) cells[en.seg_off + query_start + vi - en.seg_start] = val;
-            wsync();
-            return mx;
-        }
-        score_t max_changed = kNinf;
-        if (has) {
-            score_t *v = cells + en.seg_off + (query_start + vi - en.seg_start);
-            score_t vj = *v;
-            if ((double)val > (double)vj * cfg.rel_score_cutoff) {
-                vj = imax(vj, val);
-                *v = vj;
-                max_changed = vj;
-            }
-        }
-        max_changed = wreduce_max(max_changed);
-        wsync();
-        return max_changed;
-    }
+            score_t *c0 = t.conv_cells + en.seg_off + (query_start - s_first - en.seg_start);   // indexed by cell
+#if MGB_DEVICE_CODE
+#pragma unroll
 #endif
+            for (int c = 0; c < kCPL; ++c) {
+                const int j = j0 + c;
+                if (j >= s_first && j < size) c0[j] = S[c];
+            }
+            wsync();
+            return mx;
+        }
+        // the node was met before in this extension (cycle, re-convergent branch): the general routine, on the
+        // on-chip copy of the column
+        return update_seed_filter(e, node, query_start, sm_S + s_first, size - s_first);
+    }
 
     // extender.cpp:158-207 (every cell of [query_start, query_end) ends up at -ninf)
     MGB_HD void filter_nodes(int e, uint64_t node, int query_start, int query_end) {
@@ -1746,89 +1769,256 @@ struct ReadAligner {
     }
 
     // --------------------------------------------------------------------------------
+    // Register path: a DP column of up to 32 cells (incl. its 5 padding cells) held in registers, lane l owning
+    // cells [l * kCPL, (l + 1) * kCPL). Fuses DPTColumn::create, update_column, extend_ins_end and the flag bytes
+    // of the compact table format. In the host emulation the single lane owns all 32 cells, so the same code
+    // is exercised on machines without a GPU.
+    // --------------------------------------------------------------------------------
+    struct RegCol { score_t S[kCPL], E[kCPL], F[kCPL]; uint8_t fl[kCPL]; };
+
+    // value of cell `idx` of a lane-distributed array, broadcast to the group
+    MGB_HD static score_t cell_bcast(const score_t (&v)[kCPL], int idx) {
+        score_t x = v[0];
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int c = 1; c < kCPL; ++c) if ((idx & (kCPL - 1)) == c) x = v[c];
+        return wbcast(x, idx / kCPL);
+    }
+    // dst[j] = v[j - j0] for the lane's cells j < limit; on the device dst + j0 is aligned to kCPL cells and
+    // limit is a multiple of 8
+    MGB_HD static void store_cells(score_t *dst, int j0, const score_t (&v)[kCPL], int limit) {
+#if MGB_DEVICE_CODE
+        if (j0 >= limit) return;
+        if constexpr (kCPL == 1) dst[j0] = v[0];
+        else if constexpr (kCPL == 2) *reinterpret_cast<int2*>(dst + j0) = make_int2(v[0], v[1]);
+        else *reinterpret_cast<int4*>(dst + j0) = make_int4(v[0], v[1], v[2], v[3]);
+#else
+        for (int c = 0; c < kCPL && j0 + c < limit; ++c) dst[j0 + c] = v[c];
+#endif
+    }
+    MGB_HD static void store_flags(uint8_t *dst, int j0, const uint8_t (&v)[kCPL]) {
+#if MGB_DEVICE_CODE
+        if constexpr (kCPL == 1) dst[j0] = v[0];
+        else if constexpr (kCPL == 2) *reinterpret_cast<uint16_t*>(dst + j0) = (uint16_t)(v[0] | (v[1] << 8));
+        else *reinterpret_cast<uint32_t*>(dst + j0) = v[0] | (v[1] << 8) | (v[2] << 16) | ((uint32_t)v[3] << 24);
+#else
+        for (int c = 0; c < kCPL; ++c) dst[j0 + c] = v[c];
+#endif
+    }
+
+    // update_column (extender.cpp:209-290, max-plus scan form) + extend_ins_end (:293-328) for a child column
+    // whose n4 <= 28 and size0 <= 27. pS / pF: the parent's S / F shifted to the child's rows. Returns the final
+    // size, or -1 when the column outgrows the register path (nothing has been stored then).
+    MGB_HD int reg_column(int s, const score_t *pS, const score_t *pF, int n, int size0, int prof_base, int max_size,
+                          int code, score_t add, bool use_del, score_t cutoff, RegCol &r) {
+        const int j0 = wlane() * kCPL;
+        const int n4 = (n + 3) & ~3;
+        const score_t go = cfg.gap_open, ge = cfg.gap_ext;
+        score_t mval[kCPL], pr[kCPL], psm1[kCPL], pfv[kCPL];
+        int aloc[kCPL];
+        score_t prev = (j0 >= 1 && j0 <= n4) ? pS[j0 - 1] : kNinf;
+        int loc = INT32_MIN;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int c = 0; c < kCPL; ++c) {
+            const int j = j0 + c;
+            const bool act = j < n4;
+            const score_t ps_j = act ? pS[j] : kNinf;
+            const score_t pf_j = act ? pF[j] : kNinf;
+            pr[c] = prof_score(s, prof_base + j, code);
+            psm1[c] = prev; pfv[c] = pf_j;
+            const score_t match = (act && j) ? prev + pr[c] + add : kNinf;
+            const score_t del = (act && use_del) ? imax(ps_j + go, pf_j + ge) + add : kNinf;
+            mval[c] = imax(match, del);
+            r.F[c] = act ? del : kNinf;
+            // a[j] = m[j] + go - j*ge ; E[j+1] = prefmax(a)[j] + j*ge
+            const int a = act ? mval[c] + go - j * ge : INT32_MIN;
+            loc = imax(loc, a);
+            aloc[c] = loc;
+            prev = ps_j;                                   // pS[j] for cell j + 1 (valid while j + 1 <= n4)
+        }
+        // prefix max over the previous lanes (incl. a[-1] = E[0] + ge, E[0] = ninf)
+        const int lane_incl = imax(wscan_max(loc), kNinf + ge);
+        const int lane_excl = wshfl_up1(lane_incl, kNinf + ge);
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int c = 0; c < kCPL; ++c) {
+            const int j = j0 + c;
+            const int excl = c ? imax(lane_excl, aloc[c ? c - 1 : 0]) : lane_excl;      // prefix max over i < j
+            const score_t E_j = (j >= 1 && j <= n4) ? excl + (j - 1) * ge : kNinf;
+            score_t S_j = kNinf;
+            if (j < n4) { const score_t sv = imax(mval[c], E_j); S_j = sv > cutoff - 1 ? sv : kNinf; }
+            if (size0 > imax(1, n) && j == size0 - 1) {                                 // scalar tail (:284-289)
+                const score_t tt = imax(psm1[c] + add + pr[c], E_j);
+                if (tt >= cutoff) S_j = tt;
+            }
+            r.S[c] = S_j; r.E[c] = E_j;
+        }
+        // extend_ins_end (:293-328)
+        int size = size0;
+        if (size0 < max_size) {
+            const score_t s_last = cell_bcast(r.S, size0 - 1), e_last = cell_bcast(r.E, size0 - 1);
+            const score_t ins = imax(s_last + go, e_last + ge);
+            if (ins >= cutoff) {
+                const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;                  // ins >= cutoff
+                const uint32_t extra = cfg.ge_shift >= 0 ? diff >> cfg.ge_shift
+                                     : (ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu);
+                const uint32_t room = (uint32_t)(max_size - size0 - 1);
+                const int cnt = 1 + (int)(extra < room ? extra : room);
+                if (size0 + cnt > 27) return -1;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                for (int c = 0; c < kCPL; ++c) {
+                    const int j = j0 + c;
+                    if (j >= size0) {
+                        const bool in = j < size0 + cnt;
+                        r.S[c] = in ? ins + (j - size0) * ge : kNinf;
+                        r.E[c] = r.S[c]; r.F[c] = kNinf;
+                    }
+                }
+                size = size0 + cnt;
+            }
+        }
+        // what the backtrack asks of E and F (see CF_*)
+        score_t e_prev = wshfl_up1(r.E[kCPL - 1], kNinf);
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int c = 0; c < kCPL; ++c) {
+            r.fl[c] = (uint8_t)((r.S[c] == r.E[c] ? CF_INS : 0) | (r.E[c] == e_prev + ge ? CF_INS_EXT : 0)
+                              | (r.S[c] == r.F[c] ? CF_DEL : 0) | (r.F[c] == pfv[c] + add + ge ? CF_DEL_EXT : 0));
+            e_prev = r.E[c];
+        }
+        return size;
+    }
+
+    // --------------------------------------------------------------------------------
     // DefaultColumnExtender::extend (extender.cpp:412-772) + backtrack (:800-1034)
     //   e      extender (query strand) index, seed in slot `seed_slot`
     //   results are written to slots out_base .. out_base + n_out
+    // The reference's nested loops (queue rounds -> next_nodes -> outgoing edges) run here as ONE loop whose
+    // iteration creates one child column: `t >= n_out` means "take the next parent off the queue".
     // --------------------------------------------------------------------------------
-    MGB_HD int extend(int e, int seed_slot, score_t min_path_score, bool force_fixed_seed, int out_base) {
+    // Lock-step over the lane groups of a warp (kWarp < 32): every lane of the warp calls extend() (`act` tells
+    // whether this group has an extension to run) and the column loop runs while ANY group has work, so the
+    // groups execute it together, one child column per iteration each, instead of drifting apart.
+    MGB_HD int extend(int e, int seed_slot, score_t min_path_score, bool force_fixed_seed, int out_base, bool act) {
         const int s = e;                                 // query strand of this extender
         const AlnSlot &seed = sm.slots[seed_slot];
-        const AlnHdr sh = *seed.h;
-        const bool rc = !MGB_CANONICAL(cfg) && cx[e].rc;      // the RCDBG view is never used on CANONICAL / PRIMARY graphs
+        AlnHdr sh = AlnHdr();
+        bool rc = false;
         const int K = ix.k;
-        ++cx[e].num_ext;
-        min_path_score = imax(0, min_path_score);
-        n_cols = 0; cells_used = 0;
-        hp = sm.heap; hp_cap = sm.hcap; np = sm.nn; np_cap = sm.hcap;
-        pf_node = 0; pf_key = ~0ull; pf_slot_idx = 0;
-
         const score_t xdrop = cfg.xdrop;
-        score_t cutoff = imax(-xdrop, kNinf + 1);
-        const int start = aln_clipping(seed);
-        const int wlen = L - start;                       // |window|
-        const int seed_off_m1 = (int)sh.offset - 1;       // seed_offset
-        const int seed_seq_len = sh.seq_len;
-        const score_t partial_sum_offset = cx[s].ps[start + wlen];
-        // seed characters: for plain seeds the sequence equals the query substring (staged on chip)
-        const char *seed_seq = seed_is_query ? cx[s].q + start : seed.seq;
-        const uint64_t seed_node0 = seed.nodes[0];
+        score_t cutoff = 0;
+        int start = 0, wlen = 1, seed_off_m1 = 0, seed_seq_len = 0;
+        score_t partial_sum_offset = 0;
+        const char *seed_seq = nullptr;
+        uint64_t seed_node0 = 0;
         int res0 = -1, res1 = -1;                         // columns resident in sm.buf(0) / sm.buf(1)
-        ColMeta last_col; uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
+        ColMeta last_col = ColMeta(); uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
         bool last_band_valid = false; uint32_t last_band_mask = 0; score_t last_band_cutoff = 0;
-
-        if ((uint64_t)3 * (wlen + 16) > 3ull * caps.max_cells) { overflow = true; return 0; }
-        // committing a column is safe while cells_used <= cells_limit (room for it and the next scratch)
-        const uint32_t cells_limit = (uint32_t)(3ull * caps.max_cells - 6ull * (wlen + 16));
+        const bool reg_path = use_fast && sm.bmax >= 40 && (sm.bmax & 3) == 0;
+        uint32_t cells_limit = 0;
+        score_t min_cell_score = 0, best_score = 0;
+        int heap_n = 0, nn_n = 0;
+        bool go = act;
+        if (go) {
+            sh = *seed.h;
+            rc = !MGB_CANONICAL(cfg) && cx[e].rc;        // the RCDBG view is never used on CANONICAL / PRIMARY graphs
+            ++cx[e].num_ext;
+            min_path_score = imax(0, min_path_score);
+            n_cols = 0; cells_used = 0;
+            hp = sm.heap; hp_cap = sm.hcap; np = sm.nn; np_cap = sm.hcap;
+            pf_node = 0; pf_key = ~0ull; pf_slot_idx = 0;
+            cutoff = imax(-xdrop, kNinf + 1);
+            start = aln_clipping(seed);
+            wlen = L - start;                             // |window|
+            seed_off_m1 = (int)sh.offset - 1;             // seed_offset
+            seed_seq_len = sh.seq_len;
+            partial_sum_offset = cx[s].ps[start + wlen];
+            // seed characters: for plain seeds the sequence equals the query substring (staged on chip)
+            seed_seq = seed_is_query ? cx[s].q + start : seed.seq;
+            seed_node0 = seed.nodes[0];
+            if ((uint64_t)3 * (wlen + 16) > 3ull * caps.max_cells) { overflow = true; go = false; }
+            // committing a column is safe while cells_used <= cells_limit (room for it and the next scratch)
+            cells_limit = (uint32_t)(3ull * caps.max_cells - 6ull * (wlen + 16));
+        }
 
         // root column (:455-470)
-        {
+        if (go) {
             Scratch sc;
+            bool have_sc = true;
             if (1 + 8 <= sm.bmax) sc = scratch_smem(0);
-            else if (!scratch_arena(wlen + 1, &sc)) return 0;
-            for (int t = wlane(); t < 1 + 5; t += kWarp) { sc.S[t] = kNinf; sc.E[t] = kNinf; sc.F[t] = kNinf; }
-            wsync();
-            sc.S[0] = cfg.left_end_bonus && !start ? cfg.left_end_bonus : 0;
-            wsync();
-            int size = extend_ins_end(sc, 1, wlen + 1, cutoff);
-            if (overflow) return 0;
-            ColMeta root;
-            root.node = seed_node0; root.trail = 0; root.parent = 0xffffffffu; root.c = 0;
-            root.offset = seed_off_m1; root.max_pos = 0; root.trim = 0; root.score = 0;
-            root.is_tip = 0; root.started = 0; root.pad = 0; root.size = size;
-            root.cells_off = commit_column(sc, size);
-            if (sc.on_chip) res0 = 0;
-            m.cols[n_cols++] = root;
-            if (n_cols > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
-            stats.dp_cells += size; ++stats.dp_columns;
-            table_size_bytes = 136ull * cx[e].table_cap + 3ull * vec_capacity(1, size) * 4;
-            wsync();
+            else have_sc = scratch_arena(wlen + 1, &sc);
+            if (have_sc) {
+                for (int t = wlane(); t < 1 + 5; t += kWarp) { sc.S[t] = kNinf; sc.E[t] = kNinf; sc.F[t] = kNinf; }
+                wsync();
+                sc.S[0] = cfg.left_end_bonus && !start ? cfg.left_end_bonus : 0;
+                wsync();
+                int size = extend_ins_end(sc, 1, wlen + 1, cutoff);
+                if (!overflow) {
+                    ColMeta root;
+                    root.node = seed_node0; root.parent = 0xffffffffu; root.c = 0;
+                    root.offset = seed_off_m1; root.max_pos = 0; root.trim = 0; root.score = 0;
+                    root.is_tip = 0; root.started = 0; root.fmt = FMT_FULL; root.pad0 = root.pad1 = 0; root.size = size;
+                    root.cells_off = commit_column(sc, size);
+                    if (sc.on_chip) res0 = 0;
+                    m.cols[n_cols++] = root;
+                    if (n_cols > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
+                    stats.dp_cells += size; ++stats.dp_columns;
+                    table_size_bytes = 136ull * cx[e].table_cap + 3ull * vec_capacity(1, size) * 4;
+                    wsync();
+                }
+            }
+            if (overflow) go = false;
         }
 
         MGB_TIC(t_fwd);
-        score_t min_cell_score = 0, best_score = 0;
-        int heap_n = 0, nn_n = 0;
-        { HeapItem r0; r0.score = 0; r0.neg_off_diag = 0; r0.idx = 0; r0.max_score = 0; heap_push(heap_n, r0); }
+        if (go) { HeapItem r0; r0.score = 0; r0.neg_off_diag = 0; r0.idx = 0; r0.max_score = 0; heap_push(heap_n, r0); }
+        bool finished = false;
 
-        while (heap_n) {
-            nn_n = 0;
-            nn_push(nn_n, heap_pop(heap_n));
-            while (heap_n && hp[0].score == np[nn_n - 1].score) nn_push(nn_n, heap_pop(heap_n));
-            if (overflow) return 0;
+        // the parent being expanded and what its children share
+        uint32_t i = 0;
+        int t = 0, n_out = 0;                             // children t .. n_out - 1 of column i are still to be made
+        bool plain_out = false;                           // all added scores are 0 (not stored)
+        bool one_reg = false; uint64_t one_node = 0; uint8_t one_ch = 0;   // a single plain child, kept in registers
+        int next_offset = 0, begin = 0, size0 = 0, n = 0, shift = 0, cb = 0, pb = -1;
+        bool in_seed = false;
+        const score_t *parS = nullptr, *parF = nullptr;
+        uint8_t par_fmt = FMT_FULL;
 
-            while (nn_n) {
-                const uint32_t i = np[--nn_n].idx;
+        while (true) {
+            const bool mine = go && !overflow && !finished;
+            if (!wany_full(mine)) break;
+            if (!mine) continue;
+            if (t >= n_out) {
+                // ---------------- next parent: queue round / next_nodes (:477-504) ----------------
+                if (!nn_n) {
+                    if (!heap_n) { finished = true; continue; }
+                    nn_push(nn_n, heap_pop(heap_n));
+                    while (heap_n && hp[0].score == np[nn_n - 1].score) nn_push(nn_n, heap_pop(heap_n));
+                    if (overflow) continue;
+                }
+                i = np[--nn_n].idx;
+                t = 0; n_out = 0;
                 // `last_col` is the register copy of column `last_idx`; the popped column takes it over
-                // (nothing below the child loop's start reads `par`, the children overwrite the copy)
                 if (i != last_idx) { last_col = m.cols[i]; last_idx = i; last_band_valid = false; }
                 const ColMeta &par = last_col;
-                const int next_offset = par.offset + 1;
-                const bool in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
+                next_offset = par.offset + 1;
+                in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
+                par_fmt = par.fmt;
                 // parent cells: on chip if it is one of the two most recent columns
-                const int pb = res0 == (int)i ? 0 : (res1 == (int)i ? 1 : -1);
-                const score_t *parS, *parF;
+                pb = res0 == (int)i ? 0 : (res1 == (int)i ? 1 : -1);
                 if (pb >= 0) { parS = sm.buf(pb); parF = parS + 2 * sm.bmax; }
-                else { parS = m.cells + par.cells_off; parF = parS + 2 * (par.size + 5); }
-                const int cb = pb >= 0 ? 1 - pb : 0;      // buffer for the children
+                else {
+                    parS = m.cells + par.cells_off;
+                    parF = parS + (par.fmt == FMT_FULL ? 2 * (par.size + 5) : capr_of(par.size) + 8);
+                }
+                cb = pb >= 0 ? 1 - pb : 0;                // buffer for the children
 
                 if (parS[par.max_pos - par.trim] < best_score) {
                     double node_counter = (double)n_cols;
@@ -1842,8 +2032,8 @@ struct ReadAligner {
                     }
                 }
                 // band within the xdrop cutoff (:549-560)
-                int begin, prev_end;
-                if (i == last_idx && last_band_valid && last_band_cutoff == cutoff) {
+                int prev_end;
+                if (last_band_valid && last_band_cutoff == cutoff) {
                     // band recorded when the column was committed (same cutoff): no second pass
                     if (!last_band_mask) continue;
                     begin = ffs32(last_band_mask) - 1 + par.trim;
@@ -1859,258 +2049,273 @@ struct ReadAligner {
                 }
 
                 // call_outgoing (:330-387)
-                int n_out = 0;
-                bool plain_out = false;                   // all added scores and trails are 0 (not stored)
+                plain_out = false; one_reg = false;
                 {
-                    uint32_t seed_pos = (uint32_t)(next_offset - (int)sh.offset);
+                    const uint32_t seed_pos = (uint32_t)(next_offset - (int)sh.offset);
                     if (in_seed && next_offset < K) {
-                        sm.out_nodes[0] = seed_node0; sm.out_chars[0] = seed_seq[seed_pos];
-                        sm.out_trails[0] = 0; sm.out_scores[0] = 0; n_out = 1;
+                        one_node = seed_node0; one_ch = (uint8_t)seed_seq[seed_pos];
+                        one_reg = true; plain_out = true; n_out = 1;
                     } else if (in_seed && force_fixed_seed) {
-                        int node_i = next_offset - K + 1;
-                        uint64_t next_node = seed.nodes[node_i];
-                        sm.out_nodes[0] = next_node; sm.out_chars[0] = seed_seq[seed_pos]; sm.out_trails[0] = 0;
-                        sm.out_scores[0] = next_node ? 0 : (!par.node ? cfg.gap_ext : cfg.gap_open);
+                        const int node_i = next_offset - K + 1;
+                        const uint64_t next_node = seed.nodes[node_i];
+                        one_node = next_node; one_ch = (uint8_t)seed_seq[seed_pos];
+                        if (next_node) { one_reg = true; plain_out = true; }
+                        else {
+                            sm.out_nodes[0] = next_node; sm.out_chars[0] = one_ch;
+                            sm.out_scores[0] = !par.node ? cfg.gap_ext : cfg.gap_open;
+                            wsync();
+                        }
                         n_out = 1;
                     } else if (MGB_PRIMARY(ix)) {          // extender.cpp:361-380 (the hint equals the node's sequence)
                         n_out = canon_out(par.node, sm.out_nodes, sm.out_chars);
                         plain_out = true;
+                        wsync();
                     } else if (!rc) {
-                        n_out = outgoing_fwd(par.node, sm.out_nodes, sm.out_chars);
+                        // DBGSuccinct::call_outgoing_kmers through the adjacency record; the record of the most
+                        // recently created column was requested while its DP was computed
+                        const Adj a = (!MGB_WIDE(ix) && par.node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, par.node);
                         plain_out = true;
+                        if (a.last) {
+                            const uint32_t all = a.all, ok = a.ok & ~1u;
+                            const uint64_t first = (uint64_t)a.last - popc32(all) + 1;
+                            n_out = popc32(ok);
+                            if (n_out == 1) {
+                                const uint32_t c = (uint32_t)ffs32(ok) - 1;
+                                one_node = first + popc32(all & ((1u << c) - 1u)); one_ch = (uint8_t)cfg.letters[c];
+                                one_reg = true;
+                            } else if (n_out > 1 && n_out <= kMaxOut) {
+                                int k2 = 0;
+                                for (uint32_t c = 1; c < ix.sigma; ++c) {
+                                    if (!((ok >> c) & 1u)) continue;
+                                    sm.out_nodes[k2] = first + popc32(all & ((1u << c) - 1u)); sm.out_chars[k2] = cfg.letters[c];
+                                    ++k2;
+                                }
+                                wsync();
+                            }
+                        }
                     } else {
-                        n_out = outgoing_rc(par.node, par.trail, sm.out_nodes, sm.out_chars, sm.out_trails);
-                        for (int t = 0; t < n_out && t < kMaxOut; ++t) sm.out_scores[t] = 0;
+                        n_out = outgoing_rc(par.node, sm.out_nodes, sm.out_chars);
+                        plain_out = true;
+                        wsync();
                     }
-                    wsync();
-                    if (n_out > kMaxOut) { overflow = true; return 0; }
+                    if (n_out > kMaxOut) { overflow = true; continue; }
                 }
                 if (n_out == 0) { m.cols[i].is_tip = 1; continue; }
 
                 const int end = imin(prev_end, wlen) + 1;
-                const int size0 = end - begin;
-                const int n = prev_end - begin;           // parent rows inside the band
-                const int shift = begin - par.trim;
+                size0 = end - begin;
+                n = prev_end - begin;                     // parent rows inside the band
+                shift = begin - par.trim;
+            }
 
-                for (int t = 0; t < n_out; ++t) {
-                    uint8_t ch = sm.out_chars[t];
-                    if (ch >= 'a' && ch <= 'z') ch -= 32;      // toupper (:564)
-                    if (n_cols >= caps.max_cols) { overflow = true; return 0; }
-#if MGB_DEVICE_CODE
-                    // ---- register fast path: the whole column (incl. its 5 padding cells) fits in one
-                    // lane-per-cell pass (n4 <= 28, final size <= 27). Fuses DPTColumn::create, update_column,
-                    // extend_ins_end, the per-column scan, the table commit and the convergence filter.
-                    if (use_fast && n <= 28 && size0 <= 27 && sm.bmax >= 40) {
-                        const int j = wlane();
-                        const score_t go = cfg.gap_open, ge = cfg.gap_ext;
-                        const score_t add = plain_out ? 0 : sm.out_scores[t];
-                        {   // requests whose latency overlaps the DP below
-                            const uint64_t cnode = sm.out_nodes[t];
-                            if (!rc && cnode && !MGB_WIDE(ix) && !MGB_PRIMARY(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
-                            pf_key = cnode + (rc ? ix.n : 0);
-                            pf_slot_idx = hash_node(pf_key);
-                            pf_slot = cx[e].conv_slots[pf_slot_idx];
-                        }
-                        const int code = encode_char(ch);
-                        const int n4 = (n + 3) & ~3;
-                        const score_t *pS = parS + shift, *pF = parF + shift;
-                        const bool act = j < n4;
-                        const score_t ps_jm1 = (j >= 1 && j <= n4) ? pS[j - 1] : kNinf;
-                        const score_t ps_j = act ? pS[j] : kNinf;
-                        const score_t pf_j = act ? pF[j] : kNinf;
-                        const int pr = prof_score(s, start + begin + j, code);
-                        const score_t match = (act && j) ? ps_jm1 + pr + add : kNinf;
-                        const score_t del = (act && next_offset > 1) ? imax(ps_j + go, pf_j + ge) + add : kNinf;
-                        const score_t mval = imax(match, del);
-                        const int a = act ? mval + go - j * ge : INT32_MIN;
-                        int incl = wscan_max(a);
-                        incl = imax(incl, kNinf + ge);
-                        const int excl = wshfl_up1(incl, kNinf + ge);
-                        score_t E_j = (j >= 1 && j <= n4) ? excl + (j - 1) * ge : kNinf;
-                        score_t F_j = act ? del : kNinf;
-                        score_t S_j = kNinf;
-                        if (act) { score_t sv = imax(mval, E_j); S_j = sv > cutoff - 1 ? sv : kNinf; }
-                        if (size0 > imax(1, n) && j == size0 - 1) {               // scalar tail (:284-289)
-                            score_t tt = imax(ps_jm1 + add + pr, E_j);
-                            if (tt >= cutoff) S_j = tt;
-                        }
-                        // extend_ins_end (:293-328)
-                        int size = size0;
-                        bool fits = true;
-                        const int max_size = wlen + 1 - begin;
-                        if (size0 < max_size) {
-                            const score_t s_last = wbcast(S_j, size0 - 1), e_last = wbcast(E_j, size0 - 1);
-                            const score_t ins = imax(s_last + go, e_last + ge);
-                            if (ins >= cutoff) {
-                                const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;      // ins >= cutoff
-                                const uint32_t extra = cfg.ge_shift >= 0 ? diff >> cfg.ge_shift
-                                                     : (ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu);
-                                const uint32_t room = (uint32_t)(max_size - size0 - 1);
-                                int cnt = 1 + (int)(extra < room ? extra : room);
-                                if (size0 + cnt > 27) fits = false;
-                                else {
-                                    if (j >= size0) {
-                                        const bool in = j < size0 + cnt;
-                                        S_j = in ? ins + (j - size0) * ge : kNinf;
-                                        E_j = S_j; F_j = kNinf;
-                                    }
-                                    size = size0 + cnt;
-                                }
-                            }
-                        }
-                        if (fits) {
-                            MGB_COUNT(5);
-                            const uint32_t cap_before = cx[e].table_cap;
-                            if (n_cols + 1 > cap_before) cx[e].table_cap = cap_before ? 2 * cap_before : 1;
-                            stats.dp_cells += size; ++stats.dp_columns;
-                            // per-column scan (:643-669)
-                            const int diag_i = next_offset - seed_off_m1;
-                            const score_t extension_cutoff
-                                = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
-                            const bool cell = j < size;
-                            const score_t v = cell ? S_j : kNinf;
-                            min_cell_score = imin(min_cell_score, wreduce_min(cell && v != kNinf ? v : 0x7fffffff));
-                            const score_t gbs = wreduce_max(cell ? v : INT32_MIN);
-                            const int dj = iabs(j + begin - diag_i);
-                            const int gd = wreduce_min(cell && v == gbs ? dj : 0x7fffffff);
-                            const int gj = wreduce_min(cell && v == gbs && dj == gd ? j : 0x7fffffff);
-                            const int max_pos = gj + begin;
-                            const score_t max_val = gbs;
-                            bool has_extension = in_seed;
-                            if (!has_extension)
-                                has_extension = wballot(cell && v + cx[s].ps[start + begin + j] >= extension_cutoff) != 0;
-                            if (!in_seed && (max_val < cutoff || !has_extension))
-                                continue;                        // pop(table.size() - 1)
-                            table_size_bytes += 136ull * (cx[e].table_cap - cap_before)
-                                + 3ull * vec_capacity(size0, size) * 4;
-                            if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
-                            best_score = imax(best_score, max_val);
-                            if (cells_used > cells_limit) { overflow = true; return 0; }
-                            // commit: DP table (global) and the on-chip child buffer
-                            const int cap = size + 5;
-                            const uint32_t off = cells_used;
-                            cells_used += 3 * cap;
-                            score_t *cb_S = sm.buf(cb);
-                            if (j < cap) {
-                                score_t *dst = m.cells + off;
-                                dst[j] = S_j; dst[cap + j] = E_j; dst[2 * cap + j] = F_j;
-                                cb_S[j] = S_j; cb_S[sm.bmax + j] = E_j; cb_S[2 * sm.bmax + j] = F_j;
-                            }
-                            if (j + 32 < cap) {                  // padding cells beyond lane 31 are untouched ninf
-                                score_t *dst = m.cells + off;
-                                dst[j + 32] = kNinf; dst[cap + j + 32] = kNinf; dst[2 * cap + j + 32] = kNinf;
-                                cb_S[j + 32] = kNinf; cb_S[sm.bmax + j + 32] = kNinf; cb_S[2 * sm.bmax + j + 32] = kNinf;
-                            }
-                            ColMeta col;
-                            col.node = sm.out_nodes[t]; col.trail = plain_out ? 0 : sm.out_trails[t]; col.parent = i; col.c = ch;
-                            col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
-                            col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size; col.cells_off = off;
-                            const uint32_t idx = n_cols;
-                            m.cols[n_cols++] = col;
-                            last_col = col; last_idx = idx;
-                            last_band_mask = wballot(cell && S_j >= cutoff); last_band_cutoff = cutoff; last_band_valid = true;
-                            if (cb) res1 = (int)idx; else res0 = (int)idx;
-                            wsync();
-                            // convergence filter from registers (update_seed_filter)
-                            const int s_first = begin ? 0 : 1;
-                            const int vec_offset = start + begin - (begin ? 1 : 0);
-                            score_t converged = update_seed_filter_reg(e, col.node, vec_offset, S_j, j - s_first,
-                                                                       size - s_first);
-                            if (overflow) return 0;
-                            if (converged != kNinf) {
-                                HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
-                                it.idx = idx; it.max_score = max_val;
-                                if (nn_n && converged == np[0].score) nn_push(nn_n, it);
-                                else if (heap_n == 0 && nn_n == 0 && t + 1 == n_out) {
-                                    // sole candidate: pushing it and popping it in the next round is the
-                                    // identity; np[0] must still hold it for the tie test above
-                                    np[0] = it; nn_n = 1;
-                                } else heap_push(heap_n, it);
-                                if (overflow) return 0;
-                            }
-                            continue;
-                        }
-                    }
-#endif
-                    MGB_COUNT(6);
-                    Scratch sc;
-                    if (size0 + 8 <= sm.bmax) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
-                    else if (!scratch_arena(wlen + 1 - begin, &sc)) return 0;
-                    // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
-                    for (int j = wlane(); j < size0 + 5; j += kWarp) { sc.S[j] = kNinf; sc.E[j] = kNinf; sc.F[j] = kNinf; }
-                    wsync();
-                    const score_t add = plain_out ? 0 : sm.out_scores[t];
+            // ---------------- child t of column i (:562-770) ----------------
+            const int tc = t++;
+            uint8_t ch = one_reg ? one_ch : sm.out_chars[tc];
+            if (ch >= 'a' && ch <= 'z') ch -= 32;          // toupper (:564)
+            const uint64_t cnode = one_reg ? one_node : sm.out_nodes[tc];
+            const score_t add = plain_out ? 0 : sm.out_scores[tc];
+            if (n_cols >= caps.max_cols) { overflow = true; continue; }
+            const int code = encode_char(ch);
+            const int diag_i = next_offset - seed_off_m1;
+
+            // ---- register path: the whole column (incl. its 5 padding cells) fits 32 cells (n4 <= 28, final
+            // size <= 27). Fuses DPTColumn::create, update_column, extend_ins_end, the per-column scan, the
+            // table commit (compact format) and the convergence filter.
+            if (reg_path && n <= 28 && size0 <= 27) {
+                {   // requests whose latency overlaps the DP below
+                    if (!rc && cnode && !MGB_WIDE(ix) && !MGB_PRIMARY(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                    pf_key = cnode + (rc ? ix.n : 0);
+                    pf_slot_idx = hash_node(pf_key);
+                    pf_slot = cx[e].conv_slots[pf_slot_idx];
+                }
+                RegCol r;
+                const int size = reg_column(s, parS + shift, parF + shift, n, size0, start + begin, wlen + 1 - begin,
+                                            code, add, next_offset > 1, cutoff, r);
+                if (size >= 0) {
+                    MGB_COUNT(5);
+                    const int j0 = wlane() * kCPL;
                     const uint32_t cap_before = cx[e].table_cap;
-                    if (n_cols + 1 > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
-                    const int code = encode_char(ch);
-
-                    update_column(s, parS + shift, parF + shift, sc, size0, n, start + begin, cutoff,
-                                  code, add, next_offset > 1);
-                    const int size = extend_ins_end(sc, size0, wlen + 1 - begin, cutoff);
-                    if (overflow) return 0;
+                    if (n_cols + 1 > cap_before) cx[e].table_cap = cap_before ? 2 * cap_before : 1;
                     stats.dp_cells += size; ++stats.dp_columns;
-
                     // per-column scan (:643-669)
-                    const int diag_i = next_offset - seed_off_m1;
-                    bool has_extension = in_seed;
                     const score_t extension_cutoff
                         = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
-                    int max_pos;
-                    {
-                        score_t mn = 0x7fffffff; score_t bs = INT32_MIN; int bd = 0x7fffffff, bj = 0x7fffffff;
-                        bool he = false;
-                        for (int j = wlane(); j < size; j += kWarp) {
-                            score_t v = sc.S[j];
-                            if (v != kNinf) mn = imin(mn, v);
-                            int d = iabs(j + begin - diag_i);
-                            if (v > bs || (v == bs && d < bd)) { bs = v; bd = d; bj = j; }
-                            if (v + cx[s].ps[start + begin + j] >= extension_cutoff) he = true;
-                        }
-                        min_cell_score = imin(min_cell_score, wreduce_min(mn));
-                        score_t gbs = wreduce_max(bs);
-                        int gd = wreduce_min(bs == gbs ? bd : 0x7fffffff);
-                        int gj = wreduce_min(bs == gbs && bd == gd ? bj : 0x7fffffff);
-                        max_pos = gj + begin;
-                        if (!has_extension && wballot(he)) has_extension = true;
+                    score_t mn = 0x7fffffff, bs = INT32_MIN;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                    for (int c = 0; c < kCPL; ++c) {
+                        const bool cell = j0 + c < size;
+                        const score_t v = r.S[c];
+                        if (cell && v != kNinf) mn = imin(mn, v);
+                        if (cell) bs = imax(bs, v);
                     }
-                    const score_t max_val = sc.S[max_pos - begin];
-
+                    min_cell_score = imin(min_cell_score, wreduce_min(mn));
+                    const score_t max_val = wreduce_max(bs);
+                    int bd = 0x7fffffff; bool he = false;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                    for (int c = 0; c < kCPL; ++c) {
+                        const int j = j0 + c;
+                        const bool cell = j < size;
+                        if (cell && r.S[c] == max_val) bd = imin(bd, iabs(j + begin - diag_i));
+                        if (!in_seed && cell && r.S[c] + cx[s].ps[start + begin + j] >= extension_cutoff) he = true;
+                    }
+                    const int gd = wreduce_min(bd);
+                    int bj = 0x7fffffff;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                    for (int c = 0; c < kCPL; ++c) {
+                        const int j = j0 + c;
+                        if (j < size && r.S[c] == max_val && iabs(j + begin - diag_i) == gd) bj = imin(bj, j);
+                    }
+                    const int max_pos = wreduce_min(bj) + begin;
+                    const bool has_extension = in_seed || wballot(he) != 0;
                     if (!in_seed && (max_val < cutoff || !has_extension))
                         continue;                        // pop(table.size() - 1)
-
                     table_size_bytes += 136ull * (cx[e].table_cap - cap_before)
                         + 3ull * vec_capacity(size0, size) * 4;
-
                     if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
                     best_score = imax(best_score, max_val);
-
-                    if ((uint64_t)cells_used + 3ull * (size + 5) + 3ull * (wlen + 16) > 3ull * caps.max_cells) {
-                        overflow = true; return 0;
-                    }
+                    if (cells_used > cells_limit) { overflow = true; continue; }
+                    // commit: DP table (compact format, whole 32-byte sectors) and the on-chip child buffer
+                    const int capr = capr_of(size);
+                    const uint32_t off = (cells_used + 7u) & ~7u;
+                    cells_used = off + 2 * capr + 8;
+                    score_t *dst = m.cells + off;
+                    score_t *cb_S = sm.buf(cb);
+                    store_cells(dst, j0, r.S, capr);
+                    store_flags(reinterpret_cast<uint8_t*>(dst + capr), j0, r.fl);
+                    store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * sm.bmax, j0, r.F, 32);
                     ColMeta col;
-                    col.node = sm.out_nodes[t]; col.trail = plain_out ? 0 : sm.out_trails[t]; col.parent = i; col.c = ch;
+                    col.node = cnode; col.parent = i; col.c = ch;
                     col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
-                    col.is_tip = 0; col.started = 0; col.pad = 0; col.size = size;
-                    col.cells_off = commit_column(sc, size);
+                    col.is_tip = 0; col.started = 0; col.fmt = FMT_COMPACT; col.pad0 = col.pad1 = 0;
+                    col.size = size; col.cells_off = off;
                     const uint32_t idx = n_cols;
                     m.cols[n_cols++] = col;
-                    last_col = col; last_idx = idx; last_band_valid = false;
-                    if (sc.on_chip) { if (cb) res1 = (int)idx; else res0 = (int)idx; }
-
-                    const int vec_offset = start + begin - (begin ? 1 : 0);
+                    last_col = col; last_idx = idx;
+                    {   // band of this column under the (updated) cutoff, for when it is expanded
+                        uint32_t bits = 0;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                        for (int c = 0; c < kCPL; ++c) if (j0 + c < size && r.S[c] >= cutoff) bits |= 1u << c;
+                        last_band_mask = kCPL == 32 ? bits : wreduce_or(bits << (j0 & 31));
+                        last_band_cutoff = cutoff; last_band_valid = true;
+                    }
+                    if (cb) res1 = (int)idx; else res0 = (int)idx;
+                    wsync();
+                    // convergence filter from registers (update_seed_filter)
                     const int s_first = begin ? 0 : 1;
-                    score_t converged = update_seed_filter(e, col.node, vec_offset, sc.S + s_first, size - s_first);
-                    if (overflow) return 0;
+                    const int vec_offset = start + begin - (begin ? 1 : 0);
+                    const score_t converged = update_seed_filter_regs(e, cnode, vec_offset, r.S, s_first, size, cb_S);
+                    if (overflow) continue;
                     if (converged != kNinf) {
                         HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
                         it.idx = idx; it.max_score = max_val;
                         if (nn_n && converged == np[0].score) nn_push(nn_n, it);
-                        else heap_push(heap_n, it);
-                        if (overflow) return 0;
+                        else if (heap_n == 0 && nn_n == 0 && t == n_out) {
+                            // sole candidate: pushing it and popping it in the next round is the
+                            // identity; np[0] must still hold it for the tie test above. It is expanded from
+                            // the on-chip buffer next, so its F never has to be read from the table
+                            np[0] = it; nn_n = 1;
+                            continue;
+                        } else heap_push(heap_n, it);
+                        // the column waits in the queue: a later expansion reads its F from the table
+                        store_cells(dst + capr + 8, j0, r.F, capr);
+                        m.cols[idx].fmt = FMT_COMPACT_F; last_col.fmt = FMT_COMPACT_F;
                     }
+                    continue;
                 }
             }
+            // ---- general path: columns of any width, S | E | F in the table
+            MGB_COUNT(6);
+            if (par_fmt == FMT_COMPACT && pb >= 0) {
+                // the backtrack compares the F of a general-path column with its parent's (:976-997): write the
+                // parent's F (still on chip) into the space its compact record reserves for it
+                const ColMeta pc = m.cols[i];
+                score_t *dstF = m.cells + pc.cells_off + capr_of(pc.size) + 8;
+                for (int j = wlane(); j < pc.size + 5; j += kWarp) dstF[j] = parF[j];
+                m.cols[i].fmt = FMT_COMPACT_F; par_fmt = FMT_COMPACT_F;
+                if (last_idx == i) last_col.fmt = FMT_COMPACT_F;
+                wsync();
+            }
+            Scratch sc;
+            if (size0 + 8 <= sm.bmax) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
+            else if (!scratch_arena(wlen + 1 - begin, &sc)) continue;
+            // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
+            for (int j = wlane(); j < size0 + 5; j += kWarp) { sc.S[j] = kNinf; sc.E[j] = kNinf; sc.F[j] = kNinf; }
+            wsync();
+            const uint32_t cap_before = cx[e].table_cap;
+            if (n_cols + 1 > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
+
+            update_column(s, parS + shift, parF + shift, sc, size0, n, start + begin, cutoff,
+                          code, add, next_offset > 1);
+            const int size = extend_ins_end(sc, size0, wlen + 1 - begin, cutoff);
+            if (overflow) continue;
+            stats.dp_cells += size; ++stats.dp_columns;
+
+            // per-column scan (:643-669)
+            bool has_extension = in_seed;
+            const score_t extension_cutoff
+                = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
+            int max_pos;
+            {
+                score_t mn = 0x7fffffff; score_t bs = INT32_MIN; int bd = 0x7fffffff, bj = 0x7fffffff;
+                bool he = false;
+                for (int j = wlane(); j < size; j += kWarp) {
+                    score_t v = sc.S[j];
+                    if (v != kNinf) mn = imin(mn, v);
+                    int d = iabs(j + begin - diag_i);
+                    if (v > bs || (v == bs && d < bd)) { bs = v; bd = d; bj = j; }
+                    if (v + cx[s].ps[start + begin + j] >= extension_cutoff) he = true;
+                }
+                min_cell_score = imin(min_cell_score, wreduce_min(mn));
+                score_t gbs = wreduce_max(bs);
+                int gd = wreduce_min(bs == gbs ? bd : 0x7fffffff);
+                int gj = wreduce_min(bs == gbs && bd == gd ? bj : 0x7fffffff);
+                max_pos = gj + begin;
+                if (!has_extension && wballot(he)) has_extension = true;
+            }
+            const score_t max_val = sc.S[max_pos - begin];
+
+            if (!in_seed && (max_val < cutoff || !has_extension))
+                continue;                        // pop(table.size() - 1)
+
+            table_size_bytes += 136ull * (cx[e].table_cap - cap_before)
+                + 3ull * vec_capacity(size0, size) * 4;
+
+            if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
+            best_score = imax(best_score, max_val);
+
+            if ((uint64_t)cells_used + 3ull * (size + 5) + 3ull * (wlen + 16) > 3ull * caps.max_cells) {
+                overflow = true; continue;
+            }
+            ColMeta col;
+            col.node = cnode; col.parent = i; col.c = ch;
+            col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
+            col.is_tip = 0; col.started = 0; col.fmt = FMT_FULL; col.pad0 = col.pad1 = 0; col.size = size;
+            col.cells_off = commit_column(sc, size);
+            const uint32_t idx = n_cols;
+            m.cols[n_cols++] = col;
+            last_col = col; last_idx = idx; last_band_valid = false;
+            if (sc.on_chip) { if (cb) res1 = (int)idx; else res0 = (int)idx; }
+
+            const int vec_offset = start + begin - (begin ? 1 : 0);
+            const int s_first = begin ? 0 : 1;
+            score_t converged = update_seed_filter(e, col.node, vec_offset, sc.S + s_first, size - s_first);
+            if (overflow) continue;
+            if (converged != kNinf) {
+                HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);
+                it.idx = idx; it.max_score = max_val;
+                if (nn_n && converged == np[0].score) nn_push(nn_n, it);
+                else heap_push(heap_n, it);
+            }
         }
+        if (!go || overflow) return 0;
         wsync();
         MGB_TOC(t_fwd, 2);
 
@@ -2273,7 +2478,7 @@ struct ReadAligner {
                         const int ci = pos_t - c_t.trim, pi = pos_t - p_t.trim - 1;
                         if (c_t.parent == j - t - 1 && pos_t > 0 && ci >= 0 && ci < c_t.size && pi >= 0 && pi < p_t.size) {
                             const score_t sv = cellS(c_t, ci);
-                            const bool ins = sv == cellE(c_t, ci) && (t || cur_op == 0xffu || cur_op != OP_D);
+                            const bool ins = bt_is_ins(c_t, ci, sv) && (t || cur_op == 0xffu || cur_op != OP_D);
                             const int code = encode_char(c_t.c);
                             good = sv != kNinf && !ins
                                 && sv == cellS(p_t, pi) + c_t.score + prof_score(s, seed_clipping + pos_t, code);
@@ -2337,12 +2542,12 @@ struct ReadAligner {
 
                 if (sv == kNinf) {
                     j = 0;
-                } else if (pos && sv == cellE(col, pos - trim) && (last_op == 0xffu || last_op != OP_D)) {
+                } else if (pos && bt_is_ins(col, pos - trim, sv) && (last_op == 0xffu || last_op != OP_D)) {
                     // insertion run (:943-959)
                     bool again = true;
                     while (again) {
                         cig_add(OP_I);
-                        again = cellE(col, pos - trim) == cellE(col, pos - trim - 1) + cfg.gap_ext;
+                        again = bt_ins_ext(col, pos - trim);
                         --pos;
                     }
                 } else if (pos && pos >= trim_p + 1
@@ -2360,13 +2565,12 @@ struct ReadAligner {
                     j = col.parent;
                     col = par;
                     if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols[par.parent]; }
-                } else if (sv == cellF(col, pos - trim) && (last_op == 0xffu || last_op != OP_I)) {
+                } else if (bt_is_del(col, pos - trim, sv) && (last_op == 0xffu || last_op != OP_I)) {
                     // deletion run (:972-999)
                     bool again = true;
                     while (again && j) {
                         align_offset = imin(col.offset, k_minus_1);
-                        again = cellF(col, pos - col.trim)
-                                == cellF(par, pos - par.trim) + col.score + cfg.gap_ext;
+                        again = bt_del_ext(col, par, pos);
                         ++n_trace;
                         if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
                         m.bt_seq[n_seq++] = col.c;
@@ -2498,50 +2702,68 @@ struct ReadAligner {
     // Seeds of query strand s, in order (dbg_aligner.cpp:360-384 align_core when `both` is false,
     // :657-736 aln_both otherwise: forward extension, then backward extension of left-clipped
     // results through the reverse-complement graph view).
-    MGB_HD void align_strand(int s, bool both) {
+    // Lock-step over the lane groups of a warp: the loops below that end in the extender run while ANY group of
+    // the warp has work (wany_full) and `act` / `seed_ok` / `ext_ok` say whether THIS group takes part, so that
+    // all lanes of the warp enter the extender's column loop together (see extend()).
+    MGB_HD void align_strand(int s, bool both, bool act) {
         const int fe = s, be = 1 - s;
-        cx[fe].rc = 0;
-        if (both) cx[be].rc = MGB_CANONICAL(cfg) ? 0 : 1;     // use_rcdbg (dbg_aligner.cpp:646-650)
-        const int n_seeds_s = cx[s].n_seeds;
-        SeedRec *seeds_s = cx[s].seeds;
-        const bool implicit = cx[s].implicit_seeds != 0;
+        int n_seeds_s = 0; SeedRec *seeds_s = nullptr; bool implicit = false;
         const int nk = L >= (int)ix.k ? L - (int)ix.k + 1 : 0;
-        stats.num_seeds += n_seeds_s;
-        if (!n_seeds_s) return;
-        for (int i = implicit ? mask_next(cx[s].mask, nk, 0, true) : 0;
-             (implicit ? i < nk : i < n_seeds_s) && !overflow;
-             i = implicit ? mask_next(cx[s].mask, nk, i + 1, true) : i + 1) {
-            SeedRec sd;
-            if (implicit) {
-                sd.clip = i; sd.len = ix.k; sd.offset = 0; sd.n_nodes = 1; sd.node0 = cx[s].qnodes[i];
-                sd.alive = 1; sd.pad = 0;
-            } else {
-                sd = seeds_s[i];
-                if (!sd.alive) continue;
+        int i = 0;
+        if (act) {
+            cx[fe].rc = 0;
+            if (both) cx[be].rc = MGB_CANONICAL(cfg) ? 0 : 1;     // use_rcdbg (dbg_aligner.cpp:646-650)
+            n_seeds_s = cx[s].n_seeds;
+            seeds_s = cx[s].seeds;
+            implicit = cx[s].implicit_seeds != 0;
+            stats.num_seeds += n_seeds_s;
+            if (!n_seeds_s) act = false;
+            else if (implicit) i = mask_next(cx[s].mask, nk, 0, true);
+        }
+        while (true) {
+            // next live seed of this group (dead ones are skipped here so that a group never idles on them)
+            if (act && !implicit) while (i < n_seeds_s && !seeds_s[i].alive) ++i;
+            const bool seed_ok = act && !overflow && (implicit ? i < nk : i < n_seeds_s);
+            if (!wany_full(seed_ok)) break;
+            score_t mps_fwd = 0;
+            if (seed_ok) {
+                SeedRec sd;
+                if (implicit) {
+                    sd.clip = i; sd.len = ix.k; sd.offset = 0; sd.n_nodes = 1; sd.node0 = cx[s].qnodes[i];
+                    sd.alive = 1; sd.pad = 0;
+                } else {
+                    sd = seeds_s[i];
+                }
+                seed_to_slot(SLOT_SEED, s, sd);
+                seed_is_query = true;
+                mps_fwd = both ? cfg.min_cell_score : get_min_path_score();
             }
-            seed_to_slot(SLOT_SEED, s, sd);
-            seed_is_query = true;
-            const score_t mps_fwd = both ? cfg.min_cell_score : get_min_path_score();
             // One call site for both kinds of extension (the forward one, then the backward ones it
             // spawns): the extender is by far the largest piece of code and must exist once.
-            int n_rc = 0;
-            for (int it = 0; it <= n_rc && !overflow; ++it) {
-                if (it == 0) {
-                    set_seed(fe);
-                } else {
-                    // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
-                    if (!sm.slots[SLOT_EXT + it - 1].h->used) continue;
-                    set_seed(be);
-                    seed_is_query = false;
+            int n_rc = 0, it = 0;
+            while (true) {
+                const bool it_ok = seed_ok && !overflow && it <= n_rc;
+                if (!wany_full(it_ok)) break;
+                bool ext_ok = it_ok;
+                if (ext_ok) {
+                    if (it == 0) {
+                        set_seed(fe);
+                    } else if (!sm.slots[SLOT_EXT + it - 1].h->used) {
+                        ext_ok = false;
+                    } else {
+                        // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
+                        set_seed(be);
+                        seed_is_query = false;
+                    }
                 }
                 const int r = it - 1;
                 const int n_ext = extend(it ? be : fe, it ? SLOT_EXT + r : SLOT_SEED,
-                                         it ? get_min_path_score() : mps_fwd, it != 0, it ? SLOT_BWD : SLOT_EXT);
-                if (overflow) return;
+                                         (ext_ok && it) ? get_min_path_score() : mps_fwd, it != 0, it ? SLOT_BWD : SLOT_EXT,
+                                         ext_ok);
                 // results of this extension: one loop (and one agg_add site: the aggregator's comparison
                 // code is large) for the forward case (aggregate, then reverse-complement the clipped
                 // ones for the backward pass) and the backward case (reverse-complement back, then aggregate)
-                for (int r0 = 0; r0 < n_ext; ++r0) {
+                for (int r0 = 0; ext_ok && !overflow && r0 < n_ext; ++r0) {
                     const int slot = (it ? SLOT_BWD : SLOT_EXT) + r0;
                     // is_reversible (:652-656): on a CANONICAL-mode graph an alignment to the reverse strand
                     // with no offset is reported as its reverse complement
@@ -2568,7 +2790,7 @@ struct ReadAligner {
                         }
                         bool ok = true;
                         if (need_rc) ok = reverse_complement_for_bwd(target);
-                        if (overflow) return;
+                        if (overflow) break;
                         if (!ok) break;                                   // the alignment cannot be reversed
                         if (pass == 0) {
                             if (it != 0 && need_rc) {
@@ -2584,21 +2806,22 @@ struct ReadAligner {
                         }
                     }
                 }
-                if (it == 0) continue;
-                for (int r2 = r + 1; r2 < n_rc; ++r2) {
-                    AlnSlot &a = sm.slots[SLOT_EXT + r2];
-                    if (!a.h->used) continue;
-                    const AlnHdr h = *a.h;
-                    if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, !MGB_CANONICAL(cfg) && cx[be].rc != 0,
-                                         a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
-                        a.h->used = 0;
+                if (ext_ok && !overflow && it != 0) {
+                    for (int r2 = r + 1; r2 < n_rc; ++r2) {
+                        AlnSlot &a = sm.slots[SLOT_EXT + r2];
+                        if (!a.h->used) continue;
+                        const AlnHdr h = *a.h;
+                        if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, !MGB_CANONICAL(cfg) && cx[be].rc != 0,
+                                             a.nodes[h.n_nodes - 1], h.q_len + aln_clipping(a) - 1, h.score))
+                            a.h->used = 0;
+                    }
                 }
+                if (it_ok) ++it;
             }
-            if (overflow) return;
-            // later seeds already covered by this extension are dropped (:731-734, :379-382);
-            // independent probes, one seed per lane
-            wsync();
-            {
+            if (seed_ok && !overflow) {
+                // later seeds already covered by this extension are dropped (:731-734, :379-382);
+                // independent probes, one seed per lane
+                wsync();
                 const ConvSlot *slots = cx[fe].conv_slots; const score_t *cells = cx[fe].conv_cells;
                 const uint32_t epoch = cx[fe].conv_epoch;
                 const uint64_t *nodes_s = cx[s].qnodes; const int32_t *pss = cx[s].ps;
@@ -2628,8 +2851,9 @@ struct ReadAligner {
                             seeds_s[j].alive = 0;
                     }
                 }
+                wsync();
             }
-            wsync();
+            if (seed_ok) i = implicit ? mask_next(cx[s].mask, nk, i + 1, true) : i + 1;
         }
     }
 
@@ -2641,12 +2865,7 @@ struct ReadAligner {
         for (int base = L - 1; base >= 0; base -= kWarp) {
             int i = base - wlane();
             int v = i >= 0 ? cfg.diag[(uint8_t)cx[s].q[i]] : 0;
-#if MGB_DEVICE_CODE
-            for (int d = 1; d < 32; d <<= 1) {
-                int o = __shfl_up_sync(0xffffffffu, v, d);
-                if (wlane() >= d) v += o;
-            }
-#endif
+            v = wscan_add(v);
             v += carry;
             if (i >= 0) cx[s].ps[i] = v;
             carry = wbcast(v, kWarp - 1);
@@ -2658,11 +2877,15 @@ struct ReadAligner {
     // optional: per-position index_range results of both strands (k_subk), set before run()
     const uint32_t *subk_first[2] = { nullptr, nullptr }, *subk_last[2] = { nullptr, nullptr };
     const uint8_t *subk_len[2] = { nullptr, nullptr };
-    MGB_HD int run(int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
+    // `act`: this lane group has a read (the groups of a warp call run() together, see align_strand / extend)
+    MGB_HD int run(bool act, int L_, const char *qf, const char *qr, const uint8_t *cf, const uint8_t *cr,
                    const uint64_t *nf, const uint64_t *nr, int *order) {
         MGB_TIC(t_setup);
         L = L_;
         overflow = false; n_agg = 0; seed_is_query = false;
+        const bool both = cfg.forward_and_reverse_complement;
+        int first = 0, n_pass = 0;
+        if (act) {
         wsync();
         // per-strand context + alignment slot table (shared memory; constant indices only here)
         {
@@ -2694,7 +2917,6 @@ struct ReadAligner {
         wsync();
         stats.num_seeds = stats.num_extensions = stats.num_explored_nodes = stats.dp_columns = 0;
         stats.dp_cells = 0;
-        const bool both = cfg.forward_and_reverse_complement;
         if (MGB_CANONICAL(cfg) && MGB_PRIMARY(ix) && L >= (int)ix.k) {
             // CanonicalDBG::map_to_nodes_sequentially (:55-146) from the two per-strand maps of the stored k-mers: a
             // k-mer missing on its own strand takes the id of its reverse complement + n; the other strand's path is
@@ -2716,12 +2938,12 @@ struct ReadAligner {
         MGB_TOC(t_setup, 0);
         MGB_TIC(t_seeds);
         #pragma unroll 1
-        for (int s = 0; s < (both ? 2 : 1); ++s) {           // one call site: the seeder is large
+        for (int s = 0; s < (both ? 2 : 1) && !overflow; ++s) {           // one call site: the seeder is large
             build_seeds(s);
-            if (overflow) return 0;
+            if (overflow) break;
             if ((double)L * cfg.min_exact_match > (double)cx[s].num_matching) { cx[s].n_seeds = 0; cx[s].num_matching = 0; }
         }
-        int first = 0, n_pass = 1;
+        n_pass = 1;
         if (both) {
             // the strand with more exact-match bases first; the other only if it is close (:738-755)
             uint32_t fm = cx[0].num_matching, bm = cx[1].num_matching;
@@ -2729,12 +2951,16 @@ struct ReadAligner {
             uint32_t hi = first ? bm : fm, lo = first ? fm : bm;
             n_pass = (double)lo >= (double)hi * cfg.rel_score_cutoff ? 2 : 1;
         }
+        }   // act
         MGB_TOC(t_seeds, 1);
         MGB_TIC(t_align);
-        for (int pass = 0; pass < n_pass && !overflow; ++pass)
-            align_strand(pass ? 1 - first : first, both);
+        for (int pass = 0; ; ++pass) {
+            const bool p_ok = act && !overflow && pass < n_pass;
+            if (!wany_full(p_ok)) break;
+            align_strand(pass ? 1 - first : first, both, p_ok);
+        }
         MGB_TOC(t_align, 4);
-        if (overflow) return 0;
+        if (!act || overflow) return 0;
         stats.num_extensions += cx[0].num_ext + cx[1].num_ext;
         stats.num_explored_nodes += cx[0].explored_prev + cx[0].conv_n + cx[1].explored_prev + cx[1].conv_n;
         // AlignmentAggregator::get_alignments: descending LocalAlignmentLess order

@@ -824,9 +824,13 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             if (pass == 6) { rc = fail(MGB_ERR_OVERFLOW, "a read exceeded the largest per-read work arena"); break; }
             Caps caps = choose_caps(b.L_max, dcfg, index->view.k, scale);
             size_t stride = arena_bytes(caps);
-            // on-chip working set per warp: column buffers hold a full-width column of reads up to
-            // 248 bp; longer reads / wider columns spill to the arena scratch
-            const int bmax = b.L_max + 9 <= 256 ? (int)((b.L_max + 9 + 31) & ~31u) : 256;
+            // on-chip working set per lane group: the column buffers hold the widest column the x-drop band
+            // allows (choose_caps' estimate; at least 64 cells, the register path of the extender needs 40) of
+            // reads up to 248 bp; wider columns spill to the arena scratch
+            uint64_t band_est = (uint64_t)b.L_max + 9;
+            if (dcfg.gap_ext < 0 && dcfg.xdrop < (1 << 20))
+                band_est = std::min<uint64_t>(band_est, 2ull * (dcfg.xdrop / (-dcfg.gap_ext)) + 16 + 8);
+            const int bmax = band_est <= 256 ? std::max(64, (int)((band_est + 31) & ~31ull)) : 256;
             const int lq = b.L_max + 1 <= 512 ? (int)((b.L_max + 1 + 15) & ~15u) : 0;
             int hcap = 16;
             // test knobs: force the spill paths (arena scratch, queue migration, unstaged query)
@@ -841,7 +845,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             uint32_t n_warps = 1;
 #else
             int blocks_per_sm = 0;
-            const size_t smem_block = smem_per_warp * 4;
+            const size_t smem_block = smem_per_warp * kern_dna::kGroupsPerBlock;
             {
                 // driver queries serialise against running work: ask once per shared-memory size
                 static std::mutex occ_mu;
@@ -861,15 +865,16 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                 } else blocks_per_sm = it->second;
             }
             if (blocks_per_sm < 1) blocks_per_sm = 1;
-            uint64_t n_warps64 = (uint64_t)index->num_sms * blocks_per_sm * 4;
+            const uint64_t gpb = kern_dna::kGroupsPerBlock;       // lane groups (reads in flight) per block
+            uint64_t n_warps64 = (uint64_t)index->num_sms * blocks_per_sm * gpb;
             if (stride * n_warps64 > pass_bufs.capacity_of_next()) {
                 size_t free_b = 0, total_b = 0;
                 cudaMemGetInfo(&free_b, &total_b);
                 uint64_t mem_warps = (uint64_t)(free_b * 0.6 + pass_bufs.capacity_of_next()) / (stride ? stride : 1);
-                if (mem_warps < 4) mem_warps = 4;
-                if (n_warps64 > mem_warps) n_warps64 = mem_warps & ~3ull;
+                if (mem_warps < gpb) mem_warps = gpb;
+                if (n_warps64 > mem_warps) n_warps64 = mem_warps / gpb * gpb;
             }
-            if (n_warps64 > ((uint64_t)list.size() + 3) / 4 * 4) n_warps64 = ((uint64_t)list.size() + 3) / 4 * 4;
+            if (n_warps64 > ((uint64_t)list.size() + gpb - 1) / gpb * gpb) n_warps64 = ((uint64_t)list.size() + gpb - 1) / gpb * gpb;
             uint32_t n_warps = (uint32_t)n_warps64;
 #endif
             // output heap: generous first guess, doubled on retry passes
@@ -909,13 +914,13 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             std::vector<char> smem_emu(smem_per_warp + 64);
             WarpMem mem_emu; mem_emu.carve(d_arena, a.caps);
             WarpSmem sm_emu; sm_emu.carve(smem_emu.data(), a.bmax, a.lq, a.hcap);
-            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], mem_emu, sm_emu);
+            for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], mem_emu, sm_emu, true);
             used = *d_used;
 #else
             cudaEventRecord(ev[3], st.s);
-            CUDA_TRY(index->view.wide ? kern_any::launch_align(n_warps / 4, smem_block, st.s, a)
-                   : index->view.mode != 0 ? kern_canon::launch_align(n_warps / 4, smem_block, st.s, a)
-                                           : kern_dna::launch_align(n_warps / 4, smem_block, st.s, a));
+            CUDA_TRY(index->view.wide ? kern_any::launch_align(n_warps / (uint32_t)gpb, smem_block, st.s, a)
+                   : index->view.mode != 0 ? kern_canon::launch_align(n_warps / (uint32_t)gpb, smem_block, st.s, a)
+                                           : kern_dna::launch_align(n_warps / (uint32_t)gpb, smem_block, st.s, a));
             cudaEventRecord(ev[4], st.s);
             if ((rc = d2h(&used, d_used, 8, st))) break;
             CUDA_TRY(cudaStreamSynchronize(st.s));

@@ -136,20 +136,24 @@ struct AlignArgs {
     unsigned int *next;
 };
 
-MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm) {
+// `act`: this lane group has a read; a group without one still walks through the lock-step loops of the
+// aligner (the lane groups of a warp run them together)
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm, bool act) {
     ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
     al.use_fast = a.use_fast != 0;
-    const uint64_t b = a.offsets[r];
-    const int L = (int)(a.offsets[r + 1] - b);
+    const uint64_t b = act ? a.offsets[r] : 0;
+    const int L = act ? (int)(a.offsets[r + 1] - b) : 0;
     int order[kMaxAlt];
     const bool has_k = L >= (int)a.ix.k;
     if (a.sub_len_f) {
         al.subk_first[0] = a.sub_first_f + b; al.subk_last[0] = a.sub_last_f + b; al.subk_len[0] = a.sub_len_f + b;
         if (a.sub_len_r) { al.subk_first[1] = a.sub_first_r + b; al.subk_last[1] = a.sub_last_r + b; al.subk_len[1] = a.sub_len_r + b; }
     }
-    int n = al.run(L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
-                   has_k ? a.nodes_f + a.koff[r] : nullptr,
-                   has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + a.koff[r] : nullptr, order);
+    const uint64_t ko = (act && has_k) ? a.koff[r] : 0;
+    int n = al.run(act, L, a.qf + b, a.qr + b, a.cf + b, a.cr + b,
+                   has_k ? a.nodes_f + ko : nullptr,
+                   has_k && a.cfg.forward_and_reverse_complement ? a.nodes_r + ko : nullptr, order);
+    if (!act) return;
 #if defined(MGB_PHASE_TIMERS) && MGB_DEVICE_CODE
     if (wlane() == 0 && a.phase_out) {
         for (int p = 0; p < 8; ++p) atomicAdd((unsigned long long*)a.phase_out + p, (unsigned long long)al.phase_cycles[p]);
@@ -327,10 +331,10 @@ __global__ void __launch_bounds__(128) k_subk(SubkArgs a, uint32_t chunks_per_st
     }
 }
 
-// one warp per read strand
+// one lane group per read strand
 __global__ void __launch_bounds__(256) k_premap(SeedArgs a) {
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) / kWarp;
     const uint64_t items = (uint64_t)a.n_reads * a.n_strands;
     for (uint64_t it = warp; it < items; it += nwarps) premap_item(a, (uint32_t)(it / a.n_strands), (uint32_t)(it % a.n_strands));
 }
@@ -347,13 +351,19 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
 #ifndef MGB_ALIGN_MIN_BLOCKS
 #define MGB_ALIGN_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#ifndef MGB_ALIGN_THREADS
+#define MGB_ALIGN_THREADS 128
+#endif
+static constexpr int kAlignThreads = MGB_ALIGN_THREADS;
+static constexpr int kGroupsPerBlock = kAlignThreads / kWarp;   // reads in flight per block of k_align
+// one lane group (kWarp lanes, common.cuh) per read; kAlignThreads / kWarp groups per block
+__global__ void __launch_bounds__(kAlignThreads, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     char *arena = a.arena + (size_t)warp * a.arena_stride;
     extern __shared__ __align__(16) char smem_raw[];
     WarpSmem probe;
     const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
-    char *smem = smem_raw + (threadIdx.x >> 5) * smem_per_warp;
+    char *smem = smem_raw + (threadIdx.x / kWarp) * smem_per_warp;
     init_arena(a, arena);
     WarpMem mem;                 // the warp's arena and on-chip working set are laid out once
     mem.carve(arena, a.caps);
@@ -361,10 +371,11 @@ __global__ void __launch_bounds__(128, MGB_ALIGN_MIN_BLOCKS) k_align(const Align
     sm.carve(smem, a.bmax, a.lq, a.hcap);
     while (true) {
         unsigned int t = 0;
-        if ((threadIdx.x & 31) == 0) t = atomicAdd(a.next, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= a.n_list) break;
-        align_read(a, a.read_list[t], mem, sm);
+        if (wlane() == 0) t = atomicAdd(a.next, 1u);
+        t = wbcast(t, 0);
+        const bool have = t < a.n_list;
+        if (!wany_full(have)) break;
+        align_read(a, have ? a.read_list[t] : 0u, mem, sm, have);
     }
 }
 
@@ -380,7 +391,7 @@ cudaError_t launch_premap(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_
 cudaError_t launch_seed(unsigned grid, cudaStream_t s, const SeedArgs &a) { k_seed<<<grid, 128, 0, s>>>(a); return cudaGetLastError(); }
 #endif
 cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const AlignArgs &a) {
-    k_align<<<grid, 128, smem_block, s>>>(a);
+    k_align<<<grid, kAlignThreads, smem_block, s>>>(a);
     return cudaGetLastError();
 }
 // raises the kernel's dynamic shared memory limit to `smem_limit` and reports the resident blocks per SM
@@ -388,7 +399,7 @@ cudaError_t launch_align(unsigned grid, size_t smem_block, cudaStream_t s, const
 cudaError_t align_occupancy(size_t smem_limit, size_t smem_block, int *blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(k_align, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_align, 128, smem_block);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_align, kAlignThreads, smem_block);
 }
 
 #if !defined(MGB_WIDE_ONLY) && !defined(MGB_ALIGN_KERNEL_ONLY)
@@ -400,8 +411,8 @@ __global__ void __launch_bounds__(128) k_rc_tables(RcArgs a) {
 }
 // alphabet-independent kernels live in the first translation unit only
 __global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    uint32_t nwarps = (gridDim.x * blockDim.x) / kWarp;
     for (uint32_t r = warp; r < a.n_reads; r += nwarps) prepare_read(a, r);
 }
 __global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a) {

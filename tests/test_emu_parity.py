@@ -85,6 +85,17 @@ def test_generic_layout_on_dna_emu(monkeypatch):
         P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_general_path_emu(monkeypatch):
+    """The emulation runs the extender's register path (one lane owning all 32 cells of a column) wherever the
+    device does; with it switched off every column goes through the general path (S | E | F table format)."""
+    monkeypatch.setenv("MGB_TEST_NOFAST", "1")
+    P.check_goldens(EMU)
+    P.check_mt(EMU, True)
+    for case in P.RANDOM_CASES[:5]:
+        seed, k, G, n, L, rate, cfgf, mask, nseq = case
+        P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
+
+
 def test_seed_complexity_filter_emu():
     """CLI default `seed_complexity_filter` (sdust restated from its definition, parity with the library
     unpinned): kernels vs oracle on reads and graphs full of homopolymers / short tandem repeats."""
