@@ -166,81 +166,127 @@ enum { SLOT_SEED = 0, SLOT_TMP = 1, SLOT_EXT = 2, SLOT_BWD = 2 + kMaxAlt, SLOT_A
 // ------------------------------------------------------------------------------------
 MGB_HOSTDEV size_t align_up(size_t x) { return (x + 15) & ~(size_t)15; }
 
-struct WarpMem {
-    ColMeta *cols; score_t *cells; HeapItem *heap; HeapItem *next_nodes;
-    BtStart *starts; ConvSlot *conv_slots[2]; score_t *conv_cells[2]; SeedRec *seeds[2]; int32_t *psum[2];
-    AlnSlot slots[kNumSlots];
-    uint32_t *bt_ops; uint64_t *bt_path; char *bt_seq;
-    uint8_t *sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
-    uint32_t *sfx_first, *sfx_last; uint8_t *sfx_len;   // index_range result per query position
+// Regions of a lane group's arena as BYTE OFFSETS from its base. The layout is the same for every group, so it is
+// computed once on the host and travels in the kernel parameters (constant bank): a region's address is
+// base + constant, no pointer table has to live in registers or on the stack.
+struct WarpLayout {
+    uint64_t cols, cells, heap, next_nodes, starts, conv_slots[2], conv_cells[2], seeds[2], psum[2];
+    uint64_t slot0, slot_stride, slot_nodes, slot_seq, slot_cigar;      // alignment slot s starts at slot0 + s * slot_stride
+    uint64_t bt_ops, bt_path, bt_seq;
+    uint64_t sfx_min;       // per query position: current min_seed_length (SuffixSeeder)
+    uint64_t sfx_first, sfx_last, sfx_len;   // index_range result per query position
     // seed complexity filter: 3-mer codes / equal-3-mer masks (scratch) and, per strand, the largest start of a
     // low-complexity 3-mer interval ending at or before each 3-mer (see build_lowcx)
-    uint8_t *lc_word; uint64_t *lc_eq; int32_t *lc_max[2];
-    uint32_t *epoch_store;  // conv-table epochs survive across the reads a warp processes
+    uint64_t lc_word, lc_eq, lc_max[2];
+    uint64_t epoch_store;   // conv-table epochs survive across the reads a group processes
+    uint64_t total;
 
-    MGB_HOSTDEV size_t carve(char *base, const Caps &c) {
+    MGB_HOSTDEV size_t carve(const Caps &c) {
         size_t o = 0;
-        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return base ? base + r : (char*)nullptr; };
-        epoch_store = (uint32_t*)take(16);
-        cols = (ColMeta*)take(sizeof(ColMeta) * c.max_cols);
-        cells = (score_t*)take(sizeof(score_t) * 3 * (size_t)c.max_cells);
-        heap = (HeapItem*)take(sizeof(HeapItem) * c.max_cols);
-        next_nodes = (HeapItem*)take(sizeof(HeapItem) * c.max_cols);
-        starts = (BtStart*)take(sizeof(BtStart) * 2 * c.max_cols);
+        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return (uint64_t)r; };
+        epoch_store = take(16);
+        cols = take(sizeof(ColMeta) * c.max_cols);
+        cells = take(sizeof(score_t) * 3 * (size_t)c.max_cells);
+        heap = take(sizeof(HeapItem) * c.max_cols);
+        next_nodes = take(sizeof(HeapItem) * c.max_cols);
+        starts = take(sizeof(BtStart) * 2 * c.max_cols);
         for (int e = 0; e < 2; ++e) {
-            conv_slots[e] = (ConvSlot*)take(sizeof(ConvSlot) * c.hash_size);
-            conv_cells[e] = (score_t*)take(sizeof(score_t) * c.max_conv_cells);
-            seeds[e] = (SeedRec*)take(sizeof(SeedRec) * c.max_seeds);
-            psum[e] = (int32_t*)take(sizeof(int32_t) * (c.L_max + 8));
+            conv_slots[e] = take(sizeof(ConvSlot) * c.hash_size);
+            conv_cells[e] = take(sizeof(score_t) * c.max_conv_cells);
+            seeds[e] = take(sizeof(SeedRec) * c.max_seeds);
+            psum[e] = take(sizeof(int32_t) * (c.L_max + 8));
         }
-        for (int s = 0; s < kNumSlots; ++s) {
-            slots[s].h = (AlnHdr*)take(sizeof(AlnHdr));
-            slots[s].nodes = (uint64_t*)take(8 * (size_t)c.aln_nodes);
-            slots[s].seq = (char*)take(c.aln_seq);
-            slots[s].cigar = (uint32_t*)take(4 * (size_t)c.aln_cigar);
-        }
-        bt_ops = (uint32_t*)take(4 * (size_t)c.aln_cigar);
-        bt_path = (uint64_t*)take(8 * (size_t)c.aln_nodes);
-        bt_seq = (char*)take(c.aln_seq);
-        sfx_min = (uint8_t*)take(c.L_max + 8);
-        sfx_first = (uint32_t*)take(4 * ((size_t)c.L_max + 8)); sfx_last = (uint32_t*)take(4 * ((size_t)c.L_max + 8));
-        sfx_len = (uint8_t*)take(c.L_max + 8);
-        lc_word = (uint8_t*)take(c.L_max + 8); lc_eq = (uint64_t*)take(8 * ((size_t)c.L_max + 8));
-        lc_max[0] = (int32_t*)take(4 * ((size_t)c.L_max + 8)); lc_max[1] = (int32_t*)take(4 * ((size_t)c.L_max + 8));
+        slot0 = o;
+        take(sizeof(AlnHdr));
+        slot_nodes = take(8 * (size_t)c.aln_nodes) - slot0;
+        slot_seq = take(c.aln_seq) - slot0;
+        slot_cigar = take(4 * (size_t)c.aln_cigar) - slot0;
+        slot_stride = o - slot0;
+        o = slot0 + slot_stride * kNumSlots;
+        bt_ops = take(4 * (size_t)c.aln_cigar);
+        bt_path = take(8 * (size_t)c.aln_nodes);
+        bt_seq = take(c.aln_seq);
+        sfx_min = take(c.L_max + 8);
+        sfx_first = take(4 * ((size_t)c.L_max + 8)); sfx_last = take(4 * ((size_t)c.L_max + 8));
+        sfx_len = take(c.L_max + 8);
+        lc_word = take(c.L_max + 8); lc_eq = take(8 * ((size_t)c.L_max + 8));
+        lc_max[0] = take(4 * ((size_t)c.L_max + 8)); lc_max[1] = take(4 * ((size_t)c.L_max + 8));
+        total = o;
         return o;
     }
 };
 
-// Per-warp on-chip working set (shared memory on the device, a heap block in the host
-// emulation): two DP column buffers (parent / child ping-pong), the query strands and their
-// suffix sums, the best-first queue and the outgoing-edge scratch.
-struct WarpSmem {
-    score_t *buf0;            // two buffers, each: S[bmax] | E[bmax] | F[bmax]
-    int bmax;
-    char *q0, *q1; int32_t *psum0, *psum1; int lq;     // lq = capacity in characters (0: not staged)
-    StrandCtx *ctx;           // [2]
-    uint32_t *mask0, *mask1;  // (lq / 32 + 2) words each
-    AlnSlot *slots;           // [kNumSlots]
-    MGB_HOSTDEV score_t* buf(int b) const { return buf0 + (size_t)b * 3 * bmax; }
-    HeapItem *heap, *nn; int hcap;
-    uint64_t *out_nodes; int32_t *out_scores; uint8_t *out_chars;
+struct WarpMem {
+    char *base; const WarpLayout *lay;
+    MGB_HD ColMeta* cols() const { return (ColMeta*)(base + lay->cols); }
+    MGB_HD score_t* cells() const { return (score_t*)(base + lay->cells); }
+    MGB_HD HeapItem* heap() const { return (HeapItem*)(base + lay->heap); }
+    MGB_HD HeapItem* next_nodes() const { return (HeapItem*)(base + lay->next_nodes); }
+    MGB_HD BtStart* starts() const { return (BtStart*)(base + lay->starts); }
+    MGB_HD ConvSlot* conv_slots(int e) const { return (ConvSlot*)(base + lay->conv_slots[e]); }
+    MGB_HD score_t* conv_cells(int e) const { return (score_t*)(base + lay->conv_cells[e]); }
+    MGB_HD SeedRec* seeds(int e) const { return (SeedRec*)(base + lay->seeds[e]); }
+    MGB_HD int32_t* psum(int e) const { return (int32_t*)(base + lay->psum[e]); }
+    MGB_HD AlnSlot slot(int s) const {
+        char *p = base + lay->slot0 + (uint64_t)s * lay->slot_stride;
+        AlnSlot a; a.h = (AlnHdr*)p; a.nodes = (uint64_t*)(p + lay->slot_nodes); a.seq = p + lay->slot_seq;
+        a.cigar = (uint32_t*)(p + lay->slot_cigar);
+        return a;
+    }
+    MGB_HD uint32_t* bt_ops() const { return (uint32_t*)(base + lay->bt_ops); }
+    MGB_HD uint64_t* bt_path() const { return (uint64_t*)(base + lay->bt_path); }
+    MGB_HD char* bt_seq() const { return base + lay->bt_seq; }
+    MGB_HD uint8_t* sfx_min() const { return (uint8_t*)(base + lay->sfx_min); }
+    MGB_HD uint32_t* sfx_first() const { return (uint32_t*)(base + lay->sfx_first); }
+    MGB_HD uint32_t* sfx_last() const { return (uint32_t*)(base + lay->sfx_last); }
+    MGB_HD uint8_t* sfx_len() const { return (uint8_t*)(base + lay->sfx_len); }
+    MGB_HD uint8_t* lc_word() const { return (uint8_t*)(base + lay->lc_word); }
+    MGB_HD uint64_t* lc_eq() const { return (uint64_t*)(base + lay->lc_eq); }
+    MGB_HD int32_t* lc_max(int s) const { return (int32_t*)(base + lay->lc_max[s]); }
+    MGB_HD uint32_t* epoch_store() const { return (uint32_t*)(base + lay->epoch_store); }
+};
 
-    MGB_HOSTDEV size_t carve(char *base, int bmax_, int lq_, int hcap_) {
+// Per-group on-chip working set (shared memory on the device, a heap block in the host emulation), again as
+// offsets from the group's base: two DP column buffers (parent / child ping-pong), the query strands and their
+// suffix sums, the best-first queue and the outgoing-edge scratch.
+struct SmemLayout {
+    int bmax, lq, hcap;       // column buffer cells; staged query capacity in characters (0: not staged); queue entries
+    uint32_t buf0, psum0, psum1, q0, q1, ctx, mask0, mask1, heap, nn, out_nodes, out_scores, out_chars, total;
+    MGB_HOSTDEV size_t carve(int bmax_, int lq_, int hcap_) {
         size_t o = 0;
-        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return base ? base + r : (char*)nullptr; };
+        auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return (uint32_t)r; };
         bmax = bmax_; lq = lq_; hcap = hcap_;
-        buf0 = (score_t*)take(sizeof(score_t) * 6 * (size_t)bmax);
-        psum0 = (int32_t*)take(4 * ((size_t)lq + 8)); psum1 = (int32_t*)take(4 * ((size_t)lq + 8));
-        q0 = (char*)take((size_t)lq + 8); q1 = (char*)take((size_t)lq + 8);
-        ctx = (StrandCtx*)take(sizeof(StrandCtx) * 2);
-        mask0 = (uint32_t*)take(4 * ((size_t)lq / 32 + 2)); mask1 = (uint32_t*)take(4 * ((size_t)lq / 32 + 2));
-        slots = (AlnSlot*)take(sizeof(AlnSlot) * kNumSlots);
-        heap = (HeapItem*)take(sizeof(HeapItem) * hcap);
-        nn = (HeapItem*)take(sizeof(HeapItem) * hcap);
-        out_nodes = (uint64_t*)take(8 * kMaxOut);
-        out_scores = (int32_t*)take(4 * kMaxOut); out_chars = (uint8_t*)take(kMaxOut);
+        buf0 = take(sizeof(score_t) * 6 * (size_t)bmax);      // two buffers, each: S[bmax] | E[bmax] | F[bmax]
+        psum0 = take(4 * ((size_t)lq + 8)); psum1 = take(4 * ((size_t)lq + 8));
+        q0 = take((size_t)lq + 8); q1 = take((size_t)lq + 8);
+        ctx = take(sizeof(StrandCtx) * 2);
+        mask0 = take(4 * ((size_t)lq / 32 + 2)); mask1 = take(4 * ((size_t)lq / 32 + 2));   // (lq / 32 + 2) words each
+        heap = take(sizeof(HeapItem) * hcap);
+        nn = take(sizeof(HeapItem) * hcap);
+        out_nodes = take(8 * kMaxOut);
+        out_scores = take(4 * kMaxOut); out_chars = take(kMaxOut);
+        total = (uint32_t)o;
         return o;
     }
+};
+struct WarpSmem {
+    char *base; const SmemLayout *lay;
+    MGB_HD int bmax() const { return lay->bmax; }
+    MGB_HD int lq() const { return lay->lq; }
+    MGB_HD int hcap() const { return lay->hcap; }
+    MGB_HD score_t* buf(int b) const { return (score_t*)(base + lay->buf0) + (size_t)b * 3 * lay->bmax; }
+    MGB_HD int32_t* psum0() const { return (int32_t*)(base + lay->psum0); }
+    MGB_HD int32_t* psum1() const { return (int32_t*)(base + lay->psum1); }
+    MGB_HD char* q0() const { return base + lay->q0; }
+    MGB_HD char* q1() const { return base + lay->q1; }
+    MGB_HD StrandCtx* ctx() const { return (StrandCtx*)(base + lay->ctx); }
+    MGB_HD uint32_t* mask0() const { return (uint32_t*)(base + lay->mask0); }
+    MGB_HD uint32_t* mask1() const { return (uint32_t*)(base + lay->mask1); }
+    MGB_HD HeapItem* heap() const { return (HeapItem*)(base + lay->heap); }
+    MGB_HD HeapItem* nn() const { return (HeapItem*)(base + lay->nn); }
+    MGB_HD uint64_t* out_nodes() const { return (uint64_t*)(base + lay->out_nodes); }
+    MGB_HD int32_t* out_scores() const { return (int32_t*)(base + lay->out_scores); }
+    MGB_HD uint8_t* out_chars() const { return (uint8_t*)(base + lay->out_chars); }
 };
 
 MGB_HOSTDEV uint32_t cig_pack(uint32_t op, uint32_t len) { return (len << 3) | op; }
@@ -255,8 +301,8 @@ struct ReadAligner {
     const IndexView &ix;
     const DevConfig &cfg;
     const Caps &caps;
-    WarpMem &m;
-    WarpSmem &sm;
+    const WarpMem m;             // base + constant offsets: two small objects that live in registers
+    const WarpSmem sm;
 
     // read
     int L;
@@ -271,22 +317,22 @@ struct ReadAligner {
     uint32_t cells_used;
     int n_agg;
 
-    MGB_HD ReadAligner(const IndexView &ix_, const DevConfig &cfg_, const Caps &caps_, WarpMem &m_,
-                       WarpSmem &sm_)
-        : ix(ix_), cfg(cfg_), caps(caps_), m(m_), sm(sm_), cx(sm_.ctx) {}
+    MGB_HD ReadAligner(const IndexView &ix_, const DevConfig &cfg_, const Caps &caps_, const WarpMem &m_,
+                       const WarpSmem &sm_)
+        : ix(ix_), cfg(cfg_), caps(caps_), m(m_), sm(sm_), cx(sm_.ctx()) {}
 
     // --------------------------------------------------------------------------------
     // small helpers
     // --------------------------------------------------------------------------------
     // committed columns (layouts: see ColMeta); S always starts at cells_off
     MGB_HD static int capr_of(int size) { return (size + 5 + 7) & ~7; }
-    MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + j]; }
-    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells[(size_t)c.cells_off + (c.size + 5) + j]; }    // FMT_FULL
+    MGB_HD score_t& cellS(const ColMeta &c, int j) { return m.cells()[(size_t)c.cells_off + j]; }
+    MGB_HD score_t& cellE(const ColMeta &c, int j) { return m.cells()[(size_t)c.cells_off + (c.size + 5) + j]; }    // FMT_FULL
     MGB_HD score_t& cellF(const ColMeta &c, int j) {
-        return m.cells[(size_t)c.cells_off + (c.fmt == FMT_FULL ? 2 * (c.size + 5) : capr_of(c.size) + 8) + j];
+        return m.cells()[(size_t)c.cells_off + (c.fmt == FMT_FULL ? 2 * (c.size + 5) : capr_of(c.size) + 8) + j];
     }
     MGB_HD uint32_t cell_flags(const ColMeta &c, int j) {                                                          // compact
-        return reinterpret_cast<const uint8_t*>(m.cells + (size_t)c.cells_off + capr_of(c.size))[j];
+        return reinterpret_cast<const uint8_t*>(m.cells() + (size_t)c.cells_off + capr_of(c.size))[j];
     }
     // the backtrack's comparisons with E and F (extender.cpp:943-999), from the cells or from the flag bytes
     MGB_HD bool bt_is_ins(const ColMeta &c, int j, score_t sv) {
@@ -320,7 +366,7 @@ struct ReadAligner {
     }
 
     MGB_HD void copy_slot(int dst, int src) {
-        AlnSlot &d = sm.slots[dst]; const AlnSlot &s = sm.slots[src];
+        const AlnSlot d = m.slot(dst); const AlnSlot s = m.slot(src);
         wsync();
         AlnHdr h = *s.h;
         for (int i = wlane(); i < h.n_nodes; i += kWarp) d.nodes[i] = s.nodes[i];
@@ -332,7 +378,7 @@ struct ReadAligner {
 
     // Alignment(const Seed&, config) (alignment.hpp:154-165) materialised into a slot
     MGB_HD void seed_to_slot(int slot, int s, const SeedRec &sd) {
-        AlnSlot &a = sm.slots[slot];
+        const AlnSlot a = m.slot(slot);
         wsync();
         for (int i = wlane(); i < (int)sd.n_nodes; i += kWarp)
             a.nodes[i] = sd.n_nodes == 1 ? sd.node0 : cx[s].qnodes[sd.clip + i];
@@ -353,7 +399,7 @@ struct ReadAligner {
 
     // alignment.cpp:177-190 (no npos nodes on this path)
     MGB_HD void trim_offset(int slot) {
-        AlnSlot &a = sm.slots[slot];
+        const AlnSlot a = m.slot(slot);
         AlnHdr h = *a.h;
         if (!h.offset || h.n_nodes <= 1) return;
         int trim = imin((int)h.offset, h.n_nodes - 1);
@@ -374,7 +420,7 @@ struct ReadAligner {
     // alignment.cpp:540-561, RCDBG branch. Returns false if the alignment became empty.
     MGB_HD bool reverse_complement_slot(int slot) {
         trim_offset(slot);
-        AlnSlot &a = sm.slots[slot];
+        const AlnSlot a = m.slot(slot);
         AlnHdr h = *a.h;
         if (h.offset) { h.used = 0; h.n_nodes = 0; *a.h = h; return false; }
         wsync();
@@ -413,10 +459,10 @@ struct ReadAligner {
     // reverse complement is looked up in the graph itself. Returns false if the alignment became empty.
     MGB_HD bool reverse_complement_slot_plain(int slot) {
         trim_offset(slot);
-        AlnSlot &a = sm.slots[slot];
+        const AlnSlot a = m.slot(slot);
         AlnHdr h = *a.h;
         const int K = ix.k;
-        uint8_t *codes = (uint8_t*)m.bt_seq;                    // scratch (not in use outside backtrack)
+        uint8_t *codes = (uint8_t*)m.bt_seq();                    // scratch (not in use outside backtrack)
         auto kill = [&]() { h.used = 0; h.n_nodes = 0; *a.h = h; wsync(); return false; };
         // reverse_complement_seq_path (sequence_graph.cpp:563-573) of a.seq[0..len): complement in place, map
         auto rc_seq_path = [&](int len) {
@@ -540,7 +586,7 @@ struct ReadAligner {
     // (canonical_dbg.cpp:555-565) instead of mapping the sequence. Returns false if the alignment became empty.
     MGB_HD bool reverse_complement_slot_primary(int slot) {
         trim_offset(slot);
-        AlnSlot &a = sm.slots[slot];
+        const AlnSlot a = m.slot(slot);
         AlnHdr h = *a.h;
         const int K = ix.k;
         auto kill = [&]() { h.used = 0; h.n_nodes = 0; *a.h = h; wsync(); return false; };
@@ -571,7 +617,7 @@ struct ReadAligner {
             const int off = (int)h.offset;
             uint64_t node = a.nodes[0];
             const uint64_t base_node = node > ix.n ? node - ix.n : node;
-            uint8_t *stash = (uint8_t*)m.bt_seq;                 // scratch (not in use outside backtrack)
+            uint8_t *stash = (uint8_t*)m.bt_seq();                 // scratch (not in use outside backtrack)
             wsync();
             for (int i = wlane(); i < h.seq_len; i += kWarp) stash[i] = (uint8_t)a.seq[i];
             wsync();
@@ -614,13 +660,13 @@ struct ReadAligner {
                     a.seq[len++] = cfg.letters[label];
                 }
                 for (int i = num_first_steps; i < off; ++i) {    // last non-'$' child through the wrapper (:624-646)
-                    const int n = canon_out(node, sm.out_nodes, sm.out_chars);
+                    const int n = canon_out(node, sm.out_nodes(), sm.out_chars());
                     wsync();
                     if (n > kMaxOut) { overflow = true; return false; }
                     if (!n) return kill();
                     if (len >= (int)caps.aln_seq) { overflow = true; return false; }
-                    node = sm.out_nodes[n - 1];
-                    a.seq[len++] = (char)sm.out_chars[n - 1];
+                    node = sm.out_nodes()[n - 1];
+                    a.seq[len++] = (char)sm.out_chars()[n - 1];
                     wsync();
                 }
                 wsync();
@@ -646,11 +692,11 @@ struct ReadAligner {
                 // drop the ending that corresponds to the added prefix: first incoming node each time (:667-690)
                 for (int i = 0; i < off; ++i) {
                     uint64_t sent = 0;
-                    const int n = canon_in(node, sm.out_nodes, sm.out_chars, &sent);
+                    const int n = canon_in(node, sm.out_nodes(), sm.out_chars(), &sent);
                     wsync();
                     if (n > kMaxOut) { overflow = true; return false; }
                     if (!n && !sent) return kill();
-                    node = n ? sm.out_nodes[0] : sent;
+                    node = n ? sm.out_nodes()[0] : sent;
                     wsync();
                 }
             }
@@ -863,7 +909,7 @@ struct ReadAligner {
     MGB_HD bool has_multiple_outgoing(uint64_t node) {
         if (MGB_PRIMARY(ix)) {                               // canonical_dbg.cpp:366-380
             uint64_t sent;
-            return canon_out(node, sm.out_nodes, sm.out_chars, &sent) > 1;
+            return canon_out(node, sm.out_nodes(), sm.out_chars(), &sent) > 1;
         }
         // !get_last(fwd(node, d) - 1): the target node has more than one edge
         const Adj a = load_adj_any(ix, node);
@@ -873,7 +919,7 @@ struct ReadAligner {
     MGB_HD bool has_single_incoming(uint64_t node) {
         if (MGB_PRIMARY(ix)) {                               // canonical_dbg.cpp:382-392
             uint64_t sent;
-            int n = canon_in(node, sm.out_nodes, sm.out_chars, &sent);
+            int n = canon_in(node, sm.out_nodes(), sm.out_chars(), &sent);
             return n + (sent ? 1 : 0) == 1;
         }
         if (node == 1) return false;
@@ -945,7 +991,7 @@ struct ReadAligner {
         const uint8_t *cd = cx[s].codes;
         const int n_w = L - 2;
         if (n_w <= 0) return;
-        uint8_t *wd = m.lc_word; uint64_t *eq = m.lc_eq; int32_t *mx = m.lc_max[s];
+        uint8_t *wd = m.lc_word(); uint64_t *eq = m.lc_eq(); int32_t *mx = m.lc_max(s);
         for (int j = wlane(); j < n_w; j += kWarp) {
             const uint32_t a = cd[j], b = cd[j + 1], c = cd[j + 2];
             const bool ok = a >= 1 && a <= 4 && b >= 1 && b <= 4 && c >= 1 && c <= 4;
@@ -999,7 +1045,7 @@ struct ReadAligner {
         if (len > L - i) len = L - i;
         const int nt = len - 2;
         if (nt < 2) return false;
-        return (int)m.lc_max[s][i + nt - 1] >= i;
+        return (int)m.lc_max(s)[i + nt - 1] >= i;
     }
 
     // ExactSeeder::get_seeds (:67-93)
@@ -1131,7 +1177,7 @@ struct ReadAligner {
         const int min_len = (int)cfg.min_seed_length;
         const int stack_cap = 4 * k + 8;
         if ((uint64_t)3 * n_pos + 3 * (uint64_t)stack_cap > 3ull * caps.max_cells) { overflow = true; return; }
-        uint32_t *rc_first = (uint32_t*)m.cells, *rc_last = rc_first + n_pos;
+        uint32_t *rc_first = (uint32_t*)m.cells(), *rc_last = rc_first + n_pos;
         uint32_t *meta = rc_last + n_pos;                         // fwd length | rc length << 8
         uint32_t *stack = meta + n_pos;
         for (int i = wlane(); i < n_pos; i += kWarp) meta[i] = 0;
@@ -1145,24 +1191,24 @@ struct ReadAligner {
                 int n_here = 0; uint64_t node_here = 0;
                 if (b_next < n_base && (int)base_seeds[b_next].clip == i) {
                     node_here = base_seeds[b_next].node0; ++b_next; n_here = 1;
-                } else if (m.sfx_min[i] != k) {
-                    const int min_here = m.sfx_min[i];
-                    const int matched = m.sfx_len[i];
+                } else if (m.sfx_min()[i] != k) {
+                    const int min_here = m.sfx_min()[i];
+                    const int matched = m.sfx_len()[i];
                     if (matched >= min_here && matched > 0
                             && !(cfg.seed_complexity_filter && low_complexity(s, i, min_here))) {
                         uint64_t first_node = 0;
                         const int keep = cx[s].n_seeds;
-                        int cnt = suffix_enumerate(s, i, matched, m.sfx_first[i], m.sfx_last[i], &first_node);
+                        int cnt = suffix_enumerate(s, i, matched, m.sfx_first()[i], m.sfx_last()[i], &first_node);
                         if (overflow) return;
                         cx[s].n_seeds = keep;                     // counted only
                         const bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
-                                    && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
+                                    && m.sfx_min()[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
                         if (cnt != 0 && !skip) {
                             wsync();
-                            m.sfx_min[i] = (uint8_t)matched;
+                            m.sfx_min()[i] = (uint8_t)matched;
                             meta[i] = (uint32_t)matched;
                             int sl = matched;
-                            for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j) m.sfx_min[j] = (uint8_t)(sl--);
+                            for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min()[j]; ++j) m.sfx_min()[j] = (uint8_t)(sl--);
                             wsync();
                             n_here = cnt; node_here = first_node;
                         }
@@ -1177,14 +1223,14 @@ struct ReadAligner {
             int max_len = imin(imin((int)(cfg.max_seed_length < 0x7fffffffu ? cfg.max_seed_length : 0x7fffffffu), k - 1), L - i);
             int j_min = L - i - max_len;
             const int j_max = L - i - min_len;
-            while (j_min <= j_max && (int)m.sfx_min[j_min] > max_len) { ++j_min; --max_len; }
+            while (j_min <= j_max && (int)m.sfx_min()[j_min] > max_len) { ++j_min; --max_len; }
             if (j_min > j_max) continue;
             uint64_t first = 0, lst = 0; int matched = 0;
             boss_index_range(ix, rc_codes + i, max_len, &first, &lst, &matched, min_len);
             const int seed_length = matched;
             if (seed_length < min_len) continue;
             const int j = L - i - seed_length;
-            if (seed_length < (int)m.sfx_min[j]
+            if (seed_length < (int)m.sfx_min()[j]
                     || (cfg.seed_complexity_filter && low_complexity(s, j, seed_length)))
                 continue;
             LineCache lc;
@@ -1194,11 +1240,11 @@ struct ReadAligner {
             if (!cnt) continue;
             wsync();
             // append_suffix_seed (:195-213): longer than what the position holds -> replaces it
-            m.sfx_min[j] = (uint8_t)seed_length;
+            m.sfx_min()[j] = (uint8_t)seed_length;
             rc_first[j] = (uint32_t)lo; rc_last[j] = (uint32_t)lst;
             meta[j] = (meta[j] & 0xffu) | ((uint32_t)seed_length << 8);
             int sl = seed_length;
-            for (int jj = j + 1; jj < n_pos && sl > (int)m.sfx_min[jj]; ++jj) m.sfx_min[jj] = (uint8_t)(sl--);
+            for (int jj = j + 1; jj < n_pos && sl > (int)m.sfx_min()[jj]; ++jj) m.sfx_min()[jj] = (uint8_t)(sl--);
             wsync();
         }
         if (overflow) return;
@@ -1211,12 +1257,12 @@ struct ReadAligner {
                 if (cx[s].n_seeds >= (int)caps.max_seeds - n_base) { overflow = true; return; }
                 cx[s].seeds[cx[s].n_seeds++] = base_seeds[b_next++];
             } else {
-                const int cur = m.sfx_min[i];
+                const int cur = m.sfx_min()[i];
                 const int fl = (int)(meta[i] & 0xffu), rl_ = (int)((meta[i] >> 8) & 0xffu);
                 uint64_t cnt = 0;
                 if (fl && fl == cur) {
                     uint64_t fn = 0;
-                    cnt += (uint64_t)suffix_enumerate(s, i, fl, m.sfx_first[i], m.sfx_last[i], &fn);
+                    cnt += (uint64_t)suffix_enumerate(s, i, fl, m.sfx_first()[i], m.sfx_last()[i], &fn);
                 }
                 if (!overflow && rl_ && rl_ == cur)
                     cnt += (uint64_t)suffix_to_prefix(s, i, rc_first[i], rc_last[i], rl_, true, stack, stack_cap);
@@ -1242,7 +1288,7 @@ struct ReadAligner {
         cx[s].n_seeds = 0;
         // Exact seeder with staged query (the BASELINE configs[1] path): one k-mer seed per matched
         // k-mer, kept as a bit mask on chip instead of a seed array
-        if ((int)cfg.min_seed_length >= k && (uint32_t)k >= cfg.max_seed_length && sm.lq && L + 1 <= sm.lq) {
+        if ((int)cfg.min_seed_length >= k && (uint32_t)k >= cfg.max_seed_length && sm.lq() && L + 1 <= sm.lq()) {
             uint32_t *mask = cx[s].mask;
             const uint64_t *qn = cx[s].qnodes;
             const int nw = (nk + 31) / 32;
@@ -1295,7 +1341,7 @@ struct ReadAligner {
 
         // base (MEM) seeds first; they are merged with the sub-k seeds in query order below
         const int n_pos = L - (int)cfg.min_seed_length + 1;
-        if (!mem_only) for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min[i] = (uint8_t)cfg.min_seed_length;
+        if (!mem_only) for (int i = wlane(); i < n_pos; i += kWarp) m.sfx_min()[i] = (uint8_t)cfg.min_seed_length;
         wsync();
         mem_seeds(s, nk);
         if (mem_only) return;
@@ -1307,8 +1353,8 @@ struct ReadAligner {
         for (int i = n_base - 1; i >= 0; --i) base_seeds[i] = cx[s].seeds[i];
         for (int b = 0; b < n_base; ++b) {
             SeedRec sd = base_seeds[b];
-            for (int j = 0; j < (int)sd.n_nodes; ++j) m.sfx_min[sd.clip + j] = (uint8_t)k;
-            if ((int)(sd.clip + sd.n_nodes) < n_pos) m.sfx_min[sd.clip + sd.n_nodes] = (uint8_t)k;
+            for (int j = 0; j < (int)sd.n_nodes; ++j) m.sfx_min()[sd.clip + j] = (uint8_t)k;
+            if ((int)(sd.clip + sd.n_nodes) < n_pos) m.sfx_min()[sd.clip + sd.n_nodes] = (uint8_t)k;
         }
         wsync();
         cx[s].n_seeds = 0;
@@ -1321,12 +1367,12 @@ struct ReadAligner {
             const int g = wlane() / kGroup;
             for (int base = 0; base < n_pos; base += groups) {
                 const int i = base + g;
-                if (i < n_pos && m.sfx_min[i] != k && cx[s].sub_len && cx[s].sub_len[i] != 0xFF) {
+                if (i < n_pos && m.sfx_min()[i] != k && cx[s].sub_len && cx[s].sub_len[i] != 0xFF) {
                     if (glane() == 0) {                   // looked up by k_subk
-                        m.sfx_first[i] = cx[s].sub_first[i]; m.sfx_last[i] = cx[s].sub_last[i];
-                        m.sfx_len[i] = cx[s].sub_len[i];
+                        m.sfx_first()[i] = cx[s].sub_first[i]; m.sfx_last()[i] = cx[s].sub_last[i];
+                        m.sfx_len()[i] = cx[s].sub_len[i];
                     }
-                } else if (i < n_pos && m.sfx_min[i] != k) {
+                } else if (i < n_pos && m.sfx_min()[i] != k) {
                     const int len = imin((int)msl_u, L - i);
                     uint64_t first = 0, lst = 0; int matched = 0;
                     bool ok = len >= (int)cfg.min_seed_length;
@@ -1335,7 +1381,7 @@ struct ReadAligner {
                     // matches shorter than min_seed_length are never used below (sfx_min[i] >= min_seed_length)
                     if (ok) boss_index_range(ix, cd, imin(len, k - 1), &first, &lst, &matched, (int)cfg.min_seed_length);
                     if (glane() == 0) {
-                        m.sfx_first[i] = (uint32_t)first; m.sfx_last[i] = (uint32_t)lst; m.sfx_len[i] = (uint8_t)matched;
+                        m.sfx_first()[i] = (uint32_t)first; m.sfx_last()[i] = (uint32_t)lst; m.sfx_len()[i] = (uint8_t)matched;
                     }
                 }
             }
@@ -1357,28 +1403,28 @@ struct ReadAligner {
                 if (cx[s].n_seeds >= (int)caps.max_seeds - n_base) { overflow = true; return; }
                 cx[s].seeds[cx[s].n_seeds++] = base_seeds[b_next++];
                 n_here = 1;
-            } else if (m.sfx_min[i] != k) {
-                const int min_here = m.sfx_min[i];
-                const int matched = m.sfx_len[i];
+            } else if (m.sfx_min()[i] != k) {
+                const int min_here = m.sfx_min()[i];
+                const int matched = m.sfx_len()[i];
                 // call_nodes_with_suffix_matching_longest_prefix (:231-238): nothing below min_match_length;
                 // a low-complexity window of the current minimum length is skipped altogether (:226-229)
                 if (matched >= min_here && matched > 0
                         && !(cfg.seed_complexity_filter && low_complexity(s, i, min_here))) {
                     uint64_t first_node = 0;
                     // capacity: the scratch copy of the base seeds lives at the end of the array
-                    int cnt = suffix_enumerate(s, i, matched, m.sfx_first[i], m.sfx_last[i], &first_node);
+                    int cnt = suffix_enumerate(s, i, matched, m.sfx_first()[i], m.sfx_last()[i], &first_node);
                     if (overflow) return;
                     if (cx[s].n_seeds > (int)caps.max_seeds - n_base) { overflow = true; return; }
                     const bool skip = i >= last_full_id && cnt == 1 && last_full_id >= 1
-                                && m.sfx_min[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
+                                && m.sfx_min()[last_full_id - 1] == k && lf_count == 1 && first_node == lf_node;
                     if (cnt == 0 || skip) {
                         cx[s].n_seeds = pos_first;
                     } else {
                         // append_suffix_seed (:195-213) for every alternative node
-                        m.sfx_min[i] = (uint8_t)matched;
+                        m.sfx_min()[i] = (uint8_t)matched;
                         int sl = matched;
-                        for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min[j]; ++j)
-                            m.sfx_min[j] = (uint8_t)(sl--);
+                        for (int j = i + 1; j < n_pos && sl > (int)m.sfx_min()[j]; ++j)
+                            m.sfx_min()[j] = (uint8_t)(sl--);
                         n_here = cnt;
                         // a locus with too many alternatives is dropped at aggregation (:340-345)
                         if ((uint64_t)cnt > cfg.max_num_seeds_per_locus) cx[s].n_seeds = pos_first;
@@ -1618,10 +1664,10 @@ struct ReadAligner {
     }
     MGB_HD void heap_push(int &n, HeapItem it) {
         if (n >= hp_cap) {
-            if (hp == m.heap) { overflow = true; return; }
-            for (int t = wlane(); t < n; t += kWarp) m.heap[t] = hp[t];
+            if (hp == m.heap()) { overflow = true; return; }
+            for (int t = wlane(); t < n; t += kWarp) m.heap()[t] = hp[t];
             wsync();
-            hp = m.heap; hp_cap = caps.max_cols;
+            hp = m.heap(); hp_cap = caps.max_cols;
         }
         int i = n++;
         while (i > 0) {
@@ -1652,10 +1698,10 @@ struct ReadAligner {
     }
     MGB_HD void nn_push(int &n, HeapItem it) {
         if (n >= np_cap) {
-            if (np == m.next_nodes) { overflow = true; return; }
-            for (int t = wlane(); t < n; t += kWarp) m.next_nodes[t] = np[t];
+            if (np == m.next_nodes()) { overflow = true; return; }
+            for (int t = wlane(); t < n; t += kWarp) m.next_nodes()[t] = np[t];
             wsync();
-            np = m.next_nodes; np_cap = caps.max_cols;
+            np = m.next_nodes(); np_cap = caps.max_cols;
         }
         np[n++] = it;
     }
@@ -1676,7 +1722,7 @@ struct ReadAligner {
     struct Scratch { score_t *S, *E, *F; int cap; bool on_chip; };
 
     MGB_HD Scratch scratch_smem(int b) const {
-        Scratch r; r.S = sm.buf(b); r.E = r.S + sm.bmax; r.F = r.E + sm.bmax; r.cap = sm.bmax; r.on_chip = true;
+        Scratch r; r.S = sm.buf(b); r.E = r.S + sm.bmax(); r.F = r.E + sm.bmax(); r.cap = sm.bmax(); r.on_chip = true;
         return r;
     }
     // arena scratch above the commit area of the column in flight; `cells` must be the largest
@@ -1685,7 +1731,7 @@ struct ReadAligner {
         uint64_t need = (uint64_t)cells_used + 3ull * (cells + 8) /*commit*/ + 3ull * (cells + 8) /*scratch*/;
         if (need > 3ull * caps.max_cells) { overflow = true; return false; }
         r->cap = cells + 8;
-        r->S = m.cells + cells_used + 3ull * (cells + 8);
+        r->S = m.cells() + cells_used + 3ull * (cells + 8);
         r->E = r->S + r->cap; r->F = r->E + r->cap; r->on_chip = false;
         return true;
     }
@@ -1760,7 +1806,7 @@ struct ReadAligner {
     MGB_HD uint32_t commit_column(const Scratch &sc, int size) {
         const int cap = size + 5;
         const uint32_t off = cells_used;
-        score_t *dst = m.cells + off;
+        score_t *dst = m.cells() + off;
         for (int t = wlane(); t < cap; t += kWarp) {
             dst[t] = sc.S[t]; dst[cap + t] = sc.E[t]; dst[2 * cap + t] = sc.F[t];
         }
@@ -1908,7 +1954,7 @@ struct ReadAligner {
     // groups execute it together, one child column per iteration each, instead of drifting apart.
     MGB_HD int extend(int e, int seed_slot, score_t min_path_score, bool force_fixed_seed, int out_base, bool act) {
         const int s = e;                                 // query strand of this extender
-        const AlnSlot &seed = sm.slots[seed_slot];
+        const AlnSlot seed = m.slot(seed_slot);
         AlnHdr sh = AlnHdr();
         bool rc = false;
         const int K = ix.k;
@@ -1921,7 +1967,7 @@ struct ReadAligner {
         int res0 = -1, res1 = -1;                         // columns resident in sm.buf(0) / sm.buf(1)
         ColMeta last_col = ColMeta(); uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
         bool last_band_valid = false; uint32_t last_band_mask = 0; score_t last_band_cutoff = 0;
-        const bool reg_path = use_fast && sm.bmax >= 40 && (sm.bmax & 3) == 0;
+        const bool reg_path = use_fast && sm.bmax() >= 40 && (sm.bmax() & 3) == 0;
         uint32_t cells_limit = 0;
         score_t min_cell_score = 0, best_score = 0;
         int heap_n = 0, nn_n = 0;
@@ -1932,7 +1978,7 @@ struct ReadAligner {
             ++cx[e].num_ext;
             min_path_score = imax(0, min_path_score);
             n_cols = 0; cells_used = 0;
-            hp = sm.heap; hp_cap = sm.hcap; np = sm.nn; np_cap = sm.hcap;
+            hp = sm.heap(); hp_cap = sm.hcap(); np = sm.nn(); np_cap = sm.hcap();
             pf_node = 0; pf_key = ~0ull; pf_slot_idx = 0;
             cutoff = imax(-xdrop, kNinf + 1);
             start = aln_clipping(seed);
@@ -1952,7 +1998,7 @@ struct ReadAligner {
         if (go) {
             Scratch sc;
             bool have_sc = true;
-            if (1 + 8 <= sm.bmax) sc = scratch_smem(0);
+            if (1 + 8 <= sm.bmax()) sc = scratch_smem(0);
             else have_sc = scratch_arena(wlen + 1, &sc);
             if (have_sc) {
                 for (int t = wlane(); t < 1 + 5; t += kWarp) { sc.S[t] = kNinf; sc.E[t] = kNinf; sc.F[t] = kNinf; }
@@ -1967,7 +2013,7 @@ struct ReadAligner {
                     root.is_tip = 0; root.started = 0; root.fmt = FMT_FULL; root.pad0 = root.pad1 = 0; root.size = size;
                     root.cells_off = commit_column(sc, size);
                     if (sc.on_chip) res0 = 0;
-                    m.cols[n_cols++] = root;
+                    m.cols()[n_cols++] = root;
                     if (n_cols > cx[e].table_cap) cx[e].table_cap = cx[e].table_cap ? 2 * cx[e].table_cap : 1;
                     stats.dp_cells += size; ++stats.dp_columns;
                     table_size_bytes = 136ull * cx[e].table_cap + 3ull * vec_capacity(1, size) * 4;
@@ -2006,16 +2052,16 @@ struct ReadAligner {
                 i = np[--nn_n].idx;
                 t = 0; n_out = 0;
                 // `last_col` is the register copy of column `last_idx`; the popped column takes it over
-                if (i != last_idx) { last_col = m.cols[i]; last_idx = i; last_band_valid = false; }
+                if (i != last_idx) { last_col = m.cols()[i]; last_idx = i; last_band_valid = false; }
                 const ColMeta &par = last_col;
                 next_offset = par.offset + 1;
                 in_seed = (uint32_t)(next_offset - (int)sh.offset) < (uint32_t)seed_seq_len;
                 par_fmt = par.fmt;
                 // parent cells: on chip if it is one of the two most recent columns
                 pb = res0 == (int)i ? 0 : (res1 == (int)i ? 1 : -1);
-                if (pb >= 0) { parS = sm.buf(pb); parF = parS + 2 * sm.bmax; }
+                if (pb >= 0) { parS = sm.buf(pb); parF = parS + 2 * sm.bmax(); }
                 else {
-                    parS = m.cells + par.cells_off;
+                    parS = m.cells() + par.cells_off;
                     parF = parS + (par.fmt == FMT_FULL ? 2 * (par.size + 5) : capr_of(par.size) + 8);
                 }
                 cb = pb >= 0 ? 1 - pb : 0;                // buffer for the children
@@ -2061,13 +2107,13 @@ struct ReadAligner {
                         one_node = next_node; one_ch = (uint8_t)seed_seq[seed_pos];
                         if (next_node) { one_reg = true; plain_out = true; }
                         else {
-                            sm.out_nodes[0] = next_node; sm.out_chars[0] = one_ch;
-                            sm.out_scores[0] = !par.node ? cfg.gap_ext : cfg.gap_open;
+                            sm.out_nodes()[0] = next_node; sm.out_chars()[0] = one_ch;
+                            sm.out_scores()[0] = !par.node ? cfg.gap_ext : cfg.gap_open;
                             wsync();
                         }
                         n_out = 1;
                     } else if (MGB_PRIMARY(ix)) {          // extender.cpp:361-380 (the hint equals the node's sequence)
-                        n_out = canon_out(par.node, sm.out_nodes, sm.out_chars);
+                        n_out = canon_out(par.node, sm.out_nodes(), sm.out_chars());
                         plain_out = true;
                         wsync();
                     } else if (!rc) {
@@ -2087,20 +2133,20 @@ struct ReadAligner {
                                 int k2 = 0;
                                 for (uint32_t c = 1; c < ix.sigma; ++c) {
                                     if (!((ok >> c) & 1u)) continue;
-                                    sm.out_nodes[k2] = first + popc32(all & ((1u << c) - 1u)); sm.out_chars[k2] = cfg.letters[c];
+                                    sm.out_nodes()[k2] = first + popc32(all & ((1u << c) - 1u)); sm.out_chars()[k2] = cfg.letters[c];
                                     ++k2;
                                 }
                                 wsync();
                             }
                         }
                     } else {
-                        n_out = outgoing_rc(par.node, sm.out_nodes, sm.out_chars);
+                        n_out = outgoing_rc(par.node, sm.out_nodes(), sm.out_chars());
                         plain_out = true;
                         wsync();
                     }
                     if (n_out > kMaxOut) { overflow = true; continue; }
                 }
-                if (n_out == 0) { m.cols[i].is_tip = 1; continue; }
+                if (n_out == 0) { m.cols()[i].is_tip = 1; continue; }
 
                 const int end = imin(prev_end, wlen) + 1;
                 size0 = end - begin;
@@ -2110,10 +2156,10 @@ struct ReadAligner {
 
             // ---------------- child t of column i (:562-770) ----------------
             const int tc = t++;
-            uint8_t ch = one_reg ? one_ch : sm.out_chars[tc];
+            uint8_t ch = one_reg ? one_ch : sm.out_chars()[tc];
             if (ch >= 'a' && ch <= 'z') ch -= 32;          // toupper (:564)
-            const uint64_t cnode = one_reg ? one_node : sm.out_nodes[tc];
-            const score_t add = plain_out ? 0 : sm.out_scores[tc];
+            const uint64_t cnode = one_reg ? one_node : sm.out_nodes()[tc];
+            const score_t add = plain_out ? 0 : sm.out_scores()[tc];
             if (n_cols >= caps.max_cols) { overflow = true; continue; }
             const int code = encode_char(ch);
             const int diag_i = next_offset - seed_off_m1;
@@ -2184,18 +2230,18 @@ struct ReadAligner {
                     const int capr = capr_of(size);
                     const uint32_t off = (cells_used + 7u) & ~7u;
                     cells_used = off + 2 * capr + 8;
-                    score_t *dst = m.cells + off;
+                    score_t *dst = m.cells() + off;
                     score_t *cb_S = sm.buf(cb);
                     store_cells(dst, j0, r.S, capr);
                     store_flags(reinterpret_cast<uint8_t*>(dst + capr), j0, r.fl);
-                    store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * sm.bmax, j0, r.F, 32);
+                    store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * sm.bmax(), j0, r.F, 32);
                     ColMeta col;
                     col.node = cnode; col.parent = i; col.c = ch;
                     col.offset = next_offset; col.max_pos = max_pos; col.trim = begin; col.score = add;
                     col.is_tip = 0; col.started = 0; col.fmt = FMT_COMPACT; col.pad0 = col.pad1 = 0;
                     col.size = size; col.cells_off = off;
                     const uint32_t idx = n_cols;
-                    m.cols[n_cols++] = col;
+                    m.cols()[n_cols++] = col;
                     last_col = col; last_idx = idx;
                     {   // band of this column under the (updated) cutoff, for when it is expanded
                         uint32_t bits = 0;
@@ -2226,7 +2272,7 @@ struct ReadAligner {
                         } else heap_push(heap_n, it);
                         // the column waits in the queue: a later expansion reads its F from the table
                         store_cells(dst + capr + 8, j0, r.F, capr);
-                        m.cols[idx].fmt = FMT_COMPACT_F; last_col.fmt = FMT_COMPACT_F;
+                        m.cols()[idx].fmt = FMT_COMPACT_F; last_col.fmt = FMT_COMPACT_F;
                     }
                     continue;
                 }
@@ -2236,15 +2282,15 @@ struct ReadAligner {
             if (par_fmt == FMT_COMPACT && pb >= 0) {
                 // the backtrack compares the F of a general-path column with its parent's (:976-997): write the
                 // parent's F (still on chip) into the space its compact record reserves for it
-                const ColMeta pc = m.cols[i];
-                score_t *dstF = m.cells + pc.cells_off + capr_of(pc.size) + 8;
+                const ColMeta pc = m.cols()[i];
+                score_t *dstF = m.cells() + pc.cells_off + capr_of(pc.size) + 8;
                 for (int j = wlane(); j < pc.size + 5; j += kWarp) dstF[j] = parF[j];
-                m.cols[i].fmt = FMT_COMPACT_F; par_fmt = FMT_COMPACT_F;
+                m.cols()[i].fmt = FMT_COMPACT_F; par_fmt = FMT_COMPACT_F;
                 if (last_idx == i) last_col.fmt = FMT_COMPACT_F;
                 wsync();
             }
             Scratch sc;
-            if (size0 + 8 <= sm.bmax) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
+            if (size0 + 8 <= sm.bmax()) { sc = scratch_smem(cb); if (cb) res1 = -1; else res0 = -1; }
             else if (!scratch_arena(wlen + 1 - begin, &sc)) continue;
             // DPTColumn::create: everything (incl. padding) = ninf (extender.cpp:389-410)
             for (int j = wlane(); j < size0 + 5; j += kWarp) { sc.S[j] = kNinf; sc.E[j] = kNinf; sc.F[j] = kNinf; }
@@ -2300,7 +2346,7 @@ struct ReadAligner {
             col.is_tip = 0; col.started = 0; col.fmt = FMT_FULL; col.pad0 = col.pad1 = 0; col.size = size;
             col.cells_off = commit_column(sc, size);
             const uint32_t idx = n_cols;
-            m.cols[n_cols++] = col;
+            m.cols()[n_cols++] = col;
             last_col = col; last_idx = idx; last_band_valid = false;
             if (sc.on_chip) { if (cb) res1 = (int)idx; else res0 = (int)idx; }
 
@@ -2338,17 +2384,17 @@ struct ReadAligner {
     uint64_t table_size_bytes;
 
     MGB_HD void cig_append(int &n_ops, uint32_t op) {       // Cigar::append(op, 1)
-        if (n_ops && cig_op(m.bt_ops[n_ops - 1]) == op) m.bt_ops[n_ops - 1] += 8u;
+        if (n_ops && cig_op(m.bt_ops()[n_ops - 1]) == op) m.bt_ops()[n_ops - 1] += 8u;
         else {
             if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return; }
-            m.bt_ops[n_ops++] = cig_pack(op, 1);
+            m.bt_ops()[n_ops++] = cig_pack(op, 1);
         }
     }
 
     MGB_HD int backtrack(int e, int seed_slot, score_t min_path_score, int start, int wlen,
                          score_t min_cell_score, int out_base) {
         const int s = e;
-        const AlnSlot &seed = sm.slots[seed_slot];
+        const AlnSlot seed = m.slot(seed_slot);
         const AlnHdr sh = *seed.h;
         const int K = ix.k;
         const int seed_clipping = start;
@@ -2365,9 +2411,9 @@ struct ReadAligner {
             BtStart a, b; a.score = INT32_MIN; b.score = INT32_MIN;
             a.neg_off_diag = b.neg_off_diag = a.neg_i = b.neg_i = a.pos = b.pos = 0;
             if (i >= 1) {
-                const ColMeta col = m.cols[i];
+                const ColMeta col = m.cols()[i];
                 if (col.offset >= seed_dist) {
-                    const ColMeta par = m.cols[col.parent];
+                    const ColMeta par = m.cols()[col.parent];
                     const int code = encode_char(col.c);
                     for (int which = 0; which < 2; ++which) {
                         int start_pos;
@@ -2394,7 +2440,7 @@ struct ReadAligner {
                     }
                 }
             }
-            m.starts[2 * i] = a; m.starts[2 * i + 1] = b;
+            m.starts()[2 * i] = a; m.starts()[2 * i + 1] = b;
         }
         wsync();
 
@@ -2407,7 +2453,7 @@ struct ReadAligner {
             BtStart best; best.score = INT32_MIN; best.neg_off_diag = INT32_MIN; best.neg_i = INT32_MIN; best.pos = INT32_MIN;
             uint32_t best_idx = 0xffffffffu;
             for (uint32_t c = wlane(); c < n_cand; c += kWarp) {
-                BtStart x = m.starts[c];
+                BtStart x = m.starts()[c];
                 if (x.score == INT32_MIN) continue;
                 bool gt = x.score != best.score ? x.score > best.score
                         : x.neg_off_diag != best.neg_off_diag ? x.neg_off_diag > best.neg_off_diag
@@ -2427,13 +2473,13 @@ struct ReadAligner {
                 best.score = v0; best.neg_off_diag = v1; best.neg_i = v2; best.pos = v3;
                 best_idx = wbcast(best_idx, src);
             }
-            m.starts[best_idx].score = INT32_MIN;
+            m.starts()[best_idx].score = INT32_MIN;
             wsync();
 
             if (n_ext >= (int)cfg.num_alternative_paths) break;          // terminate_backtrack_start
             uint32_t j = (uint32_t)(-best.neg_i);
-            if (m.cols[j].started) continue;                             // skip_backtrack_start
-            m.cols[j].started = 1;
+            if (m.cols()[j].started) continue;                             // skip_backtrack_start
+            m.cols()[j].started = 1;
 
             score_t score = best.score;
             if ((int64_t)score - min_cell_score < best_score) break;
@@ -2450,16 +2496,16 @@ struct ReadAligner {
                 if (op == cur_op) { ++cur_len; return; }
                 if (cur_len) {
                     if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return; }
-                    m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+                    m.bt_ops()[n_ops++] = cig_pack(cur_op, cur_len);
                 }
                 cur_op = op; cur_len = 1;
             };
-            ColMeta col = m.cols[j];
-            ColMeta par = m.cols[col.parent];
+            ColMeta col = m.cols()[j];
+            ColMeta par = m.cols()[col.parent];
             // the grand-parent's record is requested one step ahead so that a move to the parent costs
             // no dependent round trip
             ColMeta gpar = par;
-            if (par.parent != 0xffffffffu) gpar = m.cols[par.parent];
+            if (par.parent != 0xffffffffu) gpar = m.cols()[par.parent];
             bool try_run = true;
             while (j) {
                 // Diagonal runs, one warp-wide step: lane t examines column j - t at query position
@@ -2472,8 +2518,8 @@ struct ReadAligner {
                     ColMeta c_t;
                     c_t.offset = 0; c_t.node = 0; c_t.c = 0; c_t.max_pos = -1;
                     if ((uint32_t)t < j) {
-                        c_t = m.cols[j - t];
-                        const ColMeta p_t = m.cols[j - t - 1];
+                        c_t = m.cols()[j - t];
+                        const ColMeta p_t = m.cols()[j - t - 1];
                         const int pos_t = pos - t;
                         const int ci = pos_t - c_t.trim, pi = pos_t - p_t.trim - 1;
                         if (c_t.parent == j - t - 1 && pos_t > 0 && ci >= 0 && ci < c_t.size && pi >= 0 && pi < p_t.size) {
@@ -2498,9 +2544,9 @@ struct ReadAligner {
                             overflow = true; return 0;
                         }
                         if (mine) {
-                            m.bt_seq[n_seq + t] = c_t.c;
-                            if (pos - t == c_t.max_pos) m.cols[j - t].started = 1;
-                            if (has_node) m.bt_path[n_path + popc32(node_mask & ((1u << t) - 1u))] = c_t.node;
+                            m.bt_seq()[n_seq + t] = c_t.c;
+                            if (pos - t == c_t.max_pos) m.cols()[j - t].started = 1;
+                            if (has_node) m.bt_path()[n_path + popc32(node_mask & ((1u << t) - 1u))] = c_t.node;
                         }
                         if (node_mask) path_back_nonzero = (nz_mask >> (31 - clz32(node_mask))) & 1u;
                         for (int b = 0; b < n_good; ) {          // Cigar::append per run of equal ops
@@ -2513,7 +2559,7 @@ struct ReadAligner {
                             else {
                                 if (cur_len) {
                                     if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return 0; }
-                                    m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+                                    m.bt_ops()[n_ops++] = cig_pack(cur_op, cur_len);
                                 }
                                 cur_op = op; cur_len = end - b;
                             }
@@ -2523,11 +2569,11 @@ struct ReadAligner {
                         pos -= n_good;
                         align_offset = imin(wbcast(c_t.offset, n_good - 1), k_minus_1);
                         j -= n_good;
-                        col = m.cols[j];
+                        col = m.cols()[j];
                         if (j) {
-                            par = m.cols[col.parent];
+                            par = m.cols()[col.parent];
                             gpar = par;
-                            if (par.parent != 0xffffffffu) gpar = m.cols[par.parent];
+                            if (par.parent != 0xffffffffu) gpar = m.cols()[par.parent];
                         }
                         continue;
                     }
@@ -2535,7 +2581,7 @@ struct ReadAligner {
                 try_run = true;
                 const int trim = col.trim, trim_p = par.trim;
                 align_offset = imin(col.offset, k_minus_1);
-                if (pos == col.max_pos) m.cols[j].started = 1;
+                if (pos == col.max_pos) m.cols()[j].started = 1;
                 const int code = encode_char(col.c);
                 const score_t sv = cellS(col, pos - trim);
                 const uint32_t last_op = cur_op;
@@ -2555,16 +2601,16 @@ struct ReadAligner {
                                 + prof_score(s, seed_clipping + pos, code)) {
                     ++n_trace;
                     if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
-                    m.bt_seq[n_seq++] = col.c;
+                    m.bt_seq()[n_seq++] = col.c;
                     cig_add(prof_is_match(s, seed_clipping + pos, code) ? OP_M : OP_X);
                     if (col.offset >= k_minus_1) {
                         if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
-                        m.bt_path[n_path++] = col.node; path_back_nonzero = col.node != 0;
+                        m.bt_path()[n_path++] = col.node; path_back_nonzero = col.node != 0;
                     }
                     --pos;
                     j = col.parent;
                     col = par;
-                    if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols[par.parent]; }
+                    if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols()[par.parent]; }
                 } else if (bt_is_del(col, pos - trim, sv) && (last_op == 0xffu || last_op != OP_I)) {
                     // deletion run (:972-999)
                     bool again = true;
@@ -2573,15 +2619,15 @@ struct ReadAligner {
                         again = bt_del_ext(col, par, pos);
                         ++n_trace;
                         if (n_seq >= (int)caps.aln_seq) { overflow = true; return 0; }
-                        m.bt_seq[n_seq++] = col.c;
+                        m.bt_seq()[n_seq++] = col.c;
                         cig_add(OP_D);
                         if (col.offset >= k_minus_1) {
                             if (n_path >= (int)caps.aln_nodes) { overflow = true; return 0; }
-                            m.bt_path[n_path++] = col.node; path_back_nonzero = col.node != 0;
+                            m.bt_path()[n_path++] = col.node; path_back_nonzero = col.node != 0;
                         }
                         j = col.parent;
                         col = par;
-                        if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols[par.parent]; }
+                        if (j) { par = gpar; if (par.parent != 0xffffffffu) gpar = m.cols()[par.parent]; }
                     }
                 } else {
                     break;                                   // backtracking failed
@@ -2590,31 +2636,31 @@ struct ReadAligner {
             }
             if (cur_len) {
                 if (n_ops >= (int)caps.aln_cigar - 4) { overflow = true; return 0; }
-                m.bt_ops[n_ops++] = cig_pack(cur_op, cur_len);
+                m.bt_ops()[n_ops++] = cig_pack(cur_op, cur_len);
             }
             wsync();
 
             if (n_trace >= min_trace_length && n_path && path_back_nonzero) {
-                const ColMeta cj = j ? col : m.cols[0];
+                const ColMeta cj = j ? col : m.cols()[0];
                 score_t cur_cell_score = cellS(cj, pos - cj.trim);
                 best_score = imax(best_score, score - cur_cell_score);
                 if ((int64_t)score - min_cell_score < best_score) break;
 
-                const ColMeta root = m.cols[0];
+                const ColMeta root = m.cols()[0];
                 if (score >= min_start_score
                         && (!pos || cur_cell_score == 0)
                         && (pos || cur_cell_score == cellS(root, 0))
                         && (cfg.allow_left_trim || !j)) {
                     // construct_alignment (:774-798)
-                    AlnSlot &o = sm.slots[out_base + n_ext];
+                    const AlnSlot o = m.slot(out_base + n_ext);
                     wsync();
-                    for (int t = wlane(); t < n_path; t += kWarp) o.nodes[t] = m.bt_path[n_path - 1 - t];
-                    for (int t = wlane(); t < n_seq; t += kWarp) o.seq[t] = m.bt_seq[n_seq - 1 - t];
+                    for (int t = wlane(); t < n_path; t += kWarp) o.nodes[t] = m.bt_path()[n_path - 1 - t];
+                    for (int t = wlane(); t < n_seq; t += kWarp) o.seq[t] = m.bt_seq()[n_seq - 1 - t];
                     int lead = start + pos;
                     int tail = L - start - end_pos;
                     int nc = 0;
                     if (lead) nc = 1;
-                    for (int t = wlane(); t < n_ops; t += kWarp) o.cigar[nc + t] = m.bt_ops[n_ops - 1 - t];
+                    for (int t = wlane(); t < n_ops; t += kWarp) o.cigar[nc + t] = m.bt_ops()[n_ops - 1 - t];
                     if (lead) o.cigar[0] = cig_pack(OP_S, lead);
                     nc += n_ops;
                     if (tail) o.cigar[nc++] = cig_pack(OP_S, tail);
@@ -2666,20 +2712,20 @@ struct ReadAligner {
         if (!n_agg) return kNinf;
         int mx = 0;
         for (int i = 1; i < n_agg; ++i)
-            if (aln_less(sm.slots[SLOT_AGG + mx], sm.slots[SLOT_AGG + i])) mx = i;
-        score_t cur_max = sm.slots[SLOT_AGG + mx].h->score;
+            if (aln_less(m.slot(SLOT_AGG + mx), m.slot(SLOT_AGG + i))) mx = i;
+        score_t cur_max = m.slot(SLOT_AGG + mx).h->score;
         return cur_max > 0 ? (score_t)((double)cur_max * cfg.rel_score_cutoff) : cur_max;
     }
     MGB_HD void agg_add(int slot) {
         if (!n_agg) { copy_slot(SLOT_AGG, slot); n_agg = 1; return; }
-        if (sm.slots[slot].h->score < agg_global_cutoff()) return;
+        if (m.slot(slot).h->score < agg_global_cutoff()) return;
         for (int i = 0; i < n_agg; ++i)
-            if (aln_equal(sm.slots[slot], sm.slots[SLOT_AGG + i])) return;
+            if (aln_equal(m.slot(slot), m.slot(SLOT_AGG + i))) return;
         if (n_agg < (int)cfg.num_alternative_paths) { copy_slot(SLOT_AGG + n_agg, slot); ++n_agg; return; }
         int mn = 0;
         for (int i = 1; i < n_agg; ++i)
-            if (aln_less(sm.slots[SLOT_AGG + i], sm.slots[SLOT_AGG + mn])) mn = i;
-        if (aln_less(sm.slots[slot], sm.slots[SLOT_AGG + mn])) return;
+            if (aln_less(m.slot(SLOT_AGG + i), m.slot(SLOT_AGG + mn))) mn = i;
+        if (aln_less(m.slot(slot), m.slot(SLOT_AGG + mn))) return;
         copy_slot(SLOT_AGG + mn, slot);
     }
     MGB_HD score_t get_min_path_score() { return imax(cfg.min_path_score, agg_global_cutoff()); }
@@ -2748,7 +2794,7 @@ struct ReadAligner {
                 if (ext_ok) {
                     if (it == 0) {
                         set_seed(fe);
-                    } else if (!sm.slots[SLOT_EXT + it - 1].h->used) {
+                    } else if (!m.slot(SLOT_EXT + it - 1).h->used) {
                         ext_ok = false;
                     } else {
                         // align_core(ManualSeeder(rc_of_alignments), bwd_extender, ..., force_fixed_seed = true)
@@ -2767,7 +2813,7 @@ struct ReadAligner {
                     const int slot = (it ? SLOT_BWD : SLOT_EXT) + r0;
                     // is_reversible (:652-656): on a CANONICAL-mode graph an alignment to the reverse strand
                     // with no offset is reported as its reverse complement
-                    const bool reversible = MGB_CANONICAL(cfg) && sm.slots[slot].h->orientation && !sm.slots[slot].h->offset;
+                    const bool reversible = MGB_CANONICAL(cfg) && m.slot(slot).h->orientation && !m.slot(slot).h->offset;
                     // pass 0 reports the result, pass 1 (forward case only) turns a left-clipped result into
                     // a seed of the backward extension; both go through the one reverse-complement call site
                     #pragma unroll 1
@@ -2776,7 +2822,7 @@ struct ReadAligner {
                         int target = slot;
                         if (pass == 0) {
                             if (it == 0) {
-                                add = !both || sm.slots[slot].h->score >= get_min_path_score();
+                                add = !both || m.slot(slot).h->score >= get_min_path_score();
                                 need_rc = add && reversible;              // :680-684
                                 if (need_rc) { copy_slot(SLOT_TMP, slot); target = SLOT_TMP; }
                             } else {
@@ -2785,7 +2831,7 @@ struct ReadAligner {
                             }
                         } else {
                             if (it != 0 || !both) break;
-                            if (!aln_clipping(sm.slots[slot]) || sm.slots[slot].h->offset) break;
+                            if (!aln_clipping(m.slot(slot)) || m.slot(slot).h->offset) break;
                             need_rc = true;
                         }
                         bool ok = true;
@@ -2794,10 +2840,10 @@ struct ReadAligner {
                         if (!ok) break;                                   // the alignment cannot be reversed
                         if (pass == 0) {
                             if (it != 0 && need_rc) {
-                                const AlnHdr h = *sm.slots[slot].h;
-                                int clip = aln_clipping(sm.slots[slot]), eclip = aln_end_clipping(sm.slots[slot]);
+                                const AlnHdr h = *m.slot(slot).h;
+                                int clip = aln_clipping(m.slot(slot)), eclip = aln_end_clipping(m.slot(slot));
                                 for (int t = 0; t < h.n_nodes && !overflow; ++t)
-                                    filter_nodes(fe, sm.slots[slot].nodes[t], clip, L - eclip);
+                                    filter_nodes(fe, m.slot(slot).nodes[t], clip, L - eclip);
                             }
                             if (add) agg_add(target);
                         } else {
@@ -2808,7 +2854,7 @@ struct ReadAligner {
                 }
                 if (ext_ok && !overflow && it != 0) {
                     for (int r2 = r + 1; r2 < n_rc; ++r2) {
-                        AlnSlot &a = sm.slots[SLOT_EXT + r2];
+                        const AlnSlot a = m.slot(SLOT_EXT + r2);
                         if (!a.h->used) continue;
                         const AlnHdr h = *a.h;
                         if (!check_seed_vals(cx[be].conv_slots, cx[be].conv_cells, cx[be].conv_epoch, !MGB_CANONICAL(cfg) && cx[be].rc != 0,
@@ -2891,28 +2937,24 @@ struct ReadAligner {
         {
             StrandCtx c0, c1;
             c0.q = qf; c1.q = qr; c0.codes = cf; c1.codes = cr; c0.qnodes = nf; c1.qnodes = nr;
-            c0.ps = m.psum[0]; c1.ps = m.psum[1];
-            c0.seeds = m.seeds[0]; c1.seeds = m.seeds[1];
-            c0.conv_slots = m.conv_slots[0]; c1.conv_slots = m.conv_slots[1];
-            c0.conv_cells = m.conv_cells[0]; c1.conv_cells = m.conv_cells[1];
-            c0.conv_epoch = m.epoch_store[0]; c1.conv_epoch = m.epoch_store[1];
+            c0.ps = m.psum(0); c1.ps = m.psum(1);
+            c0.seeds = m.seeds(0); c1.seeds = m.seeds(1);
+            c0.conv_slots = m.conv_slots(0); c1.conv_slots = m.conv_slots(1);
+            c0.conv_cells = m.conv_cells(0); c1.conv_cells = m.conv_cells(1);
+            c0.conv_epoch = m.epoch_store()[0]; c1.conv_epoch = m.epoch_store()[1];
             c0.conv_n = c1.conv_n = 0; c0.conv_cells_used = c1.conv_cells_used = 0;
             c0.n_seeds = c1.n_seeds = 0; c0.num_matching = c1.num_matching = 0;
             c0.table_cap = c1.table_cap = 0; c0.num_ext = c1.num_ext = 0;
             c0.explored_prev = c1.explored_prev = 0; c0.rc = c1.rc = 0;
-            c0.implicit_seeds = c1.implicit_seeds = 0; c0.mask = sm.mask0; c1.mask = sm.mask1;
+            c0.implicit_seeds = c1.implicit_seeds = 0; c0.mask = sm.mask0(); c1.mask = sm.mask1();
             c0.sub_first = subk_first[0]; c0.sub_last = subk_last[0]; c0.sub_len = subk_len[0];
             c1.sub_first = subk_first[1]; c1.sub_last = subk_last[1]; c1.sub_len = subk_len[1];
             // stage the query strands (and their suffix sums) on chip when they fit
-            if (L + 1 <= sm.lq) {
-                for (int i = wlane(); i < L; i += kWarp) { sm.q0[i] = qf[i]; sm.q1[i] = qr[i]; }
-                c0.q = sm.q0; c1.q = sm.q1; c0.ps = sm.psum0; c1.ps = sm.psum1;
+            if (L + 1 <= sm.lq()) {
+                for (int i = wlane(); i < L; i += kWarp) { sm.q0()[i] = qf[i]; sm.q1()[i] = qr[i]; }
+                c0.q = sm.q0(); c1.q = sm.q1(); c0.ps = sm.psum0(); c1.ps = sm.psum1();
             }
-            sm.ctx[0] = c0; sm.ctx[1] = c1;
-#if MGB_DEVICE_CODE
-#pragma unroll
-#endif
-            for (int t = 0; t < kNumSlots; ++t) sm.slots[t] = m.slots[t];
+            sm.ctx()[0] = c0; sm.ctx()[1] = c1;
         }
         wsync();
         stats.num_seeds = stats.num_extensions = stats.num_explored_nodes = stats.dp_columns = 0;
@@ -2967,7 +3009,7 @@ struct ReadAligner {
         for (int i = 0; i < n_agg; ++i) order[i] = i;
         for (int i = 1; i < n_agg; ++i) {
             int x = order[i], j = i - 1;
-            while (j >= 0 && aln_less(sm.slots[SLOT_AGG + order[j]], sm.slots[SLOT_AGG + x])) {
+            while (j >= 0 && aln_less(m.slot(SLOT_AGG + order[j]), m.slot(SLOT_AGG + x))) {
                 order[j + 1] = order[j]; --j;
             }
             order[j + 1] = x;

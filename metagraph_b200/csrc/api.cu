@@ -838,8 +838,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             if (const char *e = std::getenv("MGB_TEST_BMAX")) bmax_v = std::atoi(e);
             if (const char *e = std::getenv("MGB_TEST_LQ")) lq_v = std::atoi(e);
             if (const char *e = std::getenv("MGB_TEST_HCAP")) hcap = std::atoi(e);
-            WarpSmem sm_probe;
-            const size_t smem_per_warp = sm_probe.carve(nullptr, bmax_v, lq_v, hcap);
+            SmemLayout slay;
+            const size_t smem_per_warp = slay.carve(bmax_v, lq_v, hcap);
             DevBufs pass_bufs(st, wsg.w, 32);          // slot 32: the arena
 #if defined(MGB_HOST_EMU)
             uint32_t n_warps = 1;
@@ -892,7 +892,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             if ((rc = dev_zero(d_used, 8, st))) break;
             if ((rc = dev_zero(d_next, 4, st))) break;
             AlignArgs a;
-            a.ix = index->view; a.cfg = dcfg; a.caps = caps; a.bmax = bmax_v; a.lq = lq_v; a.hcap = hcap;
+            a.ix = index->view; a.cfg = dcfg; a.caps = caps; a.lay.carve(caps); a.slay = slay;
             a.use_fast = std::getenv("MGB_TEST_NOFAST") ? 0 : 1;
             a.phase_out = nullptr;
 #if defined(MGB_PHASE_TIMERS) && !defined(MGB_HOST_EMU)
@@ -912,8 +912,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 #if defined(MGB_HOST_EMU)
             init_arena(a, d_arena);
             std::vector<char> smem_emu(smem_per_warp + 64);
-            WarpMem mem_emu; mem_emu.carve(d_arena, a.caps);
-            WarpSmem sm_emu; sm_emu.carve(smem_emu.data(), a.bmax, a.lq, a.hcap);
+            const WarpMem mem_emu { d_arena, &a.lay };
+            const WarpSmem sm_emu { smem_emu.data(), &a.slay };
             for (uint32_t t = 0; t < a.n_list; ++t) align_read(a, a.read_list[t], mem_emu, sm_emu, true);
             used = *d_used;
 #else

@@ -168,8 +168,8 @@ inline Caps choose_caps(uint32_t L_max, const DevConfig &d, uint32_t k, uint32_t
 }
 
 inline size_t arena_bytes(const Caps &c) {
-    WarpMem m;
-    return m.carve(nullptr, c);
+    WarpLayout l;
+    return l.carve(c);
 }
 
 } // namespace mgb

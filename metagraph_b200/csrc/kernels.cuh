@@ -123,7 +123,8 @@ MGB_HD void subk_item(const SubkArgs &a, uint32_t r, uint32_t s, uint32_t chunk)
 
 struct AlignArgs {
     IndexView ix; DevConfig cfg; Caps caps;
-    int bmax, lq, hcap;         // on-chip working set per warp (WarpSmem)
+    WarpLayout lay;             // arena regions of a lane group (offsets)
+    SmemLayout slay;            // on-chip working set of a lane group (offsets)
     int use_fast;               // 0 disables the register fast path (test knob)
     unsigned long long *phase_out;   // MGB_PHASE_TIMERS builds: cycles per phase (setup, seeds, fwd, backtrack, align total)
     const char *qf, *qr; const uint8_t *cf, *cr; const uint64_t *offsets, *koff;
@@ -138,7 +139,7 @@ struct AlignArgs {
 
 // `act`: this lane group has a read; a group without one still walks through the lock-step loops of the
 // aligner (the lane groups of a warp run them together)
-MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &sm, bool act) {
+MGB_HD void align_read(const AlignArgs &a, uint32_t r, const WarpMem &mem, const WarpSmem &sm, bool act) {
     ReadAligner al(a.ix, a.cfg, a.caps, mem, sm);
     al.use_fast = a.use_fast != 0;
     const uint64_t b = act ? a.offsets[r] : 0;
@@ -166,7 +167,7 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &s
         // bytes: per alignment OutAln + nodes*8 + cigar*4 + seq (padded to 8)
         uint64_t bytes = 0;
         for (int i = 0; i < n; ++i) {
-            const AlnHdr ah = *mem.slots[SLOT_AGG + order[i]].h;
+            const AlnHdr ah = *mem.slot(SLOT_AGG + order[i]).h;
             bytes += sizeof(OutAln) + 8ull * ah.n_nodes + ((4ull * ah.n_cigar + 7) & ~7ull)
                    + (((uint64_t)ah.seq_len + 7) & ~7ull);
         }
@@ -183,7 +184,7 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &s
             h.n_aln = n; h.heap_off = off;
             char *p = a.heap + off;
             for (int i = 0; i < n; ++i) {
-                const AlnSlot &sl = mem.slots[SLOT_AGG + order[i]];
+                const AlnSlot sl = mem.slot(SLOT_AGG + order[i]);
                 const AlnHdr ah = *sl.h;
                 OutAln o;
                 o.orientation = ah.orientation; o.score = ah.score; o.offset = ah.offset;
@@ -204,18 +205,17 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, WarpMem &mem, WarpSmem &s
     }
     if (wlane() == 0) {
         a.hdr[r] = h;
-        mem.epoch_store[0] = sm.ctx[0].conv_epoch; mem.epoch_store[1] = sm.ctx[1].conv_epoch;
+        mem.epoch_store()[0] = sm.ctx()[0].conv_epoch; mem.epoch_store()[1] = sm.ctx()[1].conv_epoch;
     }
     wsync();
 }
 
 // once per arena: convergence-table slots start with epoch 0 (never equal to a live epoch)
 MGB_HD void init_arena(const AlignArgs &a, char *arena) {
-    WarpMem mem;
-    mem.carve(arena, a.caps);
+    const WarpMem mem { arena, &a.lay };
     for (int e = 0; e < 2; ++e)
-        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv_slots[e][i].epoch = 0;
-    if (wlane() == 0) { mem.epoch_store[0] = 0; mem.epoch_store[1] = 0; }
+        for (uint32_t i = wlane(); i < a.caps.hash_size; i += kWarp) mem.conv_slots(e)[i].epoch = 0;
+    if (wlane() == 0) { mem.epoch_store()[0] = 0; mem.epoch_store()[1] = 0; }
     wsync();
 }
 
@@ -357,18 +357,15 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
 static constexpr int kAlignThreads = MGB_ALIGN_THREADS;
 static constexpr int kGroupsPerBlock = kAlignThreads / kWarp;   // reads in flight per block of k_align
 // one lane group (kWarp lanes, common.cuh) per read; kAlignThreads / kWarp groups per block
-__global__ void __launch_bounds__(kAlignThreads, MGB_ALIGN_MIN_BLOCKS) k_align(const AlignArgs a) {
+__global__ void __launch_bounds__(kAlignThreads, MGB_ALIGN_MIN_BLOCKS) k_align(const __grid_constant__ AlignArgs a) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
     char *arena = a.arena + (size_t)warp * a.arena_stride;
     extern __shared__ __align__(16) char smem_raw[];
-    WarpSmem probe;
-    const size_t smem_per_warp = probe.carve(nullptr, a.bmax, a.lq, a.hcap);
-    char *smem = smem_raw + (threadIdx.x / kWarp) * smem_per_warp;
+    char *smem = smem_raw + (threadIdx.x / kWarp) * a.slay.total;
     init_arena(a, arena);
-    WarpMem mem;                 // the warp's arena and on-chip working set are laid out once
-    mem.carve(arena, a.caps);
-    WarpSmem sm;
-    sm.carve(smem, a.bmax, a.lq, a.hcap);
+    // the group's arena and on-chip working set: base + offsets from the kernel parameters
+    const WarpMem mem { arena, &a.lay };
+    const WarpSmem sm { smem, &a.slay };
     while (true) {
         unsigned int t = 0;
         if (wlane() == 0) t = atomicAdd(a.next, 1u);
