@@ -1580,10 +1580,10 @@ struct ReadAligner {
         return max_changed;
     }
 
-    // update_seed_filter for a column of the register path: lane l holds S[l * kCPL + c] in S[c]; the passed
-    // range is cells [s_first, size). sm_S: the same column in the on-chip child buffer.
+    // update_seed_filter (extender.cpp:100-156) for a column of the register path: lane l holds S[l * kCPL + c] in
+    // S[c]; the passed range is cells [s_first, size)
     MGB_HD score_t update_seed_filter_regs(int e, uint64_t node, int query_start, const score_t (&S)[kCPL],
-                                           int s_first, int size, const score_t *sm_S) {
+                                           int s_first, int size) {
         const int j0 = wlane() * kCPL;
         score_t mx = kNinf;
 #if MGB_DEVICE_CODE
@@ -1600,23 +1600,50 @@ struct ReadAligner {
         ConvSlot en;
         int free_at;
         int slot = conv_find(t.conv_slots, t.conv_epoch, key, &en, true, &free_at);
+        const int n_pass = size - s_first;
         if (slot < 0) {
-            slot = conv_insert(e, key, query_start, size - s_first, &en, free_at);
+            slot = conv_insert(e, key, query_start, n_pass, &en, free_at);
             if (slot < 0) return kNinf;
-            score_t *c0 = t.conv_cells + en.seg_off + (query_start - s_first - en.seg_start);   // indexed by cell
+        } else {
+            // the node was met before in this extension (seed columns share the seed's node; cycles; re-convergent
+            // branches). Disjoint from the stored range (before / after it): the values are stored as they are
+            // (:118-131); one conv_grow call site serves all three cases
+            const bool disjoint = query_start + n_pass <= en.start || query_start >= en.start + en.size;
+            const int ns = imin(query_start, en.start), ne = imax(query_start + n_pass, en.start + en.size);
+            if (ns != en.start || ne != en.start + en.size)
+                if (!conv_grow(e, slot, &en, ns, ne)) return kNinf;
+            if (!disjoint) {
+                score_t *v0 = t.conv_cells + en.seg_off + (query_start - s_first - en.seg_start);   // indexed by cell
+                score_t max_changed = kNinf;
 #if MGB_DEVICE_CODE
 #pragma unroll
 #endif
-            for (int c = 0; c < kCPL; ++c) {
-                const int j = j0 + c;
-                if (j >= s_first && j < size) c0[j] = S[c];
+                for (int c = 0; c < kCPL; ++c) {
+                    const int j = j0 + c;
+                    if (j >= s_first && j < size) {
+                        score_t vj = v0[j];
+                        if ((double)S[c] > (double)vj * cfg.rel_score_cutoff) {
+                            vj = imax(vj, S[c]);
+                            v0[j] = vj;
+                            max_changed = imax(max_changed, vj);
+                        }
+                    }
+                }
+                max_changed = wreduce_max(max_changed);
+                wsync();
+                return max_changed;
             }
-            wsync();
-            return mx;
         }
-        // the node was met before in this extension (cycle, re-convergent branch): the general routine, on the
-        // on-chip copy of the column
-        return update_seed_filter(e, node, query_start, sm_S + s_first, size - s_first);
+        score_t *c0 = t.conv_cells + en.seg_off + (query_start - s_first - en.seg_start);           // indexed by cell
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+        for (int c = 0; c < kCPL; ++c) {
+            const int j = j0 + c;
+            if (j >= s_first && j < size) c0[j] = S[c];
+        }
+        wsync();
+        return mx;
     }
 
     // extender.cpp:158-207 (every cell of [query_start, query_end) ends up at -ninf)
@@ -2040,7 +2067,173 @@ struct ReadAligner {
         while (true) {
             const bool mine = go && !overflow && !finished;
             if (!wany_full(mine)) break;
-            if (!mine) continue;
+            // ---------------- chain: the column just committed is the only candidate (:477-504 would push it and
+            // pop it again), sits in an on-chip buffer and its band under the current cutoff is known. In a
+            // linear stretch of the graph every column is like that, so this inner loop -- one child column per
+            // iteration, everything in registers, no queue traffic -- is where an extension spends its time.
+            // Anything unusual (several children, a column too wide for the register path, a seed node that is
+            // not in the graph, PRIMARY graphs) leaves the column to the general code below.
+            {
+                bool chain = mine && reg_path && L < (1 << 25) && !MGB_PRIMARY(ix) && t >= n_out && heap_n == 0 && nn_n == 1
+                             && np[0].idx == last_idx && last_band_valid && last_band_cutoff == cutoff
+                             && (res0 == (int)last_idx || res1 == (int)last_idx);
+                uint32_t ci = last_idx; uint64_t c_node = last_col.node;
+                int c_offset = last_col.offset, c_trim = last_col.trim;
+                uint32_t c_bm = last_band_mask;
+                int c_pb = res1 == (int)last_idx ? 1 : 0;
+                score_t c_maxval = 0;
+                HeapItem cur_it = HeapItem();
+                if (chain) { cur_it = np[0]; c_maxval = cur_it.max_score; }
+                uint32_t t_cap = 0, c_cols = 0; uint64_t c_cells = 0;      // table_cap / stats, written back at the end
+                if (chain) t_cap = cx[e].table_cap;
+                while (wany_full(chain)) {
+                    if (!chain) continue;
+                    // how the chain ends: END = the extension is over (nothing left in the queue), SLOW = column ci
+                    // stays the sole candidate and the general code expands it
+                    enum { GO_ON = 0, END = 1, SLOW = 2 };
+                    int stop = GO_ON;
+                    do {
+                        if (c_maxval < best_score) {
+                            if ((double)n_cols / wlen >= cfg.max_nodes_per_seq_char) { stop = END; break; }   // global_xdrop
+                            if ((double)table_size_bytes / 1000000 > cfg.max_ram_per_alignment) { stop = END; break; }
+                        }
+                        if (!c_bm) { stop = END; break; }                   // no band: no children
+                        const int begin_c = ffs32(c_bm) - 1 + c_trim;
+                        const int prev_end = 32 - clz32(c_bm) + c_trim;
+                        const int noff = c_offset + 1;
+                        const uint32_t seed_pos = (uint32_t)(noff - (int)sh.offset);
+                        const bool in_seed_c = seed_pos < (uint32_t)seed_seq_len;
+                        uint64_t cnode; uint8_t ch;
+                        // call_outgoing (:330-387), single plain child only
+                        if (in_seed_c && noff < K) {
+                            cnode = seed_node0; ch = (uint8_t)seed_seq[seed_pos];
+                        } else if (in_seed_c && force_fixed_seed) {
+                            cnode = seed.nodes[noff - K + 1]; ch = (uint8_t)seed_seq[seed_pos];
+                            if (!cnode) { stop = SLOW; break; }
+                        } else if (!rc) {
+                            const Adj a = (!MGB_WIDE(ix) && c_node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, c_node);
+                            const uint32_t ok = a.last ? (a.ok & ~1u) : 0u;
+                            if (!ok) { m.cols()[ci].is_tip = 1; stop = END; break; }
+                            if (ok & (ok - 1u)) { stop = SLOW; break; }
+                            const uint32_t c = (uint32_t)ffs32(ok) - 1;
+                            cnode = (uint64_t)a.last - popc32(a.all) + 1 + popc32(a.all & ((1u << c) - 1u));
+                            ch = (uint8_t)cfg.letters[c];
+                        } else {
+                            // RCDBG::call_outgoing_kmers through the reverse adjacency records, single incoming edge
+                            const uint2 rr = load_radj(ix, c_node);
+                            if (radj_multi(ix, rr.y)) { stop = SLOW; break; }
+                            const uint64_t edge = rr.x;
+                            ch = '$';
+                            if (in_graph(ix, edge))
+                                ch = complement_char((uint8_t)cfg.letters[radj_char(ix, load_radj(ix, edge).y)]);
+                            if (ch == '$') { m.cols()[ci].is_tip = 1; stop = END; break; }
+                            cnode = edge;
+                        }
+                        if (ch >= 'a' && ch <= 'z') ch -= 32;              // toupper (:564)
+                        if (n_cols >= caps.max_cols) { overflow = true; stop = END; break; }
+                        const int size0_c = imin(prev_end, wlen) + 1 - begin_c;
+                        const int n_c = prev_end - begin_c;
+                        if (n_c > 28 || size0_c > 27) { stop = SLOW; break; }
+                        {   // requests whose latency overlaps the DP below
+                            if (!rc && !MGB_WIDE(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
+                            pf_key = cnode + (rc ? ix.n : 0);
+                            pf_slot_idx = hash_node(pf_key);
+                            pf_slot = cx[e].conv_slots[pf_slot_idx];
+                        }
+                        const int code = encode_char(ch);
+                        const score_t *pS = sm.buf(c_pb) + (begin_c - c_trim);
+                        RegCol r;
+                        const int size = reg_column(s, pS, pS + 2 * sm.bmax(), n_c, size0_c, start + begin_c,
+                                                    wlen + 1 - begin_c, code, 0, noff > 1, cutoff, r);
+                        if (size < 0) { stop = SLOW; break; }
+                        MGB_COUNT(5);
+                        const int j0 = wlane() * kCPL;
+                        const uint32_t cap_before = t_cap;
+                        if (n_cols + 1 > t_cap) t_cap = t_cap ? 2 * t_cap : 1;
+                        c_cells += size; ++c_cols;
+                        // per-column scan (:643-669)
+                        const int diag_i = noff - seed_off_m1;
+                        score_t mn = 0x7fffffff, bs = INT32_MIN;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                        for (int c = 0; c < kCPL; ++c) {
+                            const bool cell = j0 + c < size;
+                            const score_t v = r.S[c];
+                            if (cell && v != kNinf) mn = imin(mn, v);
+                            if (cell) bs = imax(bs, v);
+                        }
+                        min_cell_score = imin(min_cell_score, wreduce_min(mn));
+                        const score_t max_val = wreduce_max(bs);
+                        int key = 0x7fffffff; bool he = false;              // (distance to the diagonal, row) of the best cell
+                        score_t ext_cut = 0;
+                        if (!in_seed_c)
+                            ext_cut = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                        for (int c = 0; c < kCPL; ++c) {
+                            const int j = j0 + c;
+                            const bool cell = j < size;
+                            if (cell && r.S[c] == max_val) key = imin(key, (iabs(j + begin_c - diag_i) << 5) | j);
+                            if (!in_seed_c && cell && r.S[c] + cx[s].ps[start + begin_c + j] >= ext_cut) he = true;
+                        }
+                        const int max_pos = (wreduce_min(key) & 31) + begin_c;
+                        if (!in_seed_c && (max_val < cutoff || !wballot(he))) {
+                            cx[e].table_cap = t_cap;                        // (the reference grew the table, then popped)
+                            stop = END; break;                              // pop(table.size() - 1): nothing left
+                        }
+                        table_size_bytes += 136ull * (t_cap - cap_before) + 3ull * vec_capacity(size0_c, size) * 4;
+                        if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
+                        best_score = imax(best_score, max_val);
+                        if (cells_used > cells_limit) { overflow = true; stop = END; break; }
+                        // commit: DP table (compact format, whole 32-byte sectors) and the on-chip child buffer
+                        const int capr = capr_of(size);
+                        const uint32_t off = (cells_used + 7u) & ~7u;
+                        cells_used = off + 2 * capr + 8;
+                        score_t *dst = m.cells() + off;
+                        score_t *cb_S = sm.buf(1 - c_pb);
+                        store_cells(dst, j0, r.S, capr);
+                        store_flags(reinterpret_cast<uint8_t*>(dst + capr), j0, r.fl);
+                        store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * sm.bmax(), j0, r.F, 32);
+                        ColMeta col;
+                        col.node = cnode; col.parent = ci; col.c = ch;
+                        col.offset = noff; col.max_pos = max_pos; col.trim = begin_c; col.score = 0;
+                        col.is_tip = 0; col.started = 0; col.fmt = FMT_COMPACT; col.pad0 = col.pad1 = 0;
+                        col.size = size; col.cells_off = off;
+                        const uint32_t idx = n_cols;
+                        m.cols()[n_cols++] = col;
+                        uint32_t bits = 0;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                        for (int c = 0; c < kCPL; ++c) if (j0 + c < size && r.S[c] >= cutoff) bits |= 1u << c;
+                        const uint32_t bm_new = kCPL == 32 ? bits : wreduce_or(bits << (j0 & 31));
+                        wsync();
+                        // convergence filter from registers (update_seed_filter)
+                        const int s_first = begin_c ? 0 : 1;
+                        const score_t converged = update_seed_filter_regs(e, cnode, start + begin_c - (begin_c ? 1 : 0), r.S,
+                                                                          s_first, size);
+                        // the new column becomes the parent
+                        ci = idx; c_node = cnode; c_offset = noff; c_trim = begin_c; c_bm = bm_new; c_pb = 1 - c_pb;
+                        c_maxval = max_val;
+                        cur_it.score = converged; cur_it.neg_off_diag = -iabs(max_pos - diag_i); cur_it.idx = idx;
+                        cur_it.max_score = max_val;
+                        if (overflow || converged == kNinf) { stop = END; break; }
+                    } while (false);
+                    if (stop != GO_ON) {
+                        chain = false;
+                        cx[e].table_cap = t_cap;
+                        stats.dp_cells += c_cells; stats.dp_columns += c_cols;
+                        // the general code finds: an empty queue (END), or column ci as the one entry of next_nodes
+                        // (SLOW); its register copy is re-read from the table, its band re-computed
+                        if (stop == END) nn_n = 0; else { np[0] = cur_it; nn_n = 1; }
+                        last_idx = 0xffffffffu; last_band_valid = false;
+                        res0 = c_pb == 0 ? (int)ci : -1; res1 = c_pb == 1 ? (int)ci : -1;
+                    }
+                }
+            }
+            if (!mine || overflow) continue;
             if (t >= n_out) {
                 // ---------------- next parent: queue round / next_nodes (:477-504) ----------------
                 if (!nn_n) {
@@ -2257,7 +2450,7 @@ struct ReadAligner {
                     // convergence filter from registers (update_seed_filter)
                     const int s_first = begin ? 0 : 1;
                     const int vec_offset = start + begin - (begin ? 1 : 0);
-                    const score_t converged = update_seed_filter_regs(e, cnode, vec_offset, r.S, s_first, size, cb_S);
+                    const score_t converged = update_seed_filter_regs(e, cnode, vec_offset, r.S, s_first, size);
                     if (overflow) continue;
                     if (converged != kNinf) {
                         HeapItem it; it.score = converged; it.neg_off_diag = -iabs(max_pos - diag_i);

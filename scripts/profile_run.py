@@ -12,6 +12,7 @@ boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=
 index = DBGSuccinctIndex(boss)
 buf, off = make_reads(genome, N, 42)
 al = B200Aligner(index, cli_defaults(K, min_seed_length=K, max_seed_length=K))
+al.set_pipeline_pieces(1)
 for i in range(STEPS):
     res = al.align_batch_raw(buf, off); st = al.stats_of(res); al.free_raw(res)
     print("step", i, "seed_ms %.2f align_ms %.2f" % (st["seed_kernel_ms"], st["align_kernel_ms"]), flush=True)

@@ -20,6 +20,7 @@ buf = np.ascontiguousarray(reads.reshape(-1)); off = np.arange(N + 1, dtype=np.u
 boss = BOSSTable.from_sequences(K, None, packed=(genome, np.array([0, G], dtype=np.uint64)), lib=lib)
 index = DBGSuccinctIndex(boss, lib=lib)
 al = B200Aligner(index, cli_defaults(K, min_exact_match=0.0))
+al.set_pipeline_pieces(1)
 for i in range(2):
     res = al.align_batch_raw(buf, off); st = al.stats_of(res); al.free_raw(res)
     print("c3 probe: seed_ms %.2f align_ms %.2f seeds %d ext %d cols %d" % (st["seed_kernel_ms"], st["align_kernel_ms"], st["num_seeds"], st["num_extensions"], st["dp_columns"]), flush=True)
