@@ -76,9 +76,15 @@ typedef struct mgb_config {
     uint8_t allow_left_trim;
     uint8_t no_backtrack;
     uint8_t seed_complexity_filter; /* sdust(T=20, W=64) on seed windows, restated from its definition (library not vendored) */
-    uint8_t reserved1[7];
+    /* What mgb_alignment_t::nodes carries (not a DBGAlignerConfig field): MGB_NODES_U64 = the node path (default),
+     * MGB_NODES_NONE = nothing (nodes == NULL, num_nodes still set) for consumers that only print alignments
+     * (the TSV branch of cli/align.cpp:254-307 never reads Alignment::get_nodes()): the node ids are 4/5 of the
+     * bytes a 150 bp alignment brings back from the device. */
+    uint8_t result_nodes;
+    uint8_t reserved1[6];
     int8_t score_matrix[128][128];
 } mgb_config_t;
+enum { MGB_NODES_U64 = 0, MGB_NODES_NONE = 1 };
 
 /* One alignment of one read (Alignment, alignment.hpp:323-331). Pointers reference memory
  * owned by the enclosing mgb_results_t. */
@@ -179,6 +185,15 @@ const mgb_alignment_t* mgb_results_alignments(const mgb_results_t *results);
 const mgb_stats_t* mgb_results_stats(const mgb_results_t *results);
 void mgb_results_free(mgb_results_t *results);
 
+/* Multi-GPU: reads shard across ranks (one process per GPU; dbg_aligner.cpp:263-354 keeps no state
+ * between reads) and rank 0 collects the per-rank results. mgb_results_export writes a result set as one
+ * relocatable byte block (the records as the kernel packed them, no pointers) into caller memory -- e.g. a pinned
+ * buffer handed to ncclSend; mgb_results_import rebuilds a result set from such a block on the receiving rank,
+ * with read_index_base added to the read indexes (the shard's first read). */
+uint64_t mgb_results_export_bytes(const mgb_results_t *results);
+int mgb_results_export(const mgb_results_t *results, void *dst, uint64_t capacity);
+int mgb_results_import(const void *block, uint64_t bytes, uint32_t read_index_base, mgb_results_t **out);
+
 /* ---- host-side construction (index build, untimed) ------------------------------------ */
 
 /* Builds BOSS arrays from sequences (batch construction incl. dummy edges). Caller frees
@@ -202,7 +217,7 @@ int mgb_boss_mask_dummy(const mgb_boss_t *boss, uint8_t *valid);
 /* Reads a graph file written by the reference (`.dbg`: DBGSuccinct::serialize, dbg_succinct.cpp:690-803 ->
  * BOSS::serialize, boss.cpp:262-277) into plain BOSS arrays for mgb_index_create(). States SMALL and STAT
  * (boss.hpp:325); DYN / FAST files are refused. *mode = DeBruijnGraph::Mode (0 BASIC, 1 CANONICAL,
- * 2 PRIMARY; only BASIC graphs can be aligned against in this build), *state = BOSS::State. The suffix
+ * 2 PRIMARY; pass it to mgb_index_set_mode), *state = BOSS::State. The suffix
  * range index and the optional .edgemask file are not read. Free with mgb_boss_free(). On failure returns
  * MGB_ERR_INVALID_ARGUMENT and mgb_dbg_last_error() describes why. */
 int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode, int *state);

@@ -88,6 +88,12 @@ def load_library(path=None):
     L.mgb_results_stats.restype = ctypes.POINTER(mgb_stats_t)
     L.mgb_results_stats.argtypes = [vp]
     L.mgb_results_free.argtypes = [vp]
+    L.mgb_results_export_bytes.restype = u64
+    L.mgb_results_export_bytes.argtypes = [vp]
+    L.mgb_results_export.restype = i
+    L.mgb_results_export.argtypes = [vp, vp, u64]
+    L.mgb_results_import.restype = i
+    L.mgb_results_import.argtypes = [vp, u64, u32, ctypes.POINTER(vp)]
     L.mgb_boss_build.restype = i
     L.mgb_boss_build.argtypes = [vp, vp, u32, u32, i, i, i, ctypes.POINTER(mgb_boss_t)]
     L.mgb_boss_free.argtypes = [ctypes.POINTER(mgb_boss_t)]
@@ -113,6 +119,7 @@ REQUIRED_SYMBOLS = [
     "mgb_last_error", "mgb_device_count", "mgb_index_create", "mgb_index_destroy", "mgb_index_num_edges",
     "mgb_index_device_bytes", "mgb_index_k", "mgb_config_init", "mgb_config_init_cli", "mgb_map_to_nodes",
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
-    "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_boss_build", "mgb_boss_free",
+    "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_results_export_bytes",
+    "mgb_results_export", "mgb_results_import", "mgb_boss_build", "mgb_boss_free",
     "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_index_set_mode",
 ]

@@ -356,6 +356,27 @@ def format_alignment(header, paths, min_path_score=0, with_nodes=False):
     return out
 
 
+def results_of_handle(L, res, seq_batch):
+    """AlignmentResults of every read of a mgb_results_t (seq_batch: the (header, sequence) pairs it was made from)"""
+    alns = L.mgb_results_alignments(res)
+    out = []
+    first, count = ctypes.c_uint64(), ctypes.c_uint32()
+    for r, (header, seq) in enumerate(seq_batch):
+        ar = AlignmentResults(seq if isinstance(seq, str) else seq.decode("latin1"))
+        L.mgb_results_read_range(res, r, ctypes.byref(first), ctypes.byref(count))
+        for i in range(first.value, first.value + count.value):
+            x = alns[i]
+            a = Alignment()
+            a.orientation = bool(x.orientation); a.score = x.score; a.offset = x.offset
+            a.query_begin = x.query_begin; a.query_len = x.query_len
+            a.nodes = np.ctypeslib.as_array(x.nodes, shape=(x.num_nodes,)).copy() if (x.num_nodes and x.nodes) else np.zeros(0, np.uint64)
+            a.sequence = ctypes.string_at(x.sequence, x.sequence_len).decode("latin1")
+            a.cigar = np.ctypeslib.as_array(x.cigar, shape=(x.num_cigar_ops,)).copy()
+            ar.append(a)
+        out.append(ar)
+    return out
+
+
 class B200Aligner:
     """IDBGAligner over the B200 kernels (Seeder = SuffixSeeder<UniMEMSeeder>, Extender =
     DefaultColumnExtender, as DBGAligner<> in dbg_aligner.hpp:42-45)."""
@@ -402,23 +423,9 @@ class B200Aligner:
         res = self.align_batch_raw(buf, offsets)
         try:
             self.last_stats = self.stats_of(res)
-            alns = self._L.mgb_results_alignments(res)
-            out = []
-            first, count = ctypes.c_uint64(), ctypes.c_uint32()
-            for r, (header, seq) in enumerate(seq_batch):
-                ar = AlignmentResults(seq if isinstance(seq, str) else seq.decode("latin1"))
-                self._L.mgb_results_read_range(res, r, ctypes.byref(first), ctypes.byref(count))
-                for i in range(first.value, first.value + count.value):
-                    x = alns[i]
-                    a = Alignment()
-                    a.orientation = bool(x.orientation); a.score = x.score; a.offset = x.offset
-                    a.query_begin = x.query_begin; a.query_len = x.query_len
-                    a.nodes = np.ctypeslib.as_array(x.nodes, shape=(x.num_nodes,)).copy() if x.num_nodes else np.zeros(0, np.uint64)
-                    a.sequence = ctypes.string_at(x.sequence, x.sequence_len).decode("latin1")
-                    a.cigar = np.ctypeslib.as_array(x.cigar, shape=(x.num_cigar_ops,)).copy()
-                    ar.append(a)
-                out.append(ar)
-                if callback:
+            out = results_of_handle(self._L, res, seq_batch)
+            if callback:
+                for (header, _), ar in zip(seq_batch, out):
                     callback(header, ar)
             return out
         finally:

@@ -39,7 +39,8 @@ class mgb_config_t(ctypes.Structure):
         ("allow_left_trim", ctypes.c_uint8),
         ("no_backtrack", ctypes.c_uint8),
         ("seed_complexity_filter", ctypes.c_uint8),
-        ("reserved1", ctypes.c_uint8 * 7),
+        ("result_nodes", ctypes.c_uint8),
+        ("reserved1", ctypes.c_uint8 * 6),
         ("score_matrix", (ctypes.c_int8 * 128) * 128),
     ]
 
@@ -127,6 +128,8 @@ class DBGAlignerConfig:
     # sdust is not vendored in the reference tree: the filter is restated from the symmetric-DUST definition
     # (parity with the library unpinned, tests/test_sdust.py); parity / bench runs keep it off
     seed_complexity_filter: bool = False
+    # mgb_config_t::result_nodes: 0 = node paths come back with the alignments, 1 = they stay on the device
+    result_nodes: int = 0
     score_matrix: list = field(default_factory=lambda: dna_scoring_matrix(2, -1, -2))
 
     def to_c(self):

@@ -56,6 +56,7 @@ struct DevConfig {
     uint32_t sigma;
     uint32_t has_complement;           // DNA: reverse complement defined
     uint32_t canonical;                // graph in CANONICAL mode (holds both strands): dbg_aligner.cpp:224-226, 646-656
+    uint32_t result_nodes;             // mgb_config_t::result_nodes (MGB_NODES_*)
 };
 
 static constexpr int kMaxAlt = 4;            // supported num_alternative_paths

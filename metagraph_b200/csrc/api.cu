@@ -254,6 +254,11 @@ struct mgb_results {
     uint64_t n_alns = 0;
     HostBuf alns_buf;
     std::vector<HostBuf> heaps;              // host copies of the output heaps (recycled on free)
+    std::vector<uint64_t> heap_bytes;        // used bytes of each heap
+    // where the packed records of read r start: heap src_heap[r], byte src_off[r] (mgb_results_export)
+    std::vector<uint64_t> src_off;
+    std::vector<uint32_t> src_heap;
+    uint32_t result_nodes = 0;
     ~mgb_results() { for (HostBuf b : heaps) hostbuf_release(b); hostbuf_release(alns_buf); }
     mgb_stats_t stats;
 };
@@ -714,6 +719,8 @@ struct Piece {
     mgb_alignment_t *alns = nullptr;
     uint64_t n_alns = 0;
     std::vector<HostBuf> heaps;
+    std::vector<uint64_t> heap_bytes;
+    uint64_t *src_off = nullptr; uint32_t *src_heap = nullptr;   // views into the enclosing mgb_results
     mgb_stats_t stats;
     int rc = 0;
     std::string err;
@@ -944,6 +951,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             tick("pass: host buffer");
             if (!heap_host.p) { rc = fail(MGB_ERR_CUDA, "host buffer allocation failed"); break; }
             res->heaps.push_back(heap_host);
+            res->heap_bytes.push_back(used);
             if (used && (rc = d2h(heap_host.p, d_heap, used, st))) break;
             if ((rc = d2h(hdr_host, d_hdr, (size_t)n_reads * sizeof(ReadHdr), st))) break;
 #if !defined(MGB_HOST_EMU)
@@ -990,6 +998,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
     // materialise mgb_alignment_t records in read order
     {
         std::vector<uint64_t> byte_off(res->first, res->first + n_reads);
+        for (uint32_t r = 0; r < n_reads; ++r) { res->src_off[r] = byte_off[r]; res->src_heap[r] = read_heap[r]; }
         uint64_t pos = 0;
         for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
         res->n_alns = pos;
@@ -1004,7 +1013,8 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                 al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
                 al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
                 p += sizeof(OutAln);
-                al.nodes = (const uint64_t*)p; p += 8ull * o->n_nodes;
+                if (dcfg.result_nodes) al.nodes = nullptr;
+                else { al.nodes = (const uint64_t*)p; p += 8ull * o->n_nodes; }
                 al.cigar = (const uint32_t*)p; p += (4ull * o->n_cigar + 7) & ~7ull;
                 al.sequence = p; p += ((uint64_t)o->seq_len + 7) & ~7ull;
                 res->alns[res->first[r] + i] = al;
@@ -1057,6 +1067,9 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     res->n_reads = n_reads;
     res->first.assign(n_reads, 0);
     res->count.assign(n_reads, 0);
+    res->src_off.assign(n_reads, 0);
+    res->src_heap.assign(n_reads, 0);
+    res->result_nodes = dcfg.result_nodes;
     const uint64_t num_alt = dcfg.num_alternative_paths;
     res->alns_buf = hostbuf_acquire(((size_t)n_reads * num_alt + 1) * sizeof(mgb_alignment_t));
     if (!res->alns_buf.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
@@ -1068,6 +1081,8 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
         pieces[i].first = res->first.data() + piece_lo(i);
         pieces[i].count = res->count.data() + piece_lo(i);
         pieces[i].alns = res->alns + (uint64_t)piece_lo(i) * num_alt;
+        pieces[i].src_off = res->src_off.data() + piece_lo(i);
+        pieces[i].src_heap = res->src_heap.data() + piece_lo(i);
     }
     if (n_pieces == 1) {
         rc = align_range(index, dcfg, seqs, offsets, 0, n_reads, &pieces[0]);
@@ -1104,7 +1119,12 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
             for (int64_t r = 0; r < n; ++r) pc.first[r] += total;
         }
         total += pc.n_alns;
+        {   // heap ids of the piece become ids in the merged list
+            const uint32_t base = (uint32_t)res->heaps.size();
+            if (base) for (uint32_t r = 0; r < pc.n_reads; ++r) pc.src_heap[r] += base;
+        }
         for (HostBuf b : pc.heaps) res->heaps.push_back(b);
+        for (uint64_t b : pc.heap_bytes) res->heap_bytes.push_back(b);
         pc.heaps.clear();
         mgb_stats_t &t = res->stats; const mgb_stats_t &u = pc.stats;
         t.num_seeds += u.num_seeds; t.num_extensions += u.num_extensions;
@@ -1115,6 +1135,109 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
     }
     res->n_alns = total;
     if (dbg_time) std::fprintf(stderr, "[mgb] merged at %.2f ms\n", since());
+    *out = res.release();
+    return MGB_OK;
+}
+
+// Relocatable form of a result set (what a rank ships to rank 0): header, per-read record counts and
+// positions, then the packed records exactly as the kernel wrote them (OutAln | nodes | cigar | sequence).
+namespace {
+struct ExportHdr { uint64_t magic, n_reads, n_alns, n_heaps, result_nodes, total_bytes; };
+const uint64_t kExportMagic = 0x3142474d53455231ull;      // "1RESMGB1"
+}
+uint64_t mgb_results_export_bytes(const mgb_results_t *r) {
+    uint64_t b = sizeof(ExportHdr) + (uint64_t)r->n_reads * (8 + 4 + 4) + 8 * r->heap_bytes.size();
+    b = (b + 15) & ~15ull;
+    for (uint64_t h : r->heap_bytes) b += (h + 15) & ~15ull;
+    return b;
+}
+int mgb_results_export(const mgb_results_t *r, void *dst, uint64_t capacity) {
+    if (!r || !dst) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    const uint64_t total = mgb_results_export_bytes(r);
+    if (capacity < total) return fail(MGB_ERR_INVALID_ARGUMENT, "export buffer too small");
+    char *p = (char*)dst;
+    ExportHdr h { kExportMagic, r->n_reads, r->n_alns, r->heap_bytes.size(), r->result_nodes, total };
+    std::memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    std::memcpy(p, r->src_off.data(), 8ull * r->n_reads); p += 8ull * r->n_reads;
+    std::memcpy(p, r->count.data(), 4ull * r->n_reads); p += 4ull * r->n_reads;
+    std::memcpy(p, r->src_heap.data(), 4ull * r->n_reads); p += 4ull * r->n_reads;
+    std::memcpy(p, r->heap_bytes.data(), 8 * r->heap_bytes.size()); p += 8 * r->heap_bytes.size();
+    p = (char*)dst + (((uint64_t)(p - (char*)dst) + 15) & ~15ull);
+    for (size_t i = 0; i < r->heaps.size(); ++i) {
+        const uint64_t n = r->heap_bytes[i];
+        const int64_t chunks = (int64_t)((n + (1 << 22) - 1) >> 22);
+        #pragma omp parallel for schedule(static) if (chunks > 4)
+        for (int64_t c = 0; c < chunks; ++c) {
+            const uint64_t lo = (uint64_t)c << 22, len = std::min<uint64_t>(1ull << 22, n - lo);
+            std::memcpy(p + lo, r->heaps[i].p + lo, len);
+        }
+        p += (n + 15) & ~15ull;
+    }
+    return MGB_OK;
+}
+int mgb_results_import(const void *blob, uint64_t bytes, uint32_t read_index_base, mgb_results_t **out) {
+    if (!blob || !out || bytes < sizeof(ExportHdr)) return fail(MGB_ERR_INVALID_ARGUMENT, "bad export blob");
+    ExportHdr h; std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != kExportMagic || h.total_bytes > bytes || h.n_reads > 0xffffffffull)
+        return fail(MGB_ERR_INVALID_ARGUMENT, "bad export blob");
+    std::unique_ptr<mgb_results> res(new mgb_results());
+    std::memset(&res->stats, 0, sizeof(res->stats));
+    const uint32_t n = (uint32_t)h.n_reads;
+    res->n_reads = n; res->n_alns = h.n_alns; res->result_nodes = (uint32_t)h.result_nodes;
+    res->first.assign(n, 0); res->count.assign(n, 0); res->src_off.assign(n, 0); res->src_heap.assign(n, 0);
+    const char *p = (const char*)blob + sizeof(h);
+    std::memcpy(res->src_off.data(), p, 8ull * n); p += 8ull * n;
+    std::memcpy(res->count.data(), p, 4ull * n); p += 4ull * n;
+    std::memcpy(res->src_heap.data(), p, 4ull * n); p += 4ull * n;
+    res->heap_bytes.assign(h.n_heaps, 0);
+    std::memcpy(res->heap_bytes.data(), p, 8 * h.n_heaps); p += 8 * h.n_heaps;
+    p = (const char*)blob + (((uint64_t)(p - (const char*)blob) + 15) & ~15ull);
+    // the records are referenced in place: one host buffer takes over the heaps
+    uint64_t heaps_total = 0;
+    for (uint64_t b : res->heap_bytes) heaps_total += (b + 15) & ~15ull;
+    if ((uint64_t)(p - (const char*)blob) + heaps_total > bytes) return fail(MGB_ERR_INVALID_ARGUMENT, "truncated export blob");
+    HostBuf hb = hostbuf_acquire(heaps_total + 16);
+    if (!hb.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
+    res->heaps.push_back(hb);
+    std::vector<uint64_t> heap_base(h.n_heaps, 0);
+    {
+        uint64_t o = 0;
+        for (size_t i = 0; i < h.n_heaps; ++i) { heap_base[i] = o; o += (res->heap_bytes[i] + 15) & ~15ull; }
+        const int64_t chunks = (int64_t)((heaps_total + (1 << 22) - 1) >> 22);
+        #pragma omp parallel for schedule(static) if (chunks > 4)
+        for (int64_t c = 0; c < chunks; ++c) {
+            const uint64_t lo = (uint64_t)c << 22, len = std::min<uint64_t>(1ull << 22, heaps_total - lo);
+            std::memcpy(hb.p + lo, p + lo, len);
+        }
+    }
+    res->alns_buf = hostbuf_acquire((h.n_alns + 1) * sizeof(mgb_alignment_t));
+    if (!res->alns_buf.p) return fail(MGB_ERR_CUDA, "host buffer allocation failed");
+    res->alns = (mgb_alignment_t*)res->alns_buf.p;
+    uint64_t pos = 0;
+    for (uint32_t r = 0; r < n; ++r) { res->first[r] = pos; pos += res->count[r]; }
+    if (pos != h.n_alns) return fail(MGB_ERR_INVALID_ARGUMENT, "inconsistent export blob");
+    const bool no_nodes = res->result_nodes != 0;
+    #pragma omp parallel for schedule(static) if (n > 20000)
+    for (int64_t r = 0; r < (int64_t)n; ++r) {
+        if (!res->count[r]) continue;
+        const char *q = hb.p + heap_base[res->src_heap[r]] + res->src_off[r];
+        for (uint32_t i = 0; i < res->count[r]; ++i) {
+            const OutAln *o = (const OutAln*)q;
+            mgb_alignment_t al;
+            std::memset(&al, 0, sizeof(al));
+            al.read_index = read_index_base + (uint32_t)r; al.orientation = (uint8_t)o->orientation; al.score = o->score;
+            al.offset = o->offset; al.query_begin = o->query_begin; al.query_len = o->query_len;
+            al.num_nodes = o->n_nodes; al.sequence_len = o->seq_len; al.num_cigar_ops = o->n_cigar;
+            q += sizeof(OutAln);
+            if (no_nodes) al.nodes = nullptr; else { al.nodes = (const uint64_t*)q; q += 8ull * o->n_nodes; }
+            al.cigar = (const uint32_t*)q; q += (4ull * o->n_cigar + 7) & ~7ull;
+            al.sequence = q; q += ((uint64_t)o->seq_len + 7) & ~7ull;
+            res->alns[res->first[r] + i] = al;
+        }
+    }
+    // after the import the records live in heap 0 at the rebased offsets
+    for (uint32_t r = 0; r < n; ++r) { res->src_off[r] += heap_base[res->src_heap[r]]; res->src_heap[r] = 0; }
+    res->heap_bytes.assign(1, heaps_total);
     *out = res.release();
     return MGB_OK;
 }

@@ -123,6 +123,8 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConf
     d->allow_left_trim = c.allow_left_trim; d->no_backtrack = c.no_backtrack;
     // is_low_complexity() is compiled to `false` in protein builds (aligner_seeder_methods.cpp:30-34)
     d->seed_complexity_filter = c.seed_complexity_filter && at.has_complement;
+    if (c.result_nodes > 1) { *err = "result_nodes must be MGB_NODES_U64 or MGB_NODES_NONE"; return MGB_ERR_INVALID_ARGUMENT; }
+    d->result_nodes = c.result_nodes;
     d->sigma = at.sigma; d->has_complement = at.has_complement ? 1 : 0;
     std::memcpy(d->letters, at.letters, sizeof(d->letters));
     std::memcpy(d->code_of, at.code_of, sizeof(d->code_of));

@@ -168,7 +168,7 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, const WarpMem &mem, const
         uint64_t bytes = 0;
         for (int i = 0; i < n; ++i) {
             const AlnHdr ah = *mem.slot(SLOT_AGG + order[i]).h;
-            bytes += sizeof(OutAln) + 8ull * ah.n_nodes + ((4ull * ah.n_cigar + 7) & ~7ull)
+            bytes += sizeof(OutAln) + (a.cfg.result_nodes ? 0ull : 8ull * ah.n_nodes) + ((4ull * ah.n_cigar + 7) & ~7ull)
                    + (((uint64_t)ah.seq_len + 7) & ~7ull);
         }
         unsigned long long off = 0;
@@ -192,9 +192,11 @@ MGB_HD void align_read(const AlignArgs &a, uint32_t r, const WarpMem &mem, const
                 o.n_nodes = ah.n_nodes; o.seq_len = ah.seq_len; o.n_cigar = ah.n_cigar;
                 if (wlane() == 0) *(OutAln*)p = o;
                 p += sizeof(OutAln);
-                uint64_t *pn = (uint64_t*)p;
-                for (int t = wlane(); t < ah.n_nodes; t += kWarp) pn[t] = sl.nodes[t];
-                p += 8ull * ah.n_nodes;
+                if (!a.cfg.result_nodes) {
+                    uint64_t *pn = (uint64_t*)p;
+                    for (int t = wlane(); t < ah.n_nodes; t += kWarp) pn[t] = sl.nodes[t];
+                    p += 8ull * ah.n_nodes;
+                }
                 uint32_t *pc = (uint32_t*)p;
                 for (int t = wlane(); t < ah.n_cigar; t += kWarp) pc[t] = sl.cigar[t];
                 p += (4ull * ah.n_cigar + 7) & ~7ull;

@@ -101,6 +101,34 @@ def random_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=1):
     return stats
 
 
+def nodeless_case(lib, seed=5, k=15, G=4000, nreads=60, L=80):
+    """mgb_config_t::result_nodes = MGB_NODES_NONE: the same alignments (TSV fields identical to the oracle's),
+    node arrays left on the device (nodes == NULL, num_nodes kept)."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    seqs = ["".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])]
+    g = O.OracleGraph(k, seqs)
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(k, seqs, lib=lib), lib=lib)
+    reads = []
+    for i in range(nreads):
+        p = int(rng.integers(0, G - L))
+        r = mutate(rng, seqs[0][p:p + L], 0.04)
+        reads.append(r.translate(COMP)[::-1] if i % 2 else r)
+    cfg = cli_defaults(k, min_exact_match=0.0)
+    exp = g.align_tsv(cfg, reads)
+    full = B200Aligner(idx, cfg).align_batch([("", r) for r in reads])
+    slim = B200Aligner(idx, dataclasses.replace(cfg, result_nodes=1)).align_batch([("", r) for r in reads])
+    n_aln = 0
+    for r, e, a, b in zip(reads, exp, full, slim):
+        assert format_alignment("", b, cfg.min_path_score) == e
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert len(y.nodes) == 0 and len(x.nodes) > 0
+            n_aln += 1
+    assert n_aln > nreads // 2
+    idx.close()
+
+
 def c1_case(lib, n_transcripts, max_len, seed=7, k=12):
     """BASELINE configs[0] shape (k=12 graph of transcripts, the transcripts themselves as reads, CLI
     defaults, ragged lengths from 59 bp up to max_len) on synthetic transcripts: related sequences

@@ -96,6 +96,10 @@ def test_general_path_emu(monkeypatch):
         P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+def test_nodeless_results_emu():
+    P.nodeless_case(EMU)
+
+
 def test_seed_complexity_filter_emu():
     """CLI default `seed_complexity_filter` (sdust restated from its definition, parity with the library
     unpinned): kernels vs oracle on reads and graphs full of homopolymers / short tandem repeats."""

@@ -58,6 +58,11 @@ def test_seed_complexity_filter_gpu():
         P.lowcx_case(LIB, seed, k, exact)
 
 
+def test_nodeless_results_gpu():
+    """MGB_NODES_NONE: identical alignments, node arrays stay on the device"""
+    P.nodeless_case(LIB)
+
+
 def test_concurrent_callers_gpu():
     """several host threads call mgb_align_batch on one index at the same time (cli/align.cpp:440-475)"""
     P.concurrent_case(LIB)

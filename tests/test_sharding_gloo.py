@@ -30,11 +30,14 @@ boss = BOSSTable.from_sequences(k, [genome], lib=EMU)
 idx = DBGSuccinctIndex(boss, lib=EMU)
 cfg = cli_defaults(k)
 lines = align_sharded(B200Aligner(idx, cfg), reads, lambda h, r: format_alignment(h, r, 0, with_nodes=True))
+# entries need not be single lines (ADVICE r1: JSON output has one line per alternative alignment)
+multi = align_sharded(B200Aligner(idx, cfg), reads, lambda h, r: h + "\n" + format_alignment(h, r, 0))
 assert shard_range(37, 0, 2) == (0, 18) and shard_range(37, 1, 2) == (18, 37)
 if rank == 0:
     g = O.OracleGraph(k, [genome])
     exp = g.align_tsv(cfg, [s for _, s in reads], headers=[h for h, _ in reads], with_nodes=True)
     assert lines == exp, (len(lines), len(exp))
+    assert len(multi) == len(reads) and all(m.split("\n")[0] == h for m, (h, _) in zip(multi, reads))
     print("SHARDING_OK", len(lines))
 else:
     assert lines is None
