@@ -54,17 +54,19 @@ class ResultGather:
         metas = [[int(x) for x in m.tolist()] for m in metas]
         if rank != self.dst:
             blk = self._send[:nbytes]
-            dist.send(blk.to(self.device, non_blocking=True) if self.on_gpu else blk, self.dst)
+            blk = blk.to(self.device, non_blocking=True) if self.on_gpu else blk
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, blk, self.dst)]):
+                q.wait()
             return None
         out = []
         bufs = {}
-        reqs = []
+        ops = []
         for r in range(world):
             if r == rank:
                 continue
             bufs[r] = torch.empty(metas[r][0], dtype=torch.uint8, device=self.device)
-            reqs.append(dist.irecv(bufs[r], r))
-        for q in reqs:
+            ops.append(dist.P2POp(dist.irecv, bufs[r], r))
+        for q in (dist.batch_isend_irecv(ops) if ops else []):
             q.wait()
         for r in range(world):
             if r == rank:
