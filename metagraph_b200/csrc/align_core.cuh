@@ -167,6 +167,32 @@ enum { SLOT_SEED = 0, SLOT_TMP = 1, SLOT_EXT = 2, SLOT_BWD = 2 + kMaxAlt, SLOT_A
 // ------------------------------------------------------------------------------------
 MGB_HOSTDEV size_t align_up(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// State handed to / taken back from the extender's chain loop (ReadAligner::chain_loop, run out of line by
+// chain_entry): the extension's constants, the column that is the sole candidate, and the running values.
+struct ChainIO {
+    bool active;                 // this lane group takes part (the groups of a warp call together)
+    int e, rc, start, wlen, seed_off_m1, sh_offset, seed_seq_len, force_fixed, seed_is_query;
+    score_t partial_sum_offset;
+    const char *seed_seq; const uint64_t *seed_nodes; uint64_t seed_node0;
+    uint32_t cells_limit;
+    uint32_t ci; uint64_t c_node; int c_offset, c_trim; uint32_t c_bm; int c_pb;
+    HeapItem cur_it;
+    score_t cutoff, best_score, min_cell_score;
+    uint64_t table_size_bytes; uint32_t n_cols, cells_used;
+    uint64_t pf_node; uint2 pf_adj;
+    int stop;                    // 1: the extension is over (queue empty), 2: column ci is left to the general code
+    bool overflow;
+    uint64_t dp_cells; uint32_t dp_columns;
+};
+struct WarpMem; struct WarpSmem;
+#if MGB_DEVICE_CODE
+static __device__ __noinline__
+#else
+static inline
+#endif
+void chain_entry(const IndexView &ix, const DevConfig &cfg, const Caps &caps, const WarpMem &m, const WarpSmem &sm, int L,
+                 ChainIO *io);
+
 // Regions of a lane group's arena as BYTE OFFSETS from its base. The layout is the same for every group, so it is
 // computed once on the host and travels in the kernel parameters (constant bank): a region's address is
 // base + constant, no pointer table has to live in registers or on the stack.
@@ -253,7 +279,9 @@ struct WarpMem {
 struct SmemLayout {
     int bmax, lq, hcap;       // column buffer cells; staged query capacity in characters (0: not staged); queue entries
     uint32_t buf0, psum0, psum1, q0, q1, ctx, mask0, mask1, heap, nn, out_nodes, out_scores, out_chars, total;
-    MGB_HOSTDEV size_t carve(int bmax_, int lq_, int hcap_) {
+    uint32_t prof0, prof1;    // DNA block layout only: per query position the scores against A, C, G, T, one byte each
+    uint32_t has_prof;
+    MGB_HOSTDEV size_t carve(int bmax_, int lq_, int hcap_, bool with_prof = false) {
         size_t o = 0;
         auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes); return (uint32_t)r; };
         bmax = bmax_; lq = lq_; hcap = hcap_;
@@ -266,6 +294,9 @@ struct SmemLayout {
         nn = take(sizeof(HeapItem) * hcap);
         out_nodes = take(8 * kMaxOut);
         out_scores = take(4 * kMaxOut); out_chars = take(kMaxOut);
+        has_prof = with_prof && lq > 0 ? 1u : 0u;
+        prof0 = prof1 = 0;
+        if (has_prof) { prof0 = take(4 * ((size_t)lq + 8)); prof1 = take(4 * ((size_t)lq + 8)); }
         total = (uint32_t)o;
         return o;
     }
@@ -288,6 +319,7 @@ struct WarpSmem {
     MGB_HD uint64_t* out_nodes() const { return (uint64_t*)(base + lay->out_nodes); }
     MGB_HD int32_t* out_scores() const { return (int32_t*)(base + lay->out_scores); }
     MGB_HD uint8_t* out_chars() const { return (uint8_t*)(base + lay->out_chars); }
+    MGB_HD uint32_t* prof4(int s) const { return (uint32_t*)(base + (s ? lay->prof1 : lay->prof0)); }
 };
 
 MGB_HOSTDEV uint32_t cig_pack(uint32_t op, uint32_t len) { return (len << 3) | op; }
@@ -1884,11 +1916,11 @@ struct ReadAligner {
     // update_column (extender.cpp:209-290, max-plus scan form) + extend_ins_end (:293-328) for a child column
     // whose n4 <= 28 and size0 <= 27. pS / pF: the parent's S / F shifted to the child's rows. Returns the final
     // size, or -1 when the column outgrows the register path (nothing has been stored then).
-    MGB_HD int reg_column(int s, const score_t *pS, const score_t *pF, int n, int size0, int prof_base, int max_size,
-                          int code, score_t add, bool use_del, score_t cutoff, RegCol &r) {
+    template <class ProfFn>
+    MGB_HD static int reg_column(ProfFn prof, const score_t *pS, const score_t *pF, int n, int size0, int max_size,
+                                 score_t add, bool use_del, score_t cutoff, score_t go, score_t ge, int ge_shift, RegCol &r) {
         const int j0 = wlane() * kCPL;
         const int n4 = (n + 3) & ~3;
-        const score_t go = cfg.gap_open, ge = cfg.gap_ext;
         score_t mval[kCPL], pr[kCPL], psm1[kCPL], pfv[kCPL];
         int aloc[kCPL];
         score_t prev = (j0 >= 1 && j0 <= n4) ? pS[j0 - 1] : kNinf;
@@ -1901,7 +1933,7 @@ struct ReadAligner {
             const bool act = j < n4;
             const score_t ps_j = act ? pS[j] : kNinf;
             const score_t pf_j = act ? pF[j] : kNinf;
-            pr[c] = prof_score(s, prof_base + j, code);
+            pr[c] = prof(j);
             psm1[c] = prev; pfv[c] = pf_j;
             const score_t match = (act && j) ? prev + pr[c] + add : kNinf;
             const score_t del = (act && use_del) ? imax(ps_j + go, pf_j + ge) + add : kNinf;
@@ -1938,7 +1970,7 @@ struct ReadAligner {
             const score_t ins = imax(s_last + go, e_last + ge);
             if (ins >= cutoff) {
                 const uint32_t diff = (uint32_t)ins - (uint32_t)cutoff;                  // ins >= cutoff
-                const uint32_t extra = cfg.ge_shift >= 0 ? diff >> cfg.ge_shift
+                const uint32_t extra = ge_shift >= 0 ? diff >> ge_shift
                                      : (ge < 0 ? diff / (uint32_t)(-ge) : 0x7fffffffu);
                 const uint32_t room = (uint32_t)(max_size - size0 - 1);
                 const int cnt = 1 + (int)(extra < room ? extra : room);
@@ -1996,6 +2028,7 @@ struct ReadAligner {
         ColMeta last_col = ColMeta(); uint32_t last_idx = 0xffffffffu;  // newest committed column (register copy)
         bool last_band_valid = false; uint32_t last_band_mask = 0; score_t last_band_cutoff = 0;
         const bool reg_path = use_fast && sm.bmax() >= 40 && (sm.bmax() & 3) == 0;
+        const bool chain_ok = !MGB_WIDE(ix) && !MGB_PRIMARY(ix) && sm.lay->has_prof && L + 1 <= sm.lq() && L < (1 << 25);
         uint32_t cells_limit = 0;
         score_t min_cell_score = 0, best_score = 0;
         int heap_n = 0, nn_n = 0;
@@ -2070,167 +2103,39 @@ struct ReadAligner {
             if (!wany_full(mine)) break;
             // ---------------- chain: the column just committed is the only candidate (:477-504 would push it and
             // pop it again), sits in an on-chip buffer and its band under the current cutoff is known. In a
-            // linear stretch of the graph every column is like that, so this inner loop -- one child column per
-            // iteration, everything in registers, no queue traffic -- is where an extension spends its time.
-            // Anything unusual (several children, a column too wide for the register path, a seed node that is
-            // not in the graph, PRIMARY graphs) leaves the column to the general code below.
+            // linear stretch of the graph every column is like that: chain_loop() (out of line, so that its
+            // code is compact and its registers its own) creates such columns one after the other until
+            // something unusual turns up, which it leaves to the general code below.
             {
-                bool chain = mine && reg_path && L < (1 << 25) && !MGB_PRIMARY(ix) && t >= n_out && heap_n == 0 && nn_n == 1
-                             && np[0].idx == last_idx && last_band_valid && last_band_cutoff == cutoff
-                             && (res0 == (int)last_idx || res1 == (int)last_idx);
-                uint32_t ci = last_idx; uint64_t c_node = last_col.node;
-                int c_offset = last_col.offset, c_trim = last_col.trim;
-                uint32_t c_bm = last_band_mask;
-                int c_pb = res1 == (int)last_idx ? 1 : 0;
-                score_t c_maxval = 0;
-                HeapItem cur_it = HeapItem();
-                if (chain) { cur_it = np[0]; c_maxval = cur_it.max_score; }
-                uint32_t t_cap = 0, c_cols = 0; uint64_t c_cells = 0;      // table_cap / stats, written back at the end
-                if (chain) t_cap = cx[e].table_cap;
-                while (wany_full(chain)) {
-                    if (!chain) continue;
-                    // how the chain ends: END = the extension is over (nothing left in the queue), SLOW = column ci
-                    // stays the sole candidate and the general code expands it
-                    enum { GO_ON = 0, END = 1, SLOW = 2 };
-                    int stop = GO_ON;
-                    do {
-                        if (c_maxval < best_score) {
-                            if ((double)n_cols / wlen >= cfg.max_nodes_per_seq_char) { stop = END; break; }   // global_xdrop
-                            if ((double)table_size_bytes / 1000000 > cfg.max_ram_per_alignment) { stop = END; break; }
-                        }
-                        if (!c_bm) { stop = END; break; }                   // no band: no children
-                        const int begin_c = ffs32(c_bm) - 1 + c_trim;
-                        const int prev_end = 32 - clz32(c_bm) + c_trim;
-                        const int noff = c_offset + 1;
-                        const uint32_t seed_pos = (uint32_t)(noff - (int)sh.offset);
-                        const bool in_seed_c = seed_pos < (uint32_t)seed_seq_len;
-                        uint64_t cnode; uint8_t ch;
-                        // call_outgoing (:330-387), single plain child only
-                        if (in_seed_c && noff < K) {
-                            cnode = seed_node0; ch = (uint8_t)seed_seq[seed_pos];
-                        } else if (in_seed_c && force_fixed_seed) {
-                            cnode = seed.nodes[noff - K + 1]; ch = (uint8_t)seed_seq[seed_pos];
-                            if (!cnode) { stop = SLOW; break; }
-                        } else if (!rc) {
-                            const Adj a = (!MGB_WIDE(ix) && c_node == pf_node) ? adj_decode(pf_adj) : load_adj_any(ix, c_node);
-                            const uint32_t ok = a.last ? (a.ok & ~1u) : 0u;
-                            if (!ok) { m.cols()[ci].is_tip = 1; stop = END; break; }
-                            if (ok & (ok - 1u)) { stop = SLOW; break; }
-                            const uint32_t c = (uint32_t)ffs32(ok) - 1;
-                            cnode = (uint64_t)a.last - popc32(a.all) + 1 + popc32(a.all & ((1u << c) - 1u));
-                            ch = (uint8_t)cfg.letters[c];
-                        } else {
-                            // RCDBG::call_outgoing_kmers through the reverse adjacency records, single incoming edge
-                            const uint2 rr = load_radj(ix, c_node);
-                            if (radj_multi(ix, rr.y)) { stop = SLOW; break; }
-                            const uint64_t edge = rr.x;
-                            ch = '$';
-                            if (in_graph(ix, edge))
-                                ch = complement_char((uint8_t)cfg.letters[radj_char(ix, load_radj(ix, edge).y)]);
-                            if (ch == '$') { m.cols()[ci].is_tip = 1; stop = END; break; }
-                            cnode = edge;
-                        }
-                        if (ch >= 'a' && ch <= 'z') ch -= 32;              // toupper (:564)
-                        if (n_cols >= caps.max_cols) { overflow = true; stop = END; break; }
-                        const int size0_c = imin(prev_end, wlen) + 1 - begin_c;
-                        const int n_c = prev_end - begin_c;
-                        if (n_c > 28 || size0_c > 27) { stop = SLOW; break; }
-                        {   // requests whose latency overlaps the DP below
-                            if (!rc && !MGB_WIDE(ix)) { pf_node = cnode; pf_adj = load_adj(ix, cnode); }
-                            pf_key = cnode + (rc ? ix.n : 0);
-                            pf_slot_idx = hash_node(pf_key);
-                            pf_slot = cx[e].conv_slots[pf_slot_idx];
-                        }
-                        const int code = encode_char(ch);
-                        const score_t *pS = sm.buf(c_pb) + (begin_c - c_trim);
-                        RegCol r;
-                        const int size = reg_column(s, pS, pS + 2 * sm.bmax(), n_c, size0_c, start + begin_c,
-                                                    wlen + 1 - begin_c, code, 0, noff > 1, cutoff, r);
-                        if (size < 0) { stop = SLOW; break; }
-                        MGB_COUNT(5);
-                        const int j0 = wlane() * kCPL;
-                        const uint32_t cap_before = t_cap;
-                        if (n_cols + 1 > t_cap) t_cap = t_cap ? 2 * t_cap : 1;
-                        c_cells += size; ++c_cols;
-                        // per-column scan (:643-669)
-                        const int diag_i = noff - seed_off_m1;
-                        score_t mn = 0x7fffffff, bs = INT32_MIN;
-#if MGB_DEVICE_CODE
-#pragma unroll
-#endif
-                        for (int c = 0; c < kCPL; ++c) {
-                            const bool cell = j0 + c < size;
-                            const score_t v = r.S[c];
-                            if (cell && v != kNinf) mn = imin(mn, v);
-                            if (cell) bs = imax(bs, v);
-                        }
-                        min_cell_score = imin(min_cell_score, wreduce_min(mn));
-                        const score_t max_val = wreduce_max(bs);
-                        int key = 0x7fffffff; bool he = false;              // (distance to the diagonal, row) of the best cell
-                        score_t ext_cut = 0;
-                        if (!in_seed_c)
-                            ext_cut = (score_t)((double)best_score * cfg.rel_score_cutoff + (double)partial_sum_offset);
-#if MGB_DEVICE_CODE
-#pragma unroll
-#endif
-                        for (int c = 0; c < kCPL; ++c) {
-                            const int j = j0 + c;
-                            const bool cell = j < size;
-                            if (cell && r.S[c] == max_val) key = imin(key, (iabs(j + begin_c - diag_i) << 5) | j);
-                            if (!in_seed_c && cell && r.S[c] + cx[s].ps[start + begin_c + j] >= ext_cut) he = true;
-                        }
-                        const int max_pos = (wreduce_min(key) & 31) + begin_c;
-                        if (!in_seed_c && (max_val < cutoff || !wballot(he))) {
-                            cx[e].table_cap = t_cap;                        // (the reference grew the table, then popped)
-                            stop = END; break;                              // pop(table.size() - 1): nothing left
-                        }
-                        table_size_bytes += 136ull * (t_cap - cap_before) + 3ull * vec_capacity(size0_c, size) * 4;
-                        if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
-                        best_score = imax(best_score, max_val);
-                        if (cells_used > cells_limit) { overflow = true; stop = END; break; }
-                        // commit: DP table (compact format, whole 32-byte sectors) and the on-chip child buffer
-                        const int capr = capr_of(size);
-                        const uint32_t off = (cells_used + 7u) & ~7u;
-                        cells_used = off + 2 * capr + 8;
-                        score_t *dst = m.cells() + off;
-                        score_t *cb_S = sm.buf(1 - c_pb);
-                        store_cells(dst, j0, r.S, capr);
-                        store_flags(reinterpret_cast<uint8_t*>(dst + capr), j0, r.fl);
-                        store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * sm.bmax(), j0, r.F, 32);
-                        ColMeta col;
-                        col.node = cnode; col.parent = ci; col.c = ch;
-                        col.offset = noff; col.max_pos = max_pos; col.trim = begin_c; col.score = 0;
-                        col.is_tip = 0; col.started = 0; col.fmt = FMT_COMPACT; col.pad0 = col.pad1 = 0;
-                        col.size = size; col.cells_off = off;
-                        const uint32_t idx = n_cols;
-                        m.cols()[n_cols++] = col;
-                        uint32_t bits = 0;
-#if MGB_DEVICE_CODE
-#pragma unroll
-#endif
-                        for (int c = 0; c < kCPL; ++c) if (j0 + c < size && r.S[c] >= cutoff) bits |= 1u << c;
-                        const uint32_t bm_new = kCPL == 32 ? bits : wreduce_or(bits << (j0 & 31));
-                        wsync();
-                        // convergence filter from registers (update_seed_filter)
-                        const int s_first = begin_c ? 0 : 1;
-                        const score_t converged = update_seed_filter_regs(e, cnode, start + begin_c - (begin_c ? 1 : 0), r.S,
-                                                                          s_first, size);
-                        // the new column becomes the parent
-                        ci = idx; c_node = cnode; c_offset = noff; c_trim = begin_c; c_bm = bm_new; c_pb = 1 - c_pb;
-                        c_maxval = max_val;
-                        cur_it.score = converged; cur_it.neg_off_diag = -iabs(max_pos - diag_i); cur_it.idx = idx;
-                        cur_it.max_score = max_val;
-                        if (overflow || converged == kNinf) { stop = END; break; }
-                    } while (false);
-                    if (stop != GO_ON) {
-                        chain = false;
-                        cx[e].table_cap = t_cap;
-                        stats.dp_cells += c_cells; stats.dp_columns += c_cols;
-                        // the general code finds: an empty queue (END), or column ci as the one entry of next_nodes
-                        // (SLOW); its register copy is re-read from the table, its band re-computed
-                        if (stop == END) nn_n = 0; else { np[0] = cur_it; nn_n = 1; }
+                const bool chain = mine && reg_path && chain_ok && t >= n_out && heap_n == 0 && nn_n == 1
+                                   && np[0].idx == last_idx && last_band_valid && last_band_cutoff == cutoff
+                                   && (res0 == (int)last_idx || res1 == (int)last_idx);
+                if (wany_full(chain)) {
+                    ChainIO io;
+                    io.active = chain;
+                    io.e = e; io.rc = rc; io.start = start; io.wlen = wlen; io.seed_off_m1 = seed_off_m1;
+                    io.sh_offset = (int)sh.offset; io.seed_seq_len = seed_seq_len; io.force_fixed = force_fixed_seed;
+                    io.seed_is_query = seed_is_query; io.partial_sum_offset = partial_sum_offset;
+                    io.seed_seq = seed_seq; io.seed_nodes = seed.nodes; io.seed_node0 = seed_node0; io.cells_limit = cells_limit;
+                    io.ci = last_idx; io.c_node = last_col.node; io.c_offset = last_col.offset; io.c_trim = last_col.trim;
+                    io.c_bm = last_band_mask; io.c_pb = res1 == (int)last_idx ? 1 : 0;
+                    io.cur_it = chain ? np[0] : HeapItem();
+                    io.cutoff = cutoff; io.best_score = best_score; io.min_cell_score = min_cell_score;
+                    io.table_size_bytes = table_size_bytes; io.n_cols = n_cols; io.cells_used = cells_used;
+                    io.pf_node = pf_node; io.pf_adj = pf_adj;
+                    io.stop = 0; io.overflow = false; io.dp_cells = 0; io.dp_columns = 0;
+                    chain_entry(ix, cfg, caps, m, sm, L, &io);
+                    if (chain) {
+                        cutoff = io.cutoff; best_score = io.best_score; min_cell_score = io.min_cell_score;
+                        table_size_bytes = io.table_size_bytes; n_cols = io.n_cols; cells_used = io.cells_used;
+                        pf_node = io.pf_node; pf_adj = io.pf_adj;
+                        stats.dp_cells += io.dp_cells; stats.dp_columns += io.dp_columns;
+                        if (io.overflow) overflow = true;
+                        // the general code finds: an empty queue (stop 1), or column ci as the one entry of
+                        // next_nodes (stop 2); its register copy is re-read from the table, its band re-computed
+                        if (io.stop == 1) nn_n = 0; else { np[0] = io.cur_it; nn_n = 1; }
                         last_idx = 0xffffffffu; last_band_valid = false;
-                        res0 = c_pb == 0 ? (int)ci : -1; res1 = c_pb == 1 ? (int)ci : -1;
+                        res0 = io.c_pb == 0 ? (int)io.ci : -1; res1 = io.c_pb == 1 ? (int)io.ci : -1;
                     }
                 }
             }
@@ -2369,8 +2274,10 @@ struct ReadAligner {
                     pf_slot = cx[e].conv_slots[pf_slot_idx];
                 }
                 RegCol r;
-                const int size = reg_column(s, parS + shift, parF + shift, n, size0, start + begin, wlen + 1 - begin,
-                                            code, add, next_offset > 1, cutoff, r);
+                const int prof_base = start + begin;
+                const int size = reg_column([&](int j) { return prof_score(s, prof_base + j, code); }, parS + shift, parF + shift,
+                                            n, size0, wlen + 1 - begin, add, next_offset > 1, cutoff, cfg.gap_open, cfg.gap_ext,
+                                            cfg.ge_shift, r);
                 if (size >= 0) {
                     MGB_COUNT(5);
                     const int j0 = wlane() * kCPL;
@@ -2568,6 +2475,273 @@ struct ReadAligner {
         for (int r = 0; r < n_res; ++r) trim_offset(out_base + r);
         MGB_TOC(t_bt, 3);
         return n_res;
+    }
+
+    // The extender's chain loop (see extend()): one child column per iteration of the column that is the sole
+    // candidate, registers only, no queue traffic. It runs out of line (chain_entry), where the kernel parameters
+    // are reached through generic pointers, so everything it reads more than once is copied into locals first.
+    // Leaves with io.stop = 1 (the extension is over: nothing is left in the queue) or 2 (column io.ci stays the
+    // sole candidate and the general code expands it: several children, a column too wide for the register path,
+    // a seed node missing from the graph, a convergence-table entry that has to move, ...).
+    MGB_HD void chain_loop(ChainIO &io) {
+        const int e = io.e, s = io.e;
+        const bool rc = io.rc != 0;
+        const int start = io.start, wlen = io.wlen, seed_off_m1 = io.seed_off_m1, sh_offset = io.sh_offset;
+        const int seed_seq_len = io.seed_seq_len, K = (int)ix.k;
+        const bool force_fixed = io.force_fixed != 0, seed_is_q = io.seed_is_query != 0;
+        const char *seed_seq = io.seed_seq; const uint64_t *seed_nodes = io.seed_nodes;
+        const uint64_t seed_node0 = io.seed_node0;
+        const score_t go = cfg.gap_open, ge = cfg.gap_ext, xdrop = cfg.xdrop;
+        const int ge_shift = cfg.ge_shift;
+        const double rsc = cfg.rel_score_cutoff, pso = (double)io.partial_sum_offset;
+        const uint32_t max_cols = caps.max_cols, hash_mask = caps.hash_size - 1;
+        const uint32_t max_conv_entries = caps.max_conv_entries, max_conv_cells = caps.max_conv_cells, hash_size = caps.hash_size;
+        const uint64_t n_edges = ix.n;
+        const uint32_t sigma = ix.sigma;
+        const uint2 *adj = ix.adj, *radj = ix.radj;
+        const uint32_t *valid = ix.valid;
+        uint32_t letters = 0;                              // '$ACGT': letters of symbols 1..4, one byte each
+        for (int c = 1; c <= 4; ++c) letters |= (uint32_t)(uint8_t)cfg.letters[c] << (8 * (c - 1));
+        ColMeta *cols = m.cols();
+        score_t *cells = m.cells();
+        StrandCtx &tc = cx[e];
+        ConvSlot *cslots = tc.conv_slots; score_t *ccells = tc.conv_cells;
+        const uint32_t epoch = tc.conv_epoch;
+        uint32_t conv_n = tc.conv_n, conv_used = tc.conv_cells_used, t_cap = tc.table_cap;
+        const int32_t *ps = cx[s].ps;
+        const uint32_t *p4 = sm.prof4(s);
+        const uint8_t *qcodes = cx[s].codes;
+        score_t *buf0 = sm.buf(0);
+        const int bmax = sm.bmax();
+        const int Lq = L;
+        const int j0 = wlane() * kCPL;
+
+        bool chain = io.active;
+        uint32_t ci = io.ci; uint64_t c_node = io.c_node;
+        int c_offset = io.c_offset, c_trim = io.c_trim, c_pb = io.c_pb;
+        uint32_t c_bm = io.c_bm;
+        HeapItem cur_it = io.cur_it;
+        score_t c_maxval = cur_it.max_score;
+        score_t cutoff = io.cutoff, best_score = io.best_score, min_cell_score = io.min_cell_score;
+        uint64_t table_bytes = io.table_size_bytes;
+        uint32_t ncols = io.n_cols, cused = io.cells_used;
+        const uint32_t cells_limit = io.cells_limit;
+        uint64_t pfn = io.pf_node; uint2 pfa = io.pf_adj;
+        uint32_t made = 0; uint64_t made_cells = 0;
+        int stop = 0;
+        bool ovf = false;
+
+        while (wany_full(chain)) {
+            if (!chain) continue;
+            do {
+                if (c_maxval < best_score) {
+                    if ((double)ncols / wlen >= cfg.max_nodes_per_seq_char) { stop = 1; break; }      // global_xdrop
+                    if ((double)table_bytes / 1000000 > cfg.max_ram_per_alignment) { stop = 1; break; }
+                }
+                if (!c_bm) { stop = 1; break; }                    // no band: no children
+                const int begin = ffs32(c_bm) - 1 + c_trim;
+                const int prev_end = 32 - clz32(c_bm) + c_trim;
+                const int noff = c_offset + 1;
+                const uint32_t seed_pos = (uint32_t)(noff - sh_offset);
+                const bool in_seed = seed_pos < (uint32_t)seed_seq_len;
+                uint64_t cnode; uint32_t code; uint8_t ch;
+                // call_outgoing (:330-387), a single plain child
+                if (in_seed && (noff < K || force_fixed)) {
+                    cnode = noff < K ? seed_node0 : seed_nodes[noff - K + 1];
+                    if (!cnode) { stop = 2; break; }               // (fixed seed: a node the graph does not have)
+                    ch = (uint8_t)seed_seq[seed_pos];
+                    code = seed_is_q ? qcodes[start + seed_pos] : cfg.code_of[ch];
+                } else if (!rc) {
+                    const uint2 a = c_node == pfn ? pfa : adj[c_node];
+                    const uint32_t all = a.y & 31u, ok = a.x ? ((a.y >> 8) & 30u) : 0u;
+                    if (!ok) { cols[ci].is_tip = 1; stop = 1; break; }
+                    if (ok & (ok - 1u)) { stop = 2; break; }
+                    code = (uint32_t)ffs32(ok) - 1;
+                    cnode = (uint64_t)a.x - popc32(all) + 1 + popc32(all & ((1u << code) - 1u));
+                    ch = (uint8_t)(letters >> (8 * (code - 1)));
+                } else {
+                    // RCDBG::call_outgoing_kmers through the reverse adjacency records, single incoming edge
+                    const uint2 rr = radj[c_node];
+                    if ((rr.y >> 3) & 1u) { stop = 2; break; }     // several incoming edges
+                    const uint64_t edge = rr.x;
+                    uint32_t c = 0;
+                    if (edge != 0 && edge <= n_edges && (!valid || ((valid[edge >> 5] >> (edge & 31)) & 1u)))
+                        c = radj[edge].y & 7u;
+                    if (!c) { cols[ci].is_tip = 1; stop = 1; break; }   // no incoming k-mer, or its first character is '$'
+                    code = sigma - c;                                   // complement
+                    ch = (uint8_t)(letters >> (8 * (code - 1)));
+                    cnode = edge;
+                }
+                if (code < 1 || code > 4) { stop = 2; break; }
+                if (ch >= 'a' && ch <= 'z') ch -= 32;              // toupper (:564)
+                if (ncols >= max_cols) { ovf = true; stop = 1; break; }
+                const int size0 = imin(prev_end, wlen) + 1 - begin;
+                const int n = prev_end - begin;
+                if (n > 28 || size0 > 27) { stop = 2; break; }
+                // requests whose latency overlaps the DP below: the child's adjacency record, its convergence slot
+                if (!rc) { pfn = cnode; pfa = adj[cnode]; }
+                const uint64_t key = cnode + (rc ? n_edges : 0);
+                uint32_t hp = ((uint32_t)key * 0x9E3779B1u) ^ ((uint32_t)(key >> 32) * 0x85EBCA77u);
+                hp = (hp ^ (hp >> 15)) & hash_mask;
+                ConvSlot sl = cslots[hp];
+
+                const score_t *pS = buf0 + (size_t)c_pb * 3 * bmax + (begin - c_trim);
+                const int prof_base = start + begin;
+                const int sh = 8 * ((int)code - 1);
+                RegCol r;
+                const int size = reg_column([&](int j) { const int x = prof_base + j;
+                                                         return x <= Lq ? (int)(int8_t)(p4[x] >> sh) : 0; },
+                                            pS, pS + 2 * bmax, n, size0, wlen + 1 - begin, 0, noff > 1, cutoff, go, ge,
+                                            ge_shift, r);
+                if (size < 0) { stop = 2; break; }
+                // per-column scan (:643-669)
+                const int diag_i = noff - seed_off_m1;
+                score_t mn = 0x7fffffff, bs = INT32_MIN;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                for (int c = 0; c < kCPL; ++c) {
+                    const bool cell = j0 + c < size;
+                    const score_t v = r.S[c];
+                    if (cell && v != kNinf) mn = imin(mn, v);
+                    if (cell) bs = imax(bs, v);
+                }
+                const score_t col_min = wreduce_min(mn);
+                const score_t max_val = wreduce_max(bs);
+                int bkey = 0x7fffffff; bool he = false;            // (distance to the diagonal, row) of the best cell
+                score_t ext_cut = 0;
+                if (!in_seed) ext_cut = (score_t)((double)best_score * rsc + pso);
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                for (int c = 0; c < kCPL; ++c) {
+                    const int j = j0 + c;
+                    const bool cell = j < size;
+                    if (cell && r.S[c] == max_val) bkey = imin(bkey, (iabs(j + begin - diag_i) << 5) | j);
+                    if (!in_seed && cell && r.S[c] + ps[start + begin + j] >= ext_cut) he = true;
+                }
+                const int max_pos = (wreduce_min(bkey) & 31) + begin;
+                // ---- convergence filter, first half (update_seed_filter, :100-156): find the node's entry. Cases
+                // that move data around are left to the general code before anything has been written
+                const int s_first = begin ? 0 : 1;
+                const int qstart = start + begin - (begin ? 1 : 0);
+                const int n_pass = size - s_first;
+                bool hit = false;
+                {
+                    uint32_t probes = 0;
+                    while (sl.epoch == epoch && sl.key != key && probes < hash_size) { hp = (hp + 1) & hash_mask; sl = cslots[hp]; ++probes; }
+                    hit = sl.epoch == epoch && sl.key == key;
+                }
+                int new_end = 0;
+                if (!hit) {
+                    const int seg_start = imax(0, qstart - 8);
+                    const int seg_cap = imin(Lq + 1, qstart + n_pass + 8) - seg_start;
+                    if (conv_n >= max_conv_entries || 2 * (conv_n + 1) > hash_size || conv_used + seg_cap > max_conv_cells) {
+                        stop = 2; break;                           // (the general code reports the overflow)
+                    }
+                    sl.key = key; sl.epoch = epoch; sl.start = qstart; sl.size = n_pass;
+                    sl.seg_start = seg_start; sl.seg_cap = seg_cap; sl.seg_off = conv_used;
+                } else {
+                    // the node was met before (seed columns share the seed's node): only the in-place cases -- the
+                    // passed range overlaps the stored one and ends at or after its end, inside the segment
+                    new_end = imax(qstart + n_pass, sl.start + sl.size);
+                    if (qstart < sl.start || qstart >= sl.start + sl.size || new_end > sl.seg_start + sl.seg_cap) {
+                        stop = 2; break;
+                    }
+                }
+
+                const uint32_t cap_before = t_cap;
+                if (ncols + 1 > t_cap) t_cap = t_cap ? 2 * t_cap : 1;
+                made_cells += size; ++made;
+                min_cell_score = imin(min_cell_score, col_min);
+                if (!in_seed && (max_val < cutoff || !wballot(he))) { stop = 1; break; }   // pop(table.size() - 1)
+
+                table_bytes += 136ull * (t_cap - cap_before) + 3ull * vec_capacity(size0, size) * 4;
+                if ((int64_t)max_val - cutoff > xdrop) cutoff = max_val - xdrop;
+                best_score = imax(best_score, max_val);
+                if (cused > cells_limit) { ovf = true; stop = 1; break; }
+                // ---- commit: DP table (compact format, whole 32-byte sectors) and the on-chip child buffer
+                const int capr = capr_of(size);
+                const uint32_t off = (cused + 7u) & ~7u;
+                cused = off + 2 * capr + 8;
+                score_t *dst = cells + off;
+                score_t *cb_S = buf0 + (size_t)(1 - c_pb) * 3 * bmax;
+                store_cells(dst, j0, r.S, capr);
+                store_flags(reinterpret_cast<uint8_t*>(dst + capr), j0, r.fl);
+                store_cells(cb_S, j0, r.S, 32); store_cells(cb_S + 2 * bmax, j0, r.F, 32);
+                ColMeta col;
+                col.node = cnode; col.parent = ci; col.c = ch;
+                col.offset = noff; col.max_pos = max_pos; col.trim = begin; col.score = 0;
+                col.is_tip = 0; col.started = 0; col.fmt = FMT_COMPACT; col.pad0 = col.pad1 = 0;
+                col.size = size; col.cells_off = off;
+                const uint32_t idx = ncols;
+                cols[ncols++] = col;
+                uint32_t bits = 0;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                for (int c = 0; c < kCPL; ++c) if (j0 + c < size && r.S[c] >= cutoff) bits |= 1u << c;
+                const uint32_t bm_new = kCPL == 32 ? bits : wreduce_or(bits << (j0 & 31));
+
+                // ---- convergence filter, second half
+                score_t converged;
+                score_t *c0 = ccells + sl.seg_off + (qstart - s_first - sl.seg_start);              // indexed by cell
+                if (!hit) {
+                    conv_used += sl.seg_cap; ++conv_n;
+                    cslots[hp] = sl;
+                    score_t mx = kNinf;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                    for (int c = 0; c < kCPL; ++c) {
+                        const int j = j0 + c;
+                        if (j >= s_first && j < size) { c0[j] = r.S[c]; mx = imax(mx, r.S[c]); }
+                    }
+                    converged = wreduce_max(mx);
+                } else {
+                    const int old_end = sl.start + sl.size;
+                    if (new_end > old_end) {                       // vec.resize(n, ninf)
+                        score_t *cseg = ccells + sl.seg_off;
+                        for (int p = old_end + wlane(); p < new_end; p += kWarp) cseg[p - sl.seg_start] = kNinf;
+                        sl.size = new_end - sl.start;
+                        cslots[hp] = sl;
+                        wsync();
+                    }
+                    score_t max_changed = kNinf;
+#if MGB_DEVICE_CODE
+#pragma unroll
+#endif
+                    for (int c = 0; c < kCPL; ++c) {
+                        const int j = j0 + c;
+                        if (j >= s_first && j < size) {
+                            score_t vj = c0[j];
+                            if ((double)r.S[c] > (double)vj * rsc) {
+                                vj = imax(vj, r.S[c]);
+                                c0[j] = vj;
+                                max_changed = imax(max_changed, vj);
+                            }
+                        }
+                    }
+                    converged = wreduce_max(max_changed);
+                }
+                wsync();
+                // the new column becomes the parent
+                ci = idx; c_node = cnode; c_offset = noff; c_trim = begin; c_bm = bm_new; c_pb = 1 - c_pb;
+                c_maxval = max_val;
+                cur_it.score = converged; cur_it.neg_off_diag = -iabs(max_pos - diag_i); cur_it.idx = idx;
+                cur_it.max_score = max_val;
+                if (converged == kNinf) { stop = 1; break; }
+            } while (false);
+            if (stop) chain = false;
+        }
+        if (io.active) {
+            tc.table_cap = t_cap; tc.conv_n = conv_n; tc.conv_cells_used = conv_used;
+            io.ci = ci; io.c_pb = c_pb; io.cur_it = cur_it;
+            io.cutoff = cutoff; io.best_score = best_score; io.min_cell_score = min_cell_score;
+            io.table_size_bytes = table_bytes; io.n_cols = ncols; io.cells_used = cused;
+            io.pf_node = pfn; io.pf_adj = pfa;
+            io.stop = stop; io.overflow = ovf; io.dp_cells = made_cells; io.dp_columns = made;
+        }
     }
 
     long long phase_cycles[8] = {0,0,0,0,0,0,0,0};   // MGB_PHASE_TIMERS: setup, seeds, fwd loop, backtrack, rest
@@ -3113,6 +3287,23 @@ struct ReadAligner {
         wsync();
     }
 
+    // DNA block layout: scores of query position x (1-based, as prof_score) against A, C, G, T in one word, so that
+    // the chain loop reads one shared-memory word per DP cell instead of the query character and then the table
+    MGB_HD void build_prof4(int s) {
+        uint32_t *p4 = sm.prof4(s);
+        const char *q = cx[s].q;
+        for (int x = wlane(); x < sm.lq() + 8; x += kWarp) {
+            uint32_t w = 0;
+            if (x >= 1 && x <= L) {
+                const uint8_t ch = (uint8_t)q[x - 1];
+                w = (uint32_t)(uint8_t)cfg.prof[1][ch] | ((uint32_t)(uint8_t)cfg.prof[2][ch] << 8)
+                  | ((uint32_t)(uint8_t)cfg.prof[3][ch] << 16) | ((uint32_t)(uint8_t)cfg.prof[4][ch] << 24);
+            }
+            p4[x] = w;
+        }
+        wsync();
+    }
+
     // whole pipeline for one read; returns the number of alignments left in SLOT_AGG.. (sorted)
     // optional: per-position index_range results of both strands (k_subk), set before run()
     const uint32_t *subk_first[2] = { nullptr, nullptr }, *subk_last[2] = { nullptr, nullptr };
@@ -3170,6 +3361,7 @@ struct ReadAligner {
         }
         build_psum(0);
         if (both) build_psum(1);
+        if (!MGB_WIDE(ix) && sm.lay->has_prof && L + 1 <= sm.lq()) { build_prof4(0); if (both) build_prof4(1); }
         if (cfg.seed_complexity_filter) { build_lowcx(0); if (both) build_lowcx(1); }
         MGB_TOC(t_setup, 0);
         MGB_TIC(t_seeds);
@@ -3211,5 +3403,17 @@ struct ReadAligner {
         return n_agg;
     }
 };
+
+#if MGB_DEVICE_CODE
+static __device__ __noinline__
+#else
+static inline
+#endif
+void chain_entry(const IndexView &ix, const DevConfig &cfg, const Caps &caps, const WarpMem &m, const WarpSmem &sm, int L,
+                 ChainIO *io) {
+    ReadAligner al(ix, cfg, caps, m, sm);
+    al.L = L;
+    al.chain_loop(*io);
+}
 
 } // namespace mgb

@@ -846,7 +846,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
             if (const char *e = std::getenv("MGB_TEST_LQ")) lq_v = std::atoi(e);
             if (const char *e = std::getenv("MGB_TEST_HCAP")) hcap = std::atoi(e);
             SmemLayout slay;
-            const size_t smem_per_warp = slay.carve(bmax_v, lq_v, hcap);
+            const size_t smem_per_warp = slay.carve(bmax_v, lq_v, hcap, !index->view.wide);
             DevBufs pass_bufs(st, wsg.w, 32);          // slot 32: the arena
 #if defined(MGB_HOST_EMU)
             uint32_t n_warps = 1;
