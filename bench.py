@@ -199,7 +199,8 @@ def workload(name, world):
     if name == "c2":
         G = env_int("BENCH_GENOME", 100_000_000)
         n_rank = env_int("BENCH_READS", 1_000_000)
-        cfg = cli_defaults(K, min_seed_length=K, max_seed_length=K, result_nodes=env_int("BENCH_RESULT_NODES", 1))
+        cfg = cli_defaults(K, min_seed_length=K, max_seed_length=K, result_nodes=env_int("BENCH_RESULT_NODES", 1),
+                           no_exact_path_shortcut=bool(env_int("BENCH_NO_SHORTCUT", 0)))
         text = ("%d synthetic %d bp DNA reads/GPU (50%% rc, error-free) vs k=%d BOSS graph of a %d bp random "
                 "genome, exact-match seeder, CLI-default scoring" % (n_rank, READ_LEN, K, G))
         return dict(name="c2 (BASELINE configs[1])", text=text, G=G, n_rank=n_rank, n_total=n_rank * world, cfg=cfg,
@@ -208,7 +209,8 @@ def workload(name, world):
     n_total = env_int("BENCH_READS", 10_000_000)
     chunk = min(CHUNK, max(1, n_total // (8 * 5)))        # 40 chunks at least: 1, 2, 4 and 8 ranks take whole chunks
     n_total = max(chunk * world, n_total // (chunk * world) * (chunk * world))
-    cfg = cli_defaults(K, min_exact_match=0.0, result_nodes=env_int("BENCH_RESULT_NODES", 1))
+    cfg = cli_defaults(K, min_exact_match=0.0, result_nodes=env_int("BENCH_RESULT_NODES", 1),
+                       no_exact_path_shortcut=bool(env_int("BENCH_NO_SHORTCUT", 0)))
     text = ("%d synthetic %d bp DNA reads in total (50%% rc, 5%% errors: 80/10/10 substitution/insertion/deletion) vs "
             "k=%d BOSS graph of a %d bp random genome, CLI-default seeder (MEM + sub-k seeds), min_exact_match 0, "
             "CLI-default scoring" % (n_total, READ_LEN, K, G))
@@ -245,6 +247,8 @@ def main():
               "read_len": READ_LEN, "k": K, "genome_bp": G, "seeder": wl["seeder"],
               "result_nodes": "none (TSV consumer: cli/align.cpp:254-307 prints no node ids)" if cfg.result_nodes
                               else "u64 node path per alignment",
+              "exact_path_shortcut": "off" if cfg.no_exact_path_shortcut else "on (reads whose k-mers all match: the "
+                                     "extension is provably {L}= along them and is not run; same results, DESIGN.md)",
               "cpu_arm_suffix_index": CPU_SUFFIX_INDEX,
               "l2_policy": "inputs larger than L2 (index + node arrays + per-group arenas >> 126 MB)",
               "parallelism": "reads sharded x%d, index replicated" % world}
@@ -383,6 +387,23 @@ def main():
         sampler.start()
     stats = [step(False) for _ in range(args.steps)]
     barrier()
+    # the same region with the exact-path shortcut switched off (every extension runs): what the roofline / GCUPS
+    # lines describe, and the device-timed rate without the shortcut
+    stats_full = stats
+    if not cfg.no_exact_path_shortcut:
+        import dataclasses
+        aligner_full = B200Aligner(index, dataclasses.replace(cfg, no_exact_path_shortcut=True))
+        def step_full():
+            res = aligner_full.align_batch_raw(buf, offsets)
+            st = aligner_full.stats_of(res)
+            n_aln, chk = score_sum(res)
+            aligner_full.free_raw(res)
+            return st, n_aln, chk
+        step_full()
+        barrier()
+        stats_full = [step_full() for _ in range(args.steps)]
+        barrier()
+        assert [c for _, _, c in stats_full] == [c for _, _, c in stats], "the shortcut changed the results"
     aligner.set_pipeline_pieces(0)
     for _ in range(args.warmup):
         step(True)
@@ -395,14 +416,17 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     dev_ms = sum(s["seed_kernel_ms"] + s["align_kernel_ms"] for s, _, _ in stats)
-    seed_ms = sum(s["seed_kernel_ms"] for s, _, _ in stats) / args.steps
-    align_ms = sum(s["align_kernel_ms"] for s, _, _ in stats) / args.steps
-    t = torch.tensor([dev_ms, wall * 1e3, float(np.mean(gather_ms)) if gather_ms else 0.0], dtype=torch.float64, device=dev)
+    # kernel times and DP counts of the full run (shortcut off) feed the roofline lines
+    seed_ms = sum(s["seed_kernel_ms"] for s, _, _ in stats_full) / args.steps
+    align_ms = sum(s["align_kernel_ms"] for s, _, _ in stats_full) / args.steps
+    dev_ms_full = sum(s["seed_kernel_ms"] + s["align_kernel_ms"] for s, _, _ in stats_full)
+    t = torch.tensor([dev_ms, wall * 1e3, float(np.mean(gather_ms)) if gather_ms else 0.0, dev_ms_full],
+                     dtype=torch.float64, device=dev)
     tot = torch.tensor([sum(c for _, _, c in stats), sum(a for _, a, _ in stats)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max, gather_ms_max = t.tolist()
+    dev_ms_max, wall_ms_max, gather_ms_max, dev_ms_full_max = t.tolist()
     if rank == 0:
         # what rank 0 gathered in region B must be what the ranks computed in region A
         assert sum(c for _, _, c in stats_e2e) == int(tot[0].item()), "gathered results differ from the per-rank results"
@@ -412,7 +436,7 @@ def main():
         total_reads = N * world
         value = total_reads * args.steps / (dev_ms_max / 1e3)
         e2e = total_reads * args.steps / (wall_ms_max / 1e3)
-        st = stats[-1][0]
+        st = stats_full[-1][0]
         st_e2e = stats_e2e[-1][0]
         peak, peak_kind = measured_peaks()
         # dominant kernel and its algorithmic bytes per launch (DESIGN.md "Roofline")
@@ -461,7 +485,10 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": kms},
-            "kernels_ms_per_step": {"prepare+seed": seed_ms, "align": align_ms},
+            "kernels_ms_per_step": {"prepare+seed": seed_ms, "align": align_ms,
+                                    "align_with_shortcut": sum(s["align_kernel_ms"] for s, _, _ in stats) / args.steps},
+            "without_exact_path_shortcut": {"value": total_reads * args.steps / (dev_ms_full_max / 1e3), "unit": "reads/s",
+                                            "ms_per_step": dev_ms_full_max / args.steps},
             # seeding against the HBM roofline (SURVEY 8d model of algorithmic bytes per read, both strands)
             "seeding": {"bound": "hbm", "kernel": "k_prepare+k_premap+k_seed(+k_subk)", "achieved": seed_gbs, "peak": peak,
                         "unit": "GB/s", "frac": seed_gbs / peak, "algorithmic_bytes_per_launch": int(seed_alg),

@@ -81,7 +81,12 @@ typedef struct mgb_config {
      * (the TSV branch of cli/align.cpp:254-307 never reads Alignment::get_nodes()): the node ids are 4/5 of the
      * bytes a 150 bp alignment brings back from the device. */
     uint8_t result_nodes;
-    uint8_t reserved1[6];
+    /* 1 = never take the exact-path shortcut: when every k-mer of a strand is in the graph, the seed at query
+     * position 0 extends, provably, to the whole read matched along those nodes (DESIGN.md "Exact-path shortcut":
+     * conditions on the scores, proof, what the reference does instead); the kernel then writes that alignment
+     * without running the extension. Results are identical either way; the switch exists for measurements. */
+    uint8_t no_exact_path_shortcut;
+    uint8_t reserved1[5];
     int8_t score_matrix[128][128];
 } mgb_config_t;
 enum { MGB_NODES_U64 = 0, MGB_NODES_NONE = 1 };

@@ -40,7 +40,8 @@ class mgb_config_t(ctypes.Structure):
         ("no_backtrack", ctypes.c_uint8),
         ("seed_complexity_filter", ctypes.c_uint8),
         ("result_nodes", ctypes.c_uint8),
-        ("reserved1", ctypes.c_uint8 * 6),
+        ("no_exact_path_shortcut", ctypes.c_uint8),
+        ("reserved1", ctypes.c_uint8 * 5),
         ("score_matrix", (ctypes.c_int8 * 128) * 128),
     ]
 
@@ -130,6 +131,8 @@ class DBGAlignerConfig:
     seed_complexity_filter: bool = False
     # mgb_config_t::result_nodes: 0 = node paths come back with the alignments, 1 = they stay on the device
     result_nodes: int = 0
+    # mgb_config_t::no_exact_path_shortcut: True = always run the extension (measurements; results are identical)
+    no_exact_path_shortcut: bool = False
     score_matrix: list = field(default_factory=lambda: dna_scoring_matrix(2, -1, -2))
 
     def to_c(self):

@@ -57,6 +57,7 @@ struct DevConfig {
     uint32_t has_complement;           // DNA: reverse complement defined
     uint32_t canonical;                // graph in CANONICAL mode (holds both strands): dbg_aligner.cpp:224-226, 646-656
     uint32_t result_nodes;             // mgb_config_t::result_nodes (MGB_NODES_*)
+    uint32_t exact_shortcut;           // the scores allow the exact-path shortcut (lower_config) and it is not switched off
 };
 
 static constexpr int kMaxAlt = 4;            // supported num_alternative_paths
@@ -2055,6 +2056,40 @@ struct ReadAligner {
             cells_limit = (uint32_t)(3ull * caps.max_cells - 6ull * (wlen + 16));
         }
 
+        // ---------------- exact-path shortcut: every k-mer of this strand is in the graph and the seed
+        // starts the read. The extension below would walk exactly those nodes first (their columns hold the best
+        // score so far, so the queue pops them before anything else), the backtrack would start from the last of
+        // them at the end of the read -- every other start scores less: a shorter alignment misses matches and the
+        // end bonus, any mismatch or gap costs more than the match it replaces, and another path cannot spell the
+        // same characters -- and walk the diagonal back: {L}=, the read's own nodes. lower_config() checked what this
+        // needs from the scores (cfg.exact_shortcut).
+        shortcut_hit = false;
+        if (go && cfg.exact_shortcut && !force_fixed_seed && seed_is_query && start == 0 && sh.offset == 0 && !rc
+                && !MGB_CANONICAL(cfg) && !MGB_PRIMARY(ix) && L >= K && cx[s].qnodes != nullptr) {
+            const uint64_t *qn = cx[s].qnodes;
+            const int nk = L - K + 1;
+            bool miss = false;
+            for (int i2 = wlane(); i2 < nk; i2 += kWarp) miss = miss || qn[i2] == 0;
+            const score_t full = cx[s].ps[0] - cx[s].ps[L] + cfg.left_end_bonus + cfg.right_end_bonus;
+            if (!wballot(miss) && full >= min_path_score) {
+                if ((int)caps.aln_nodes < nk || (int)caps.aln_seq < L || (int)caps.aln_cigar < 1) overflow = true;
+                else {
+                    const AlnSlot o = m.slot(out_base);
+                    wsync();
+                    for (int i2 = wlane(); i2 < nk; i2 += kWarp) o.nodes[i2] = qn[i2];
+                    for (int i2 = wlane(); i2 < L; i2 += kWarp) o.seq[i2] = cx[s].q[i2];
+                    o.cigar[0] = cig_pack(OP_M, L);
+                    AlnHdr h;
+                    h.q_len = L; h.n_nodes = nk; h.seq_len = L; h.n_cigar = 1; h.score = full; h.offset = 0;
+                    h.orientation = sh.orientation; h.used = 1;
+                    *o.h = h;
+                    wsync();
+                    shortcut_hit = true;
+                }
+                go = false;
+            }
+        }
+
         // root column (:455-470)
         if (go) {
             Scratch sc;
@@ -2462,6 +2497,7 @@ struct ReadAligner {
                 else heap_push(heap_n, it);
             }
         }
+        if (shortcut_hit) return 1;
         if (!go || overflow) return 0;
         wsync();
         MGB_TOC(t_fwd, 2);
@@ -2746,6 +2782,7 @@ struct ReadAligner {
 
     long long phase_cycles[8] = {0,0,0,0,0,0,0,0};   // MGB_PHASE_TIMERS: setup, seeds, fwd loop, backtrack, rest
     bool seed_is_query;          // the seed in SLOT_SEED is a plain query substring
+    bool shortcut_hit = false;   // the last extend() call took the exact-path shortcut
     bool use_fast = true;        // register fast path for narrow columns (device only)
     uint64_t pf_node; uint2 pf_adj;        // software prefetch: adjacency record of the newest column
     uint64_t pf_key; ConvSlot pf_slot; uint32_t pf_slot_idx;   // ... and its first conv-table probe
@@ -3232,7 +3269,22 @@ struct ReadAligner {
                 }
                 if (it_ok) ++it;
             }
-            if (seed_ok && !overflow) {
+            if (seed_ok && !overflow && shortcut_hit) {
+                // exact-path shortcut: the extension it replaces covers every later seed of the strand (their last
+                // node and position lie on the matched path with at least the seed's score)
+                wsync();
+                if (implicit) {
+                    uint32_t *mask = cx[s].mask;
+                    for (int w = i >> 5; 32 * w < nk; ++w) {
+                        const uint32_t keep = 32 * w + 31 <= i ? ~0u : (32 * w > i ? 0u : ((2u << (i & 31)) - 1u));
+                        mask[w] &= keep;
+                    }
+                } else {
+                    for (int j = i + 1 + wlane(); j < n_seeds_s; j += kWarp) seeds_s[j].alive = 0;
+                }
+                shortcut_hit = false;
+                wsync();
+            } else if (seed_ok && !overflow) {
                 // later seeds already covered by this extension are dropped (:731-734, :379-382);
                 // independent probes, one seed per lane
                 wsync();

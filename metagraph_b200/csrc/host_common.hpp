@@ -1,6 +1,7 @@
 // Host-side helpers shared by the C-ABI implementation: config validation / lowering
 // (DBGAligner ctor, dbg_aligner.cpp:33-61) and arena sizing.
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -125,6 +126,23 @@ inline int lower_config(const mgb_config_t &c, uint32_t k, int alphabet, DevConf
     d->seed_complexity_filter = c.seed_complexity_filter && at.has_complement;
     if (c.result_nodes > 1) { *err = "result_nodes must be MGB_NODES_U64 or MGB_NODES_NONE"; return MGB_ERR_INVALID_ARGUMENT; }
     d->result_nodes = c.result_nodes;
+    {   // exact-path shortcut (align_core.cuh extend()): one reported alignment, backtracking on, every letter of the
+        // alphabet scores strictly best against itself and positively, gaps cost, the end bonuses are not negative
+        // and the left one (plus a match) is not outweighed by the right one (later seeds are covered)
+        bool ok = !c.no_exact_path_shortcut && c.num_alternative_paths == 1 && !c.no_backtrack
+                  && c.gap_opening_penalty < 0 && c.gap_extension_penalty < 0
+                  && c.left_end_bonus >= 0 && c.right_end_bonus >= 0 && !std::getenv("MGB_NO_EXACT_SHORTCUT");
+        for (uint32_t i = 1; i < at.sigma && ok; ++i) {
+            const int q = (unsigned char)at.letters[i];
+            const int m = c.score_matrix[q][q];
+            if (m <= 0 || m + c.left_end_bonus < c.right_end_bonus || !std::strchr(at.valid_upper, q)) ok = false;
+            for (uint32_t x = 1; x < at.sigma && ok; ++x) {
+                const int g = (unsigned char)at.letters[x];
+                if (g != q && c.score_matrix[g][q] >= m) ok = false;
+            }
+        }
+        d->exact_shortcut = ok ? 1 : 0;
+    }
     d->sigma = at.sigma; d->has_complement = at.has_complement ? 1 : 0;
     std::memcpy(d->letters, at.letters, sizeof(d->letters));
     std::memcpy(d->code_of, at.code_of, sizeof(d->code_of));

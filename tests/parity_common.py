@@ -101,6 +101,48 @@ def random_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=1):
     return stats
 
 
+def exact_shortcut_case(lib, seed, k, cfg, nseq=3, G=3000, nreads=80, L=90):
+    """Reads that match a path of the graph exactly (the exact-path shortcut of the extender applies to them) on a
+    graph with variants and a tandem repeat, mixed with reads carrying errors; kernels (shortcut on) == oracle, and
+    the shortcut switched off gives the same lines."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    base = "".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])
+    unit = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 7)])
+    base = base[:G // 2] + unit * 12 + base[G // 2:]                 # a tandem repeat: nodes met more than once
+    seqs = [base] + [mutate(rng, base, 0.01) for _ in range(nseq - 1)]
+    g = O.OracleGraph(k, seqs)
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(k, seqs, lib=lib), lib=lib)
+    reads = []
+    for i in range(nreads):
+        sq = seqs[int(rng.integers(0, len(seqs)))]
+        p = int(rng.integers(0, len(sq) - L))
+        r = sq[p:p + L] if i % 4 else mutate(rng, sq[p:p + L], 0.03)
+        reads.append(r.translate(COMP)[::-1] if i % 3 == 0 else r)
+    reads.append(base[G // 2 - 20:G // 2 + 60])                      # runs into the repeat
+    reads.append("ACGT" * (L // 4))
+    exp = g.align_tsv(cfg, reads, with_nodes=True)
+    got, _ = run_lines(idx, cfg, reads)
+    bad = [i for i in range(len(reads)) if exp[i] != got[i]]
+    assert not bad, (seed, bad[:3], exp[bad[0]], got[bad[0]])
+    got2, _ = run_lines(idx, dataclasses.replace(cfg, no_exact_path_shortcut=True), reads)
+    assert got2 == got
+    full = sum(1 for r, l in zip(reads, got) if ("\t%d=\t" % len(r)) in l)
+    assert full >= nreads // 2
+    idx.close()
+
+
+EXACT_SHORTCUT_CASES = [
+    (101, 21, lambda k: cli_defaults(k)),                                           # MEM + sub-k seeds
+    (102, 21, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k)),     # exact seeds (bench config)
+    (103, 12, lambda k: cli_defaults(k, min_exact_match=0.0, left_end_bonus=0, right_end_bonus=0)),
+    (104, 15, lambda k: cli_defaults(k, right_end_bonus=9)),                        # right bonus above match + left: no shortcut
+    (105, 17, lambda k: cli_defaults(k, forward_and_reverse_complement=False)),
+    (106, 13, lambda k: struct_defaults(xdrop=20, min_seed_length=k, max_seed_length=k)),
+    (107, 19, lambda k: cli_defaults(k, num_alternative_paths=2)),                  # two reported paths: no shortcut
+]
+
+
 def nodeless_case(lib, seed=5, k=15, G=4000, nreads=60, L=80):
     """mgb_config_t::result_nodes = MGB_NODES_NONE: the same alignments (TSV fields identical to the oracle's),
     node arrays left on the device (nodes == NULL, num_nodes kept)."""

@@ -96,6 +96,12 @@ def test_general_path_emu(monkeypatch):
         P.random_case(EMU, seed, k, G, n, L, rate, cfgf(k), mask, nseq)
 
 
+@pytest.mark.parametrize("case", P.EXACT_SHORTCUT_CASES, ids=[str(c[0]) for c in P.EXACT_SHORTCUT_CASES])
+def test_exact_path_shortcut_emu(case):
+    seed, k, cfgf = case
+    P.exact_shortcut_case(EMU, seed, k, cfgf(k))
+
+
 def test_nodeless_results_emu():
     P.nodeless_case(EMU)
 

@@ -58,6 +58,13 @@ def test_seed_complexity_filter_gpu():
         P.lowcx_case(LIB, seed, k, exact)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", P.EXACT_SHORTCUT_CASES, ids=[str(c[0]) for c in P.EXACT_SHORTCUT_CASES])
+def test_exact_path_shortcut_gpu(case):
+    seed, k, cfgf = case
+    P.exact_shortcut_case(LIB, seed, k, cfgf(k))
+
+
 def test_nodeless_results_gpu():
     """MGB_NODES_NONE: identical alignments, node arrays stay on the device"""
     P.nodeless_case(LIB)
