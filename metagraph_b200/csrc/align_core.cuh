@@ -186,8 +186,10 @@ struct ChainIO {
     uint64_t dp_cells; uint32_t dp_columns;
 };
 struct WarpMem; struct WarpSmem;
-#if MGB_DEVICE_CODE
+#if MGB_DEVICE_CODE && defined(MGB_CHAIN_NOINLINE)
 static __device__ __noinline__
+#elif MGB_DEVICE_CODE
+static __device__ __forceinline__
 #else
 static inline
 #endif
@@ -1937,12 +1939,12 @@ struct ReadAligner {
             pr[c] = prof(j);
             psm1[c] = prev; pfv[c] = pf_j;
             const score_t match = (act && j) ? prev + pr[c] + add : kNinf;
-            const score_t del = (act && use_del) ? imax(ps_j + go, pf_j + ge) + add : kNinf;
+            // (DPX add-max forms of max(S + go, F + ge) and of the running maximum)
+            const score_t del = (act && use_del) ? iaddmax(ps_j, go, pf_j + ge) + add : kNinf;
             mval[c] = imax(match, del);
             r.F[c] = act ? del : kNinf;
             // a[j] = m[j] + go - j*ge ; E[j+1] = prefmax(a)[j] + j*ge
-            const int a = act ? mval[c] + go - j * ge : INT32_MIN;
-            loc = imax(loc, a);
+            if (act) loc = iaddmax(mval[c], go - j * ge, loc);
             aloc[c] = loc;
             prev = ps_j;                                   // pS[j] for cell j + 1 (valid while j + 1 <= n4)
         }
@@ -3456,8 +3458,10 @@ struct ReadAligner {
     }
 };
 
-#if MGB_DEVICE_CODE
+#if MGB_DEVICE_CODE && defined(MGB_CHAIN_NOINLINE)
 static __device__ __noinline__
+#elif MGB_DEVICE_CODE
+static __device__ __forceinline__
 #else
 static inline
 #endif

@@ -218,6 +218,8 @@ struct DevBufs {
 // opaque types
 // ---------------------------------------------------------------------------------------
 struct mgb_index {
+    // owns its device buffers and cached workspaces: every error path of mgb_index_create releases what was uploaded
+    ~mgb_index();
     IndexView view;            // device pointers (host pointers in the emulation build)
     int device = 0;
     uint64_t device_bytes = 0;
@@ -245,6 +247,13 @@ struct mgb_index {
     std::vector<uint2> radj_host;
 #endif
 };
+
+mgb_index::~mgb_index() {
+#if !defined(MGB_HOST_EMU)
+    if (!bufs.empty()) { cudaSetDevice(device); for (void *p : bufs) cudaFree(p); }
+#endif
+    for (Workspace *w : ws_free) delete w;
+}
 
 struct mgb_results {
     uint32_t n_reads = 0;
@@ -425,7 +434,7 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
             uint64_t blocks = std::min<uint64_t>((nxt_num + 31) / 32, (uint64_t)idx->num_sms * 32);
             e = idx->view.wide ? kern_any::launch_sfx_extend((unsigned)blocks, sa) : kern_dna::launch_sfx_extend((unsigned)blocks, sa);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
-            if (e != cudaSuccess) { cudaFree(nxt); return fail(MGB_ERR_CUDA, std::string("k_sfx_extend: ") + cudaGetErrorString(e)); }
+            if (e != cudaSuccess) { cudaFree(nxt); return fail(MGB_ERR_CUDA, std::string("k_sfx_extend: ") + cudaGetErrorString(e)); }   // (idx's destructor frees the rest)
             // the previous level is no longer needed (the host-built one is freed with the index)
             if (len > sfx_host + 1) {
                 cudaFree((void*)cur);
@@ -447,7 +456,10 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         if (e == cudaSuccess) e = cudaMalloc((void**)&c1, n + 1);
         if (e == cudaSuccess) e = cudaMalloc((void**)&multi, n + 1);
         if (e == cudaSuccess) e = cudaMalloc((void**)&radj, (n + 1) * sizeof(uint2));
-        if (e != cudaSuccess) return fail(MGB_ERR_CUDA, std::string("cudaMalloc(radj): ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            cudaFree(bwd_arr); cudaFree(c0); cudaFree(c1); cudaFree(multi); cudaFree(radj);     // cudaFree(nullptr) is a no-op
+            return fail(MGB_ERR_CUDA, std::string("cudaMalloc(radj): ") + cudaGetErrorString(e));
+        }
         cudaMemset(bwd_arr, 0, 4); cudaMemset(c0, 0, 1); cudaMemset(c1, 0, 1); cudaMemset(multi, 0, 1);
         cudaMemset(radj, 0, sizeof(uint2));
         RadjArgs ra { idx->view, bwd_arr, c0, c1, multi, radj, n };
@@ -510,15 +522,7 @@ int mgb_index_set_mode(mgb_index_t *index, int mode) {
     return MGB_OK;
 }
 
-void mgb_index_destroy(mgb_index_t *index) {
-    if (!index) return;
-#if !defined(MGB_HOST_EMU)
-    cudaSetDevice(index->device);
-    for (void *p : index->bufs) cudaFree(p);
-#endif
-    for (Workspace *w : index->ws_free) delete w;
-    delete index;
-}
+void mgb_index_destroy(mgb_index_t *index) { delete index; }
 
 uint64_t mgb_index_num_edges(const mgb_index_t *index) { return index->view.n; }
 uint64_t mgb_index_device_bytes(const mgb_index_t *index) { return index->device_bytes; }

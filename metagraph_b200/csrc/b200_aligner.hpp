@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -147,10 +148,14 @@ class B200Aligner
             seqs += batch[i].second;
             offsets[i + 1] = seqs.size();
         }
-        mgb_results_t *res = nullptr;
+        mgb_results_t *res_raw = nullptr;
         int rc = mgb_align_batch(index_.handle(), &c_, seqs.data(), offsets.data(),
-                                 (uint32_t)batch.size(), &res);
+                                 (uint32_t)batch.size(), &res_raw);
         if (rc != MGB_OK) throw std::runtime_error(mgb_last_error());
+        // freed on every way out, a throwing callback included
+        struct ResultsFree { void operator()(mgb_results_t *r) const { mgb_results_free(r); } };
+        std::unique_ptr<mgb_results_t, ResultsFree> res_guard(res_raw);
+        const mgb_results_t *res = res_raw;
         const mgb_alignment_t *alns = mgb_results_alignments(res);
         for (size_t i = 0; i < batch.size(); ++i) {
             uint64_t first; uint32_t count;
@@ -190,7 +195,6 @@ class B200Aligner
 #endif
             callback(batch[i].first, std::move(paths));
         }
-        mgb_results_free(res);
     }
 
     Results align(const std::string &query) const {   // IDBGAligner::align (dbg_aligner.cpp:22-31)

@@ -120,6 +120,14 @@ inline int nth_set32(uint32_t x, int t) {
 }
 #endif
 
+// max(a + b, c): one DPX instruction (VIADDMNMX) on the device
+MGB_HD int iaddmax(int a, int b, int c) {
+#if MGB_DEVICE_CODE
+    return __viaddmax_s32(a, b, c);
+#else
+    return a + b > c ? a + b : c;
+#endif
+}
 MGB_HOSTDEV int imin(int a, int b) { return a < b ? a : b; }
 MGB_HOSTDEV int imax(int a, int b) { return a > b ? a : b; }
 MGB_HOSTDEV int iabs(int a) { return a < 0 ? -a : a; }
