@@ -651,8 +651,8 @@ int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, St
         const uint64_t pb = std::min<uint64_t>((items + 7) / 8, (uint64_t)index->num_sms * 16);
         CUDA_TRY(index->view.wide ? kern_any::launch_premap((unsigned)pb, st.s, a) : kern_dna::launch_premap((unsigned)pb, st.s, a));
     }
-    // 32 quads per block; enough blocks to fill the machine, grid-stride beyond that
-    uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
+    // one strand per lane, 128 strands per block; enough blocks to fill the machine, grid-stride beyond that
+    uint64_t blocks = std::min<uint64_t>((items + 127) / 128, (uint64_t)index->num_sms * 16);
     CUDA_TRY(index->view.wide ? kern_any::launch_seed((unsigned)blocks, st.s, a) : kern_dna::launch_seed((unsigned)blocks, st.s, a));
 #endif
     return 0;
@@ -812,8 +812,9 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
                     for (uint32_t c = 0; c < chunks; ++c) subk_item(sk, r, s2, c);
 #else
             if (!rc) {
-                const uint64_t items = (uint64_t)n_reads * sk.n_strands * chunks;
-                const uint64_t blocks = std::min<uint64_t>((items + 31) / 32, (uint64_t)index->num_sms * 16);
+                // one warp per 32 query positions of a strand, 4 warps per block
+                const uint64_t items = (uint64_t)n_reads * sk.n_strands * ((chunks * kSubkChunk + 31) / 32);
+                const uint64_t blocks = std::min<uint64_t>((items + 3) / 4, (uint64_t)index->num_sms * 16);
                 CUDA_TRY(index->view.wide ? kern_any::launch_subk((unsigned)blocks, st.s, sk, chunks)
                                           : kern_dna::launch_subk((unsigned)blocks, st.s, sk, chunks));
             }

@@ -322,14 +322,74 @@ __global__ void __launch_bounds__(128) k_sfx_extend(SfxArgs a) {
     for (uint64_t o = quad; o < total; o += nquads) sfx_extend_item(a, o);
 }
 
+// Sub-k lookups (subk_item) for 32 query positions of one strand per warp. Most positions end with one load: the
+// first sfx_len characters do not occur in the graph, and a miss in a suffix-range table no longer than
+// min_seed_length is final (boss_index_range). So every LANE first settles its own position against the table;
+// only the survivors (a matched prefix of at least sfx_len characters: near an error on the matching strand) go
+// through the quad-cooperative range search, 8 at a time. (One quad per position kept 4 lanes on every one-load
+// miss.) Same results as subk_item(), which the host emulation still runs.
 __global__ void __launch_bounds__(128) k_subk(SubkArgs a, uint32_t chunks_per_strand) {
-    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    const uint64_t per_read = (uint64_t)a.n_strands * chunks_per_strand;
+    const IndexView &ix = a.ix;
+    const int K = (int)ix.k;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t blocks32 = (chunks_per_strand * (uint32_t)kSubkChunk + 31) / 32;    // 32-position blocks per strand
+    const uint64_t per_read = (uint64_t)a.n_strands * blocks32;
     const uint64_t items = (uint64_t)a.n_reads * per_read;
-    for (uint64_t it = quad; it < items; it += nquads) {
+    const int S = (int)ix.sfx_len;
+    const uint64_t base = ix.sigma - 1;
+    for (uint64_t it = warp; it < items; it += nwarps) {
         const uint32_t r = (uint32_t)(it / per_read), rem = (uint32_t)(it % per_read);
-        subk_item(a, r, rem / chunks_per_strand, rem % chunks_per_strand);
+        const uint32_t s = rem / blocks32, blk = rem % blocks32;
+        const uint64_t b = a.offsets[r];
+        const int L = (int)(a.offsets[r + 1] - b);
+        if (L < (int)a.min_seed_length) continue;
+        const int n_pos = L - (int)a.min_seed_length + 1;
+        const uint8_t *codes = (s ? a.cr : a.cf) + b;
+        const uint64_t *nodes = L >= K ? (s ? a.nodes_r : a.nodes_f) + a.koff[r] : nullptr;
+        uint32_t *of = (s ? a.first_r : a.first_f) + b, *ol = (s ? a.last_r : a.last_f) + b;
+        uint8_t *on = (s ? a.len_r : a.len_f) + b;
+        const int nk = L >= K ? L - K + 1 : 0;
+        const int i = (int)blk * 32 + lane;
+        // ---- per lane: positions that need no search
+        bool survivor = false;
+        int len = 0;
+        if (i < n_pos) {
+            if (i < nk && nodes && nodes[i] != 0) {
+                of[i] = 0; ol[i] = 0; on[i] = 0xFF;                 // a full k-mer matches here: not computed
+            } else {
+                len = (int)a.max_len < L - i ? (int)a.max_len : L - i;
+                bool ok = len >= (int)a.min_seed_length;
+                bool zero = false;
+                for (int t = 0; t < len && ok; ++t) { const uint32_t c = codes[i + t]; ok = c < ix.sigma; zero = zero || c == 0; }
+                const int qlen = len < K - 1 ? len : K - 1;         // what boss_index_range is asked for
+                survivor = ok;
+                if (ok && S && S <= qlen && S <= (int)a.min_seed_length && !zero && S > 1) {
+                    uint64_t slot = 0;
+                    for (int j = S - 1; j >= 0; --j) slot = slot * base + (codes[i + j] - 1);
+                    const uint32_t rl = ldg32(ix.sfx + 2 * slot), ru1 = ldg32(ix.sfx + 2 * slot + 1);
+                    if (rl >= ru1) survivor = false;                // empty range: matched = 0, final
+                }
+                if (!survivor) { of[i] = 0; ol[i] = 0; on[i] = 0; }
+            }
+        }
+        // ---- the survivors, 8 per round, one quad each
+        uint32_t todo = __ballot_sync(0xffffffffu, survivor);
+        while (todo) {
+            // the (lane >> 2)-th set bit of `todo` is this quad's position, if there are that many
+            const int q = lane >> 2;
+            const int src = popc32(todo) > q ? nth_set32(todo, q + 1) : -1;
+            if (src >= 0) {
+                const int pi = (int)blk * 32 + src;
+                const int plen = (int)a.max_len < L - pi ? (int)a.max_len : L - pi;
+                uint64_t first = 0, lst = 0; int matched = 0;
+                boss_index_range(ix, codes + pi, plen < K - 1 ? plen : K - 1, &first, &lst, &matched, (int)a.min_seed_length);
+                if (glane() == 0) { of[pi] = (uint32_t)first; ol[pi] = (uint32_t)lst; on[pi] = (uint8_t)matched; }
+            }
+            // drop the (up to) 8 lowest set bits
+            for (int t = 0; t < 8 && todo; ++t) todo &= todo - 1;
+        }
     }
 }
 
@@ -341,11 +401,104 @@ __global__ void __launch_bounds__(256) k_premap(SeedArgs a) {
     for (uint64_t it = warp; it < items; it += nwarps) premap_item(a, (uint32_t)(it / a.n_strands), (uint32_t)(it % a.n_strands));
 }
 
+// BOSS::map_to_edges (boss.cpp:996-1045) for 32 read strands per warp, one per lane. The two regimes of the walk
+// have opposite shapes, so the warp alternates between them instead of letting every strand run its own loop:
+//   cold  a k-mer is looked up from scratch (BOSS::index: suffix-range table + tighten_range steps over 64-byte
+//         blocks): quad-cooperative, 8 strands at a time, the strand's state fetched from / returned to its lane;
+//   warm  the next k-mer is the child of the current edge: ONE 8-byte adjacency load per step and lane, 32
+//         independent pointer chases per warp, all lanes in the same three-instruction-deep loop.
+// (One quad per strand running both regimes kept 8 of 32 lanes busy on average: 8 quads in 8 different states.)
+// Same results as map_to_edges() in seed_core.cuh, which the host emulation still runs.
 __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
-    uint64_t quad = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    uint64_t nquads = ((uint64_t)gridDim.x * blockDim.x) >> 2;
-    uint64_t items = (uint64_t)a.n_reads * a.n_strands;
-    for (uint64_t it = quad; it < items; it += nquads) seed_item(a, it);
+    const IndexView &ix = a.ix;
+    const int K = (int)ix.k;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t items = (uint64_t)a.n_reads * a.n_strands;
+    const int S = (ix.sfx_len && (int)ix.sfx_len <= K - 1) ? (int)ix.sfx_len : 0;
+    const uint64_t base = ix.sigma - 1;
+    for (uint64_t chunk = warp * 32; chunk < items; chunk += nwarps * 32) {
+        const uint64_t item = chunk + lane;
+        // this lane's strand
+        const uint8_t *codes = nullptr; uint64_t *out = nullptr; const uint32_t *hints = nullptr;
+        int nk = 0;
+        if (item < items) {
+            const uint32_t r = (uint32_t)(item / a.n_strands), s = (uint32_t)(item % a.n_strands);
+            const uint64_t b = a.offsets[r];
+            const int L = (int)(a.offsets[r + 1] - b);
+            nk = L >= K ? L - K + 1 : 0;
+            codes = (s ? a.cr : a.cf) + b;
+            out = (s ? a.nodes_r : a.nodes_f) + a.koff[r];
+            hints = a.hinted ? (s ? a.hint_r : a.hint_f) + (a.koff[r] >> 5) + r : nullptr;
+        }
+        int pos = 0;                 // first k-mer not resolved yet
+        uint64_t edge = 0;           // warm: the edge of k-mer pos - 1
+        while (__any_sync(0xffffffffu, pos < nk)) {
+            // ---- cold: strands without an edge look for their next k-mer that exists, 8 strands per round
+            for (int t = 0; t < 4; ++t) {
+                const int src = 8 * t + (lane >> 2);                   // the strand this quad serves in round t
+                const bool need = __shfl_sync(0xffffffffu, (int)(edge == 0 && pos < nk), src) != 0;
+                const uint64_t codes_s = __shfl_sync(0xffffffffu, (unsigned long long)codes, src);
+                const uint64_t hints_s = __shfl_sync(0xffffffffu, (unsigned long long)hints, src);
+                const uint64_t out_s = __shfl_sync(0xffffffffu, (unsigned long long)out, src);
+                const int nk_s = __shfl_sync(0xffffffffu, nk, src);
+                int i = __shfl_sync(0xffffffffu, pos, src);
+                uint64_t found = 0;
+                if (need) {                                            // uniform within the quad
+                    const uint8_t *cd = (const uint8_t*)codes_s;
+                    const uint32_t *hn = (const uint32_t*)hints_s;
+                    LineCache lc;
+                    for (; i < nk_s; ++i) {
+                        if (hn) { i = next_hint(hn, nk_s, i); if (i >= nk_s) break; }
+                        // map_to_edge (boss.hpp:766-777)
+                        bool valid = true, zero = false;
+                        for (int j = 0; j < K; ++j) { const uint32_t c = cd[i + j]; valid = valid && c < ix.sigma; zero = zero || c == 0; }
+                        uint64_t e = 0;
+                        if (valid) {
+                            if (S && !zero) {
+                                uint64_t slot = 0;
+                                for (int j = S - 1; j >= 0; --j) slot = slot * base + (cd[i + j] - 1);
+                                e = boss_index_slot(ix, cd + i, K - 1, slot);
+                            } else {
+                                e = boss_index(ix, cd + i, K - 1);
+                            }
+                            if (e) e = pick_edge(ix, lc, e, cd[i + K - 1]);
+                        }
+                        if (e) { found = e; break; }
+                    }
+                    if (found && glane() == 0) ((uint64_t*)out_s)[i] = in_graph(ix, found) ? found : 0;
+                }
+                // back to the strand's lane: served by quad (lane & 7) in round lane >> 3
+                const uint64_t f_back = __shfl_sync(0xffffffffu, (unsigned long long)found, 4 * (lane & 7));
+                const int i_back = __shfl_sync(0xffffffffu, i, 4 * (lane & 7));
+                if ((lane >> 3) == t && edge == 0 && pos < nk) {
+                    edge = f_back;
+                    pos = f_back ? i_back + 1 : nk;                    // nothing left to find: the strand is done
+                }
+            }
+            // ---- warm: every lane with an edge follows it (boss.cpp:1024-1043) until a k-mer is missing
+            while (__any_sync(0xffffffffu, edge != 0 && pos < nk)) {
+                if (edge != 0 && pos < nk) {
+                    const uint32_t c = codes[pos + K - 1];
+                    if (c >= ix.sigma) {                               // invalid character: this k-mer and the walk end
+                        out[pos] = 0; edge = 0; ++pos;
+                    } else if (!MGB_WIDE(ix)) {
+                        const uint2 ar = load_adj(ix, edge);
+                        edge = adj_child(ar, c);
+                        out[pos] = (edge && ((ar.y >> (8 + c)) & 1u)) ? edge : 0;
+                        ++pos;
+                    } else {
+                        const Adj ar = load_adj_any(ix, edge);
+                        edge = adj_child(ar, c);
+                        out[pos] = (edge && ((ar.ok >> c) & 1u)) ? edge : 0;
+                        ++pos;
+                    }
+                }
+            }
+            if (pos >= nk) edge = 0;
+        }
+    }
 }
 
 #endif // MGB_ALIGN_KERNEL_ONLY
