@@ -435,10 +435,14 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
         int pos = 0;                 // first k-mer not resolved yet
         uint64_t edge = 0;           // warm: the edge of k-mer pos - 1
         while (__any_sync(0xffffffffu, pos < nk)) {
-            // ---- cold: strands without an edge look for their next k-mer that exists, 8 strands per round
-            for (int t = 0; t < 4; ++t) {
-                const int src = 8 * t + (lane >> 2);                   // the strand this quad serves in round t
-                const bool need = __shfl_sync(0xffffffffu, (int)(edge == 0 && pos < nk), src) != 0;
+            if (pos >= nk) edge = 0;
+            // ---- cold: strands without an edge look for their next k-mer that exists. The quads take the waiting
+            // strands in lane order, 8 per round (quad q serves the q-th waiting lane)
+            uint32_t waiting = __ballot_sync(0xffffffffu, edge == 0 && pos < nk);
+            while (waiting) {
+                const int q = lane >> 2;
+                const bool need = popc32(waiting) > q;
+                const int src = need ? nth_set32(waiting, q + 1) : 0;
                 const uint64_t codes_s = __shfl_sync(0xffffffffu, (unsigned long long)codes, src);
                 const uint64_t hints_s = __shfl_sync(0xffffffffu, (unsigned long long)hints, src);
                 const uint64_t out_s = __shfl_sync(0xffffffffu, (unsigned long long)out, src);
@@ -469,17 +473,25 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
                     }
                     if (found && glane() == 0) ((uint64_t*)out_s)[i] = in_graph(ix, found) ? found : 0;
                 }
-                // back to the strand's lane: served by quad (lane & 7) in round lane >> 3
-                const uint64_t f_back = __shfl_sync(0xffffffffu, (unsigned long long)found, 4 * (lane & 7));
-                const int i_back = __shfl_sync(0xffffffffu, i, 4 * (lane & 7));
-                if ((lane >> 3) == t && edge == 0 && pos < nk) {
+                // back to the strand's lane: the r-th waiting lane was served by quad r (if r < 8)
+                const int my_rank = popc32(waiting & ((1u << lane) - 1u));
+                const bool served = ((waiting >> lane) & 1u) && my_rank < 8;
+                const uint64_t f_back = __shfl_sync(0xffffffffu, (unsigned long long)found, 4 * (my_rank & 7));
+                const int i_back = __shfl_sync(0xffffffffu, i, 4 * (my_rank & 7));
+                if (served) {
                     edge = f_back;
                     pos = f_back ? i_back + 1 : nk;                    // nothing left to find: the strand is done
                 }
+                for (int t = 0; t < 8 && waiting; ++t) waiting &= waiting - 1;
             }
-            // ---- warm: every lane with an edge follows it (boss.cpp:1024-1043) until a k-mer is missing
-            while (__any_sync(0xffffffffu, edge != 0 && pos < nk)) {
-                if (edge != 0 && pos < nk) {
+            // ---- warm: every lane with an edge follows it (boss.cpp:1024-1043) until its next k-mer is missing; the
+            // warp goes back to cold lookups once 8 strands wait for one (a full round of quads), or nobody is warm
+            while (true) {
+                const bool warm = edge != 0 && pos < nk;
+                // one warp reduction counts both kinds of lanes: warm ones in the low byte, waiting ones above
+                const uint32_t cnt = __reduce_add_sync(0xffffffffu, warm ? 1u : ((edge == 0 && pos < nk) ? 256u : 0u));
+                if (!(cnt & 255u) || (cnt >> 8) >= 8u) break;
+                if (warm) {
                     const uint32_t c = codes[pos + K - 1];
                     if (c >= ix.sigma) {                               // invalid character: this k-mer and the walk end
                         out[pos] = 0; edge = 0; ++pos;

@@ -120,6 +120,23 @@ def test_c1_shape_emu():
     assert full >= n - 2
 
 
+def test_c1_transcripts_subset_emu():
+    """the first 40 records of the configs[0] fixture (up to 4.5 kbp) against the graph of all 1000"""
+    import oracle_lib as O
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex
+    from metagraph_b200.config import cli_defaults
+    from test_oracle_golden import GOLD, read_fasta
+    _, seqs = read_fasta(os.path.join(GOLD, "transcripts_1000.fa"))
+    boss = BOSSTable.from_sequences(12, seqs, lib=EMU)
+    idx = DBGSuccinctIndex(boss, lib=EMU)
+    cfg = cli_defaults(12)
+    reads = seqs[:40]
+    got, _ = P.run_lines(idx, cfg, reads)
+    exp = O.OracleGraph(12, arrays=(boss.W, boss.last, boss.F)).align_tsv(cfg, reads, with_nodes=True, threads=8)
+    assert got == exp
+    idx.close()
+
+
 def test_random_emu_in_pieces(monkeypatch):
     """mgb_align_batch splits big batches into pieces run by two host threads; force the split on a
     small batch (ragged piece boundaries, results merged in read order)."""

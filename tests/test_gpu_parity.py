@@ -124,3 +124,64 @@ def test_c2_scale_properties():
     exp = o.align_tsv(cfg, reads[:2000], with_nodes=True, threads=8)
     got = [format_alignment("", r, 0, with_nodes=True) for r in res[:2000]]
     assert got == exp
+
+
+def test_c1_transcripts_1000_gpu():
+    """BASELINE configs[0] on the reference's own fixture: tests/data/transcripts_1000.fa (1000 records, 59 bp ..
+    11 666 bp), k = 12 graph of the transcripts, the transcripts themselves as reads at CLI defaults. Kernels ==
+    oracle line by line (node paths included); SURVEY 8c expects every read to align to itself end to end."""
+    import os
+    import oracle_lib as O
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex
+    from metagraph_b200.config import cli_defaults
+    from test_oracle_golden import GOLD, read_fasta
+    names, seqs = read_fasta(os.path.join(GOLD, "transcripts_1000.fa"))
+    assert len(seqs) == 1000 and sum(len(s) for s in seqs) == 1490627
+    k = 12
+    boss = BOSSTable.from_sequences(k, seqs)
+    idx = DBGSuccinctIndex(boss)
+    cfg = cli_defaults(k)
+    got, _ = P.run_lines(idx, cfg, seqs)
+    g = O.OracleGraph(k, arrays=(boss.W, boss.last, boss.F))
+    exp = g.align_tsv(cfg, seqs, with_nodes=True, threads=16)
+    bad = [i for i in range(len(seqs)) if exp[i] != got[i]]
+    assert not bad, (bad[:3], len(seqs[bad[0]]), exp[bad[0]][:200], got[bad[0]][:200])
+    full = sum(1 for s_, l in zip(seqs, got) if l.split("\t")[6] == "%d=" % len(s_) and int(l.split("\t")[4]) == 2 * len(s_) + 10)
+    assert full >= 990, full
+    idx.close()
+
+
+@pytest.mark.parametrize("which", ["dna", "protein"])
+def test_example_dbg_graphs_gpu(which):
+    """The two graph files the reference ships (examples/data/graphs/*.dbg, written by `metagraph build`): loaded
+    with mgb_dbg_load, uploaded, and aligned against on the device; kernels == oracle on the example queries."""
+    import os
+    import oracle_lib as O
+    from metagraph_b200.aligner import BOSSTable, DBGSuccinctIndex
+    from metagraph_b200.config import cli_defaults
+    import test_dbg_loader as T
+    dbg, fa, qfa, alpha, code = [c for c in T.CASES if c[3] == which][0]
+    t = BOSSTable.from_dbg(os.path.join(T.EX, dbg))
+    idx = DBGSuccinctIndex(t)
+    reads = T.fasta(os.path.join(T.EX, qfa)) + [s[3:50] for s in T.fasta(os.path.join(T.EX, fa))]
+    cfg = cli_defaults(t.k, alphabet=alpha)
+    g = O.OracleGraph(t.k, arrays=(t.W, t.last, t.F), alphabet=alpha)
+    exp = g.align_tsv(cfg, reads, with_nodes=True)
+    got, _ = P.run_lines(idx, cfg, reads)
+    assert got == exp
+    idx.close()
+
+
+def test_cpp_shim_on_device(tmp_path):
+    """tests/cpp/test_shim.cpp (the IDBGAligner-shaped C++ shim) linked against the product library libmgb.so"""
+    import subprocess
+    from metagraph_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.dirname(_lib.DEFAULT_LIB)
+    exe = str(tmp_path / "test_shim_dev")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "test_shim.cpp"),
+                           "-o", exe, "-L" + lib_dir, "-l:libmgb.so", "-Wl,-rpath," + lib_dir, "-fopenmp"])
+    dbg = os.path.join(root, "tests", "golden", "example_graphs", "test_DNA_graph.dbg")
+    out = subprocess.run([exe, dbg], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "q1\tAGCTNCGAGGCCAA\t4=1X9=\t24" in out.stdout and "dbg\t36=" in out.stdout

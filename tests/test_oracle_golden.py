@@ -228,3 +228,17 @@ def test_map_count_kmers_golden():
     _, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
     g = O.OracleGraph(11, seqs, mask=True)
     assert [_map_counts(g.map_to_nodes(r)) for r in reads] == MAP_COUNTS
+
+
+def test_c1_transcripts_1000_oracle():
+    """BASELINE configs[0] fixture (tests/data/transcripts_1000.fa: 1000 records, 1 490 627 bp, 59 .. 11 666 bp): k = 12
+    graph of the transcripts, CLI defaults. The reference stores no expected output for it; SURVEY 8c states what the
+    algorithm must give -- every read aligns to itself, CIGAR {L}=, score 2L + 10 -- and the restatement does."""
+    from metagraph_b200.config import cli_defaults
+    names, seqs = read_fasta(os.path.join(GOLD, "transcripts_1000.fa"))
+    assert len(seqs) == 1000 and sum(len(s) for s in seqs) == 1490627
+    g = O.OracleGraph(12, seqs)
+    out = g.align_tsv(cli_defaults(12), seqs, threads=8)
+    for s_, l in zip(seqs, out):
+        f = l.split("\t")
+        assert f[2] == "+" and f[3] == s_ and int(f[4]) == 2 * len(s_) + 10 and f[6] == "%d=" % len(s_) and f[7] == "0"
