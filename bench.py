@@ -321,6 +321,8 @@ def main():
     index = DBGSuccinctIndex(boss, device=local_rank)
     index_s = time.time() - t0
     aligner = B200Aligner(index, cfg)
+    # torchrun pins OMP_NUM_THREADS=1: give this rank its share of the host cores for result unpacking
+    aligner._L.mgb_set_host_threads(max(1, min(32, host_threads // max(world, 1))))
 
     buf_np, off_np = rank_reads(wl, genome, rank, world)
     del genome

@@ -106,6 +106,8 @@ def load_library(path=None):
     L.mgb_dbg_last_error.restype = ctypes.c_char_p
     L.mgb_set_pipeline_pieces.restype = None
     L.mgb_set_pipeline_pieces.argtypes = [u32]
+    L.mgb_set_host_threads.restype = None
+    L.mgb_set_host_threads.argtypes = [i]
     _libs[path] = L
     return L
 
@@ -121,5 +123,5 @@ REQUIRED_SYMBOLS = [
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
     "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_results_export_bytes",
     "mgb_results_export", "mgb_results_import", "mgb_boss_build", "mgb_boss_free",
-    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_index_set_mode",
+    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_index_set_mode",
 ]

@@ -18,6 +18,9 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 
 #include "../../include/mgb.h"
 #if !defined(MGB_HOST_EMU)
@@ -1035,6 +1038,14 @@ static std::atomic<uint32_t> g_max_pieces{0};      // 0 = automatic
 extern "C" {
 
 void mgb_set_pipeline_pieces(uint32_t max_pieces) { g_max_pieces.store(max_pieces); }
+
+void mgb_set_host_threads(int n) {
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
                     const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out) {
