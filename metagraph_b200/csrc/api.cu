@@ -351,7 +351,7 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         std::vector<uint32_t> bwd_arr(n + 1, 0);
         std::vector<uint8_t> c0(n + 1, 0), c1(n + 1, 0), multi(n + 1, 0);
         idx->radj_host.assign(n + 1, uint2{0, 0});
-        RadjArgs ra { idx->view, bwd_arr.data(), c0.data(), c1.data(), multi.data(), idx->radj_host.data(), n };
+        RadjArgs ra { idx->view, bwd_arr.data(), c0.data(), c1.data(), multi.data(), idx->radj_host.data(), n, nullptr };
         for (uint64_t e = 1; e <= n; ++e) radj_bwd_item(ra, e);
         for (uint32_t r = 0; r + 2 < k; ++r) {
             for (uint64_t e = 1; e <= n; ++e) ra.c_nxt[e] = ra.c_cur[bwd_arr[e]];
@@ -465,20 +465,51 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         }
         cudaMemset(bwd_arr, 0, 4); cudaMemset(c0, 0, 1); cudaMemset(c1, 0, 1); cudaMemset(multi, 0, 1);
         cudaMemset(radj, 0, sizeof(uint2));
-        RadjArgs ra { idx->view, bwd_arr, c0, c1, multi, radj, n };
+        // k-mer hash index (index.cuh kh_*): DNA block layout, k <= 31 (62-bit keys). The k-mer of every edge falls out
+        // of the gather rounds below; 12 bytes per slot at a load factor of 0.7. Skipped (the seeding kernel then looks
+        // k-mers up through the suffix-range table and tighten_range) if the memory is not there or MGB_NO_KMER_HASH is set.
+        unsigned long long *kmer = nullptr, *kh_keys = nullptr; uint32_t *kh_vals = nullptr;
+        const uint64_t kh_slots = (uint64_t)((double)(n + 1) / 0.7) + 64;
+        if (!idx->view.wide && k >= 3 && k <= 31 && !std::getenv("MGB_NO_KMER_HASH")) {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            if ((double)free_b > 1.2 * (8.0 * (n + 1) + 12.0 * kh_slots) + 16e9
+                    && cudaMalloc((void**)&kmer, (n + 1) * 8) == cudaSuccess) {
+                if (cudaMalloc((void**)&kh_keys, kh_slots * 8) != cudaSuccess
+                        || cudaMalloc((void**)&kh_vals, kh_slots * 4) != cudaSuccess) {
+                    cudaGetLastError();
+                    cudaFree(kmer); cudaFree(kh_keys); cudaFree(kh_vals);
+                    kmer = nullptr; kh_keys = nullptr; kh_vals = nullptr;
+                } else {
+                    cudaMemset(kmer, 0xFF, 8);                  // position 0: no k-mer
+                    cudaMemset(kh_keys, 0, kh_slots * 8);
+                }
+            } else cudaGetLastError();
+        }
+        RadjArgs ra { idx->view, bwd_arr, c0, c1, multi, radj, n, kmer };
         const unsigned grid = (unsigned)idx->num_sms * 16;
         e = idx->view.wide ? kern_any::launch_radj_bwd(grid, ra) : kern_dna::launch_radj_bwd(grid, ra);
         for (uint32_t r = 0; r + 2 < k; ++r) {          // k - 2 bwd steps
-            kern_dna::k_radj_gather<<<grid, 256>>>(ra);
+            kern_dna::k_radj_gather<<<grid, 256>>>(ra, 2 * ((int)k - 3 - (int)r));
             std::swap(ra.c_cur, ra.c_nxt);
         }
         kern_dna::k_radj_pack<<<grid, 256>>>(ra, radj_multi_shift(idx->view));
+        if (kmer) kern_dna::k_kmer_insert<<<grid, 256>>>(kmer, n, kh_keys, kh_vals, kh_slots);
+        if (e == cudaSuccess) e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        cudaFree(bwd_arr); cudaFree(c0); cudaFree(c1); cudaFree(multi);
-        if (e != cudaSuccess) { cudaFree(radj); return fail(MGB_ERR_CUDA, std::string("radj build: ") + cudaGetErrorString(e)); }
+        cudaFree(bwd_arr); cudaFree(c0); cudaFree(c1); cudaFree(multi); cudaFree(kmer);
+        if (e != cudaSuccess) {
+            cudaFree(radj); cudaFree(kh_keys); cudaFree(kh_vals);
+            return fail(MGB_ERR_CUDA, std::string("radj / k-mer hash build: ") + cudaGetErrorString(e));
+        }
         idx->bufs.push_back(radj);
         idx->device_bytes += (n + 1) * sizeof(uint2);
         idx->view.radj = radj;
+        if (kh_keys) {
+            idx->bufs.push_back(kh_keys); idx->bufs.push_back(kh_vals);
+            idx->device_bytes += kh_slots * 12;
+            idx->view.kh_keys = kh_keys; idx->view.kh_vals = kh_vals; idx->view.kh_slots = kh_slots;
+        }
     }
 #endif
     *out = idx.release();
@@ -634,6 +665,7 @@ int launch_seed(const mgb_index_t *index, const Batch &b, uint32_t n_strands, St
     // first pass (k_premap): rules out the k-mers the suffix-range table has no node for; the node arrays
     // are zero-filled, so the second pass only visits what is left
     const bool premap = index->view.sfx_len && index->view.sfx_len <= index->view.k - 1 && b.total_kmers
+                        && !index->view.kh_slots               // (the k-mer hash index answers every k-mer with one load)
                         && !std::getenv("MGB_TEST_NOPREMAP");
     if (premap) {
         const size_t words = (size_t)(b.total_kmers >> 5) + b.n_reads + 2;

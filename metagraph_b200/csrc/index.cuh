@@ -50,6 +50,13 @@ struct IndexView {
     const uint32_t *sfx;        // 2 words per indexed suffix: [begin, end) edge range
     const uint2 *adj;           // per edge: forward adjacency record (see adj_* below), or nullptr
     const uint2 *radj;          // per edge: reverse adjacency record (see load_radj), or nullptr
+    // k-mer -> edge hash index (DNA block layout, k <= 31; kh_slots == 0: absent). Open addressing, linear probing:
+    // kh_keys[i] = packed k-mer | 1 << 63 (0 = empty), kh_vals[i] = its BOSS edge. What BOSS::map_to_edge
+    // (boss.hpp:766-777: index() over k-1 characters, then pick_edge) answers with ~60 dependent block loads, this
+    // answers with one or two: HBM capacity traded for latency, as with the adjacency records.
+    const unsigned long long *kh_keys;
+    const uint32_t *kh_vals;
+    uint64_t kh_slots;
     uint64_t n;                 // number of edges (ids 1..n)
     uint32_t nblk;
     uint32_t k;                 // DBG k; BOSS node length = k - 1
@@ -617,6 +624,29 @@ MGB_HD void boss_index_range(const IndexView &ix, const uint8_t *codes, int len,
     *first = succ_last(ix, lc, rl);
     *lst = ru;
     *matched = i;
+}
+
+// ---------------------------------------------------------------------------------------
+// k-mer hash index: key = sum over positions p of (code_p - 1) << 2p (codes 1..4), k <= 31
+// ---------------------------------------------------------------------------------------
+MGB_HD uint64_t kh_slot_of(uint64_t key, uint64_t slots) {
+    const uint64_t h = key * 0x9E3779B97F4A7C15ull;
+#if MGB_DEVICE_CODE
+    return __umul64hi(h ^ (h >> 29), slots);
+#else
+    return (uint64_t)(((unsigned __int128)(h ^ (h >> 29)) * slots) >> 64);
+#endif
+}
+// edge of the k-mer `key62`, 0 if the graph does not have it
+MGB_HD uint64_t kh_lookup(const IndexView &ix, uint64_t key62) {
+    const uint64_t key = key62 | (1ull << 63);
+    uint64_t i = kh_slot_of(key, ix.kh_slots);
+    while (true) {
+        const uint64_t k = ix.kh_keys[i];
+        if (k == key) return ix.kh_vals[i];
+        if (k == 0) return 0;
+        if (++i == ix.kh_slots) i = 0;
+    }
 }
 
 } // namespace mgb

@@ -238,7 +238,11 @@ MGB_HD void sfx_extend_item(const SfxArgs &a, uint64_t o) {
 // Reverse adjacency construction (index.cuh load_radj): per edge bwd(e) + "source node has several
 // incoming edges", then k-2 gather rounds c_{j+1}[e] = c_j[bwd(e)] that move the last node character
 // (boss.cpp:679-690) to the first position of the k-mer.
-struct RadjArgs { IndexView ix; uint32_t *bwd_arr; uint8_t *c_cur; uint8_t *c_nxt; uint8_t *multi; uint2 *radj; uint64_t n; };
+struct RadjArgs { IndexView ix; uint32_t *bwd_arr; uint8_t *c_cur; uint8_t *c_nxt; uint8_t *multi; uint2 *radj; uint64_t n;
+                  // k-mer hash index build (nullptr: not built): the packed k-mer of every edge, accumulated over the same
+                  // gather rounds that move the node's last character to the first position
+                  unsigned long long *kmer; };
+static constexpr unsigned long long kKmerBad = ~0ull;      // the k-mer holds a '$'
 inline uint32_t radj_multi_shift(const IndexView &ix) { return ix.wide ? 7u : 3u; }   // index.cuh radj_multi
 
 MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
@@ -250,6 +254,14 @@ MGB_HD void radj_bwd_item(const RadjArgs &a, uint64_t e) {
         uint32_t w;
         succ_W2(a.ix, lc, x + 1, d, &w);
         multi = w == d + a.ix.sigma;
+    }
+    if (a.kmer) {
+        // last two characters of the k-mer: the edge label and the node's last character
+        const uint32_t lab = lc.get_W(a.ix, e) % a.ix.sigma;
+        const uint32_t K = a.ix.k;
+        if (glane() == 0)
+            a.kmer[e] = (lab == 0 || d == 0) ? kKmerBad
+                      : ((unsigned long long)(lab - 1) << (2 * (K - 1))) | ((unsigned long long)(d - 1) << (2 * (K - 2)));
     }
     if (glane() == 0) { a.bwd_arr[e] = (uint32_t)x; a.c_cur[e] = (uint8_t)d; a.multi[e] = (uint8_t)multi; }
 }
@@ -416,6 +428,44 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t items = (uint64_t)a.n_reads * a.n_strands;
+    if (ix.kh_slots) {
+        // ---- with the k-mer hash index: one strand per lane from start to end. Every k-mer costs one load: the
+        // adjacency record while the walk is warm, a hash probe (+ the value on a hit) when it is not; the packed
+        // k-mer is a rolling value. Every lane of a warp makes the same number of steps for reads of one length.
+        const uint32_t sigma = ix.sigma;
+        for (uint64_t item = warp * 32 + lane; item < items; item += nwarps * 32) {
+            const uint32_t r = (uint32_t)(item / a.n_strands), s = (uint32_t)(item % a.n_strands);
+            const uint64_t b = a.offsets[r];
+            const int L = (int)(a.offsets[r + 1] - b);
+            if (L < K) continue;
+            const int nk = L - K + 1;
+            const uint8_t *codes = (s ? a.cr : a.cf) + b;
+            uint64_t *out = (s ? a.nodes_r : a.nodes_f) + a.koff[r];
+            unsigned long long key = 0;
+            int last_bad = -1;
+            for (int j = 0; j < K - 1; ++j) {
+                const uint32_t c = codes[j];
+                if (c < 1 || c >= sigma) last_bad = j;
+                key = (key >> 2) | ((unsigned long long)((c - 1) & 3u) << (2 * (K - 1)));
+            }
+            uint64_t edge = 0;
+            for (int pos = 0; pos < nk; ++pos) {
+                const uint32_t c = codes[pos + K - 1];
+                if (c < 1 || c >= sigma) last_bad = pos + K - 1;
+                key = (key >> 2) | ((unsigned long long)((c - 1) & 3u) << (2 * (K - 1)));
+                if (last_bad >= pos) { edge = 0; continue; }           // an invalid character in the window (out[] is zero-filled)
+                if (edge) {                                            // warm (boss.cpp:1024-1043)
+                    const uint2 ar = load_adj(ix, edge);
+                    edge = adj_child(ar, c);
+                    if (edge && ((ar.y >> (8 + c)) & 1u)) out[pos] = edge;
+                } else {                                               // cold (map_to_edge, boss.hpp:766-777)
+                    edge = kh_lookup(ix, key);
+                    if (edge && in_graph(ix, edge)) out[pos] = edge;
+                }
+            }
+        }
+        return;
+    }
     const int S = (ix.sfx_len && (int)ix.sfx_len <= K - 1) ? (int)ix.sfx_len : 0;
     const uint64_t base = ix.sigma - 1;
     for (uint64_t chunk = warp * 32; chunk < items; chunk += nwarps * 32) {
@@ -579,10 +629,32 @@ __global__ void __launch_bounds__(256) k_prepare(PrepArgs a) {
     uint32_t nwarps = (gridDim.x * blockDim.x) / kWarp;
     for (uint32_t r = warp; r < a.n_reads; r += nwarps) prepare_read(a, r);
 }
-__global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a) {
+// round r (0-based) brings character k - 3 - r of every edge's k-mer to c_nxt[e]; kmer_shift = 2 * (k - 3 - r)
+__global__ void __launch_bounds__(256) k_radj_gather(RadjArgs a, int kmer_shift) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = 1 + t; e <= a.n; e += nt) a.c_nxt[e] = a.c_cur[a.bwd_arr[e]];
+    for (uint64_t e = 1 + t; e <= a.n; e += nt) {
+        const uint8_t c = a.c_cur[a.bwd_arr[e]];
+        a.c_nxt[e] = c;
+        if (a.kmer) {
+            const unsigned long long km = a.kmer[e];
+            if (km != kKmerBad) a.kmer[e] = c == 0 ? kKmerBad : (km | ((unsigned long long)(c - 1) << kmer_shift));
+        }
+    }
+}
+// k-mer hash index: one slot per k-mer without '$' (every such edge spells a distinct k-mer)
+__global__ void __launch_bounds__(256) k_kmer_insert(const unsigned long long *kmer, uint64_t n, unsigned long long *keys,
+                                                     uint32_t *vals, uint64_t slots) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t nt = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = 1 + t; e <= n; e += nt) {
+        const unsigned long long km = kmer[e];
+        if (km == kKmerBad) continue;
+        const unsigned long long key = km | (1ull << 63);
+        uint64_t i = kh_slot_of(key, slots);
+        while (atomicCAS(keys + i, 0ull, key) != 0ull) { if (++i == slots) i = 0; }
+        vals[i] = (uint32_t)e;
+    }
 }
 __global__ void __launch_bounds__(256) k_radj_pack(RadjArgs a, uint32_t multi_shift) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
