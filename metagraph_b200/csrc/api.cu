@@ -372,6 +372,16 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     idx->num_sms = prop.multiProcessorCount;
+    {   // Every access of this path to the index and to the per-read arenas is a single 8 .. 64-byte record at a
+        // data-dependent address; L2 fetches 128-byte lines from HBM for them (k_seed: 146 bytes of DRAM traffic per
+        // 8-byte adjacency / 32-byte hash-bucket access). MGB_L2_FETCH=32 / 64 asks for smaller fetches (process-wide).
+        // (measured: 32-byte fetches cut k_seed's DRAM bytes from 35 to 12 GB per 1 M reads and made it SLOWER, 12.9 ->
+        // 15.7 ms: the access rate, not the bytes, is what HBM limits here. Left at the default unless MGB_L2_FETCH is set.)
+        size_t gran = 0;
+        if (const char *e = std::getenv("MGB_L2_FETCH")) gran = (size_t)std::atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     {   // keep stream-ordered allocations cached between calls
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -469,7 +479,7 @@ int mgb_index_create(const uint8_t *W, const uint8_t *last, uint64_t n_plus_1, c
         // of the gather rounds below; 12 bytes per slot at a load factor of 0.7. Skipped (the seeding kernel then looks
         // k-mers up through the suffix-range table and tighten_range) if the memory is not there or MGB_NO_KMER_HASH is set.
         unsigned long long *kmer = nullptr, *kh_keys = nullptr; uint32_t *kh_vals = nullptr;
-        const uint64_t kh_slots = (uint64_t)((double)(n + 1) / 0.7) + 64;
+        const uint64_t kh_slots = (((uint64_t)((double)(n + 1) / 0.7) + 64) + 3) & ~3ull;     // whole buckets of 4
         if (!idx->view.wide && k >= 3 && k <= 31 && !std::getenv("MGB_NO_KMER_HASH")) {
             size_t free_b = 0, total_b = 0;
             cudaMemGetInfo(&free_b, &total_b);

@@ -449,19 +449,42 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs a) {
                 key = (key >> 2) | ((unsigned long long)((c - 1) & 3u) << (2 * (K - 1)));
             }
             uint64_t edge = 0;
+            const unsigned long long *keys = ix.kh_keys;
+            const uint64_t slots = ix.kh_slots;
+            // one step per k-mer, written with selects rather than branches: the lanes of a warp are in different
+            // regimes (warm / cold / inside an invalid window) at the same step and should still issue together
             for (int pos = 0; pos < nk; ++pos) {
                 const uint32_t c = codes[pos + K - 1];
                 if (c < 1 || c >= sigma) last_bad = pos + K - 1;
                 key = (key >> 2) | ((unsigned long long)((c - 1) & 3u) << (2 * (K - 1)));
-                if (last_bad >= pos) { edge = 0; continue; }           // an invalid character in the window (out[] is zero-filled)
-                if (edge) {                                            // warm (boss.cpp:1024-1043)
-                    const uint2 ar = load_adj(ix, edge);
-                    edge = adj_child(ar, c);
-                    if (edge && ((ar.y >> (8 + c)) & 1u)) out[pos] = edge;
-                } else {                                               // cold (map_to_edge, boss.hpp:766-777)
-                    edge = kh_lookup(ix, key);
-                    if (edge && in_graph(ix, edge)) out[pos] = edge;
+                const bool ok = last_bad < pos;                        // no invalid character in the window
+                const bool warm = ok && edge != 0, cold = ok && edge == 0;
+                const unsigned long long want = key | (1ull << 63);
+                uint64_t slot = kh_slot_of(want, slots);
+                uint2 ar = make_uint2(0u, 0u);
+                ulonglong2 ka = make_ulonglong2(0ull, 0ull), kb = ka;
+                if (warm) ar = load_adj(ix, edge);                     // boss.cpp:1024-1043
+                if (cold) {                                            // map_to_edge (boss.hpp:766-777): the k-mer's bucket
+                    ka = __ldg(reinterpret_cast<const ulonglong2*>(keys + slot));
+                    kb = __ldg(reinterpret_cast<const ulonglong2*>(keys + slot + 2));
                 }
+                int h = ka.x == want ? 0 : ka.y == want ? 1 : kb.x == want ? 2 : kb.y == want ? 3 : -1;
+                // a full bucket without the k-mer: its run goes on in the next buckets (rare at this load factor)
+                bool more = cold && h < 0 && ka.x != 0 && ka.y != 0 && kb.x != 0 && kb.y != 0;
+                while (more) {
+                    slot += 4; if (slot >= slots) slot = 0;
+                    ka = __ldg(reinterpret_cast<const ulonglong2*>(keys + slot));
+                    kb = __ldg(reinterpret_cast<const ulonglong2*>(keys + slot + 2));
+                    h = ka.x == want ? 0 : ka.y == want ? 1 : kb.x == want ? 2 : kb.y == want ? 3 : -1;
+                    more = h < 0 && ka.x != 0 && ka.y != 0 && kb.x != 0 && kb.y != 0;
+                }
+                uint64_t found = 0;
+                if (cold && h >= 0) found = ix.kh_vals[slot + h];
+                const uint64_t child = adj_child(ar, c);              // 0 for lanes that are not warm (ar = 0)
+                const bool child_ok = (ar.y >> (8 + c)) & 1u;
+                edge = warm ? child : found;                           // (0 when the window is invalid)
+                const bool store = warm ? (child != 0 && child_ok) : (found != 0 && in_graph(ix, found));
+                if (store) out[pos] = edge;
             }
         }
         return;
