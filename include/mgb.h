@@ -37,6 +37,7 @@ extern "C" {
 #define MGB_ERR_UNSUPPORTED (-4)  /* a configuration or graph the kernels do not serve (chaining, labels, ...) */
 #define MGB_ERR_OVERFLOW (-5)     /* a read exceeded the largest per-read work arena */
 #define MGB_ERR_NO_DEVICE (-6)
+#define MGB_ERR_NO_MEMORY (-7)    /* host allocation failed (index construction) */
 
 #define MGB_ALPHABET_DNA 0      /* "$ACGT", sigma = 5 (kmer/alphabets.hpp:64-79) */
 #define MGB_ALPHABET_PROTEIN 1  /* "$ABCDEFGHIJKLMNOPQRSTUVWYZX", sigma = 27 (kmer/alphabets.hpp:29-38) */
@@ -217,6 +218,8 @@ typedef struct mgb_boss {
 } mgb_boss_t;
 int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t k,
                    int alphabet, int force_source_dummies, int num_threads, mgb_boss_t *out);
+/* Text for the last failed mgb_boss_build() on this thread ("" after a success). */
+const char* mgb_boss_last_error(void);
 void mgb_boss_free(mgb_boss_t *boss);
 /* Dummy-k-mer mask as DBGSuccinct::mask_dummy_kmers computes it (dbg_succinct.cpp:917-932);
  * valid must hold n_plus_1 bytes. */

@@ -13,7 +13,7 @@ DEFAULT_LIB = os.path.join(_HERE, "_lib", "libmgb.so")
 
 MGB_OK = 0
 ERRORS = {-1: "INVALID_ARGUMENT", -2: "CUDA", -3: "BAD_CONFIG", -4: "UNSUPPORTED", -5: "OVERFLOW",
-          -6: "NO_DEVICE"}
+          -6: "NO_DEVICE", -7: "NO_MEMORY"}
 
 
 class MgbError(RuntimeError):
@@ -104,6 +104,7 @@ def load_library(path=None):
     L.mgb_dbg_load.restype = i
     L.mgb_dbg_load.argtypes = [ctypes.c_char_p, ctypes.POINTER(mgb_boss_t), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.mgb_dbg_last_error.restype = ctypes.c_char_p
+    L.mgb_boss_last_error.restype = ctypes.c_char_p
     L.mgb_set_pipeline_pieces.restype = None
     L.mgb_set_pipeline_pieces.argtypes = [u32]
     L.mgb_set_host_threads.restype = None
@@ -123,5 +124,5 @@ REQUIRED_SYMBOLS = [
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
     "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_results_export_bytes",
     "mgb_results_export", "mgb_results_import", "mgb_boss_build", "mgb_boss_free",
-    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_index_set_mode",
+    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_boss_last_error", "mgb_index_set_mode",
 ]

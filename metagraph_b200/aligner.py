@@ -53,7 +53,7 @@ class BOSSTable:
         rc = L.mgb_boss_build(buf.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k, int(alphabet),
                               int(force_source_dummies), threads, ctypes.byref(b))
         if rc:
-            raise _lib.MgbError(rc, "mgb_boss_build failed")
+            raise _lib.MgbError(rc, "mgb_boss_build: " + L.mgb_boss_last_error().decode())
         try:
             n1 = b.n_plus_1
             W = np.ctypeslib.as_array(b.W, shape=(n1,)).copy()

@@ -8,6 +8,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <parallel/algorithm>
@@ -16,6 +18,8 @@
 #include "../../include/mgb.h"
 
 namespace {
+
+thread_local std::string g_boss_err;
 
 typedef unsigned __int128 u128;
 thread_local std::string g_build_err;
@@ -203,7 +207,11 @@ int build_with_key(const Alpha &al, const char *seqs, const uint64_t *offsets, u
     const uint64_t n_total = real.size() + dummy.size();
     uint8_t *W = (uint8_t*)std::malloc(n_total + 2);
     uint8_t *last = (uint8_t*)std::malloc(n_total + 2);
-    if (!W || !last) { std::free(W); std::free(last); return MGB_ERR_INVALID_ARGUMENT; }
+    if (!W || !last) {
+        std::free(W); std::free(last);
+        g_boss_err = "out of host memory for W / last (" + std::to_string(2 * (n_total + 2)) + " bytes)";
+        return MGB_ERR_NO_MEMORY;
+    }
     W[0] = 0; last[0] = 0;
     std::memset(out->F, 0, sizeof(out->F));
     uint64_t curpos = 1;
@@ -254,19 +262,31 @@ int build_with_key(const Alpha &al, const char *seqs, const uint64_t *offsets, u
 
 extern "C" {
 
+const char* mgb_boss_last_error(void) { return g_boss_err.c_str(); }
+
 int mgb_boss_build(const char *seqs, const uint64_t *offsets, uint32_t n_seqs, uint32_t K,
                    int alphabet, int force_source_dummies, int num_threads, mgb_boss_t *out) {
-    if (!offsets || !out || (n_seqs && !seqs)) return MGB_ERR_INVALID_ARGUMENT;
-    if (alphabet != MGB_ALPHABET_DNA && alphabet != MGB_ALPHABET_PROTEIN) return MGB_ERR_UNSUPPORTED;
-    if (K < 2) return MGB_ERR_INVALID_ARGUMENT;
+    auto fail = [](int rc, const std::string &why) { g_boss_err = why; return rc; };
+    g_boss_err.clear();
+    if (!offsets || !out || (n_seqs && !seqs)) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    if (alphabet != MGB_ALPHABET_DNA && alphabet != MGB_ALPHABET_PROTEIN)
+        return fail(MGB_ERR_UNSUPPORTED, "unknown alphabet " + std::to_string(alphabet));
+    if (K < 2) return fail(MGB_ERR_INVALID_ARGUMENT, "k must be at least 2");
     const Alpha al = alphabet == MGB_ALPHABET_PROTEIN ? make_protein() : make_dna();
-    if ((uint64_t)K * al.bits > 256) return MGB_ERR_UNSUPPORTED;      // DNA: k <= 85, protein: k <= 51
+    if ((uint64_t)K * al.bits > 256)                                   // DNA: k <= 85, protein: k <= 51
+        return fail(MGB_ERR_UNSUPPORTED, "k = " + std::to_string(K) + " does not fit the 256-bit (k+1)-mer keys");
     if (num_threads < 1) num_threads = omp_get_max_threads();
     omp_set_num_threads(num_threads);
-    // MGB_TEST_WIDE_KEYS=1 (tests): every graph through the 256-bit instantiation
-    if ((uint64_t)K * al.bits <= 128 && !std::getenv("MGB_TEST_WIDE_KEYS"))
-        return build_with_key<u128>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
-    return build_with_key<Wide256>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
+    try {
+        // MGB_TEST_WIDE_KEYS=1 (tests): every graph through the 256-bit instantiation
+        if ((uint64_t)K * al.bits <= 128 && !std::getenv("MGB_TEST_WIDE_KEYS"))
+            return build_with_key<u128>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
+        return build_with_key<Wide256>(al, seqs, offsets, n_seqs, K, alphabet, force_source_dummies, num_threads, out);
+    } catch (const std::bad_alloc &) {
+        return fail(MGB_ERR_NO_MEMORY, "out of host memory while sorting the (k+1)-mers");
+    } catch (const std::exception &e) {
+        return fail(MGB_ERR_INVALID_ARGUMENT, e.what());
+    }
 }
 
 void mgb_boss_free(mgb_boss_t *b) {

@@ -43,7 +43,14 @@ thread_local std::string g_load_err;
 struct Reader {
     std::vector<uint8_t> b;
     size_t p = 0;
-    void need(size_t n) const { if (p + n > b.size()) throw std::runtime_error("unexpected end of file"); }
+    // overflow-safe: a corrupt length field must not wrap around the bound
+    void need(uint64_t n) const { if (n > b.size() - p) throw std::runtime_error("unexpected end of file"); }
+    // number of 64-bit words of a vector of `bits` bits, checked against what is left of the file
+    uint64_t words_of(uint64_t bits) const {
+        const uint64_t nw = bits / 64 + (bits % 64 != 0);
+        if (nw > (b.size() - p) / 8) throw std::runtime_error("vector longer than the file");
+        return nw;
+    }
     uint64_t be() { need(8); uint64_t v = 0; for (int i = 0; i < 8; ++i) v = (v << 8) | b[p + i]; p += 8; return v; }
     uint64_t le() { need(8); uint64_t v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | b[p + i]; p += 8; return v; }
     uint8_t u8() { need(1); return b[p++]; }
@@ -58,6 +65,7 @@ struct Bits {
     bool get(uint64_t i) const { return (w[i >> 6] >> (i & 63)) & 1u; }
     uint64_t get_int(uint64_t pos, unsigned len) const {     // len <= 64, bits [pos, pos + len)
         if (!len) return 0;
+        if (len > 64 || (pos >> 6) + 1 >= w.size()) throw std::runtime_error("bit vector read out of range");
         uint64_t lo = w[pos >> 6] >> (pos & 63);
         unsigned got = 64 - (unsigned)(pos & 63);
         if (got < len) lo |= w[(pos >> 6) + 1] << got;
@@ -66,8 +74,7 @@ struct Bits {
 };
 Bits read_bits(Reader &r) {
     Bits v; v.size = r.le();
-    const uint64_t nw = (v.size + 63) / 64;
-    r.need(nw * 8);
+    const uint64_t nw = r.words_of(v.size);
     v.w.resize(nw + 1, 0);
     for (uint64_t i = 0; i < nw; ++i) v.w[i] = r.le();
     return v;
@@ -82,20 +89,20 @@ Ints read_ints(Reader &r) {
     Ints v;
     const uint64_t sz = r.le();
     v.width = r.u8();
+    if (v.width < 1 || v.width > 64) throw std::runtime_error("int_vector width " + std::to_string(v.width));
     v.bits.size = sz;
-    const uint64_t nw = (sz + 63) / 64;
-    r.need(nw * 8);
+    const uint64_t nw = r.words_of(sz);
     v.bits.w.resize(nw + 1, 0);
     for (uint64_t i = 0; i < nw; ++i) v.bits.w[i] = r.le();
     return v;
 }
-void skip_ints64(Reader &r) { const uint64_t sz = r.le(); r.skip((sz + 63) / 64 * 8); }   // int_vector<64>
+void skip_ints64(Reader &r) { const uint64_t sz = r.le(); r.skip(r.words_of(sz) * 8); }   // int_vector<64>
 // sdsl::select_support_mcl: #args; if any: superblocks, a flag vector, one vector per 4096 args
 void skip_select_mcl(Reader &r) {
     const uint64_t cnt = r.le();
     if (!cnt) return;
     read_ints(r);
-    const uint64_t sb = (cnt + 4095) >> 12;
+    const uint64_t sb = cnt / 4096 + (cnt % 4096 != 0);
     Bits mini_or_long = read_bits(r);
     (void)mini_or_long;
     for (uint64_t i = 0; i < sb; ++i) read_ints(r);
@@ -134,17 +141,18 @@ Bits read_rrr(Reader &r) {
     Bits btnr = read_bits(r);
     read_ints(r);                // sampled pointers into btnr
     read_ints(r);                // sampled ranks
-    Bits out; out.size = size; out.w.assign((size + 63) / 64 + 2, 0);
+    if (size / kRrrBlock > bt.size()) throw std::runtime_error("rrr_vector: block class array too short");
+    Bits out; out.size = size; out.w.assign(size / 64 + 3, 0);
     const Binomial &B = binom();
     uint64_t pos = 0;
-    const uint64_t nblocks = (size + kRrrBlock - 1) / kRrrBlock;
+    const uint64_t nblocks = size / kRrrBlock + (size % kRrrBlock != 0);
     if (bt.size() < nblocks) throw std::runtime_error("rrr_vector: block class array too short");
     const uint64_t full = (1ull << kRrrBlock) - 1;
     for (uint64_t i = 0; i < nblocks; ++i) {
         const unsigned k = (unsigned)bt[i];
         if (k > (unsigned)kRrrBlock) throw std::runtime_error("rrr_vector: bad block class");
         const unsigned sp = B.space[k];
-        if (pos + sp > btnr.size + 64) throw std::runtime_error("rrr_vector: offsets overrun");
+        if (pos > btnr.size || sp > btnr.size - pos) throw std::runtime_error("rrr_vector: offsets overrun");
         const uint64_t nr = btnr.get_int(pos, sp);
         pos += sp;
         // blocks with more than half of the bits set are stored complemented
@@ -165,12 +173,15 @@ Bits read_sd(Reader &r) {
     Ints low = read_ints(r);
     Bits high = read_bits(r);
     skip_select_mcl(r); skip_select_mcl(r);
-    Bits out; out.size = size; out.w.assign((size + 63) / 64 + 1, 0);
+    if (wl > 63) throw std::runtime_error("sd_vector: bad low width");
+    if (size / 64 > (uint64_t)r.b.size() * 64) throw std::runtime_error("sd_vector: length field larger than the file allows");
+    Bits out; out.size = size; out.w.assign(size / 64 + 2, 0);
     uint64_t ones = 0;
     for (uint64_t i = 0; i < high.size; ++i) {
         if (!high.get(i)) continue;
         const uint64_t hi = i - ones;                    // number of zeros before this one
         if (ones >= low.size()) throw std::runtime_error("sd_vector: low part too short");
+        if (wl && (hi >> (64 - wl))) throw std::runtime_error("sd_vector: position out of range");
         const uint64_t v = (hi << wl) | low[ones];
         if (v >= size) throw std::runtime_error("sd_vector: position out of range");
         out.w[v >> 6] |= 1ull << (v & 63);
@@ -182,7 +193,9 @@ Bits read_sd(Reader &r) {
 // --- wt_huff ---------------------------------------------------------------------------------------
 struct WtNode { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child[2]; };
 void wt_decode(const Bits &bv, const std::vector<WtNode> &nodes, uint16_t v, const std::vector<uint64_t> &idx,
-               std::vector<uint8_t> &out) {
+               std::vector<uint8_t> &out, unsigned depth = 0) {
+    // a Huffman tree over <= 2 * 27 symbols is at most that deep: anything deeper is a cycle in a corrupt file
+    if (depth > 64) throw std::runtime_error("wt_huff: tree too deep (cycle?)");
     const WtNode &nd = nodes.at(v);
     if (nd.child[0] == 0xffff) {                         // leaf: bv_pos_rank holds the symbol
         for (uint64_t i : idx) out[i] = (uint8_t)nd.bv_pos_rank;
@@ -190,11 +203,11 @@ void wt_decode(const Bits &bv, const std::vector<WtNode> &nodes, uint16_t v, con
     }
     std::vector<uint64_t> l, rr;
     for (uint64_t j = 0; j < idx.size(); ++j) {
-        if (nd.bv_pos + j >= bv.size) throw std::runtime_error("wt_huff: node beyond the bit vector");
+        if (nd.bv_pos >= bv.size || j >= bv.size - nd.bv_pos) throw std::runtime_error("wt_huff: node beyond the bit vector");
         (bv.get(nd.bv_pos + j) ? rr : l).push_back(idx[j]);
     }
-    wt_decode(bv, nodes, nd.child[0], l, out);
-    wt_decode(bv, nodes, nd.child[1], rr, out);
+    wt_decode(bv, nodes, nd.child[0], l, out, depth + 1);
+    wt_decode(bv, nodes, nd.child[1], rr, out, depth + 1);
 }
 std::vector<uint8_t> read_wt_huff(Reader &r, bool rrr) {
     const uint64_t n = r.le();
@@ -210,6 +223,8 @@ std::vector<uint8_t> read_wt_huff(Reader &r, bool rrr) {
         nd.parent = r.le16(); nd.child[0] = r.le16(); nd.child[1] = r.le16();
     }
     r.skip(256 * 2 + 256 * 8);                           // symbol -> leaf, symbol -> path
+    if (n > bv.size + 1 && n_nodes > 1) throw std::runtime_error("wt_huff: more symbols than tree bits");
+    if (n > (uint64_t)r.b.size() * 64) throw std::runtime_error("wt_huff: length field larger than the file allows");
     std::vector<uint8_t> out(n, 0);
     if (n) {
         if (nodes.empty()) throw std::runtime_error("wt_huff: empty tree");
@@ -241,6 +256,9 @@ int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode_out, int *state_ou
         std::vector<uint64_t> F(nf);
         for (auto &f : F) f = r.be();
         const uint64_t k_node = r.be();
+        // node length k_node = k - 1; the device keys hold k <= 85 DNA / k <= 51 protein characters (mgb.h)
+        if (k_node < 1 || k_node + 1 > (nf == 27 ? 51u : 85u))
+            throw std::runtime_error("k = " + std::to_string(k_node + 1) + " is outside the supported range");
         const uint64_t state = r.be();
         if (state_out) *state_out = (int)state;
         if (state != 1 && state != 3)

@@ -74,3 +74,55 @@ def test_loader_rejects_garbage(tmp_path):
     p.write_bytes(b"\x00" * 64)
     with pytest.raises(_lib.MgbError):
         BOSSTable.from_dbg(str(p), lib=EMU)
+
+
+MUTATE = r'''
+import os, sys
+sys.path.insert(0, ROOT)
+import numpy as np
+from metagraph_b200 import _lib
+from metagraph_b200.aligner import BOSSTable
+src = open(SRC, "rb").read()
+rng = np.random.default_rng(11)
+ok = bad = 0
+def attempt(buf):
+    global ok, bad
+    open(TMP, "wb").write(bytes(buf))
+    try:
+        BOSSTable.from_dbg(TMP, lib=EMU); ok += 1
+    except _lib.MgbError:
+        bad += 1
+# every 8-byte field in turn replaced by all-ones / a huge length / a small wrong value
+for off in range(0, len(src) - 8, 8 if len(src) < 3500 else 16):
+    for patt in (b"\xff" * 8, b"\x00" * 7 + b"\x80", b"\x01" + b"\x00" * 7):
+        b = bytearray(src); b[off:off + 8] = patt; attempt(b)
+# random single-byte damage (also hits the width bytes and the 16-bit tree links)
+for _ in range(600):
+    b = bytearray(src); b[int(rng.integers(0, len(src)))] = int(rng.integers(0, 256)); attempt(b)
+# truncation at every length up to the first KB, then sparsely
+for n in list(range(0, 1024, 7)) + list(range(1024, len(src), 131)):
+    attempt(src[:n])
+print("MUTATIONS_DONE", ok, bad)
+'''
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[3] for c in CASES])
+def test_loader_survives_damaged_files(case, tmp_path):
+    """ADVICE r1: a malformed file must end in MgbError (or load, if the damage hit a part the loader skips) —
+    never in a crash, a hang or an out-of-memory kill. Run in a child so that a crash fails this test only."""
+    import sys
+    script = tmp_path / "mutate.py"
+    script.write_text("ROOT = %r\nEMU = %r\nSRC = %r\nTMP = %r\n" % (ROOT, EMU, os.path.join(EX, case[0]),
+                                                                   str(tmp_path / "m.dbg")) + MUTATE)
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-1000:] + out.stderr[-3000:]
+    assert "MUTATIONS_DONE" in out.stdout
+    ok, bad = map(int, out.stdout.split("MUTATIONS_DONE")[1].split()[:2])
+    assert bad > 300          # most damage is detected; the rest hit rank/select payloads the loader skips
+
+
+def test_boss_build_reports_why():
+    with pytest.raises(_lib.MgbError, match="256-bit"):
+        BOSSTable.from_sequences(90, ["ACGT" * 50], lib=EMU)
+    with pytest.raises(_lib.MgbError, match="at least 2"):
+        BOSSTable.from_sequences(1, ["ACGT" * 50], lib=EMU)
