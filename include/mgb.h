@@ -182,7 +182,8 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
  * then do not overlap), 0 = automatic (default). Process-wide. */
 void mgb_set_pipeline_pieces(uint32_t max_pieces);
 /* Host threads for the unpacking of results (mgb_align_batch, mgb_results_export / import): launchers such as
- * torchrun start every rank with OMP_NUM_THREADS=1; a rank that owns cores/ranks of them says so here. Process-wide. */
+ * torchrun start every rank with OMP_NUM_THREADS=1; a rank that owns cores/ranks of them says so here. Process-wide.
+ * The library never uses more than 16 threads per call for this work whatever the setting (the loops are short). */
 void mgb_set_host_threads(int num_threads);
 
 uint32_t mgb_results_num_reads(const mgb_results_t *results);

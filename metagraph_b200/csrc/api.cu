@@ -22,6 +22,19 @@
 #include <omp.h>
 #endif
 
+// Threads per OpenMP team of the result-unpacking loops. They are short, memory-bound loops that run on two
+// pipeline lanes at once: beyond a few cores they gain nothing, and with one team per lane as wide as a
+// 128-thread host the teams spend their time spinning against each other (measured: a 36 ms call took 470 ms,
+// profiles/r2_e2e_probe.txt). mgb_set_host_threads() can only lower the number.
+[[maybe_unused]] static inline int host_team() {
+#if defined(_OPENMP)
+    const int n = omp_get_max_threads();
+    return n < 16 ? (n < 1 ? 1 : n) : 16;
+#else
+    return 1;
+#endif
+}
+
 #include "../../include/mgb.h"
 #if !defined(MGB_HOST_EMU)
 #define MGB_NARROW_ONLY 1        // this translation unit's kernels: DNA block layout only (see kernels.cuh)
@@ -876,7 +889,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
         std::vector<uint32_t> list(n_reads);
         for (uint32_t r = 0; r < n_reads; ++r) list[r] = r;
         uint32_t scale = 1;
-        float align_ms = 0, d2h_ms = 0;
+        float align_ms = 0, d2h_ms = 0; (void)align_ms; (void)d2h_ms;
         for (int pass = 0; !rc && !list.empty(); ++pass, scale *= 4) {
             if (pass == 6) { rc = fail(MGB_ERR_OVERFLOW, "a read exceeded the largest per-read work arena"); break; }
             Caps caps = choose_caps(b.L_max, dcfg, index->view.k, scale);
@@ -1052,7 +1065,7 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
         uint64_t pos = 0;
         for (uint32_t r = 0; r < n_reads; ++r) { res->first[r] = pos; pos += res->count[r]; }
         res->n_alns = pos;
-        #pragma omp parallel for schedule(static) if (n_reads > 20000)
+        #pragma omp parallel for schedule(static) num_threads(host_team()) if (n_reads > 20000)
         for (int64_t r = 0; r < (int64_t)n_reads; ++r) {
             const char *p = res->heaps[read_heap[r]].p + byte_off[r];
             for (uint32_t i = 0; i < res->count[r]; ++i) {
@@ -1155,9 +1168,14 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
                 if (pc.rc) { pc.err = g_err; failed.store(true); }
             }
         };
-        std::thread other(lane);
+        // two host threads keep two pieces in flight (MGB_TEST_LANES: measurement knob)
+        uint32_t n_lanes = 2;
+        if (const char *e = std::getenv("MGB_TEST_LANES")) n_lanes = std::max(1, std::atoi(e));
+        n_lanes = std::min(n_lanes, n_pieces);
+        std::vector<std::thread> others;
+        for (uint32_t t = 1; t < n_lanes; ++t) others.emplace_back(lane);
         lane();
-        other.join();
+        for (std::thread &t : others) t.join();
         for (Piece &pc : pieces)
             if (pc.rc) return fail(pc.rc, pc.err);
     }
@@ -1173,7 +1191,7 @@ int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const 
         }
         if (total) {
             const int64_t n = pc.n_reads;
-            #pragma omp parallel for schedule(static) if (n > 50000)
+            #pragma omp parallel for schedule(static) num_threads(host_team()) if (n > 50000)
             for (int64_t r = 0; r < n; ++r) pc.first[r] += total;
         }
         total += pc.n_alns;
@@ -1224,7 +1242,7 @@ int mgb_results_export(const mgb_results_t *r, void *dst, uint64_t capacity) {
     for (size_t i = 0; i < r->heaps.size(); ++i) {
         const uint64_t n = r->heap_bytes[i];
         const int64_t chunks = (int64_t)((n + (1 << 22) - 1) >> 22);
-        #pragma omp parallel for schedule(static) if (chunks > 4)
+        #pragma omp parallel for schedule(static) num_threads(host_team()) if (chunks > 4)
         for (int64_t c = 0; c < chunks; ++c) {
             const uint64_t lo = (uint64_t)c << 22, len = std::min<uint64_t>(1ull << 22, n - lo);
             std::memcpy(p + lo, r->heaps[i].p + lo, len);
@@ -1262,7 +1280,7 @@ int mgb_results_import(const void *blob, uint64_t bytes, uint32_t read_index_bas
         uint64_t o = 0;
         for (size_t i = 0; i < h.n_heaps; ++i) { heap_base[i] = o; o += (res->heap_bytes[i] + 15) & ~15ull; }
         const int64_t chunks = (int64_t)((heaps_total + (1 << 22) - 1) >> 22);
-        #pragma omp parallel for schedule(static) if (chunks > 4)
+        #pragma omp parallel for schedule(static) num_threads(host_team()) if (chunks > 4)
         for (int64_t c = 0; c < chunks; ++c) {
             const uint64_t lo = (uint64_t)c << 22, len = std::min<uint64_t>(1ull << 22, heaps_total - lo);
             std::memcpy(hb.p + lo, p + lo, len);
@@ -1275,7 +1293,7 @@ int mgb_results_import(const void *blob, uint64_t bytes, uint32_t read_index_bas
     for (uint32_t r = 0; r < n; ++r) { res->first[r] = pos; pos += res->count[r]; }
     if (pos != h.n_alns) return fail(MGB_ERR_INVALID_ARGUMENT, "inconsistent export blob");
     const bool no_nodes = res->result_nodes != 0;
-    #pragma omp parallel for schedule(static) if (n > 20000)
+    #pragma omp parallel for schedule(static) num_threads(host_team()) if (n > 20000)
     for (int64_t r = 0; r < (int64_t)n; ++r) {
         if (!res->count[r]) continue;
         const char *q = hb.p + heap_base[res->src_heap[r]] + res->src_off[r];
