@@ -1089,6 +1089,9 @@ static int align_range(const mgb_index_t *index, const DevConfig &dcfg, const ch
 }
 
 static std::atomic<uint32_t> g_max_pieces{0};      // 0 = automatic
+#if defined(MGB_HOST_EMU)
+extern "C" { unsigned long long mgb_emu_whole_read_hits = 0; }
+#endif
 
 extern "C" {
 

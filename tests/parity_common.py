@@ -101,6 +101,17 @@ def random_case(lib, seed, k, G, nreads, L, rate, cfg, mask=False, nseq=1):
     return stats
 
 
+def whole_read_hits(lib):
+    """test counter of the host-emulation build (None for the product library)"""
+    import ctypes
+    from metagraph_b200 import _lib
+    L = _lib.load_library(lib)
+    try:
+        return ctypes.c_ulonglong.in_dll(L, "mgb_emu_whole_read_hits").value
+    except ValueError:
+        return None
+
+
 def exact_shortcut_case(lib, seed, k, cfg, nseq=3, G=3000, nreads=80, L=90):
     """Reads that match a path of the graph exactly (the exact-path shortcut of the extender applies to them) on a
     graph with variants and a tandem repeat, mixed with reads carrying errors; kernels (shortcut on) == oracle, and
@@ -122,11 +133,19 @@ def exact_shortcut_case(lib, seed, k, cfg, nseq=3, G=3000, nreads=80, L=90):
     reads.append(base[G // 2 - 20:G // 2 + 60])                      # runs into the repeat
     reads.append("ACGT" * (L // 4))
     exp = g.align_tsv(cfg, reads, with_nodes=True)
+    hits0 = whole_read_hits(lib)
     got, _ = run_lines(idx, cfg, reads)
+    hits1 = whole_read_hits(lib)
     bad = [i for i in range(len(reads)) if exp[i] != got[i]]
     assert not bad, (seed, bad[:3], exp[bad[0]], got[bad[0]])
     got2, _ = run_lines(idx, dataclasses.replace(cfg, no_exact_path_shortcut=True), reads)
     assert got2 == got
+    if hits0 is not None:
+        # host emulation: the whole-read form of the shortcut (exact seeder, both strands) answered reads in the first
+        # run exactly when the configuration allows it, and none with the shortcut switched off
+        exact = cfg.min_seed_length == k and cfg.max_seed_length == k and cfg.forward_and_reverse_complement
+        assert (hits1 - hits0 >= nreads // 3) if exact else (hits1 == hits0), (hits0, hits1, exact)
+        assert whole_read_hits(lib) == hits1
     full = sum(1 for r, l in zip(reads, got) if ("\t%d=\t" % len(r)) in l)
     assert full >= nreads // 2
     idx.close()
@@ -140,6 +159,64 @@ EXACT_SHORTCUT_CASES = [
     (105, 17, lambda k: cli_defaults(k, forward_and_reverse_complement=False)),
     (106, 13, lambda k: struct_defaults(xdrop=20, min_seed_length=k, max_seed_length=k)),
     (107, 19, lambda k: cli_defaults(k, num_alternative_paths=2)),                  # two reported paths: no shortcut
+]
+
+def whole_read_case(lib, seed, k, cfg, G=2500, L=70):
+    """Reads around the whole-read form of the exact-path shortcut (exact seeder, both strands): reads that are paths
+    of the graph on either strand, reads whose other strand has k-mers in the graph as well (the graph holds a region
+    and its reverse complement; palindromes), reads of length k and k - 1, reads with an 'N' or one wrong base, a read
+    that leaves the graph at its last base. Kernels == oracle, shortcut on and off."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    base = "".join(np.array(list("ACGT"))[rng.integers(0, 4, G)])
+    region = base[300:300 + 3 * L]
+    pal = "".join(np.array(list("ACGT"))[rng.integers(0, 4, L // 2)])
+    pal = pal + pal.translate(COMP)[::-1]                              # its own reverse complement
+    seqs = [base, region.translate(COMP)[::-1], pal + base[:40]]
+    g = O.OracleGraph(k, seqs)
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(k, seqs, lib=lib), lib=lib)
+    reads = []
+    for i in range(40):
+        p = int(rng.integers(0, G - L))
+        r = base[p:p + L]
+        reads.append(r.translate(COMP)[::-1] if i % 2 else r)
+    for off in (0, 7, L, 2 * L - 3):                                   # both strands are paths of the graph
+        reads.append(region[off:off + L]); reads.append(region[off:off + L].translate(COMP)[::-1])
+    reads.append(base[290:290 + L])                                    # runs into the doubled region: other strand matches in part
+    reads.append(base[300 + 3 * L - 20:300 + 3 * L - 20 + L])
+    reads.append(pal); reads.append(pal[3:] + base[:3])
+    for n in (k - 1, k, k + 1, 2 * k):
+        reads.append(base[1000:1000 + n]); reads.append(base[1200:1200 + n].translate(COMP)[::-1])
+    r = base[1500:1500 + L]
+    reads.append(r[:30] + "N" + r[31:]); reads.append(r[:L - 1] + ("A" if r[L - 1] != "A" else "C"))
+    reads.append(("T" if r[0] != "T" else "G") + r[1:]); reads.append(r[:k + 3] + ("A" if r[k + 3] != "A" else "C") + r[k + 4:])
+    reads.append(base[G - L:] ); reads.append(base[G - L + 1:] + "A")
+    reads.append("acgt" + base[2000:2000 + L - 4].lower())            # lower case input
+    exp = g.align_tsv(cfg, reads, with_nodes=True)
+    hits0 = whole_read_hits(lib)
+    got, _ = run_lines(idx, cfg, reads)
+    hits = None if hits0 is None else whole_read_hits(lib) - hits0
+    bad = [i for i in range(len(reads)) if exp[i] != got[i]]
+    assert not bad, (seed, bad[:5], reads[bad[0]], exp[bad[0]], got[bad[0]])
+    got2, _ = run_lines(idx, dataclasses.replace(cfg, no_exact_path_shortcut=True), reads)
+    assert got2 == got
+    idx.close()
+    return hits
+
+
+WHOLE_READ_CASES = [
+    # (seed, k, config, whether the whole-read form may answer reads at all)
+    (201, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k), True),
+    (202, 21, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, rel_score_cutoff=0.0), True),
+    (203, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, min_path_score=151), False),   # above 2 * L + 10
+    (204, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, min_path_score=100), True),    # some reads pass
+    (205, 17, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, seed_complexity_filter=True), False),
+    (206, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, min_exact_match=1.0), True),
+    (207, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, min_cell_score=120), True),    # forward min path score
+    (208, 13, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, left_end_bonus=0, right_end_bonus=0,
+                                     min_exact_match=0.0), True),
+    (209, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, forward_and_reverse_complement=False), False),
+    (210, 15, lambda k: cli_defaults(k, min_seed_length=k, max_seed_length=k, max_num_seeds_per_locus=1), True),
 ]
 
 

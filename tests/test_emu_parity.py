@@ -201,3 +201,10 @@ def test_boss_build_large_k(k):
     W, last, F, valid = O.OracleGraph(k, seqs, mask=True).arrays()
     assert (boss.W == W).all() and (boss.last == last).all() and (boss.F == F).all()
     assert (boss.dummy_mask(lib=EMU) == valid).all()
+
+
+@pytest.mark.parametrize("case", P.WHOLE_READ_CASES, ids=[str(c[0]) for c in P.WHOLE_READ_CASES])
+def test_whole_read_shortcut_emu(case):
+    seed, k, cfgf, may = case
+    hits = P.whole_read_case(EMU, seed, k, cfgf(k))
+    assert (hits > 10) if may else (hits == 0), hits

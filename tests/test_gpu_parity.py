@@ -59,6 +59,13 @@ def test_seed_complexity_filter_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", P.WHOLE_READ_CASES, ids=[str(c[0]) for c in P.WHOLE_READ_CASES])
+def test_whole_read_shortcut_gpu(case):
+    seed, k, cfgf, _ = case
+    P.whole_read_case(LIB, seed, k, cfgf(k))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", P.EXACT_SHORTCUT_CASES, ids=[str(c[0]) for c in P.EXACT_SHORTCUT_CASES])
 def test_exact_path_shortcut_gpu(case):
     seed, k, cfgf = case
