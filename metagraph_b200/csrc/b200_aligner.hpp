@@ -57,11 +57,15 @@ class B200Graph {
         const auto &boss = dbg.get_boss();
         const uint64_t n1 = boss.num_edges() + 1;
         std::vector<uint8_t> W(n1, 0), last(n1, 0), valid;
+        // get_W is a wavelet-tree access (a few rank operations): read-only, so all cores share the pass; for a
+        // graph that is on disk anyway the .dbg constructor above decodes the tree level by level instead
+        #pragma omp parallel for schedule(static)
         for (uint64_t i = 1; i < n1; ++i) { W[i] = boss.get_W(i); last[i] = boss.get_last(i); }
         std::vector<uint64_t> F(boss.alph_size);
         for (size_t c = 0; c < F.size(); ++c) F[c] = boss.get_F(c);
         if (dbg.get_mask()) {
             valid.assign(n1, 0);
+            #pragma omp parallel for schedule(static)
             for (uint64_t i = 1; i < n1; ++i) valid[i] = (*dbg.get_mask())[i];
         }
         if (mgb_index_create(W.data(), last.data(), n1, F.data(), valid.empty() ? nullptr : valid.data(),
