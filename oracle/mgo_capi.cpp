@@ -132,6 +132,16 @@ uint64_t mgo_map_to_nodes(void *g, const char *seq, uint64_t len, uint64_t *out)
     return nodes.size();
 }
 
+// First node DBGSuccinct::call_nodes_with_suffix_matching_longest_prefix reports for `str` (0: none), what
+// `metagraph align --map --align-length L` with L < k keeps per position (cli/align.cpp:113-131).
+uint64_t mgo_suffix_match_first(void *g, const char *str, uint64_t len, uint64_t min_match_length) {
+    const DBGSuccinct *dbg = static_cast<DBGSuccinct*>(g);
+    uint64_t first = 0;
+    dbg->call_nodes_with_suffix_matching_longest_prefix(std::string_view(str, len),
+        [&](uint64_t node, uint64_t) { if (!first) first = node; }, min_match_length);
+    return first;
+}
+
 // Outgoing (rc = 0) or RCDBG-outgoing (rc = 1) (node, char) pairs in reference order.
 int mgo_call_outgoing(void *g, uint64_t node, int rc, uint64_t *nodes, char *chars) {
     GraphView v { static_cast<DBGSuccinct*>(g), rc != 0 };

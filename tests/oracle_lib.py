@@ -124,6 +124,13 @@ class OracleGraph:
         n = lib().mgo_map_to_nodes(self.h, seq.encode(), len(seq), out.ctypes.data)
         return out[:n].copy()
 
+    def suffix_match_first(self, s, min_match_length):
+        """first node of call_nodes_with_suffix_matching_longest_prefix (0: none)"""
+        f = lib().mgo_suffix_match_first
+        f.restype = ctypes.c_uint64
+        f.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64]
+        return int(f(self.h, s.encode(), len(s), min_match_length))
+
     def outgoing(self, node, rc=False):
         import numpy as np
         nodes = np.zeros(64, np.uint64)

@@ -230,6 +230,21 @@ def test_map_count_kmers_golden():
     assert [_map_counts(g.map_to_nodes(r)) for r in reads] == MAP_COUNTS
 
 
+MAP_COUNTS_SUBK = ["3/141/3", "141/141/141", "141/141/141", "1/141/1", "141/141/141", "4/141/4", "3/141/3"]
+
+
+def test_map_count_kmers_subk_golden():
+    """`metagraph align --map --count-kmers --align-length 10` on the k = 11 MT graph (integration_tests/test_align.py:
+    90-122, cli/align.cpp:113-131): per 10-mer the first node of call_nodes_with_suffix_matching_longest_prefix —
+    pins BOSS::index_range + the enumeration of the nodes that end with the match (SURVEY 8a rows a6, a14)."""
+    _, seqs = read_fasta(os.path.join(GOLD, "genome.MT.fa"))
+    _, reads = read_fastq(os.path.join(GOLD, "genome_MT1.fq"))
+    for mask in (False, True):           # the CLI drops the mask before mapping (cli/align.cpp:336-339); same counts
+        g = O.OracleGraph(11, seqs, mask=mask)
+        got = [_map_counts([g.suffix_match_first(r[i:i + 10], 10) for i in range(len(r) - 9)]) for r in reads]
+        assert got == MAP_COUNTS_SUBK
+
+
 def test_c1_transcripts_1000_oracle():
     """BASELINE configs[0] fixture (tests/data/transcripts_1000.fa: 1000 records, 1 490 627 bp, 59 .. 11 666 bp): k = 12
     graph of the transcripts, CLI defaults. The reference stores no expected output for it; SURVEY 8c states what the
