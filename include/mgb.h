@@ -13,6 +13,7 @@
  *   mgb_map_to_nodes      <- map_to_nodes_sequentially() (graph/representation/base/
  *                            sequence_graph.cpp:541-551 -> dbg_succinct.cpp:285-305 ->
  *                            boss.cpp:996-1045 BOSS::map_to_edges)
+ *   mgb_config_check      <- DBGAligner::DBGAligner (graph/alignment/dbg_aligner.cpp:26-60)
  *   mgb_align_batch       <- IDBGAligner::align_batch (graph/alignment/dbg_aligner.hpp:32-33,
  *                            dbg_aligner.cpp:251-355) with Seeder = SuffixSeeder<UniMEMSeeder>,
  *                            Extender = DefaultColumnExtender
@@ -165,6 +166,12 @@ uint32_t mgb_index_k(const mgb_index_t *index);
  * dependency is restated here) — set it to 1 for flag-free `metagraph align` behaviour. */
 void mgb_config_init(mgb_config_t *config);
 void mgb_config_init_cli(mgb_config_t *config, uint32_t k, int alphabet);
+
+/* What the DBGAligner constructor checks (dbg_aligner.cpp:37-60: seed-length normalisation, check_config_scores ->
+ * std::runtime_error("Error: sum of min_cell_score and lowest penalty too low.")) plus what this build does not serve:
+ * MGB_OK, MGB_ERR_BAD_CONFIG or MGB_ERR_UNSUPPORTED with the text in mgb_last_error(). mgb_align_batch makes the same
+ * check; this entry point lets a binding fail at construction time, as the reference does. No device work. */
+int mgb_config_check(const mgb_index_t *index, const mgb_config_t *config);
 
 /* Exact seeding only: node ids of all k-mers of each sequence (0 = not in graph), forward
  * strand. seqs: concatenated characters, offsets[n_seqs + 1]. out_nodes must hold

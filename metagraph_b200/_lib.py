@@ -74,6 +74,8 @@ def load_library(path=None):
     L.mgb_index_k.argtypes = [vp]
     L.mgb_config_init.argtypes = [ctypes.POINTER(mgb_config_t)]
     L.mgb_config_init_cli.argtypes = [ctypes.POINTER(mgb_config_t), u32, i]
+    L.mgb_config_check.restype = i
+    L.mgb_config_check.argtypes = [vp, ctypes.POINTER(mgb_config_t)]
     L.mgb_map_to_nodes.restype = i
     L.mgb_map_to_nodes.argtypes = [vp, vp, vp, u32, vp]
     L.mgb_align_batch.restype = i
@@ -124,5 +126,5 @@ REQUIRED_SYMBOLS = [
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
     "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_results_export_bytes",
     "mgb_results_export", "mgb_results_import", "mgb_boss_build", "mgb_boss_free",
-    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_boss_last_error", "mgb_index_set_mode",
+    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_boss_last_error", "mgb_config_check", "mgb_index_set_mode",
 ]

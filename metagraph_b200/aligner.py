@@ -386,6 +386,9 @@ class B200Aligner:
         self.config = config or DBGAlignerConfig()
         self._L = graph._L
         self.last_stats = None
+        # the DBGAligner constructor throws for a configuration it cannot run (dbg_aligner.cpp:55-56)
+        c = self.config.to_c() if not isinstance(self.config, mgb_config_t) else self.config
+        _lib.check(self._L, self._L.mgb_config_check(self.graph.handle, ctypes.byref(c)))
 
     def get_graph(self):
         return self.graph

@@ -1105,6 +1105,14 @@ void mgb_set_host_threads(int n) {
 #endif
 }
 
+int mgb_config_check(const mgb_index_t *index, const mgb_config_t *config) {
+    if (!index || !config) return fail(MGB_ERR_INVALID_ARGUMENT, "null argument");
+    DevConfig dcfg;
+    std::string err;
+    const int rc = lower_config(*config, index->view.k, index->alphabet, &dcfg, &err);
+    return rc ? fail(rc, err) : MGB_OK;
+}
+
 int mgb_align_batch(const mgb_index_t *index, const mgb_config_t *config, const char *seqs,
                     const uint64_t *offsets, uint32_t n_reads, mgb_results_t **out) {
     if (!index || !config || !offsets || !out || (!seqs && n_reads && offsets[n_reads]))

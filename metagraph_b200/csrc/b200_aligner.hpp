@@ -128,13 +128,13 @@ class B200Aligner
     typedef mtg::graph::align::AlignmentResults Results;
     B200Aligner(const mtg::graph::DeBruijnGraph &graph, const B200Graph &index,
                 const mtg::graph::align::DBGAlignerConfig &config)
-          : graph_(graph), index_(index), config_(config) { lower(config); }
+          : graph_(graph), index_(index), config_(config) { lower(config); check(); }
     const mtg::graph::DeBruijnGraph& get_graph() const override { return graph_; }
     const mtg::graph::align::DBGAlignerConfig& get_config() const override { return config_; }
     bool has_coordinates() const override { return false; }
 #else
     typedef AlignmentResults Results;
-    B200Aligner(const B200Graph &index, const mgb_config_t &config) : index_(index), c_(config) {}
+    B200Aligner(const B200Graph &index, const mgb_config_t &config) : index_(index), c_(config) { check(); }
     const mgb_config_t& get_config() const { return c_; }
     bool has_coordinates() const { return false; }
 #endif
@@ -209,6 +209,10 @@ class B200Aligner
     }
 
   private:
+    // the DBGAligner constructor throws for a configuration it cannot run (dbg_aligner.cpp:55-56): so does this one
+    void check() const {
+        if (mgb_config_check(index_.handle(), &c_) != MGB_OK) throw std::runtime_error(mgb_last_error());
+    }
 #ifdef MGB_WITH_METAGRAPH
     void lower(const mtg::graph::align::DBGAlignerConfig &c) {
         std::memset(&c_, 0, sizeof(c_));

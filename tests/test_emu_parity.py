@@ -208,3 +208,22 @@ def test_whole_read_shortcut_emu(case):
     seed, k, cfgf, may = case
     hits = P.whole_read_case(EMU, seed, k, cfgf(k))
     assert (hits > 10) if may else (hits == 0), hits
+
+
+def test_bad_min_cell_score_emu():
+    """tests/graph/test_aligner.cpp:85-92 (bad_min_cell_score): the aligner's constructor throws for a configuration
+    whose min_cell_score + lowest penalty underflows — here at construction too (mgb_config_check), with the
+    reference's message, and the restatement agrees."""
+    import oracle_lib as O
+    from metagraph_b200 import _lib
+    from metagraph_b200.aligner import B200Aligner, BOSSTable, DBGSuccinctIndex
+    from metagraph_b200.config import INT32_MIN, dna_scoring_matrix, struct_defaults
+    cfg = struct_defaults(score_matrix=dna_scoring_matrix(2, -1, -2), min_cell_score=INT32_MIN, min_path_score=INT32_MIN)
+    idx = DBGSuccinctIndex(BOSSTable.from_sequences(3, [], lib=EMU), lib=EMU)      # build_graph_batch(3, {})
+    with pytest.raises(_lib.MgbError, match="sum of min_cell_score and lowest penalty too low") as e:
+        B200Aligner(idx, cfg)
+    assert e.value.code == -3                                                       # MGB_ERR_BAD_CONFIG
+    with pytest.raises(RuntimeError, match="sum of min_cell_score and lowest penalty too low"):
+        O.OracleGraph(3, []).align_tsv(cfg, ["ACGT"])
+    B200Aligner(idx, struct_defaults(score_matrix=dna_scoring_matrix(2, -1, -2)))   # the same graph with a sane config
+    idx.close()
