@@ -246,7 +246,7 @@ struct mgb_index {
 #endif
     int alphabet = MGB_ALPHABET_DNA;
     AlphabetTables at;
-    // working memory recycled between calls (at most 3 sets are kept)
+    // working memory recycled between calls (at most 4 sets are kept)
     mutable std::mutex ws_mu;
     mutable std::vector<Workspace*> ws_free;
     Workspace* ws_acquire() const {
@@ -256,7 +256,7 @@ struct mgb_index {
     }
     void ws_release(Workspace *w) const {
         std::lock_guard<std::mutex> lk(ws_mu);
-        if (ws_free.size() < 3) ws_free.push_back(w); else delete w;
+        if (ws_free.size() < 4) ws_free.push_back(w); else delete w;
     }
 #if defined(MGB_HOST_EMU)
     HostIndex host;

@@ -43,9 +43,8 @@ def run(tag, pieces=None, lanes=None, threads=None, reps=4):
         tag, np.mean([x[0] for x in t]), np.mean([x[1] for x in t]), np.mean([x[2] for x in t]),
         np.mean([sum(x[:3]) for x in t])), flush=True)
 al.set_pipeline_pieces(0)
+L.mgb_set_host_threads(32)
 run("default (8 pieces, 2 lanes)")
-os.environ["MGB_DEBUG"] = "1"; sys.stderr.write("== split of one default call\n"); step(); os.environ.pop("MGB_DEBUG")
-for pieces, lanes in ((4, 2), (8, 3), (8, 4), (12, 3), (16, 4), (16, 2), (2, 2), (1, 1)):
-    run("%d pieces, %d lanes" % (pieces, lanes), pieces, lanes)
-run("8 pieces, 3 lanes, 32 host threads", 8, 3, 32)
-run("8 pieces, 3 lanes, 8 host threads", 8, 3, 8)
+for pieces, lanes in ((8, 3), (8, 4), (6, 3), (12, 3), (12, 4), (16, 4), (4, 2), (4, 4), (6, 2), (8, 2)):
+    run("%d pieces, %d lanes" % (pieces, lanes), pieces, lanes, reps=6)
+os.environ["MGB_DEBUG"] = "1"; sys.stderr.write("== split of one default call (8 pieces, 2 lanes)\n"); run("split", 8, 2, reps=1); os.environ.pop("MGB_DEBUG")
