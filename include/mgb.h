@@ -240,6 +240,15 @@ int mgb_boss_mask_dummy(const mgb_boss_t *boss, uint8_t *valid);
  * range index and the optional .edgemask file are not read. Free with mgb_boss_free(). On failure returns
  * MGB_ERR_INVALID_ARGUMENT and mgb_dbg_last_error() describes why. */
 int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode, int *state);
+/* The file's own index of suffix ranges (BOSS::serialize_suffix_ranges / load_suffix_ranges, boss.cpp:396-426; what
+ * BOSS::get_initial_range consults, boss.hpp:638-664), decoded: *suffix_len = indexed suffix length s (0: the file has
+ * none), ranges[2 i], ranges[2 i + 1] = first edge and one past the last edge of the nodes whose last s characters
+ * are the i-th s-mer (index = sum over positions p of (code_p - 1) (sigma - 1)^p; an empty range has both equal).
+ * mgb_index_create builds its own, deeper table on the device and does not need this one: the entry point exists for
+ * callers that keep using the file's table and for checking one against the other. Free with
+ * mgb_dbg_free_suffix_ranges(). */
+int mgb_dbg_load_suffix_ranges(const char *path, uint32_t *suffix_len, uint64_t **ranges, uint64_t *n_ranges);
+void mgb_dbg_free_suffix_ranges(uint64_t *ranges);
 const char* mgb_dbg_last_error(void);
 
 #ifdef __cplusplus

@@ -126,5 +126,5 @@ REQUIRED_SYMBOLS = [
     "mgb_align_batch", "mgb_results_num_reads", "mgb_results_read_range", "mgb_results_num_alignments",
     "mgb_results_alignments", "mgb_results_stats", "mgb_results_free", "mgb_results_export_bytes",
     "mgb_results_export", "mgb_results_import", "mgb_boss_build", "mgb_boss_free",
-    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_boss_last_error", "mgb_config_check", "mgb_index_set_mode",
+    "mgb_boss_mask_dummy", "mgb_set_pipeline_pieces", "mgb_set_host_threads", "mgb_dbg_load", "mgb_dbg_last_error", "mgb_boss_last_error", "mgb_config_check", "mgb_dbg_load_suffix_ranges", "mgb_dbg_free_suffix_ranges", "mgb_index_set_mode",
 ]

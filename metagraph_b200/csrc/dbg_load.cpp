@@ -235,6 +235,46 @@ std::vector<uint8_t> read_wt_huff(Reader &r, bool rrr) {
     return out;
 }
 
+// BOSS::serialize (boss.cpp:262-277) followed by the graph mode (dbg_succinct.cpp:780-803); leaves the reader at
+// the optional suffix-range index
+struct ParsedBoss { uint64_t nf = 0, k_node = 0, state = 0, mode = 0; std::vector<uint64_t> F; std::vector<uint8_t> W; Bits last; };
+void parse_boss(Reader &r, ParsedBoss &b) {
+    uint64_t &nf = b.nf, &k_node = b.k_node, &state = b.state, &mode = b.mode;
+    std::vector<uint64_t> &F = b.F; std::vector<uint8_t> &W = b.W; Bits &last = b.last;
+    nf = r.be();
+    if (nf != 5 && nf != 27) throw std::runtime_error("unsupported alphabet size " + std::to_string(nf));
+    F.assign(nf, 0);
+    for (auto &f : F) f = r.be();
+    k_node = r.be();
+    // node length k_node = k - 1; the device keys hold k <= 85 DNA / k <= 51 protein characters (mgb.h)
+    if (k_node < 1 || k_node + 1 > (nf == 27 ? 51u : 85u))
+        throw std::runtime_error("k = " + std::to_string(k_node + 1) + " is outside the supported range");
+    state = r.be();
+    if (state != 1 && state != 3)
+        throw std::runtime_error("BOSS state " + std::to_string(state) + " (DYN / FAST) is not supported; "
+                                 "convert the graph with `metagraph transform --state small|stat`");
+    W = read_wt_huff(r, state == 1);
+    const uint64_t logsigma = r.be();
+    (void)logsigma;
+    if (state == 1) {
+        const uint64_t code = r.be();               // bit_vector_adaptive::VectorCode
+        if (code == 0) last = read_rrr(r);
+        else if (code == 1) last = read_sd(r);
+        else throw std::runtime_error("unsupported `last` representation " + std::to_string(code));
+    } else {
+        last = read_bits(r);
+        r.be();                                      // number of set bits
+        skip_ints64(r);                              // rank_support_v5
+        skip_select_mcl(r);                          // select_support_mcl<1>; select_support_scan<0> stores nothing
+    }
+    mode = r.be();
+}
+void read_file(const char *path, Reader &r) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in.good()) throw std::runtime_error(std::string("cannot open ") + path);
+    r.b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+}
+
 } // namespace
 
 extern "C" {
@@ -244,42 +284,14 @@ const char* mgb_dbg_last_error(void) { return g_load_err.c_str(); }
 int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode_out, int *state_out) {
     if (!path || !out) return MGB_ERR_INVALID_ARGUMENT;
     std::memset(out, 0, sizeof(*out));
+    ParsedBoss pb;
     try {
         Reader r;
-        {
-            std::ifstream in(path, std::ios::binary);
-            if (!in.good()) throw std::runtime_error(std::string("cannot open ") + path);
-            r.b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
-        }
-        const uint64_t nf = r.be();
-        if (nf != 5 && nf != 27) throw std::runtime_error("unsupported alphabet size " + std::to_string(nf));
-        std::vector<uint64_t> F(nf);
-        for (auto &f : F) f = r.be();
-        const uint64_t k_node = r.be();
-        // node length k_node = k - 1; the device keys hold k <= 85 DNA / k <= 51 protein characters (mgb.h)
-        if (k_node < 1 || k_node + 1 > (nf == 27 ? 51u : 85u))
-            throw std::runtime_error("k = " + std::to_string(k_node + 1) + " is outside the supported range");
-        const uint64_t state = r.be();
+        read_file(path, r);
+        parse_boss(r, pb);
+        const uint64_t nf = pb.nf, k_node = pb.k_node, state = pb.state, mode = pb.mode;
+        const std::vector<uint64_t> &F = pb.F; const std::vector<uint8_t> &W = pb.W; const Bits &last = pb.last;
         if (state_out) *state_out = (int)state;
-        if (state != 1 && state != 3)
-            throw std::runtime_error("BOSS state " + std::to_string(state) + " (DYN / FAST) is not supported; "
-                                     "convert the graph with `metagraph transform --state small|stat`");
-        std::vector<uint8_t> W = read_wt_huff(r, state == 1);
-        const uint64_t logsigma = r.be();
-        (void)logsigma;
-        Bits last;
-        if (state == 1) {
-            const uint64_t code = r.be();               // bit_vector_adaptive::VectorCode
-            if (code == 0) last = read_rrr(r);
-            else if (code == 1) last = read_sd(r);
-            else throw std::runtime_error("unsupported `last` representation " + std::to_string(code));
-        } else {
-            last = read_bits(r);
-            r.be();                                      // number of set bits
-            skip_ints64(r);                              // rank_support_v5
-            skip_select_mcl(r);                          // select_support_mcl<1>; select_support_scan<0> stores nothing
-        }
-        const uint64_t mode = r.be();
         if (mode_out) *mode_out = (int)mode;
         // consistency: sizes, W range, F against the decoded arrays (boss_chunk.cpp:105-123)
         const uint64_t n1 = W.size();
@@ -316,8 +328,57 @@ int mgb_dbg_load(const char *path, mgb_boss_t *out, int *mode_out, int *state_ou
         return MGB_OK;
     } catch (const std::exception &e) {
         g_load_err = e.what();
+        if (state_out) *state_out = (int)pb.state;       // a refused DYN / FAST file still says what it is
         return MGB_ERR_INVALID_ARGUMENT;
     }
 }
+
+int mgb_dbg_load_suffix_ranges(const char *path, uint32_t *suffix_len, uint64_t **ranges, uint64_t *n_ranges) {
+    if (!path || !suffix_len || !ranges || !n_ranges) return MGB_ERR_INVALID_ARGUMENT;
+    *suffix_len = 0; *ranges = nullptr; *n_ranges = 0;
+    try {
+        Reader r;
+        read_file(path, r);
+        ParsedBoss pb;
+        parse_boss(r, pb);
+        if (r.p == r.b.size()) return MGB_OK;            // written without the index (boss.cpp:402-426 tolerates that)
+        // BOSS::serialize_suffix_ranges (boss.cpp:396-400): the length, then an sd_vector whose i-th set bit sits at
+        // range value i + i (build_suffix_ranges_sd, boss.cpp:99-118; get_suffix_range(i) = select1(i + 1) - i)
+        const uint64_t len = r.be();
+        if (len == 0) {
+            // `metagraph build` without an index still writes the (empty) vector: both example graphs end like this,
+            // which pins the field order of the container (size, low width, low parts, high parts, two select supports)
+            const Bits none = read_sd(r);
+            if (none.size != 0 || r.p != r.b.size()) throw std::runtime_error("trailing bytes after an empty suffix-range index");
+            return MGB_OK;
+        }
+        if (len > pb.k_node) throw std::runtime_error("bad index of suffix ranges");
+        uint64_t expect = 2;
+        for (uint64_t i = 0; i < len; ++i) {
+            if (expect > (1ull << 40) / (pb.nf - 1)) throw std::runtime_error("bad index of suffix ranges");
+            expect *= pb.nf - 1;
+        }
+        const Bits sd = read_sd(r);
+        if (r.p != r.b.size()) throw std::runtime_error("trailing bytes after the suffix-range index");
+        if (sd.size != pb.W.size() + expect) throw std::runtime_error("suffix-range index does not fit the graph");
+        uint64_t *out = (uint64_t*)std::malloc(expect * sizeof(uint64_t));
+        if (!out) { g_load_err = "out of host memory"; return MGB_ERR_NO_MEMORY; }
+        uint64_t i = 0;
+        for (uint64_t w = 0; w < sd.w.size() && i <= expect; ++w)
+            for (uint64_t bits = sd.w[w]; bits; bits &= bits - 1) {
+                const uint64_t pos = w * 64 + (uint64_t)__builtin_ctzll(bits);
+                if (i < expect) out[i] = pos - i;
+                ++i;
+            }
+        if (i != expect) { std::free(out); throw std::runtime_error("suffix-range index: wrong number of entries"); }
+        *suffix_len = (uint32_t)len; *ranges = out; *n_ranges = expect;
+        return MGB_OK;
+    } catch (const std::exception &e) {
+        g_load_err = e.what();
+        return MGB_ERR_INVALID_ARGUMENT;
+    }
+}
+
+void mgb_dbg_free_suffix_ranges(uint64_t *ranges) { std::free(ranges); }
 
 } // extern "C"

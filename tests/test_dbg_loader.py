@@ -126,3 +126,138 @@ def test_boss_build_reports_why():
         BOSSTable.from_sequences(90, ["ACGT" * 50], lib=EMU)
     with pytest.raises(_lib.MgbError, match="at least 2"):
         BOSSTable.from_sequences(1, ["ACGT" * 50], lib=EMU)
+
+
+# ---- the file's own suffix-range index (BOSS::serialize_suffix_ranges) ------------------------------------------
+# The two example graphs were written without it, so there is no reference-made fixture: PARITY UNPINNED. What is
+# checked: an sd_vector written here from the library's published layout (sdsl sd_vector<>: size, low-part width,
+# low parts, unary-coded high parts, two select supports) with the values build_suffix_ranges_sd produces for the
+# oracle's table decodes back to that table.
+def _le64(x):
+    return int(x).to_bytes(8, "little")
+
+
+def _int_vector(values, width):
+    nbits = len(values) * width
+    words = np.zeros((nbits + 63) // 64 + 1, dtype=np.uint64)
+    for i, v in enumerate(values):
+        pos = i * width
+        words[pos >> 6] |= np.uint64((int(v) << (pos & 63)) & 0xFFFFFFFFFFFFFFFF)
+        if (pos & 63) + width > 64:
+            words[(pos >> 6) + 1] |= np.uint64(int(v) >> (64 - (pos & 63)))
+    return _le64(nbits) + bytes([width]) + words[:(nbits + 63) // 64].tobytes()
+
+
+def _bit_vector(positions, nbits):
+    words = np.zeros((nbits + 63) // 64, dtype=np.uint64)
+    for p in positions:
+        words[p >> 6] |= np.uint64(1 << (p & 63))
+    return _le64(nbits) + words.tobytes()
+
+
+def _sd_vector(ones, size):
+    m, n = len(ones), size
+    logm, logn = m.bit_length(), n.bit_length()         # bits::hi(x) + 1
+    if logm == logn:
+        logm -= 1
+    wl = logn - logm
+    low = [v & ((1 << wl) - 1) for v in ones]
+    high = [(v >> wl) + i for i, v in enumerate(ones)]
+    out = _le64(size) + bytes([wl]) + _int_vector(low, wl) + _bit_vector(high, m + (1 << logm))
+    return out + _le64(0) + _le64(0)                     # select supports written with no arguments
+
+
+def _suffix_table(g_arrays, k, s, sigma=5):
+    """ranges of every s-mer suffix by brute force over the node labels of the BOSS table"""
+    W, last, F = g_arrays
+    n1 = len(W)
+    lastc = np.zeros(n1, dtype=np.int64)
+    for c in range(sigma):
+        lo = int(F[c]) + 1
+        hi = int(F[c + 1]) if c + 1 < sigma else n1 - 1
+        lastc[lo:hi + 1] = c
+    # bwd: the edge that leads to the node of edge i = select of the (rank of node among those ending in c)-th c edge
+    order = {c: [i for i in range(1, n1) if W[i] == c] for c in range(1, sigma)}
+    node_rank = np.zeros(n1, dtype=np.int64)             # rank of the node of edge i among nodes with its last char
+    cnt = {c: 0 for c in range(sigma)}
+    prev_end = 0
+    for i in range(1, n1):
+        node_rank[i] = cnt[int(lastc[i])]
+        if last[i]:
+            cnt[int(lastc[i])] += 1
+    def bwd(i):
+        c = int(lastc[i])
+        return order[c][int(node_rank[i])] if c else 0
+    labels = []
+    for i in range(n1):
+        x, lab = i, []
+        for _ in range(s):
+            if x == 0:
+                lab.append(0); continue
+            lab.append(int(lastc[x])); x = bwd(x)
+        labels.append(lab)                               # last character first
+    table = {}
+    for i in range(1, n1):
+        lab = labels[i]
+        if 0 in lab:
+            continue
+        idx = 0
+        for c in lab:                                    # boss.cpp:3190-3212: the character prepended last is the most significant
+            idx = idx * (sigma - 1) + (c - 1)
+        a = table.setdefault(idx, [i, i + 1])
+        a[1] = i + 1
+    return table
+
+
+def test_suffix_range_index_roundtrip(tmp_path):
+    import ctypes
+    L = _lib.load_library(EMU)
+    src = open(os.path.join(EX, "test_DNA_graph.dbg"), "rb").read()
+    t = BOSSTable.from_dbg(os.path.join(EX, "test_DNA_graph.dbg"), lib=EMU)
+    sl, rp, n = ctypes.c_uint32(), ctypes.POINTER(ctypes.c_uint64)(), ctypes.c_uint64()
+    f = L.mgb_dbg_load_suffix_ranges
+    f.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.POINTER(ctypes.c_uint64)),
+                  ctypes.POINTER(ctypes.c_uint64)]
+    for name in ("test_DNA_graph.dbg", "test_Protein_graph.dbg"):     # "no index" = length 0 + an empty sd_vector, read to EOF
+        assert f(os.path.join(EX, name).encode(), sl, rp, n) == 0 and sl.value == 0 and n.value == 0
+    s = 4
+    table = _suffix_table((t.W, t.last, t.F), t.k, s)
+    n_ranges = 2 * 4 ** s
+    flat = [1] * n_ranges
+    for idx, (a, b) in table.items():
+        flat[2 * idx], flat[2 * idx + 1] = a, b
+    aligned = list(flat)                                  # build_suffix_ranges_sd, boss.cpp:99-118
+    aligned[0] = max(aligned[0], 1)
+    for i in range(1, n_ranges):
+        aligned[i] = max(aligned[i], aligned[i - 1] - (i - 1)) + i
+    p = tmp_path / "with_index.dbg"
+    # the example graph ends with the 50 bytes of "no index": length 0 and an empty sd_vector (decoded to EOF above)
+    assert src[-50:-42] == bytes(8) and src[-25] == 64
+    src = src[:-50]
+    p.write_bytes(src + int(s).to_bytes(8, "big") + _sd_vector(aligned, len(t.W) + n_ranges))
+    assert f(str(p).encode(), sl, rp, n) == 0, L.mgb_dbg_last_error()
+    assert sl.value == s and n.value == n_ranges
+    got = np.ctypeslib.as_array(rp, (n_ranges,)).copy()
+    L.mgb_dbg_free_suffix_ranges(rp)
+    for i in range(0, n_ranges, 2):
+        if flat[i] < flat[i + 1]:
+            assert (int(got[i]), int(got[i + 1])) == (flat[i], flat[i + 1])
+        else:
+            assert got[i] >= got[i + 1] or got[i] == got[i + 1]          # empty stays empty
+    assert sum(1 for i in range(0, n_ranges, 2) if got[i] < got[i + 1]) == len(table) > 10
+    # the table agrees with the oracle's view of the same graph: an s-mer has a range iff the graph has a node ending in it
+    g = O.OracleGraph(t.k, arrays=(t.W, t.last, t.F))
+    seqs = fasta(os.path.join(EX, "test_DNA_sequences.fa"))
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for sq in seqs:
+        for j in range(len(sq) - s + 1):
+            sm = sq[j:j + s]
+            idx = 0
+            for ch in reversed(sm):
+                idx = idx * 4 + code[ch]
+            if j + s >= t.k:                              # the s-mer ends a real k-mer of the graph
+                assert got[2 * idx] < got[2 * idx + 1], sm
+    del g
+    # damage: a length that disagrees with the graph is refused
+    p.write_bytes(src + int(s + 1).to_bytes(8, "big") + _sd_vector(aligned, len(t.W) + n_ranges))
+    assert f(str(p).encode(), sl, rp, n) != 0
